@@ -1,0 +1,262 @@
+// Shared device helpers for the seghiero_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SH_OK 0
+#define SH_ERR_BAD_ARG (-1)
+#define SH_ERR_UNSUPPORTED (-2)
+
+#define SH_DT_F32 0
+#define SH_DT_BF16 1
+#define SH_DT_F16 2
+
+#define SH_IGNORE 255
+#define SH_NUM_SMS 148
+
+#define SH_CHECK_LAUNCH()                          \
+  do {                                             \
+    cudaError_t e__ = cudaGetLastError();          \
+    if (e__ != cudaSuccess) return (int)e__;       \
+  } while (0)
+
+namespace sh {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// natural log through the MUFU lg2 (abs error ~1e-7 for arguments in [1e-8, 2])
+__device__ __forceinline__ float fast_log(float x) { return lg2(x) * kLn2; }
+
+// e^x and sigmoid(x) from ONE ex2 and ONE rcp.  x is clamped so that e^x stays
+// finite; for x > 17 sigmoid rounds to 1.0f in fp32 anyway, for x < -87 to 0.
+struct SigExp {
+  float v;  // e^x
+  float s;  // sigmoid(x)
+};
+__device__ __forceinline__ SigExp sig_exp(float x) {
+  float xc = fminf(fmaxf(x, -87.0f), 80.0f);
+  SigExp r;
+  r.v = ex2(xc * kLog2e);
+  r.s = r.v * rcp(1.0f + r.v);
+  if (x != x) r.s = x;  // NaN propagates like torch.sigmoid
+  return r;
+}
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <>
+__device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+// N consecutive elements -> fp32.  Vector path needs (ptr) aligned to N*sizeof(T).
+template <typename T, int N>
+struct VecIO;
+
+template <>
+struct VecIO<float, 4> {
+  static __device__ __forceinline__ void load(const float* p, float (&o)[4]) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&o)[4]) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(o[0], o[1], o[2], o[3]));
+  }
+};
+template <>
+struct VecIO<float, 2> {
+  static __device__ __forceinline__ void load(const float* p, float (&o)[2]) {
+    float2 v = __ldg(reinterpret_cast<const float2*>(p));
+    o[0] = v.x; o[1] = v.y;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&o)[2]) {
+    __stcs(reinterpret_cast<float2*>(p), make_float2(o[0], o[1]));
+  }
+};
+template <>
+struct VecIO<__nv_bfloat16, 4> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&o)[4]) {
+    uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    o[0] = __uint_as_float(v.x << 16); o[1] = __uint_as_float(v.x & 0xffff0000u);
+    o[2] = __uint_as_float(v.y << 16); o[3] = __uint_as_float(v.y & 0xffff0000u);
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&o)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(o[2], o[3]);
+    uint2 v;
+    v.x = *reinterpret_cast<uint32_t*>(&a);
+    v.y = *reinterpret_cast<uint32_t*>(&b);
+    __stcs(reinterpret_cast<uint2*>(p), v);
+  }
+};
+template <>
+struct VecIO<__nv_bfloat16, 2> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&o)[2]) {
+    uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(p));
+    o[0] = __uint_as_float(v << 16); o[1] = __uint_as_float(v & 0xffff0000u);
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&o)[2]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]);
+    __stcs(reinterpret_cast<uint32_t*>(p), *reinterpret_cast<uint32_t*>(&a));
+  }
+};
+template <>
+struct VecIO<__half, 4> {
+  static __device__ __forceinline__ void load(const __half* p, float (&o)[4]) {
+    uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    __half2 a = *reinterpret_cast<__half2*>(&v.x), b = *reinterpret_cast<__half2*>(&v.y);
+    float2 fa = __half22float2(a), fb = __half22float2(b);
+    o[0] = fa.x; o[1] = fa.y; o[2] = fb.x; o[3] = fb.y;
+  }
+  static __device__ __forceinline__ void store(__half* p, const float (&o)[4]) {
+    __half2 a = __floats2half2_rn(o[0], o[1]), b = __floats2half2_rn(o[2], o[3]);
+    uint2 v;
+    v.x = *reinterpret_cast<uint32_t*>(&a);
+    v.y = *reinterpret_cast<uint32_t*>(&b);
+    __stcs(reinterpret_cast<uint2*>(p), v);
+  }
+};
+template <>
+struct VecIO<__half, 2> {
+  static __device__ __forceinline__ void load(const __half* p, float (&o)[2]) {
+    uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(p));
+    float2 f = __half22float2(*reinterpret_cast<__half2*>(&v));
+    o[0] = f.x; o[1] = f.y;
+  }
+  static __device__ __forceinline__ void store(__half* p, const float (&o)[2]) {
+    __half2 a = __floats2half2_rn(o[0], o[1]);
+    __stcs(reinterpret_cast<uint32_t*>(p), *reinterpret_cast<uint32_t*>(&a));
+  }
+};
+
+
+template <>
+struct VecIO<__nv_bfloat16, 8> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&o)[8]) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      o[2 * k] = __uint_as_float(w[k] << 16);
+      o[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&o)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(o[2 * k], o[2 * k + 1]);
+      w[k] = *reinterpret_cast<uint32_t*>(&a);
+    }
+    __stcs(reinterpret_cast<uint4*>(p), make_uint4(w[0], w[1], w[2], w[3]));
+  }
+};
+template <>
+struct VecIO<__half, 8> {
+  static __device__ __forceinline__ void load(const __half* p, float (&o)[8]) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 f = __half22float2(*reinterpret_cast<__half2*>(&w[k]));
+      o[2 * k] = f.x;
+      o[2 * k + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void store(__half* p, const float (&o)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      __half2 a = __floats2half2_rn(o[2 * k], o[2 * k + 1]);
+      w[k] = *reinterpret_cast<uint32_t*>(&a);
+    }
+    __stcs(reinterpret_cast<uint4*>(p), make_uint4(w[0], w[1], w[2], w[3]));
+  }
+};
+
+// Guarded N-element load/store: vector when `vec_ok` and fully in range, scalar otherwise.
+template <typename T, int N>
+__device__ __forceinline__ void load_n(const T* base, long idx, long limit, bool vec_ok, float (&o)[N]) {
+  if (vec_ok && idx + N <= limit) {
+    VecIO<T, N>::load(base + idx, o);
+  } else {
+#pragma unroll
+    for (int k = 0; k < N; ++k) o[k] = (idx + k < limit) ? to_f32<T>(base[idx + k]) : 0.0f;
+  }
+}
+template <typename T, int N>
+__device__ __forceinline__ void store_n(T* base, long idx, long limit, bool vec_ok, const float (&o)[N]) {
+  if (vec_ok && idx + N <= limit) {
+    VecIO<T, N>::store(base + idx, o);
+  } else {
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      if (idx + k < limit) base[idx + k] = from_f32<T>(o[k]);
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ long long warp_sum(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of K floats per thread; result valid in thread 0..K-1 of warp 0
+// (element k in thread k).  `scratch` needs K * (blockDim.x/32) floats.
+template <int K>
+__device__ __forceinline__ float block_sum_k(float (&v)[K], float* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    float r = warp_sum(v[k]);
+    if (lane == 0) scratch[k * nwarp + warp] = r;
+  }
+  __syncthreads();
+  float out = 0.0f;
+  if (threadIdx.x < K) {
+    for (int w = 0; w < nwarp; ++w) out += scratch[threadIdx.x * nwarp + w];
+  }
+  __syncthreads();
+  return out;
+}
+
+}  // namespace sh

@@ -1,0 +1,192 @@
+// Target builders (integer gathers) and the hierarchical argmax decode.
+// HBM-bound streaming kernels; all results are bit-exact integers.
+#include "common.cuh"
+
+namespace sh {
+
+// ---------------------------------------------------------------------------
+// Target builders.  Reference: models/loss/hiera_triplet_loss.py:11-38 (range
+// test, later bucket wins -> precomputed LUT), models/loss/rmi_hiera_triplet_loss.py
+// :21-63 (gather with literal-255 passthrough), dataset/dataloader.py:166-177
+// (plain gather).  torch advanced indexing wraps negative indices, so do we.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_targets_two_level(const long long* __restrict__ label,
+                                                           long long* __restrict__ coarse, long n,
+                                                           const int* __restrict__ lut, int lut_size) {
+  long i = (blockIdx.x * (long)blockDim.x + threadIdx.x) * 2;
+  const long stride = (long)gridDim.x * blockDim.x * 2;
+  for (; i < n; i += stride) {
+    if (i + 1 < n) {
+      longlong2 t = *reinterpret_cast<const longlong2*>(label + i);
+      longlong2 o;
+      o.x = (t.x >= 0 && t.x < lut_size) ? lut[t.x] : SH_IGNORE;
+      o.y = (t.y >= 0 && t.y < lut_size) ? lut[t.y] : SH_IGNORE;
+      *reinterpret_cast<longlong2*>(coarse + i) = o;
+    } else {
+      long long t = label[i];
+      coarse[i] = (t >= 0 && t < lut_size) ? lut[t] : SH_IGNORE;
+    }
+  }
+}
+
+// mode 0: three-level builder (255 passes through, two maps); mode 1: dataloader gather (one map, no passthrough)
+__global__ void __launch_bounds__(256) k_targets_gather(const long long* __restrict__ label,
+                                                        long long* __restrict__ out_a, long long* __restrict__ out_b,
+                                                        long n, const long long* __restrict__ map_a,
+                                                        const long long* __restrict__ map_b, int map_size,
+                                                        int passthrough_255, int* __restrict__ err) {
+  long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (; i < n; i += stride) {
+    long long t = label[i];
+    long long a = SH_IGNORE, b = SH_IGNORE;
+    if (!(passthrough_255 && t == SH_IGNORE)) {
+      long long u = t < 0 ? t + map_size : t;
+      if (u >= 0 && u < map_size) {
+        a = map_a[u];
+        if (map_b) b = map_b[u];
+      } else {
+        bad = true;
+      }
+    }
+    out_a[i] = a;
+    if (out_b) out_b[i] = b;
+  }
+  if (bad) atomicOr(err, 1);
+}
+
+// ---------------------------------------------------------------------------
+// Decode: independent per-level argmax over channel slices (infer.py:303-312),
+// first max wins, NaN counts as max (torch.argmax).  Optional fine-level pixel
+// accuracy counts (train.py:37-49, 382-385).  Logits are read exactly once.
+// ---------------------------------------------------------------------------
+template <typename T, int VEC, typename OutT>
+__global__ void __launch_bounds__(256) k_decode(const T* __restrict__ x, int B, int C, long HW, int n0, int n1, int n2,
+                                                OutT* __restrict__ o0, OutT* __restrict__ o1, OutT* __restrict__ o2,
+                                                const long long* __restrict__ label,
+                                                unsigned long long* __restrict__ counts, int vec_ok) {
+  const long groups_per_img = (HW + VEC - 1) / VEC;
+  const long total = groups_per_img * B;
+  long long correct = 0, valid = 0;
+  for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+    const int b = (int)(g / groups_per_img);
+    const long p = (g - (long)b * groups_per_img) * VEC;
+    const T* base = x + (long)b * C * HW;
+    int c0 = 0;
+#pragma unroll
+    for (int lvl = 0; lvl < 3; ++lvl) {
+      const int k = lvl == 0 ? n0 : (lvl == 1 ? n1 : n2);
+      OutT* out = lvl == 0 ? o0 : (lvl == 1 ? o1 : o2);
+      if (k <= 0 || out == nullptr) { c0 += max(k, 0); continue; }
+      float best[VEC];
+      int arg[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) { best[v] = 0.f; arg[v] = -1; }
+#pragma unroll 4
+      for (int c = 0; c < k; ++c) {
+        float val[VEC];
+        load_n<T, VEC>(base + (long)(c0 + c) * HW, p, HW, vec_ok != 0, val);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          // take if first, strictly greater, or first NaN
+          bool take = (arg[v] < 0) || (val[v] > best[v]) || (val[v] != val[v] && best[v] == best[v]);
+          if (take) { best[v] = val[v]; arg[v] = c; }
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        if (p + v < HW) {
+          out[(long)b * HW + p + v] = (OutT)arg[v];
+          if (lvl == 0 && label != nullptr) {
+            long long t = label[(long)b * HW + p + v];
+            if (t != SH_IGNORE) { valid++; correct += (t == arg[v]); }
+          }
+        }
+      }
+      c0 += k;
+    }
+  }
+  if (label != nullptr && counts != nullptr) {
+    correct = warp_sum(correct);
+    valid = warp_sum(valid);
+    if ((threadIdx.x & 31) == 0 && valid) {
+      atomicAdd(counts, (unsigned long long)correct);
+      atomicAdd(counts + 1, (unsigned long long)valid);
+    }
+  }
+}
+
+template <typename T, typename OutT>
+static int launch_decode(const void* x, int B, int C, long HW, int n0, int n1, int n2, void* o0, void* o1, void* o2,
+                         const long long* label, unsigned long long* counts, cudaStream_t st) {
+  constexpr int VEC = sizeof(T) == 4 ? 4 : 8;  // 128-bit loads
+  bool vec_ok = (HW % VEC == 0) && ((uintptr_t)x % (VEC * sizeof(T)) == 0);
+  long groups = ((HW + VEC - 1) / VEC) * B;
+  long blocks = (groups + 255) / 256;
+  if (blocks > SH_NUM_SMS * 16L) blocks = SH_NUM_SMS * 16L;
+  if (blocks < 1) blocks = 1;
+  k_decode<T, VEC, OutT><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, B, C, HW, n0, n1, n2, (OutT*)o0, (OutT*)o1,
+                                                            (OutT*)o2, label, counts, vec_ok ? 1 : 0);
+  SH_CHECK_LAUNCH();
+  return SH_OK;
+}
+
+}  // namespace sh
+
+extern "C" {
+
+int sh_targets_two_level(const long long* label, long long* coarse, long n, const int* lut, int lut_size,
+                         void* stream) {
+  if (n <= 0) return SH_OK;
+  if (((uintptr_t)label | (uintptr_t)coarse) % 16) return SH_ERR_BAD_ARG;
+  long blocks = (n / 2 + 255) / 256;
+  if (blocks > SH_NUM_SMS * 16L) blocks = SH_NUM_SMS * 16L;
+  if (blocks < 1) blocks = 1;
+  sh::k_targets_two_level<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(label, coarse, n, lut, lut_size);
+  SH_CHECK_LAUNCH();
+  return SH_OK;
+}
+
+int sh_targets_three_level(const long long* label, long long* mid, long long* high, long n, const long long* f2m,
+                           const long long* f2h, int n_fine, int* err_flag, void* stream) {
+  if (n <= 0) return SH_OK;
+  long blocks = (n + 255) / 256;
+  if (blocks > SH_NUM_SMS * 16L) blocks = SH_NUM_SMS * 16L;
+  sh::k_targets_gather<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(label, mid, high, n, f2m, f2h, n_fine, 1,
+                                                                          err_flag);
+  SH_CHECK_LAUNCH();
+  return SH_OK;
+}
+
+int sh_targets_gather(const long long* label, long long* out, long n, const long long* map, int map_size,
+                      int* err_flag, void* stream) {
+  if (n <= 0) return SH_OK;
+  long blocks = (n + 255) / 256;
+  if (blocks > SH_NUM_SMS * 16L) blocks = SH_NUM_SMS * 16L;
+  sh::k_targets_gather<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(label, out, nullptr, n, map, nullptr,
+                                                                          map_size, 0, err_flag);
+  SH_CHECK_LAUNCH();
+  return SH_OK;
+}
+
+int sh_decode(const void* logits, int dtype, int B, int C, long HW, int n0, int n1, int n2, void* out0, void* out1,
+              void* out2, int out_is_u8, const long long* label, unsigned long long* counts, void* stream) {
+  if (B <= 0 || HW <= 0) return SH_OK;
+  if (n0 + (n1 > 0 ? n1 : 0) + (n2 > 0 ? n2 : 0) > C) return SH_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+#define SH_DECODE_DISPATCH(T)                                                                                  \
+  return out_is_u8 ? sh::launch_decode<T, unsigned char>(logits, B, C, HW, n0, n1, n2, out0, out1, out2, label, \
+                                                         counts, st)                                            \
+                   : sh::launch_decode<T, long long>(logits, B, C, HW, n0, n1, n2, out0, out1, out2, label,     \
+                                                     counts, st)
+  switch (dtype) {
+    case SH_DT_F32: SH_DECODE_DISPATCH(float);
+    case SH_DT_BF16: SH_DECODE_DISPATCH(__nv_bfloat16);
+    case SH_DT_F16: SH_DECODE_DISPATCH(__half);
+  }
+#undef SH_DECODE_DISPATCH
+  return SH_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

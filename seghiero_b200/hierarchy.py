@@ -1,0 +1,92 @@
+"""Host-side hierarchy tables (small int32 arrays) consumed by the CUDA kernels.
+
+Pure Python/numpy so it can be unit-tested without a GPU.  Semantics follow the
+reference's per-class Python loops:
+  two-level  : models/loss/hiera_triplet_loss.py:28-36, 81-92
+  three-level: models/loss/rmi_hiera_triplet_loss.py:379-442
+  triplet    : models/loss/tree_triplet_loss.py:32-36, models/loss/rmi_tree_triplet_loss.py:28-45
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import numpy as np
+
+IGNORE = 255
+
+
+def two_level_tables(n_fine: int, hiera_index: Sequence[Sequence[int]]):
+    """-> (int32 blob [bstart][bend][owner][fb_ptr][fb_idx][lut], n_fb, lut_size)."""
+    nc = len(hiera_index)
+    bstart = np.array([max(0, min(int(s), n_fine)) for s, _ in hiera_index], dtype=np.int32)
+    bend = np.array([max(0, min(int(e), n_fine)) for _, e in hiera_index], dtype=np.int32)
+    bend = np.maximum(bend, bstart)
+    owner = np.full(n_fine, -1, dtype=np.int32)           # last bucket containing f (later bucket wins)
+    members = [[] for _ in range(n_fine)]
+    for i in range(nc):
+        for f in range(bstart[i], bend[i]):
+            owner[f] = i
+            members[f].append(i)
+    fb_ptr = np.zeros(n_fine + 1, dtype=np.int32)
+    fb_idx = []
+    for f in range(n_fine):
+        fb_idx.extend(members[f])
+        fb_ptr[f + 1] = len(fb_idx)
+    # target LUT follows the RAW ranges (labels >= n_fine are an error in the loss, but the
+    # standalone target builder accepts any range the caller wrote)
+    lut_size = max([int(e) for _, e in hiera_index] + [1])
+    lut = np.full(lut_size, IGNORE, dtype=np.int32)
+    for i, (s, e) in enumerate(hiera_index):
+        lo, hi = max(int(s), 0), min(int(e), lut_size)
+        if hi > lo:
+            lut[lo:hi] = i
+    blob = np.concatenate([bstart, bend, owner, fb_ptr, np.array(fb_idx, dtype=np.int32), lut]).astype(np.int32)
+    return blob, len(fb_idx), lut_size
+
+
+def three_level_tables(n_fine: int, n_mid: int, n_high: int, fine_to_mid, fine_to_high):
+    """-> (int32 blob [f2m][f2h][mh_ptr][mh_idx][hsmask], n_mh).  Validates the maps."""
+    f2m = np.asarray(fine_to_mid, dtype=np.int64).reshape(-1)
+    f2h = np.asarray(fine_to_high, dtype=np.int64).reshape(-1)
+    if f2m.size != n_fine or f2h.size != n_fine:
+        raise ValueError("fine_to_mid / fine_to_high must have n_fine entries")
+    if (f2m < 0).any() or (f2m >= n_mid).any():
+        raise ValueError("fine_to_mid holds ids outside [0, n_mid)")
+    if (f2h < 0).any() or (f2h >= n_high).any():
+        raise ValueError("fine_to_high holds ids outside [0, n_high) (uninitialised map?)")
+    if n_high > 32:
+        raise ValueError("n_high > 32 is not supported")
+    if n_fine + n_mid + n_high > 255:
+        raise ValueError("more than 255 channels are not supported")
+    # Ms(h) = {f2m[f] : f2h[f]==h};  mh list of mid m = highs whose Ms contains m
+    mh = [sorted({int(f2h[f]) for f in range(n_fine) if f2m[f] == m}) for m in range(n_mid)]
+    mh_ptr = np.zeros(n_mid + 1, dtype=np.int32)
+    mh_idx = []
+    hsmask = np.zeros(n_mid, dtype=np.uint32)
+    for m in range(n_mid):
+        mh_idx.extend(mh[m])
+        mh_ptr[m + 1] = len(mh_idx)
+        for h in mh[m]:                                   # Hs(m) = {f2h[f] : f in F(m)} -- the same set
+            hsmask[m] |= np.uint32(1) << np.uint32(h)
+    blob = np.concatenate([f2m.astype(np.int32), f2h.astype(np.int32), mh_ptr,
+                           np.array(mh_idx, dtype=np.int32), hsmask.view(np.int32)]).astype(np.int32)
+    return blob, len(mh_idx)
+
+
+def triplet_tables_hierarchy(hiera_map: Sequence[int], hiera_index: Sequence[Sequence[int]]):
+    """mode 0: per class c the bucket [lo, hi) = hiera_index[hiera_map[c]][0], [-1]."""
+    lo = np.array([int(hiera_index[hiera_map[c]][0]) for c in range(len(hiera_map))], dtype=np.int32)
+    hi = np.array([int(hiera_index[hiera_map[c]][-1]) for c in range(len(hiera_map))], dtype=np.int32)
+    return np.concatenate([lo, hi]), len(hiera_map)
+
+
+def triplet_tables_id_lists(upper_ids: Sequence[int], lower_ids: Sequence[int]):
+    """mode 1: group id per label value (0 = upper, 1 = lower, -1 = neither)."""
+    grp = np.full(256, -1, dtype=np.int32)
+    for v in lower_ids:
+        if 0 <= int(v) < 256:
+            grp[int(v)] = 1
+    for v in upper_ids:                                   # `if ii in upper_ids` is tested first
+        if 0 <= int(v) < 256:
+            grp[int(v)] = 0
+    return grp, 256

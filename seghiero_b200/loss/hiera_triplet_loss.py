@@ -1,0 +1,52 @@
+"""HieraTripletLoss -- drop-in for models/loss/hiera_triplet_loss.py:110-211 on sm_100a kernels."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .tree_triplet_loss import TreeTripletLoss
+
+
+class HieraTripletLoss(nn.Module):
+    """2-level (fine -> coarse) hierarchical BCE + softmax CE + scheduled triplet loss.
+
+    Constructor and forward signatures are the reference's.  `use_sigmoid`, `weight`,
+    `cls_score_before` and `**kwargs` are accepted and ignored exactly as there.  Differences
+    that a caller can observe (all documented in DESIGN.md):
+      * no host synchronisation: `step`, the `ready` gate and the schedule stay on the device;
+        consequently `embedding.grad` is a zero tensor (not None) when no triplet class was found;
+      * labels outside [0, num_classes) U {255} (where the reference's F.one_hot raises) make the
+        loss NaN; pass `strict=True` to get the RuntimeError at the cost of one sync per call;
+      * CUDA tensors only.
+    """
+
+    def __init__(self, num_classes: int, hiera_map: list, hiera_index: list, ignore_index: int = 255,
+                 use_sigmoid: bool = False, loss_weight: float = 1.0, strict: bool = False):
+        super().__init__()
+        if ignore_index != 255:
+            raise ValueError("only ignore_index=255 is supported (the reference's builders hard-code 255)")
+        self.num_classes = num_classes
+        self.hiera_map = hiera_map
+        self.hiera_index = hiera_index
+        self.ignore_index = ignore_index
+        self.triplet_loss_fn = TreeTripletLoss(num_classes=len(hiera_map), hiera_map=hiera_map,
+                                               hiera_index=hiera_index, ignore_index=ignore_index)
+        self.loss_weight = loss_weight
+        self.strict = strict
+        self.last_stats: dict = {}
+
+    def forward(self, step, embedding, cls_score_before, cls_score, label, weight=None, **kwargs):
+        cfg = ops.Hier2Config(n_fine=int(self.num_classes), n_coarse=len(self.hiera_index),
+                              hiera_map=list(self.hiera_map), hiera_index=[list(r) for r in self.hiera_index],
+                              loss_weight=float(self.loss_weight))
+        self.last_stats = {}
+        step_d = ops.step_tensor(step, cls_score.device)
+        loss = ops.HieraTriplet2Fn.apply(cls_score, embedding, label, step_d, cfg, self.last_stats)
+        if self.strict:
+            if int(self.last_stats["counts"][2].item()):
+                raise RuntimeError("Class values must be smaller than num_classes.")
+            st = self.last_stats.get("triplet")
+            if st is not None and int(st.status[1].item()):
+                raise IndexError("label outside hiera_map in the triplet term")
+        return loss

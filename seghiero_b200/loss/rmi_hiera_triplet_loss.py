@@ -1,0 +1,80 @@
+"""RMIHieraTripletLoss -- drop-in for models/loss/rmi_hiera_triplet_loss.py:180-546 on sm_100a kernels."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import hierarchy as H
+from .. import ops
+from .rmi_tree_triplet_loss import TreeTripletLoss
+
+
+class RMIHieraTripletLoss(nn.Module):
+    """3-level (fine -> mid -> high) tree BCE + RMI lower bound + softmax CE + scheduled triplet.
+
+    Same constructor / forward as the reference; `rmi_pool_*`, `weight`, `cls_score_before` and
+    `**kwargs` are accepted and ignored as there (rmi_radius must be 3, the only value the reference's
+    arithmetic is defined for with its 9x9 matrices).  The maps are validated (ids inside the level
+    sizes) instead of silently indexing garbage.  Observable differences: see HieraTripletLoss.
+    """
+
+    def __init__(self, n_fine: int, n_mid: int, n_high: int, fine_to_mid: torch.Tensor, fine_to_high: torch.Tensor,
+                 rmi_radius: int = 3, rmi_pool_way: int = 0, rmi_pool_size: int = 3, rmi_pool_stride: int = 3,
+                 loss_weight_lambda: float = 0.5, loss_weight: float = 1.0, ignore_index: int = 255,
+                 strict: bool = False):
+        super().__init__()
+        assert fine_to_mid.dtype == torch.long
+        assert fine_to_high.dtype == torch.long
+        assert fine_to_mid.numel() == n_fine
+        assert fine_to_high.numel() == n_fine
+        if ignore_index != 255:
+            raise ValueError("only ignore_index=255 is supported (the reference's builders hard-code 255)")
+        if rmi_radius != 3:
+            raise ValueError("rmi_radius must be 3")
+        self.n_fine, self.n_mid, self.n_high = n_fine, n_mid, n_high
+        self.fine_to_mid = fine_to_mid.clone()
+        self.fine_to_high = fine_to_high.clone()
+        self.ignore_index = ignore_index
+        self.rmi_radius = rmi_radius
+        self.rmi_pool_way = rmi_pool_way
+        self.rmi_pool_size = rmi_pool_size
+        self.rmi_pool_stride = rmi_pool_stride
+        assert self.rmi_pool_size == self.rmi_pool_stride
+        if n_fine > 15:
+            self.upper_ids = [1, 2, 3, 4, 5, 6, 7, 10, 11, 13, 14, 15]
+            self.lower_ids = [8, 9, 12, 16, 17, 18, 19]
+        else:
+            self.upper_ids = [1, 2, 3, 4]
+            self.lower_ids = [5, 6]
+        self.loss_weight_lambda = loss_weight_lambda
+        self.loss_weight = loss_weight
+        self.half_d = self.rmi_radius * self.rmi_radius
+        self.d = 2 * self.half_d
+        self.kernel_padding = self.rmi_pool_size // 2
+        self.triplet_loss = TreeTripletLoss(num_classes=self.n_fine, upper_ids=self.upper_ids,
+                                            lower_ids=self.lower_ids, ignore_index=self.ignore_index)
+        self.strict = strict
+        self.last_stats: dict = {}
+        # validate once on the host (raises ValueError on out-of-range map entries)
+        H.three_level_tables(n_fine, n_mid, n_high, self.fine_to_mid.cpu().numpy(), self.fine_to_high.cpu().numpy())
+
+    def forward(self, step, embedding, cls_score_before, cls_score, label, weight=None, **kwargs):
+        cfg = ops.Hier3Config(
+            n_fine=int(self.n_fine), n_mid=int(self.n_mid), n_high=int(self.n_high),
+            fine_to_mid=tuple(int(v) for v in self.fine_to_mid.tolist()),
+            fine_to_high=tuple(int(v) for v in self.fine_to_high.tolist()),
+            upper_ids=tuple(self.upper_ids), lower_ids=tuple(self.lower_ids),
+            lam=float(self.loss_weight_lambda), loss_weight=float(self.loss_weight),
+            total_steps=160000.0 if self.n_fine > 15 else 60000.0,
+            use_triplet=self.triplet_loss is not None)
+        self.last_stats = {}
+        step_d = ops.step_tensor(step, cls_score.device)
+        loss = ops.RMIHieraTriplet3Fn.apply(cls_score, embedding, label, step_d, cfg, self.last_stats)
+        if self.strict:
+            ws = self.last_stats["workspace"]
+            if int(ws[16:24].view(torch.int64).item()):
+                raise RuntimeError("Class values must be smaller than num_classes.")
+            st = self.last_stats.get("triplet")
+            if st is not None and int(st.status[1].item()):
+                raise ValueError("list.remove(x): x not in list (label in neither upper_ids nor lower_ids)")
+        return loss

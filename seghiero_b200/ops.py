@@ -1,0 +1,381 @@
+"""Host side of the C-ABI custom ops: tensor plumbing, workspaces and autograd glue.
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; every
+computation is a kernel of libseghiero_b200.so.  Nothing here touches the host
+inside forward/backward (no .item(), no .tolist()): `step`, the `ready` gate and
+`grad_output` stay on the device.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+from . import hierarchy as H
+
+_DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+_table_cache: dict = {}
+
+
+def _p(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("seghiero_b200 runs on CUDA tensors only (there is no CPU fallback)")
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype not in _DT:
+        raise TypeError(f"unsupported dtype {t.dtype}; use float32, bfloat16 or float16")
+    return _DT[t.dtype]
+
+
+def _labels(label: torch.Tensor) -> torch.Tensor:
+    if label.dtype != torch.int64:
+        label = label.long()
+    return label.contiguous()
+
+
+def device_table(key, builder, device):
+    """numpy int32 table -> cached device tensor (built once per device)."""
+    k = (key, str(device))
+    hit = _table_cache.get(k)
+    if hit is None:
+        arr = builder()
+        extra = arr[1:] if isinstance(arr, tuple) else ()
+        arr0 = arr[0] if isinstance(arr, tuple) else arr
+        hit = (torch.from_numpy(np.ascontiguousarray(arr0)).to(device), *extra)
+        _table_cache[k] = hit
+    return hit
+
+
+def step_tensor(step, device) -> torch.Tensor:
+    if isinstance(step, torch.Tensor):
+        return step.detach().reshape(-1)[:1].to(device=device, dtype=torch.float64)
+    return torch.tensor([float(step)], dtype=torch.float64, device=device)
+
+
+def _world_ready(status: torch.Tensor) -> None:
+    """`ready` = every rank found >= 1 triplet class (hiera_triplet_loss.py:193-198), as one
+    device-side MIN all-reduce instead of an all_gather + host sync."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(status[:1], op=dist.ReduceOp.MIN)
+
+
+# ----------------------------------------------------------------------------------------------
+# targets / decode
+# ----------------------------------------------------------------------------------------------
+def targets_two_level(label: torch.Tensor, hiera_index):
+    _need_cuda(label)
+    lab = _labels(label)
+    key = ("lut2", tuple(tuple(int(v) for v in r) for r in hiera_index))
+
+    def build():
+        size = max([int(e) for _, e in hiera_index] + [1])
+        lut = np.full(size, H.IGNORE, dtype=np.int32)
+        for i, (s, e) in enumerate(hiera_index):
+            lo, hi = max(int(s), 0), min(int(e), size)
+            if hi > lo:
+                lut[lo:hi] = i
+        return lut
+    (lut,) = device_table(key, build, lab.device)
+    out = torch.empty_like(lab)
+    with torch.cuda.device(lab.device):
+        _lib.call("sh_targets_two_level", _p(lab), _p(out), lab.numel(), _p(lut), lut.numel(), _stream())
+    return out.to(label.dtype) if label.dtype != torch.int64 else out
+
+
+def targets_three_level(label: torch.Tensor, fine_to_mid: torch.Tensor, fine_to_high: torch.Tensor, check=True):
+    _need_cuda(label)
+    lab = _labels(label)
+    f2m = fine_to_mid.to(device=lab.device, dtype=torch.int64).contiguous()
+    f2h = fine_to_high.to(device=lab.device, dtype=torch.int64).contiguous()
+    mid, high = torch.empty_like(lab), torch.empty_like(lab)
+    err = torch.zeros(1, dtype=torch.int32, device=lab.device)
+    with torch.cuda.device(lab.device):
+        _lib.call("sh_targets_three_level", _p(lab), _p(mid), _p(high), lab.numel(), _p(f2m), _p(f2h), f2m.numel(),
+                  _p(err), _stream())
+    if check and int(err.item()):
+        raise IndexError("fine label out of range for fine_to_mid / fine_to_high")
+    return mid, high
+
+
+def targets_gather(fine_mask: torch.Tensor, level_map: torch.Tensor, check=True):
+    _need_cuda(fine_mask)
+    lab = _labels(fine_mask)
+    m = level_map.to(device=lab.device, dtype=torch.int64).contiguous()
+    out = torch.empty_like(lab)
+    err = torch.zeros(1, dtype=torch.int32, device=lab.device)
+    with torch.cuda.device(lab.device):
+        _lib.call("sh_targets_gather", _p(lab), _p(out), lab.numel(), _p(m), m.numel(), _p(err), _stream())
+    if check and int(err.item()):
+        raise IndexError("index out of range in target gather")
+    return out
+
+
+def hierarchical_argmax(logits: torch.Tensor, level_sizes: Sequence[int], label: Optional[torch.Tensor] = None,
+                        out_dtype=torch.int64):
+    """Per-level argmax over channel slices (+ fine pixel-accuracy counts when `label` is given).
+    Returns (list of [B,H,W] predictions, counts int64[2] = (#correct, #valid) or None)."""
+    _need_cuda(logits)
+    if out_dtype not in (torch.int64, torch.uint8):
+        raise TypeError("out_dtype must be torch.int64 or torch.uint8")
+    x = logits.contiguous()
+    b, c = x.shape[0], x.shape[1]
+    hw = x[0, 0].numel()
+    sizes = [int(s) for s in level_sizes] + [0, 0]
+    n0, n1, n2 = sizes[:3]
+    if len(level_sizes) > 3 or n0 + n1 + n2 > c:
+        raise ValueError("level_sizes must be <= 3 levels and fit the channel count")
+    outs = [torch.empty((b,) + tuple(x.shape[2:]), dtype=out_dtype, device=x.device) if n > 0 else None
+            for n in (n0, n1, n2)]
+    counts = None
+    lab = None
+    if label is not None:
+        lab = _labels(label)
+        counts = torch.zeros(2, dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("sh_decode", _p(x), _dtype_code(x), b, c, hw, n0, n1, n2, _p(outs[0]), _p(outs[1]), _p(outs[2]),
+                  1 if out_dtype == torch.uint8 else 0, _p(lab), _p(counts), _stream())
+    return [o for o in outs if o is not None], counts
+
+
+# ----------------------------------------------------------------------------------------------
+# triplet
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class TripletState:
+    mode: int
+    ncls: int
+    max_triplet: int
+    dims: tuple
+    sel: torch.Tensor
+    kcount: torch.Tensor
+    tl: torch.Tensor
+    trip: torch.Tensor      # [loss, #classes] float32
+    status: torch.Tensor    # [ready, error] int32
+    lab_ds: torch.Tensor
+
+
+def triplet_forward(feats: torch.Tensor, label: torch.Tensor, mode: int, tab: torch.Tensor, ncls: int,
+                    max_triplet: int = 200) -> TripletState:
+    _need_cuda(feats, label)
+    b, d, h, w = feats.shape
+    hh, ww = label.shape[-2:]
+    dev = feats.device
+    rows = b * h * w
+    lab_ds = torch.empty(rows, dtype=torch.int32, device=dev)
+    sel = torch.empty(ncls * 3 * max_triplet, dtype=torch.int32, device=dev)
+    kcount = torch.empty(ncls, dtype=torch.int32, device=dev)
+    tl = torch.empty(ncls * max_triplet, dtype=torch.float32, device=dev)
+    trip = torch.empty(2, dtype=torch.float32, device=dev)
+    status = torch.empty(2, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("sh_triplet_forward", _p(feats), _dtype_code(feats), _p(label), b, d, h, w, hh, ww, mode, _p(tab),
+                  ncls, max_triplet, _p(lab_ds), _p(sel), _p(kcount), _p(tl), _p(trip), _p(status), _stream())
+    return TripletState(mode, ncls, max_triplet, (b, d, h, w), sel, kcount, tl, trip, status, lab_ds)
+
+
+def triplet_backward(feats: torch.Tensor, st: TripletState, tscale: torch.Tensor,
+                     gscale: Optional[torch.Tensor]) -> torch.Tensor:
+    b, d, h, w = st.dims
+    gfeat = torch.empty((b, d, h, w), dtype=torch.float32, device=feats.device)
+    with torch.cuda.device(feats.device):
+        _lib.call("sh_triplet_backward", _p(feats), _dtype_code(feats), b, d, h, w, st.ncls, st.max_triplet,
+                  _p(st.sel), _p(st.kcount), _p(st.tl), _p(st.trip), _p(tscale), _p(gscale), _p(gfeat), _stream())
+    return gfeat if feats.dtype == torch.float32 else gfeat.to(feats.dtype)
+
+
+class TripletFn(torch.autograd.Function):
+    """Standalone triplet loss value (mean over classes); 0 when no class contributes."""
+
+    @staticmethod
+    def forward(ctx, feats, label, mode, tab, ncls, max_triplet, holder):
+        feats_c = feats.contiguous()
+        st = triplet_forward(feats_c, _labels(label), mode, tab, ncls, max_triplet)
+        holder["state"] = st
+        ctx.st = st
+        ctx.save_for_backward(feats_c)
+        return st.trip[0].clone()
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        (feats,) = ctx.saved_tensors
+        one = torch.ones(1, dtype=torch.float32, device=feats.device)
+        g = gout.detach().to(torch.float32).reshape(1).contiguous()
+        return triplet_backward(feats, ctx.st, one, g), None, None, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# two-level fused loss
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class Hier2Config:
+    n_fine: int
+    n_coarse: int
+    hiera_map: list
+    hiera_index: list
+    loss_weight: float
+    total_steps: float = 80000.0
+    eps: float = 1e-8
+
+
+class HieraTriplet2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cls_score, embedding, label, step_d, cfg: Hier2Config, stats: dict):
+        _need_cuda(cls_score, label, embedding)
+        x = cls_score.contiguous()
+        lab = _labels(label)
+        dev = x.device
+        b, c = x.shape[0], x.shape[1]
+        hw = x[0, 0].numel()
+        if c != cfg.n_fine + cfg.n_coarse:
+            raise ValueError(f"cls_score has {c} channels, expected n_fine+n_coarse={cfg.n_fine + cfg.n_coarse}")
+        if tuple(lab.shape) != (b,) + tuple(x.shape[2:]):
+            raise ValueError("label must be [B,H,W] matching cls_score")
+        key = ("h2", cfg.n_fine, tuple(tuple(int(v) for v in r) for r in cfg.hiera_index))
+        tab, n_fb, lut_size = device_table(key, lambda: H.two_level_tables(cfg.n_fine, cfg.hiera_index), dev)
+
+        st = None
+        if embedding is not None:
+            tkey = ("t0", tuple(int(v) for v in cfg.hiera_map), key[2])
+            ttab, ncls = device_table(tkey, lambda: H.triplet_tables_hierarchy(cfg.hiera_map, cfg.hiera_index), dev)
+            emb = embedding.contiguous()
+            st = triplet_forward(emb, lab, 0, ttab, ncls)
+            _world_ready(st.status)
+
+        want_grad = ctx.needs_input_grad[0]
+        grad = torch.empty_like(x) if want_grad else None
+        lab8 = torch.empty(b * hw, dtype=torch.uint8, device=dev)
+        counts = torch.empty(4, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            grid = _lib.load().sh_bce2_grid(b, hw, c, cfg.n_coarse)
+            partials = torch.empty(grid * 4, dtype=torch.float32, device=dev)
+            sums = torch.empty(4, dtype=torch.float64, device=dev)
+            out = torch.empty(4, dtype=torch.float32, device=dev)
+            _lib.call("sh_bce2_fwdbwd", _p(x), _dtype_code(x), _p(lab), _p(grad), b, hw, cfg.n_fine, cfg.n_coarse,
+                      _p(tab), n_fb, lut_size, cfg.eps, cfg.loss_weight, _p(lab8), _p(counts), _p(partials), _p(sums),
+                      _stream())
+            _lib.call("sh_loss2_final", _p(sums), _p(counts), cfg.n_fine, cfg.n_coarse, float(b * hw), _p(step_d),
+                      cfg.total_steps, _p(st.trip) if st else None, _p(st.status) if st else None, cfg.loss_weight,
+                      _p(out), _stream())
+        stats.update(sums=sums, counts=counts, out=out, triplet=st)
+        ctx.grad = grad
+        ctx.st = st
+        ctx.out = out
+        ctx.emb = emb if st is not None else None
+        return out[0].clone()
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        g = gout.detach().to(torch.float32).reshape(1).contiguous()
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = ctx.grad
+            if gx is None:
+                raise RuntimeError("seghiero_b200: backward through the fused loss can run only once")
+            ctx.grad = None
+            with torch.cuda.device(gx.device):
+                _lib.call("sh_scale_inplace", _p(gx), _dtype_code(gx), gx.numel(), _p(g), _stream())
+        gemb = None
+        if ctx.st is not None and ctx.needs_input_grad[1]:
+            gemb = triplet_backward(ctx.emb, ctx.st, ctx.out[1:2], g)
+        return gx, gemb, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# three-level fused loss
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class Hier3Config:
+    n_fine: int
+    n_mid: int
+    n_high: int
+    fine_to_mid: tuple
+    fine_to_high: tuple
+    upper_ids: tuple
+    lower_ids: tuple
+    lam: float
+    loss_weight: float
+    total_steps: float
+    use_triplet: bool = True
+
+
+class RMIHieraTriplet3Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cls_score, embedding, label, step_d, cfg: Hier3Config, stats: dict):
+        _need_cuda(cls_score, label, embedding)
+        x = cls_score.contiguous()
+        lab = _labels(label)
+        dev = x.device
+        if x.dim() != 4:
+            raise ValueError("cls_score must be [B,C,H,W]")
+        b, c, hh, ww = x.shape
+        if c != cfg.n_fine + cfg.n_mid + cfg.n_high:
+            raise ValueError(f"cls_score has {c} channels, expected {cfg.n_fine + cfg.n_mid + cfg.n_high}")
+        if tuple(lab.shape) != (b, hh, ww):
+            raise ValueError("label must be [B,H,W] matching cls_score")
+        if hh < 5 or ww < 5:
+            raise ValueError("the RMI term needs H, W >= 5")
+        key = ("h3", cfg.n_fine, cfg.n_mid, cfg.n_high, cfg.fine_to_mid, cfg.fine_to_high)
+        tab, n_mh = device_table(key, lambda: H.three_level_tables(cfg.n_fine, cfg.n_mid, cfg.n_high,
+                                                                   cfg.fine_to_mid, cfg.fine_to_high), dev)
+        st = None
+        if embedding is not None and cfg.use_triplet:
+            tkey = ("t1", cfg.upper_ids, cfg.lower_ids)
+            ttab, ncls = device_table(tkey, lambda: H.triplet_tables_id_lists(cfg.upper_ids, cfg.lower_ids), dev)
+            emb = embedding.contiguous()
+            st = triplet_forward(emb, lab, 1, ttab, ncls)
+            _world_ready(st.status)
+        with torch.cuda.device(dev):
+            lib = _lib.load()
+            nbytes = lib.sh_rmi3_workspace_bytes(b, hh, ww, cfg.n_fine, cfg.n_mid, cfg.n_high)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            out = torch.empty(4, dtype=torch.float32, device=dev)
+            _lib.call("sh_rmi3_forward", _p(x), _dtype_code(x), _p(lab), b, hh, ww, cfg.n_fine, cfg.n_mid, cfg.n_high,
+                      _p(tab), n_mh, cfg.lam, cfg.loss_weight, _p(ws), _stream())
+            _lib.call("sh_loss3_final", b, hh, ww, cfg.n_fine, cfg.n_mid, cfg.n_high, _p(ws), cfg.lam, _p(step_d),
+                      cfg.total_steps, _p(st.trip) if st else None, _p(st.status) if st else None, cfg.loss_weight,
+                      _p(out), _stream())
+        stats.update(out=out, triplet=st, workspace=ws)
+        ctx.cfg = cfg
+        ctx.tab, ctx.n_mh = tab, n_mh
+        ctx.st = st
+        ctx.out = out
+        ctx.ws = ws if ctx.needs_input_grad[0] else None
+        ctx.x = x if ctx.needs_input_grad[0] else None
+        ctx.emb = emb if st is not None else None
+        return out[0].clone()
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        g = gout.detach().to(torch.float32).reshape(1).contiguous()
+        cfg = ctx.cfg
+        gx = None
+        if ctx.needs_input_grad[0]:
+            x = ctx.x
+            b, c, hh, ww = x.shape
+            gx = torch.empty_like(x)
+            with torch.cuda.device(x.device):
+                _lib.call("sh_rmi3_backward", _p(x), _dtype_code(x), _p(gx), b, hh, ww, cfg.n_fine, cfg.n_mid,
+                          cfg.n_high, _p(ctx.tab), ctx.n_mh, cfg.loss_weight, _p(ctx.ws), _p(g), _stream())
+        gemb = None
+        if ctx.st is not None and ctx.needs_input_grad[1]:
+            gemb = triplet_backward(ctx.emb, ctx.st, ctx.out[1:2], g)
+        return gx, gemb, None, None, None, None

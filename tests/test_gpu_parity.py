@@ -1,0 +1,360 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs the CPU oracle and the golden vectors
+generated from the reference.  Tolerances are north_star's: integers bit-exact, fp32 1e-5 relative,
+bf16 inputs 2e-2 relative."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import hiera_oracle as O
+from tests.util import F2H, F2M, HI, HM, blob_labels, iid_labels, rel, to_np
+
+pytestmark = pytest.mark.gpu
+FP32_TOL = 1e-5
+BF16_TOL = 2e-2
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import seghiero_b200
+    from seghiero_b200 import _lib
+    _lib.load()
+    assert torch.cuda.is_available()
+    return seghiero_b200
+
+
+def _x_from_golden(g):
+    x = torch.from_numpy(g["x"])
+    if "is_bf16" in g and bool(g["is_bf16"]):
+        x = x.bfloat16()
+    return x
+
+
+# ------------------------------------------------------------------------------------------------
+# integer paths
+# ------------------------------------------------------------------------------------------------
+def test_targets_bit_exact(sb):
+    g = torch.Generator().manual_seed(5)
+    lab = iid_labels(g, 3, 37, 53, 19, 0.2)
+    lab[0, 0, :5] = torch.tensor([19, 300, -1, 254, 18])
+    out = sb.targets_two_level(lab.cuda(), HI)
+    assert np.array_equal(out.cpu().numpy(), O.targets_two_level(lab.numpy(), HI)[1])
+    out = sb.targets_two_level(lab.cuda(), [[0, 5], [3, 9], [20, 400]])    # overlap + beyond n_fine
+    assert np.array_equal(out.cpu().numpy(), O.targets_two_level(lab.numpy(), [[0, 5], [3, 9], [20, 400]])[1])
+    lab3 = iid_labels(g, 2, 40, 31, 19, 0.2)
+    mid, high = sb.targets_three_level(lab3.cuda(), torch.tensor(F2M), torch.tensor(F2H))
+    _, om, oh = O.targets_three_level(lab3.numpy(), F2M, F2H)
+    assert np.array_equal(mid.cpu().numpy(), om) and np.array_equal(high.cpu().numpy(), oh)
+    lab3[0, 0, 0] = -2     # torch indexing wraps negatives
+    mid, _ = sb.targets_three_level(lab3.cuda(), torch.tensor(F2M), torch.tensor(F2H))
+    assert np.array_equal(mid.cpu().numpy(), O.targets_three_level(lab3.numpy(), F2M, F2H)[1])
+    lab3[0, 0, 0] = 19
+    with pytest.raises(IndexError):
+        sb.targets_three_level(lab3.cuda(), torch.tensor(F2M), torch.tensor(F2H))
+    fm = torch.randint(0, 19, (64, 48), generator=g)
+    out = sb.targets_gather(fm.cuda(), torch.tensor(F2H))
+    assert np.array_equal(out.cpu().numpy(), O.targets_dataloader(fm.numpy(), F2H))
+    fm[3, 3] = 255
+    with pytest.raises(IndexError):
+        sb.targets_gather(fm.cuda(), torch.tensor(F2H))
+    empty = sb.targets_two_level(torch.zeros(0, 4, 4, dtype=torch.long).cuda(), HI)
+    assert empty.numel() == 0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_decode_bit_exact(sb, golden, dtype):
+    g = golden("decode")
+    x = torch.from_numpy(g["x"]).to(dtype)
+    preds, counts = sb.hierarchical_argmax(x.cuda(), [19, 7, 2], torch.from_numpy(g["label"]).cuda())
+    ref = O.argmax_decode(x.float(), [19, 7, 2])
+    for p, r in zip(preds, ref):
+        assert np.array_equal(p.cpu().numpy(), r)
+    if dtype != torch.float16:
+        assert np.array_equal(preds[0].cpu().numpy(), g["pf"])
+        assert counts.tolist() == [int(g["correct"]), int(g["total"])]
+    # ragged width (scalar path), two levels, uint8 output
+    gen = torch.Generator().manual_seed(9)
+    x = torch.randn(3, 26, 17, 23, generator=gen).to(dtype)
+    preds, _ = sb.hierarchical_argmax(x.cuda(), [19, 7], out_dtype=torch.uint8)
+    ref = O.argmax_decode(x.float(), [19, 7])
+    assert len(preds) == 2
+    for p, r in zip(preds, ref):
+        assert p.dtype == torch.uint8 and np.array_equal(p.cpu().numpy().astype(np.int64), r)
+
+
+# ------------------------------------------------------------------------------------------------
+# triplet
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(2, 16, 8, 12, 32, 48), (2, 32, 7, 9, 50, 70), (1, 256, 16, 32, 64, 128)])
+def test_triplet_hierarchy(sb, shape):
+    b, d, h, w, hh, ww = shape
+    g = torch.Generator().manual_seed(b * 100 + d)
+    lab = blob_labels(g, b, hh, ww, 19, 5, 0.1)
+    emb = F.normalize(torch.randn(b, d, h, w, generator=g), dim=1)
+    e_ref = emb.clone().requires_grad_(True)
+    ref, cnt = O.triplet_hierarchy(e_ref, lab.numpy(), HM, HI)
+    ref.backward()
+    mod = sb.TreeTripletLoss(19, HM, HI)
+    e = emb.cuda().requires_grad_(True)
+    loss, count = mod(e, lab.cuda())
+    loss.backward()
+    assert int(count.item()) == cnt and count.dtype == torch.int64 and count.shape == (1,)
+    assert abs(float(loss) - float(ref)) <= FP32_TOL * abs(float(ref))
+    assert rel(to_np(e.grad), to_np(e_ref.grad)) <= FP32_TOL
+    # max_triplet honoured
+    ref2, _ = O.triplet_hierarchy(emb, lab.numpy(), HM, HI, max_triplet=3)
+    loss2, _ = mod(emb.cuda(), lab.cuda(), max_triplet=3)
+    assert abs(float(loss2) - float(ref2)) <= FP32_TOL * abs(float(ref2))
+
+
+def test_triplet_id_lists_and_edge_cases(sb):
+    g = torch.Generator().manual_seed(77)
+    lab = blob_labels(g, 2, 40, 56, 19, 4, 0.1)
+    emb = F.normalize(torch.randn(2, 24, 10, 14, generator=g), dim=1)
+    upper, lower = O.id_lists_for(19)
+    e_ref = emb.clone().requires_grad_(True)
+    ref, cnt = O.triplet_id_lists(e_ref, lab.numpy(), upper, lower)
+    ref.backward()
+    mod = sb.IdListTreeTripletLoss(19, upper, lower)
+    e = emb.cuda().requires_grad_(True)
+    loss, count = mod(e, lab.cuda())
+    loss.backward()
+    assert int(count.item()) == cnt
+    assert abs(float(loss) - float(ref)) <= FP32_TOL * abs(float(ref))
+    assert rel(to_np(e.grad), to_np(e_ref.grad)) <= FP32_TOL
+    # nothing to mine -> (None, [0])
+    void = torch.full((2, 40, 56), 255, dtype=torch.long)
+    loss, count = mod(emb.cuda(), void.cuda())
+    assert loss is None and count.tolist() == [0]
+    loss, count = sb.TreeTripletLoss(19, HM, HI)(emb.cuda(), void.cuda())
+    assert loss is None and count.tolist() == [0]
+    # class in neither list -> ValueError
+    with pytest.raises(ValueError):
+        sb.IdListTreeTripletLoss(9, [1, 2, 3, 4], [5, 6])(emb.cuda(), torch.full((2, 40, 56), 8).cuda())
+
+
+# ------------------------------------------------------------------------------------------------
+# two-level module
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["two_level_blob", "two_level_iid", "two_level_bf16", "two_level_allvoid"])
+def test_two_level_golden(sb, golden, name):
+    g = golden(name)
+    bf16 = bool(g["is_bf16"])
+    tol = BF16_TOL if bf16 else FP32_TOL
+    x = _x_from_golden(g).cuda().requires_grad_(True)
+    emb = torch.from_numpy(g["emb"]).cuda().requires_grad_(True)
+    mod = sb.HieraTripletLoss(19, HM, HI, loss_weight=float(g["loss_weight"]))
+    loss = mod(torch.tensor([int(g["step"])]), emb, None, x, torch.from_numpy(g["label"]).cuda())
+    loss.backward()
+    assert loss.dtype == torch.float32 and loss.dim() == 0
+    assert abs(float(loss) - float(g["loss"])) <= tol * abs(float(g["loss"]))
+    assert rel(to_np(x.grad), g["dx"]) <= tol
+    assert x.grad.dtype == x.dtype
+    if bool(g["demb_none"]):
+        assert float(emb.grad.abs().max()) == 0.0
+    else:
+        assert rel(to_np(emb.grad), g["demb"]) <= FP32_TOL
+    st = mod.last_stats
+    assert int(st["triplet"].trip[1].item()) == int(g["count"][0])
+
+
+@pytest.mark.parametrize("case", [
+    dict(b=2, h=33, w=47, hi=HI, hm=HM, step=0, dtype=torch.float32, labels="iid"),          # ragged W, step 0
+    dict(b=1, h=64, w=96, hi=HI, hm=HM, step=40000, dtype=torch.float32, labels="blob"),
+    dict(b=3, h=16, w=260, hi=HI, hm=HM, step=160000, dtype=torch.float32, labels="blob"),   # > one CTA chunk
+    dict(b=2, h=32, w=32, hi=[[0, 4], [2, 6], [6, 7]], hm=[0, 0, 1, 1, 1, 1, 2, 0, 0], step=80000,
+         dtype=torch.float32, labels="iid"),                                                  # overlapping buckets + orphans
+    dict(b=2, h=24, w=40, hi=HI, hm=HM, step=80000, dtype=torch.float16, labels="blob"),
+])
+def test_two_level_vs_oracle(sb, case):
+    g = torch.Generator().manual_seed(case["h"] * 7 + case["w"])
+    nf = len(case["hm"])
+    nc = len(case["hi"])
+    b, h, w = case["b"], case["h"], case["w"]
+    lab = (iid_labels(g, b, h, w, nf, 0.15) if case["labels"] == "iid" else blob_labels(g, b, h, w, nf, 6, 0.1))
+    x = (torch.randn(b, nf + nc, h, w, generator=g) * 3).to(case["dtype"])
+    x[0, :, 0, 0] = torch.linspace(-30, 30, nf + nc).to(case["dtype"])       # saturated logits
+    eh, ew = max(h // 8, 1), max(w // 8, 1)
+    emb = F.normalize(torch.randn(b, 12, eh, ew, generator=g), dim=1)
+    xr = x.clone().requires_grad_(True)
+    er = emb.clone().requires_grad_(True)
+    ref, parts = O.hiera_triplet_loss(case["step"], er, xr, lab, nf, case["hm"], case["hi"], loss_weight=1.3)
+    (ref * 0.7).backward()
+    xc = x.cuda().requires_grad_(True)
+    ec = emb.cuda().requires_grad_(True)
+    mod = sb.HieraTripletLoss(nf, case["hm"], case["hi"], loss_weight=1.3)
+    loss = mod(torch.tensor([case["step"]]).cuda(), ec, None, xc, lab.cuda())
+    (loss * 0.7).backward()                                                  # non-unit grad_output
+    tol = FP32_TOL if case["dtype"] == torch.float32 else BF16_TOL
+    assert abs(float(loss) - float(ref)) <= tol * abs(float(ref)), (float(loss), float(ref), parts)
+    assert rel(to_np(xc.grad), to_np(xr.grad)) <= tol
+    if er.grad is not None and float(er.grad.abs().max()) > 0:
+        assert rel(to_np(ec.grad), to_np(er.grad)) <= 10 * FP32_TOL
+    else:
+        assert float(ec.grad.abs().max()) == 0.0
+
+
+def test_two_level_forward_only_and_errors(sb):
+    g = torch.Generator().manual_seed(3)
+    lab = iid_labels(g, 1, 16, 16, 19, 0.1)
+    x = torch.randn(1, 26, 16, 16, generator=g)
+    emb = F.normalize(torch.randn(1, 8, 2, 2, generator=g), dim=1)
+    mod = sb.HieraTripletLoss(19, HM, HI)
+    with torch.no_grad():
+        loss = mod(torch.tensor([5]), emb.cuda(), None, x.cuda(), lab.cuda())
+    ref, _ = O.hiera_triplet_loss(5, emb, x, lab, 19, HM, HI)
+    assert abs(float(loss) - float(ref)) <= FP32_TOL * abs(float(ref))
+    with pytest.raises(RuntimeError):
+        mod(torch.tensor([5]), emb, None, x, lab)                            # CPU tensors: no fallback
+    lab_bad = lab.clone()
+    lab_bad[0, 0, 0] = 19
+    assert torch.isnan(mod(torch.tensor([5]), emb.cuda(), None, x.cuda(), lab_bad.cuda()))
+    with pytest.raises(RuntimeError):
+        sb.HieraTripletLoss(19, HM, HI, strict=True)(torch.tensor([5]), emb.cuda(), None, x.cuda(), lab_bad.cuda())
+
+
+# ------------------------------------------------------------------------------------------------
+# three-level module
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["three_level_blob", "three_level_iid", "three_level_small", "three_level_bf16"])
+def test_three_level_golden(sb, golden, name):
+    g = golden(name)
+    bf16 = bool(g["is_bf16"])
+    tol = BF16_TOL if bf16 else FP32_TOL
+    nf, nm, nh = int(g["nf"]), int(g["nm"]), int(g["nh"])
+    for tag, lam in (("", float(g["lam"])), ("_lam0", 0.0)):
+        x = _x_from_golden(g).cuda().requires_grad_(True)
+        emb = torch.from_numpy(g["emb"]).cuda().requires_grad_(True)
+        mod = sb.RMIHieraTripletLoss(nf, nm, nh, torch.from_numpy(g["f2m"]), torch.from_numpy(g["f2h"]),
+                                     loss_weight_lambda=lam, loss_weight=float(g["loss_weight"]))
+        loss = mod(torch.tensor([int(g["step"])]), emb, None, x, torch.from_numpy(g["label"]).cuda())
+        loss.backward()
+        assert abs(float(loss) - float(g["loss" + tag])) <= tol * abs(float(g["loss" + tag])), (tag, float(loss))
+        assert rel(to_np(x.grad), g["dx" + tag]) <= tol, (tag, rel(to_np(x.grad), g["dx" + tag]))
+        if tag == "" and not bool(g["demb_none"]):
+            assert rel(to_np(emb.grad), g["demb"]) <= FP32_TOL
+        assert int(mod.last_stats["triplet"].trip[1].item()) == int(g["count"][0])
+
+
+def test_three_level_flat_predictions(sb, golden):
+    g = golden("three_level_flat")
+    x = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+    mod = sb.RMIHieraTripletLoss(19, 7, 2, torch.tensor(F2M), torch.tensor(F2H))
+    loss = mod(torch.tensor([0]), torch.zeros(1, 4, 2, 2).cuda(), None, x, torch.from_numpy(g["label"]).cuda())
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) <= FP32_TOL * abs(float(g["loss"]))
+    assert rel(to_np(x.grad), g["dx"]) <= 1e-3      # rank-deficient regime: the reference itself is noisy
+
+
+@pytest.mark.parametrize("case", [
+    dict(b=2, h=37, w=50, labels="iid", step=0, lam=0.5, dtype=torch.float32),               # ragged, scalar path
+    dict(b=1, h=48, w=132, labels="blob", step=100000, lam=1.0, dtype=torch.float32),        # 3 tiles wide, 3 tall
+    dict(b=2, h=21, w=64, labels="blob", step=200000, lam=0.25, dtype=torch.float32),
+    dict(b=1, h=5, w=5, labels="iid", step=0, lam=0.5, dtype=torch.float32),                 # minimum size: all frame but 1
+    dict(b=1, h=40, w=72, labels="blob", step=100000, lam=0.5, dtype=torch.float16),
+])
+def test_three_level_vs_oracle(sb, case):
+    g = torch.Generator().manual_seed(case["h"] * 11 + case["w"])
+    b, h, w = case["b"], case["h"], case["w"]
+    lab = (iid_labels(g, b, h, w, 19, 0.15) if case["labels"] == "iid" else blob_labels(g, b, h, w, 19, 7, 0.1))
+    x = (torch.randn(b, 28, h, w, generator=g) * 2).to(case["dtype"])
+    eh, ew = max(h // 8, 1), max(w // 8, 1)
+    emb = F.normalize(torch.randn(b, 12, eh, ew, generator=g), dim=1)
+    xr = x.clone().requires_grad_(True)
+    er = emb.clone().requires_grad_(True)
+    ref, parts = O.rmi_hiera_triplet_loss(case["step"], er, xr, lab, 19, 7, 2, F2M, F2H,
+                                          loss_weight_lambda=case["lam"], loss_weight=0.9)
+    (ref * 1.5).backward()
+    xc = x.cuda().requires_grad_(True)
+    ec = emb.cuda().requires_grad_(True)
+    mod = sb.RMIHieraTripletLoss(19, 7, 2, torch.tensor(F2M), torch.tensor(F2H), loss_weight_lambda=case["lam"],
+                                 loss_weight=0.9)
+    loss = mod(torch.tensor([case["step"]]).cuda(), ec, None, xc, lab.cuda())
+    (loss * 1.5).backward()
+    tol = FP32_TOL if case["dtype"] == torch.float32 else BF16_TOL
+    rmi_gpu = float(mod.last_stats["out"][2].item())
+    assert abs(rmi_gpu - parts["rmi"]) <= tol * abs(parts["rmi"]), (rmi_gpu, parts["rmi"])
+    assert abs(float(loss) - float(ref)) <= tol * abs(float(ref)), (float(loss), float(ref), parts)
+    assert rel(to_np(xc.grad), to_np(xr.grad)) <= tol
+    if er.grad is not None and float(er.grad.abs().max()) > 0:
+        assert rel(to_np(ec.grad), to_np(er.grad)) <= 10 * FP32_TOL
+
+
+def test_three_level_large_hierarchy(sb):
+    """150/30/6 classes (config 4 shape family); triplet undefined in the reference for ids >= 20
+     so it is disabled on both sides."""
+    g = torch.Generator().manual_seed(4)
+    nf, nm, nh = 150, 30, 6
+    f2m = [f // 5 for f in range(nf)]
+    f2h = [f // 25 for f in range(nf)]
+    lab = blob_labels(g, 1, 24, 72, nf, 5, 0.1)
+    x = torch.randn(1, nf + nm + nh, 24, 72, generator=g) * 2
+    xr = x.clone().requires_grad_(True)
+    ref, parts = O.rmi_hiera_triplet_loss(0, None, xr, lab, nf, nm, nh, f2m, f2h, with_triplet=False)
+    ref.backward()
+    mod = sb.RMIHieraTripletLoss(nf, nm, nh, torch.tensor(f2m), torch.tensor(f2h))
+    mod.triplet_loss = None
+    xc = x.cuda().requires_grad_(True)
+    loss = mod(torch.tensor([0]), None, None, xc, lab.cuda())
+    loss.backward()
+    assert abs(float(loss) - float(ref)) <= FP32_TOL * abs(float(ref)), (float(loss), float(ref), parts)
+    assert rel(to_np(xc.grad), to_np(xr.grad)) <= FP32_TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size, size-independent properties (BASELINE configs 2, 3, 5)
+# ------------------------------------------------------------------------------------------------
+def test_full_size_properties(sb):
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(1234)
+    # config 5 family: decode at 4 x 2048 x 2048 against torch.argmax on the same device
+    x = torch.randn(4, 28, 1024, 2048, generator=g, device=dev, dtype=torch.bfloat16)
+    preds, _ = sb.hierarchical_argmax(x, [19, 7, 2])
+    assert torch.equal(preds[0], x[:, :19].argmax(1))
+    assert torch.equal(preds[1], x[:, 19:26].argmax(1))
+    assert torch.equal(preds[2], x[:, 26:].argmax(1))
+    # targets: gather == composition property  high = map_mh[mid]
+    lab = torch.randint(0, 19, (8, 1024, 2048), generator=g, device=dev)
+    lab[torch.rand(8, 1024, 2048, generator=g, device=dev) < 0.1] = 255
+    mid, high = sb.targets_three_level(lab, torch.tensor(F2M), torch.tensor(F2H))
+    m2h = torch.tensor([0, 0, 0, 0, 0, 1, 1] + [255] * 249, device=dev)
+    assert torch.equal(high, m2h[mid])
+    assert torch.equal(mid == 255, lab == 255)
+    del x, preds
+    # config 2 shape: linearity in loss_weight and run-to-run determinism
+    x = torch.randn(4, 26, 512, 1024, generator=g, device=dev).bfloat16().requires_grad_(True)
+    lab2 = lab[:4, :512, :1024].contiguous()
+    emb = F.normalize(torch.randn(4, 256, 16, 32, generator=g, device=dev), dim=1)
+    outs = []
+    for lw in (1.0, 2.0, 1.0):
+        mod = sb.HieraTripletLoss(19, HM, HI, loss_weight=lw)
+        x.grad = None
+        loss = mod(torch.tensor([100000], device=dev), emb, None, x, lab2)
+        loss.backward()
+        outs.append((float(loss), x.grad.float().clone()))
+    assert outs[0][0] == outs[2][0] and torch.equal(outs[0][1], outs[2][1])            # deterministic
+    assert abs(outs[1][0] - 2 * outs[0][0]) <= 1e-6 * abs(outs[1][0])
+    assert rel(to_np(outs[1][1]), 2 * to_np(outs[0][1])) <= 1e-2                       # bf16 rounding of grads
+    # config 3 shape (one sample): RMI r_bc of a batch == r_bc of its samples; loss finite
+    x3 = (torch.randn(2, 28, 1024, 2048, generator=g, device=dev) * 2).requires_grad_(True)
+    lab3 = lab[:2].contiguous()
+    emb3 = F.normalize(torch.randn(2, 256, 32, 64, generator=g, device=dev), dim=1)
+    mod = sb.RMIHieraTripletLoss(19, 7, 2, torch.tensor(F2M), torch.tensor(F2H))
+    loss = mod(torch.tensor([100000], device=dev), emb3, None, x3, lab3)
+    loss.backward()
+    assert torch.isfinite(loss) and torch.isfinite(x3.grad).all()
+    rmi_batch = float(mod.last_stats["out"][2])
+    rmis = []
+    for i in range(2):
+        m1 = sb.RMIHieraTripletLoss(19, 7, 2, torch.tensor(F2M), torch.tensor(F2H))
+        m1(torch.tensor([100000], device=dev), emb3[i:i + 1], None, x3[i:i + 1].detach(), lab3[i:i + 1])
+        rmis.append(float(m1.last_stats["out"][2]))
+    assert abs(rmi_batch - 0.5 * (rmis[0] + rmis[1])) <= 1e-5 * abs(rmi_batch)
+    # directional derivative check of the full-size gradient (fp32, central difference)
+    d = torch.randn_like(x3) * 1e-2
+    with torch.no_grad():
+        lp = mod(torch.tensor([100000], device=dev), emb3, None, x3 + d, lab3)
+        lm = mod(torch.tensor([100000], device=dev), emb3, None, x3 - d, lab3)
+    fd = (float(lp) - float(lm)) / 2
+    an = float((x3.grad.double() * d.double()).sum())
+    assert abs(fd - an) <= 2e-2 * max(abs(an), 1e-6), (fd, an)
