@@ -1,0 +1,460 @@
+#!/usr/bin/env python
+"""Benchmark of the hierarchical-loss hot path (BASELINE.json metric: hier-loss fwd+bwd Gpix/s and
+fraction of the HBM roofline).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU arm (oracle port, rank 0 only)
+
+A "step" is one forward+backward of the loss module over one synthetic batch (per rank; weak scaling).
+Default workload = BASELINE config 3 (the configuration the target is quoted on):
+RMIHieraTripletLoss, 19->7->2 classes, logits fp32 [8, 28, 1024, 2048] per GPU, labels L-blob (32x32
+constant tiles, 10 % ignore), embedding [8, 256, 32, 64].  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+HI_19_7 = [[0, 2], [2, 5], [5, 8], [8, 10], [10, 11], [11, 13], [13, 19]]
+HM_19_7 = [0, 0, 1, 1, 1, 2, 2, 2, 3, 3, 4, 5, 5, 6, 6, 6, 6, 6, 6]
+F2H_19 = [0] * 11 + [1] * 8
+
+WORKLOADS = {
+    # name: kind, levels, B, H, W, dtype, algorithmic bytes/pixel formula pieces
+    "cfg3": dict(kind="3level", nf=19, nm=7, nh=2, B=8, H=1024, W=2048, dtype="fp32",
+                 desc="config 3: RMIHieraTripletLoss 19/7/2, 1024x2048, batch 8/GPU, fp32 logits"),
+    "cfg3-bf16": dict(kind="3level", nf=19, nm=7, nh=2, B=8, H=1024, W=2048, dtype="bf16",
+                      desc="config 3 with bf16 logits"),
+    "cfg2": dict(kind="2level", nf=19, nc=7, B=16, H=512, W=1024, dtype="bf16",
+                 desc="config 2: HieraTripletLoss 19/7, 512x1024, batch 16, bf16 logits"),
+    "cfg4": dict(kind="3level", nf=150, nm=30, nh=6, B=32, H=512, W=512, dtype="fp32", triplet=False,
+                 desc="config 4: 150/30/6 classes, 512x512, batch 32/GPU (triplet undefined in the reference, off)"),
+    "cfg5": dict(kind="decode", nf=19, nm=7, nh=2, B=64, H=2048, W=2048, dtype="bf16",
+                 desc="config 5: hierarchical argmax decode, 2048x2048, batch 64, bf16 logits"),
+}
+
+
+def algorithmic_bytes_per_px(w):
+    e = 4 if w["dtype"] == "fp32" else 2
+    if w["kind"] == "3level":
+        c = w["nf"] + w["nm"] + w["nh"]
+        return dict(total=3 * c * e + 16, pass1=c * e + 8, pass2=2 * c * e + 8)
+    if w["kind"] == "2level":
+        c = w["nf"] + w["nc"]
+        return dict(total=2 * c * e + 8, fused=2 * c * e + 8)
+    c = w["nf"] + w["nm"] + w["nh"]
+    return dict(total=c * e + 3 * 8, decode=c * e + 3 * 8)   # int64 outputs like torch.argmax
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                 parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+class StageTimer:
+    """Brackets every kernel-level stage of the multi-kernel C entry points with CUDA events."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.pending, self.open = [], {}
+
+    def start(self, name, bit):
+        ev = self.torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.open[(name, bit)] = ev
+
+    def stop(self, name, bit):
+        ev = self.torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.pending.append(((name, bit), self.open.pop((name, bit)), ev))
+
+    def totals(self):
+        out = {}
+        for key, a, b in self.pending:
+            t, n = out.get(key, (0.0, 0))
+            out[key] = (t + a.elapsed_time(b), n + 1)
+        return out
+
+
+def make_labels(torch, gen, b, h, w, n_fine, kind, dev):
+    if kind == "iid":
+        lab = torch.randint(0, n_fine, (b, h, w), generator=gen, device=dev)
+        lab[torch.rand(b, h, w, generator=gen, device=dev) < 0.1] = 255
+        return lab
+    tile = 32
+    th, tw = (h + tile - 1) // tile, (w + tile - 1) // tile
+    c = torch.randint(0, n_fine, (b, th, tw), generator=gen, device=dev)
+    c[torch.rand(b, th, tw, generator=gen, device=dev) < 0.1] = 255
+    return c.repeat_interleave(tile, 1).repeat_interleave(tile, 2)[:, :h, :w].contiguous()
+
+
+def hierarchy_maps(w):
+    if w["nf"] == 19:
+        return HM_19_7, F2H_19
+    return [f // 5 for f in range(w["nf"])], [f // 25 for f in range(w["nf"])]
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores, bounded sample of the workload
+# ------------------------------------------------------------------------------------------------
+def cpu_sample_shape(w):
+    if w["kind"] == "decode":
+        return 4, 512, 512
+    if w["kind"] == "2level":
+        return 2, 256, 512
+    return (1, 512, 1024) if w["nf"] <= 32 else (1, 256, 256)
+
+
+def run_cpu_oracle(w, steps, warmup, label_kind):
+    import torch
+    import torch.nn.functional as F
+    from oracle import hiera_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    b, h, wd = cpu_sample_shape(w)
+    g = torch.Generator().manual_seed(1234)
+    lab = make_labels(torch, g, b, h, wd, w["nf"], label_kind, "cpu")
+    dt = torch.float32 if w["dtype"] == "fp32" else torch.bfloat16
+    f2m, f2h = hierarchy_maps(w)
+    if w["kind"] == "decode":
+        x = torch.randn(b, w["nf"] + w["nm"] + w["nh"], h, wd, generator=g).to(dt)
+
+        def step():
+            O.argmax_decode(x, [w["nf"], w["nm"], w["nh"]])
+    elif w["kind"] == "2level":
+        x = (torch.randn(b, w["nf"] + w["nc"], h, wd, generator=g) * 2).to(dt).requires_grad_(True)
+        emb = F.normalize(torch.randn(b, 256, h // 32, wd // 32, generator=g), dim=1).requires_grad_(True)
+
+        def step():
+            x.grad = None
+            emb.grad = None
+            loss, _ = O.hiera_triplet_loss(100000, emb, x, lab, w["nf"], HM_19_7, HI_19_7)
+            loss.backward()
+    else:
+        x = (torch.randn(b, w["nf"] + w["nm"] + w["nh"], h, wd, generator=g) * 2).to(dt).requires_grad_(True)
+        emb = F.normalize(torch.randn(b, 256, h // 32, wd // 32, generator=g), dim=1).requires_grad_(True)
+        trip = w.get("triplet", True)
+
+        def step():
+            x.grad = None
+            emb.grad = None
+            loss, _ = O.rmi_hiera_triplet_loss(100000, emb, x, lab, w["nf"], w["nm"], w["nh"], f2m, f2h,
+                                               with_triplet=trip)
+            loss.backward()
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt_s = (time.perf_counter() - t0) / max(steps, 1)
+    px = b * h * wd
+    return dict(value=px / dt_s / 1e9, unit="Gpix/s", cores=cores, kind="port",
+                sample=f"oracle port (torch-CPU restatement of the reference loss), {b}x{h}x{wd} crop of the "
+                       f"workload, fwd+bwd, {steps} steps, all {cores} host threads", ms_per_step=dt_s * 1e3)
+
+
+def run_reference_arm(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    res = run_cpu_oracle(w, steps, 1, args.labels)
+    line = {
+        "impl": "reference", "metric": "hier_loss_fwd_bwd_throughput", "value": res["value"], "unit": "Gpix/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": res["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "description": w["desc"], "labels": args.labels},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": "Gpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, w):
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    import seghiero_b200 as sb
+    from seghiero_b200 import ops
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
+    steps = max(args.steps, 1)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    b, h, wd = args.batch or w["B"], w["H"], w["W"]
+    dt = torch.float32 if w["dtype"] == "fp32" else torch.bfloat16
+    px = b * h * wd
+    f2m, f2h = hierarchy_maps(w)
+    lab = make_labels(torch, g, b, h, wd, w["nf"], args.labels, dev)
+    step_t = torch.tensor([100000], device=dev)
+    grads_out = []
+
+    if w["kind"] == "decode":
+        c = w["nf"] + w["nm"] + w["nh"]
+        x = torch.randn(b, c, h, wd, generator=g, device=dev, dtype=torch.float32).to(dt)
+        emb = None
+
+        def step():
+            preds, counts = sb.hierarchical_argmax(x, [w["nf"], w["nm"], w["nh"]], lab)
+            return counts
+        host_in = [x]
+    else:
+        if w["kind"] == "2level":
+            c = w["nf"] + w["nc"]
+            mod = sb.HieraTripletLoss(w["nf"], HM_19_7, HI_19_7)
+        else:
+            c = w["nf"] + w["nm"] + w["nh"]
+            mod = sb.RMIHieraTripletLoss(w["nf"], w["nm"], w["nh"], torch.tensor(f2m), torch.tensor(f2h))
+            if not w.get("triplet", True):
+                mod.triplet_loss = None
+        x = (torch.randn(b, c, h, wd, generator=g, device=dev) * 2).to(dt).requires_grad_(True)
+        emb = F.normalize(torch.randn(b, 256, h // 32, wd // 32, generator=g, device=dev), dim=1).requires_grad_(True)
+        use_emb = emb if (w["kind"] == "2level" or w.get("triplet", True)) else None
+
+        def step():
+            x.grad = None
+            emb.grad = None
+            loss = mod(step_t, use_emb, None, x, lab)
+            loss.backward()
+            if world > 1:   # scalar loss sum across ranks (the path's only data collective besides `ready`)
+                dist.all_reduce(loss.detach(), op=dist.ReduceOp.SUM)
+            return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+
+    # ---- timed region: K steps, device-timed, stage events on --------------------------------------
+    timer = StageTimer()
+    ops.STAGE_TIMER = timer
+    ops.LAUNCHES["n"] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            out = step()
+        e1.record()
+        barrier()
+    ops.STAGE_TIMER = None
+    launches = ops.LAUNCHES["n"]
+    elapsed = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
+    ms_total = float(elapsed.item())
+    ms_step = ms_total / steps
+    value = world * px / (ms_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (from the stage events of the same timed region) ------------
+    ab = algorithmic_bytes_per_px(w)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    stage_names = {("sh_rmi3_forward", 1): "k3_prep", ("sh_rmi3_forward", 2): "k3_pass1",
+                   ("sh_rmi3_forward", 4): "k3_frame1", ("sh_rmi3_forward", 8): "k3_finalize",
+                   ("sh_rmi3_backward", 1): "k3_pass2", ("sh_rmi3_backward", 2): "k3_frame2",
+                   ("sh_bce2_fwdbwd", 1): "k_prep2", ("sh_bce2_fwdbwd", 2): "k_bce2_fused",
+                   ("sh_bce2_fwdbwd", 4): "k_reduce_partials"}
+    stage_bytes = {"k3_pass1": ab.get("pass1"), "k3_pass2": ab.get("pass2"), "k_bce2_fused": ab.get("fused")}
+    stages = {stage_names[k]: t / n for k, (t, n) in timer.totals().items() if k in stage_names}
+    roofline = None
+    traffic_tab = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_per_px.json")) as fh:
+            traffic_tab = json.load(fh)
+    except OSError:
+        pass
+    cand = {k: v for k, v in stages.items() if stage_bytes.get(k)}
+    if cand:
+        top = max(cand, key=cand.get)
+        achieved = stage_bytes[top] * px / (cand[top] * 1e-3) / 1e9
+        tr = traffic_tab.get(f"{args.workload}:{top}")
+        roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": (tr * px if tr else None),
+                    "algorithmic_bytes_per_launch": stage_bytes[top] * px, "ms_per_launch": cand[top],
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                    "whole_step_frac": ab["total"] * px / (ms_step * 1e-3) / 1e9 / peak}
+    elif w["kind"] == "decode":
+        achieved = ab["total"] * px / (ms_step * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_decode", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": ab["total"] * px,
+                    "ms_per_launch": ms_step,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"}
+
+    # ---- end-to-end through the public API with HOST buffers -----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        if w["kind"] == "decode":
+            hx = torch.empty(x.shape, dtype=x.dtype, pin_memory=True).copy_(x)
+            hlab = torch.empty(lab.shape, dtype=lab.dtype, pin_memory=True).copy_(lab)
+            hout = [torch.empty((b, h, wd), dtype=torch.int64, pin_memory=True) for _ in range(3)]
+
+            def e2e_step():
+                xd = hx.to(dev, non_blocking=True)
+                ld = hlab.to(dev, non_blocking=True)
+                preds, counts = sb.hierarchical_argmax(xd, [w["nf"], w["nm"], w["nh"]], ld)
+                for o, p in zip(hout, preds):
+                    o.copy_(p, non_blocking=True)
+                return counts.cpu()
+            h2d = hx.numel() * hx.element_size() + hlab.numel() * 8
+            d2h = 3 * b * h * wd * 8 + 16
+        else:
+            hx = torch.empty(x.shape, dtype=x.dtype, pin_memory=True).copy_(x.detach())
+            hlab = torch.empty(lab.shape, dtype=lab.dtype, pin_memory=True).copy_(lab)
+            hemb = torch.empty(emb.shape, dtype=emb.dtype, pin_memory=True).copy_(emb.detach())
+            hgx = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+            hge = torch.empty(emb.shape, dtype=emb.dtype, pin_memory=True)
+
+            def e2e_step():
+                xd = hx.to(dev, non_blocking=True).requires_grad_(True)
+                ld = hlab.to(dev, non_blocking=True)
+                ed = hemb.to(dev, non_blocking=True).requires_grad_(True)
+                loss = mod(step_t, ed if use_emb is not None else None, None, xd, ld)
+                loss.backward()
+                hgx.copy_(xd.grad, non_blocking=True)
+                if ed.grad is not None:
+                    hge.copy_(ed.grad, non_blocking=True)
+                return loss.cpu()          # device->host read of the step's result (syncs)
+            h2d = hx.numel() * hx.element_size() + hlab.numel() * 8 + hemb.numel() * hemb.element_size()
+            d2h = hgx.numel() * hgx.element_size() + hge.numel() * hge.element_size() + 4
+        e2e_step()
+        barrier()
+        k2 = max(2, min(steps, 5))
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(k2):
+            e2e_step()
+        a1.record()
+        barrier()
+        el = torch.tensor([a0.elapsed_time(a1) / k2], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * px / (float(el.item()) * 1e-3) / 1e9, "unit": "Gpix/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": float(el.item()),
+               "steps": k2, "note": "pinned host buffers -> H2D -> fwd+bwd -> D2H of loss and gradients"}
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        res = run_cpu_oracle(w, 2, 1, args.labels)
+        cpu_base = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": "hier_loss_fwd_bwd_throughput", "value": value, "unit": "Gpix/s", "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if w["dtype"] == "fp32" else "bf16 in / f32 accumulate",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "description": w["desc"], "labels": args.labels,
+                       "batch_per_gpu": b, "pixels_per_step_per_gpu": px,
+                       "l2": "inputs larger than L2 (logits %.2f GB per GPU)" % (x.numel() * x.element_size() / 1e9),
+                       "parallelism": f"dp{world} by sample, no data-path collective"},
+            "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clk.summary(), "kernel_ms": stages,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--labels", default="blob", choices=["blob", "iid"])
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -4,7 +4,9 @@
  * its own).  Every entry point takes plain device pointers, sizes and a
  * cudaStream_t passed as void*; nothing here names a torch type.  All pointers are caller-owned
  * device memory (PyTorch's caching allocator in the shipped host code); the library keeps no global
- * state, allocates nothing and launches only on the given stream.  Return value: 0 on success,
+ * state, allocates nothing and launches only on the given stream.  `stages` arguments are bit masks
+ * selecting which kernels of a multi-kernel entry point run (-1 = all; bench.py brackets single kernels
+ * with CUDA events this way).  Return value: 0 on success,
  * a negative SH_ERR_* code for bad arguments, or a positive cudaError_t from the launch.
  *
  * dtype codes: 0 = float32, 1 = bfloat16, 2 = float16 (logits / embeddings / gradients).
@@ -57,7 +59,8 @@ int sh_bce2_grid(int B, long HW, int C, int n_coarse);
  * #valid coarse, label-range error flag. */
 int sh_bce2_fwdbwd(const void* logits, int dtype, const long long* label, void* grad, int B, long HW, int n_fine,
                    int n_coarse, const int* hier_tab, int n_fb, int lut_size, float eps, float loss_weight,
-                   unsigned char* lab8, unsigned long long* counts, float* partials, double* sums, void* stream);
+                   unsigned char* lab8, unsigned long long* counts, float* partials, double* sums, int stages,
+                   void* stream);
 
 /* Scalar assembly incl. the cosine schedule and ready gate (hiera_triplet_loss.py:188-211), on device.
  * out[0] = loss, out[1] = ready*factor*loss_weight (scale for the triplet backward). */
@@ -81,7 +84,8 @@ int sh_rmi3_workspace_offsets(int B, int H, int W, int nf, int nm, int nh, size_
  * sh_loss3_final need in `workspace`.
  * hier_tab (device int32): [f2m nf][f2h nf][mh_ptr nm+1][mh_idx n_mh][hsmask nm]. */
 int sh_rmi3_forward(const void* logits, int dtype, const long long* label, int B, int H, int W, int nf, int nm, int nh,
-                    const int* hier_tab, int n_mh, float lam, float loss_weight, void* workspace, void* stream);
+                    const int* hier_tab, int n_mh, float lam, float loss_weight, void* workspace, int stages,
+                    void* stream);
 
 /* out[0] = loss, out[1] = ready*factor*loss_weight, out[2] = rmi term. */
 int sh_loss3_final(int B, int H, int W, int nf, int nm, int nh, void* workspace, float lam, const double* step,
@@ -91,7 +95,7 @@ int sh_loss3_final(int B, int H, int W, int nf, int nm, int nh, void* workspace,
 /* Pass 2: d loss / d logits written once (grad_out = device scalar handed over by autograd). */
 int sh_rmi3_backward(const void* logits, int dtype, void* grad, int B, int H, int W, int nf, int nm, int nh,
                      const int* hier_tab, int n_mh, float loss_weight, void* workspace, const float* grad_out,
-                     void* stream);
+                     int stages, void* stream);
 
 /* ---- triplet: TreeTripletLoss.forward, models/loss/tree_triplet_loss.py:15-65 (mode 0) and
  *      models/loss/rmi_tree_triplet_loss.py:14-70 (mode 1) ------------------------------------- */

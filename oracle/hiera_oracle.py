@@ -376,7 +376,7 @@ def hiera_triplet_loss(step, embedding, x, label, num_classes, hiera_map, hiera_
     if ready and trip is not None:
         loss = loss + factor * trip.double()
     parts = dict(hiera=float(hiera.detach()), ce=[float(ce_f.detach()), float(ce_c.detach())],
-                 triplet=None if trip is None else float(trip), count=count, factor=factor,
+                 triplet=None if trip is None else float(trip.detach()), count=count, factor=factor,
                  targets=(tf, tc))
     return (loss * loss_weight).float(), parts
 
@@ -403,7 +403,7 @@ def rmi_hiera_triplet_loss(step, embedding, x, label, n_fine, n_mid, n_high, fin
     if ready and trip is not None:
         loss = loss + factor * trip.double()
     parts = dict(hiera=float(hiera.detach()), rmi=float(rmi.detach()), ce=[float(c.detach()) for c in ce],
-                 triplet=None if trip is None else float(trip), count=count, factor=factor,
+                 triplet=None if trip is None else float(trip.detach()), count=count, factor=factor,
                  targets=(tf, tm, th))
     return (loss * loss_weight).float(), parts
 

@@ -37,17 +37,19 @@ def main():
     ap.add_argument("--labels", default="blob")
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--dtype", default="")
+    ap.add_argument("--h", type=int, default=0)
+    ap.add_argument("--w", type=int, default=0)
     a = ap.parse_args()
     dev = "cuda"
     g = torch.Generator(device=dev).manual_seed(1234)
     if a.cfg == "2":
-        b, h, w, dt = a.batch or 16, 512, 1024, torch.bfloat16
+        b, h, w, dt = a.batch or 16, a.h or 512, a.w or 1024, torch.bfloat16
         dt = {"": dt, "fp32": torch.float32, "bf16": torch.bfloat16}[a.dtype]
         x = (torch.randn(b, 26, h, w, generator=g, device=dev) * 2).to(dt).requires_grad_(True)
         mod = sb.HieraTripletLoss(19, HM, HI)
         bpp = 2 * 26 * x.element_size() + 8
     else:
-        b, h, w, dt = a.batch or 8, 1024, 2048, torch.float32
+        b, h, w, dt = a.batch or 8, a.h or 1024, a.w or 2048, torch.float32
         dt = {"": dt, "fp32": torch.float32, "bf16": torch.bfloat16}[a.dtype]
         x = (torch.randn(b, 28, h, w, generator=g, device=dev) * 2).to(dt).requires_grad_(True)
         mod = sb.RMIHieraTripletLoss(19, 7, 2, torch.tensor(F2M), torch.tensor(F2H))

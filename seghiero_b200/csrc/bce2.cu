@@ -307,7 +307,7 @@ int sh_bce2_grid(int B, long HW, int C, int n_coarse) {
 int sh_bce2_fwdbwd(const void* logits, int dtype, const long long* label, void* grad /* nullable */, int B, long HW,
                    int n_fine, int n_coarse, const int* hier_tab, int n_fb, int lut_size, float eps, float loss_weight,
                    unsigned char* lab8 /* [B*HW] */, unsigned long long* counts /* [4], zeroed by callee */,
-                   float* partials /* [grid*4] */, double* sums /* [4] */, void* stream) {
+                   float* partials /* [grid*4] */, double* sums /* [4] */, int stages, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (B <= 0 || HW <= 0 || n_fine <= 0 || n_coarse <= 0 || n_fine + n_coarse > 255) return SH_ERR_BAD_ARG;
   sh::Hier2 h;
@@ -319,24 +319,28 @@ int sh_bce2_fwdbwd(const void* logits, int dtype, const long long* label, void* 
   h.fb_idx = h.fb_ptr + n_fine + 1;
   h.lut = h.fb_idx + n_fb;
   h.lut_size = lut_size;
-  cudaError_t e = cudaMemsetAsync(counts, 0, 4 * sizeof(unsigned long long), st);
-  if (e != cudaSuccess) return (int)e;
-  const long n = (long)B * HW;
-  long pb = (n + 255) / 256;
-  if (pb > SH_NUM_SMS * 8L) pb = SH_NUM_SMS * 8L;
-  sh::k_prep2<<<(unsigned)pb, 256, 0, st>>>(label, lab8, n, n_fine, h.lut, lut_size, counts);
-  SH_CHECK_LAUNCH();
+  if (stages & 1) {
+    cudaError_t e = cudaMemsetAsync(counts, 0, 4 * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return (int)e;
+    const long n = (long)B * HW;
+    long pb = (n + 255) / 256;
+    if (pb > SH_NUM_SMS * 8L) pb = SH_NUM_SMS * 8L;
+    sh::k_prep2<<<(unsigned)pb, 256, 0, st>>>(label, lab8, n, n_fine, h.lut, lut_size, counts);
+    SH_CHECK_LAUNCH();
+  }
   const int grid = sh_bce2_grid(B, HW, n_fine + n_coarse, n_coarse);
-  int rc;
-  switch (dtype) {
+  int rc = SH_OK;
+  if (stages & 2) switch (dtype) {
     case SH_DT_F32: rc = sh::launch_bce2<float>(logits, lab8, grad, B, HW, h, eps, loss_weight, counts, partials, grid, st); break;
     case SH_DT_BF16: rc = sh::launch_bce2<__nv_bfloat16>(logits, lab8, grad, B, HW, h, eps, loss_weight, counts, partials, grid, st); break;
     case SH_DT_F16: rc = sh::launch_bce2<__half>(logits, lab8, grad, B, HW, h, eps, loss_weight, counts, partials, grid, st); break;
     default: return SH_ERR_UNSUPPORTED;
   }
   if (rc != SH_OK) return rc;
-  sh::k_reduce_partials<<<1, 256, 0, st>>>(partials, grid, 4, sums);
-  SH_CHECK_LAUNCH();
+  if (stages & 4) {
+    sh::k_reduce_partials<<<1, 256, 0, st>>>(partials, grid, 4, sums);
+    SH_CHECK_LAUNCH();
+  }
   return SH_OK;
 }
 

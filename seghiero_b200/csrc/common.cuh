@@ -45,18 +45,27 @@ __device__ __forceinline__ float rcp(float x) {
 // natural log through the MUFU lg2 (abs error ~1e-7 for arguments in [1e-8, 2])
 __device__ __forceinline__ float fast_log(float x) { return lg2(x) * kLn2; }
 
-// e^x and sigmoid(x) from ONE ex2 and ONE rcp.  x is clamped so that e^x stays
-// finite; for x > 17 sigmoid rounds to 1.0f in fp32 anyway, for x < -87 to 0.
+// e^x and sigmoid(x) from one ex2 and two rcp.  The sigmoid follows torch's own formula
+// 1/(1+e^-x) INCLUDING its fp32 rounding of (1 + e^-x): the reference takes log(1 - s + eps) of that
+// quantised value, so large positive logits must saturate exactly the way torch does.
+//   w = e^-|x| ;  x >= 0: s = 1/(1+w) (refined to a correctly rounded reciprocal), e^x = 1/w
+//                 x <  0: s = w/(1+w),                                               e^x = w
+// |x| is clamped to 80 so that sums of e^x over a level's channels stay finite.
 struct SigExp {
   float v;  // e^x
   float s;  // sigmoid(x)
 };
 __device__ __forceinline__ SigExp sig_exp(float x) {
-  float xc = fminf(fmaxf(x, -87.0f), 80.0f);
+  const float ax = fminf(fabsf(x), 80.0f);
+  const float w = ex2(-ax * kLog2e);
+  const float y = 1.0f + w;
+  const float q0 = rcp(y);
+  const float q = fmaf(q0, fmaf(-y, q0, 1.0f), q0);   // one Newton step: IEEE-quality 1/y
+  const bool pos = x >= 0.0f;
   SigExp r;
-  r.v = ex2(xc * kLog2e);
-  r.s = r.v * rcp(1.0f + r.v);
-  if (x != x) r.s = x;  // NaN propagates like torch.sigmoid
+  r.s = pos ? q : w * q;
+  r.v = pos ? rcp(w) : w;
+  if (x != x) { r.s = x; r.v = x; }
   return r;
 }
 

@@ -307,14 +307,18 @@ __global__ void __launch_bounds__(256) k3_frame2(const T* __restrict__ x, T* __r
 
 template <typename T>
 static int run_backward3(const void* x, void* grad, int B, int H, int W, const Hier3& h, const Ws3& ws, float eps,
-                         float lw, const float* gscale, cudaStream_t st) {
+                         float lw, const float* gscale, int stages, cudaStream_t st) {
   const int C = h.nf + h.nm + h.nh;
   const bool vec_ok = ((W & 3) == 0) && ((uintptr_t)x % (4 * sizeof(T)) == 0) && ((uintptr_t)grad % (4 * sizeof(T)) == 0);
   dim3 g2((W + kTW - 1) / kTW, (H + 15) / 16, B);
-  k3_pass2<T><<<g2, 256, 0, st>>>((const T*)x, (T*)grad, B, H, W, h, ws, eps, lw, gscale, vec_ok ? 1 : 0);
-  SH_CHECK_LAUNCH();
-  k3_frame2<T><<<dim3(B * C, ws.nseg), 256, 0, st>>>((const T*)x, (T*)grad, B, H, W, h, ws, gscale);
-  SH_CHECK_LAUNCH();
+  if (stages & 1) {
+    k3_pass2<T><<<g2, 256, 0, st>>>((const T*)x, (T*)grad, B, H, W, h, ws, eps, lw, gscale, vec_ok ? 1 : 0);
+    SH_CHECK_LAUNCH();
+  }
+  if (stages & 2) {
+    k3_frame2<T><<<dim3(B * C, ws.nseg), 256, 0, st>>>((const T*)x, (T*)grad, B, H, W, h, ws, gscale);
+    SH_CHECK_LAUNCH();
+  }
   return SH_OK;
 }
 
@@ -324,15 +328,15 @@ extern "C" {
 
 int sh_rmi3_backward(const void* logits, int dtype, void* grad, int B, int H, int W, int nf, int nm, int nh,
                      const int* hier_tab, int n_mh, float loss_weight, void* workspace, const float* grad_out,
-                     void* stream) {
+                     int stages, void* stream) {
   if (B <= 0 || H < 5 || W < 5 || nf + nm + nh > 255) return SH_ERR_BAD_ARG;
   sh::Ws3 ws = sh::ws3_layout(workspace, B, H, W, nf, nm, nh);
   sh::Hier3 h = sh::hier3_from_tab(hier_tab, nf, nm, nh, n_mh);
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case SH_DT_F32: return sh::run_backward3<float>(logits, grad, B, H, W, h, ws, 1e-6f, loss_weight, grad_out, st);
-    case SH_DT_BF16: return sh::run_backward3<__nv_bfloat16>(logits, grad, B, H, W, h, ws, 1e-6f, loss_weight, grad_out, st);
-    case SH_DT_F16: return sh::run_backward3<__half>(logits, grad, B, H, W, h, ws, 1e-6f, loss_weight, grad_out, st);
+    case SH_DT_F32: return sh::run_backward3<float>(logits, grad, B, H, W, h, ws, 1e-6f, loss_weight, grad_out, stages, st);
+    case SH_DT_BF16: return sh::run_backward3<__nv_bfloat16>(logits, grad, B, H, W, h, ws, 1e-6f, loss_weight, grad_out, stages, st);
+    case SH_DT_F16: return sh::run_backward3<__half>(logits, grad, B, H, W, h, ws, 1e-6f, loss_weight, grad_out, stages, st);
   }
   return SH_ERR_UNSUPPORTED;
 }

@@ -717,13 +717,15 @@ __global__ void __launch_bounds__(256) k_reduce_partials3(const float* __restric
 
 template <typename T>
 static int run_forward3(const void* x, const long long* label, int B, int H, int W, const Hier3& h, const Ws3& ws,
-                        float eps, double scale, cudaStream_t st) {
+                        float eps, double scale, int stages, cudaStream_t st) {
   const int C = h.nf + h.nm + h.nh;
-  cudaError_t e = cudaMemsetAsync(ws.counts, 0, 4 * sizeof(unsigned long long), st);
-  if (e != cudaSuccess) return (int)e;
-  dim3 gp((W + kTW - 1) / kTW, (H + 15) / 16, B);
-  k3_prep<<<gp, 256, 0, st>>>(label, B, H, W, h, ws.lab8, ws.flags, ws.counts);
-  SH_CHECK_LAUNCH();
+  if (stages & 1) {
+    cudaError_t e = cudaMemsetAsync(ws.counts, 0, 4 * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return (int)e;
+    dim3 gp((W + kTW - 1) / kTW, (H + 15) / 16, B);
+    k3_prep<<<gp, 256, 0, st>>>(label, B, H, W, h, ws.lab8, ws.flags, ws.counts);
+    SH_CHECK_LAUNCH();
+  }
   const int th = ws.th, PX = th * kTW;
   size_t smem = (size_t)(th + 2) * kPitch * 4 + (size_t)(h.nm + h.nh) * PX * 5 + 64 * 4 + 3 * (size_t)(th + 4) * kLabPitch;
   smem = (smem + 15) & ~(size_t)15;
@@ -732,16 +734,22 @@ static int run_forward3(const void* x, const long long* label, int B, int H, int
   auto kern = k3_pass1<T>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 g1(ws.tiles_x, ws.tiles_y, B);
-  kern<<<g1, th * kStrips, smem, st>>>((const T*)x, B, H, W, h, ws, eps, vec_ok ? 1 : 0);
-  SH_CHECK_LAUNCH();
+  if (stages & 2) {
+    kern<<<g1, th * kStrips, smem, st>>>((const T*)x, B, H, W, h, ws, eps, vec_ok ? 1 : 0);
+    SH_CHECK_LAUNCH();
+  }
   const int nseg = ws.nseg;
-  k3_frame1<T><<<dim3(B * C, nseg), 256, 0, st>>>((const T*)x, B, H, W, h, ws);
-  SH_CHECK_LAUNCH();
-  const long ntiles = (long)ws.tiles_x * ws.tiles_y * B;
-  k_reduce_partials3<<<1, 256, 0, st>>>(ws.bcepart, ntiles, 8, ws.sums);
-  SH_CHECK_LAUNCH();
-  k3_finalize<<<B * C, 64, 0, st>>>(B, C, (long)ws.tiles_x * ws.tiles_y, nseg, ws, scale);
-  SH_CHECK_LAUNCH();
+  if (stages & 4) {
+    k3_frame1<T><<<dim3(B * C, nseg), 256, 0, st>>>((const T*)x, B, H, W, h, ws);
+    SH_CHECK_LAUNCH();
+  }
+  if (stages & 8) {
+    const long ntiles = (long)ws.tiles_x * ws.tiles_y * B;
+    k_reduce_partials3<<<1, 256, 0, st>>>(ws.bcepart, ntiles, 8, ws.sums);
+    SH_CHECK_LAUNCH();
+    k3_finalize<<<B * C, 64, 0, st>>>(B, C, (long)ws.tiles_x * ws.tiles_y, nseg, ws, scale);
+    SH_CHECK_LAUNCH();
+  }
   return SH_OK;
 }
 
@@ -764,7 +772,8 @@ int sh_rmi3_workspace_offsets(int B, int H, int W, int nf, int nm, int nh, size_
 
 // hier_tab (device int32): [f2m nf][f2h nf][mh_ptr nm+1][mh_idx n_mh][hsmask nm]
 int sh_rmi3_forward(const void* logits, int dtype, const long long* label, int B, int H, int W, int nf, int nm, int nh,
-                    const int* hier_tab, int n_mh, float lam, float loss_weight, void* workspace, void* stream) {
+                    const int* hier_tab, int n_mh, float lam, float loss_weight, void* workspace, int stages,
+                    void* stream) {
   if (B <= 0 || H < 5 || W < 5 || nf <= 0 || nm <= 0 || nh <= 0 || nf + nm + nh > 255 || nh > 32)
     return SH_ERR_BAD_ARG;
   sh::Ws3 ws = sh::ws3_layout(workspace, B, H, W, nf, nm, nh);
@@ -772,9 +781,9 @@ int sh_rmi3_forward(const void* logits, int dtype, const long long* label, int B
   const double scale = (double)lam * (double)loss_weight / (9.0 * B);
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case SH_DT_F32: return sh::run_forward3<float>(logits, label, B, H, W, h, ws, 1e-6f, scale, st);
-    case SH_DT_BF16: return sh::run_forward3<__nv_bfloat16>(logits, label, B, H, W, h, ws, 1e-6f, scale, st);
-    case SH_DT_F16: return sh::run_forward3<__half>(logits, label, B, H, W, h, ws, 1e-6f, scale, st);
+    case SH_DT_F32: return sh::run_forward3<float>(logits, label, B, H, W, h, ws, 1e-6f, scale, stages, st);
+    case SH_DT_BF16: return sh::run_forward3<__nv_bfloat16>(logits, label, B, H, W, h, ws, 1e-6f, scale, stages, st);
+    case SH_DT_F16: return sh::run_forward3<__half>(logits, label, B, H, W, h, ws, 1e-6f, scale, stages, st);
   }
   return SH_ERR_UNSUPPORTED;
 }

@@ -21,6 +21,38 @@ from . import hierarchy as H
 _DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 _table_cache: dict = {}
 
+# kernels launched per C-ABI call (per stage bit for the multi-kernel entry points); bench.py reads
+# LAUNCHES["n"] to report how many of OUR kernels ran inside its timed region
+_KERNELS = {
+    "sh_targets_two_level": 1, "sh_targets_three_level": 1, "sh_targets_gather": 1, "sh_decode": 1,
+    "sh_loss2_final": 1, "sh_loss3_final": 1, "sh_scale_inplace": 1, "sh_triplet_forward": 4,
+    "sh_triplet_backward": 1,
+    ("sh_bce2_fwdbwd", 1): 1, ("sh_bce2_fwdbwd", 2): 1, ("sh_bce2_fwdbwd", 4): 1,
+    ("sh_rmi3_forward", 1): 1, ("sh_rmi3_forward", 2): 1, ("sh_rmi3_forward", 4): 1, ("sh_rmi3_forward", 8): 2,
+    ("sh_rmi3_backward", 1): 1, ("sh_rmi3_backward", 2): 1,
+}
+LAUNCHES = {"n": 0}
+STAGE_TIMER = None   # bench.py installs an object with start(name, bit) / stop(name, bit)
+
+
+def _call(name, *args):
+    _lib.call(name, *args)
+    LAUNCHES["n"] += _KERNELS.get(name, 0)
+
+
+def _staged(name, bits, make_args):
+    """Run a multi-kernel entry point.  Normally one C call with every stage bit set; with a stage
+    timer installed, one call per stage so that each kernel can be bracketed by CUDA events."""
+    timer = STAGE_TIMER
+    if timer is None:
+        _lib.call(name, *make_args(sum(bits)))
+    else:
+        for bit in bits:
+            timer.start(name, bit)
+            _lib.call(name, *make_args(bit))
+            timer.stop(name, bit)
+    LAUNCHES["n"] += sum(_KERNELS[(name, b)] for b in bits)
+
 
 def _p(t: Optional[torch.Tensor]):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
@@ -94,7 +126,7 @@ def targets_two_level(label: torch.Tensor, hiera_index):
     (lut,) = device_table(key, build, lab.device)
     out = torch.empty_like(lab)
     with torch.cuda.device(lab.device):
-        _lib.call("sh_targets_two_level", _p(lab), _p(out), lab.numel(), _p(lut), lut.numel(), _stream())
+        _call("sh_targets_two_level", _p(lab), _p(out), lab.numel(), _p(lut), lut.numel(), _stream())
     return out.to(label.dtype) if label.dtype != torch.int64 else out
 
 
@@ -106,7 +138,7 @@ def targets_three_level(label: torch.Tensor, fine_to_mid: torch.Tensor, fine_to_
     mid, high = torch.empty_like(lab), torch.empty_like(lab)
     err = torch.zeros(1, dtype=torch.int32, device=lab.device)
     with torch.cuda.device(lab.device):
-        _lib.call("sh_targets_three_level", _p(lab), _p(mid), _p(high), lab.numel(), _p(f2m), _p(f2h), f2m.numel(),
+        _call("sh_targets_three_level", _p(lab), _p(mid), _p(high), lab.numel(), _p(f2m), _p(f2h), f2m.numel(),
                   _p(err), _stream())
     if check and int(err.item()):
         raise IndexError("fine label out of range for fine_to_mid / fine_to_high")
@@ -120,7 +152,7 @@ def targets_gather(fine_mask: torch.Tensor, level_map: torch.Tensor, check=True)
     out = torch.empty_like(lab)
     err = torch.zeros(1, dtype=torch.int32, device=lab.device)
     with torch.cuda.device(lab.device):
-        _lib.call("sh_targets_gather", _p(lab), _p(out), lab.numel(), _p(m), m.numel(), _p(err), _stream())
+        _call("sh_targets_gather", _p(lab), _p(out), lab.numel(), _p(m), m.numel(), _p(err), _stream())
     if check and int(err.item()):
         raise IndexError("index out of range in target gather")
     return out
@@ -148,7 +180,7 @@ def hierarchical_argmax(logits: torch.Tensor, level_sizes: Sequence[int], label:
         lab = _labels(label)
         counts = torch.zeros(2, dtype=torch.int64, device=x.device)
     with torch.cuda.device(x.device):
-        _lib.call("sh_decode", _p(x), _dtype_code(x), b, c, hw, n0, n1, n2, _p(outs[0]), _p(outs[1]), _p(outs[2]),
+        _call("sh_decode", _p(x), _dtype_code(x), b, c, hw, n0, n1, n2, _p(outs[0]), _p(outs[1]), _p(outs[2]),
                   1 if out_dtype == torch.uint8 else 0, _p(lab), _p(counts), _stream())
     return [o for o in outs if o is not None], counts
 
@@ -184,7 +216,7 @@ def triplet_forward(feats: torch.Tensor, label: torch.Tensor, mode: int, tab: to
     trip = torch.empty(2, dtype=torch.float32, device=dev)
     status = torch.empty(2, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        _lib.call("sh_triplet_forward", _p(feats), _dtype_code(feats), _p(label), b, d, h, w, hh, ww, mode, _p(tab),
+        _call("sh_triplet_forward", _p(feats), _dtype_code(feats), _p(label), b, d, h, w, hh, ww, mode, _p(tab),
                   ncls, max_triplet, _p(lab_ds), _p(sel), _p(kcount), _p(tl), _p(trip), _p(status), _stream())
     return TripletState(mode, ncls, max_triplet, (b, d, h, w), sel, kcount, tl, trip, status, lab_ds)
 
@@ -194,7 +226,7 @@ def triplet_backward(feats: torch.Tensor, st: TripletState, tscale: torch.Tensor
     b, d, h, w = st.dims
     gfeat = torch.empty((b, d, h, w), dtype=torch.float32, device=feats.device)
     with torch.cuda.device(feats.device):
-        _lib.call("sh_triplet_backward", _p(feats), _dtype_code(feats), b, d, h, w, st.ncls, st.max_triplet,
+        _call("sh_triplet_backward", _p(feats), _dtype_code(feats), b, d, h, w, st.ncls, st.max_triplet,
                   _p(st.sel), _p(st.kcount), _p(st.tl), _p(st.trip), _p(tscale), _p(gscale), _p(gfeat), _stream())
     return gfeat if feats.dtype == torch.float32 else gfeat.to(feats.dtype)
 
@@ -267,10 +299,10 @@ class HieraTriplet2Fn(torch.autograd.Function):
             partials = torch.empty(grid * 4, dtype=torch.float32, device=dev)
             sums = torch.empty(4, dtype=torch.float64, device=dev)
             out = torch.empty(4, dtype=torch.float32, device=dev)
-            _lib.call("sh_bce2_fwdbwd", _p(x), _dtype_code(x), _p(lab), _p(grad), b, hw, cfg.n_fine, cfg.n_coarse,
-                      _p(tab), n_fb, lut_size, cfg.eps, cfg.loss_weight, _p(lab8), _p(counts), _p(partials), _p(sums),
-                      _stream())
-            _lib.call("sh_loss2_final", _p(sums), _p(counts), cfg.n_fine, cfg.n_coarse, float(b * hw), _p(step_d),
+            _staged("sh_bce2_fwdbwd", (1, 2, 4), lambda st_bits: (
+                _p(x), _dtype_code(x), _p(lab), _p(grad), b, hw, cfg.n_fine, cfg.n_coarse, _p(tab), n_fb, lut_size,
+                cfg.eps, cfg.loss_weight, _p(lab8), _p(counts), _p(partials), _p(sums), st_bits, _stream()))
+            _call("sh_loss2_final", _p(sums), _p(counts), cfg.n_fine, cfg.n_coarse, float(b * hw), _p(step_d),
                       cfg.total_steps, _p(st.trip) if st else None, _p(st.status) if st else None, cfg.loss_weight,
                       _p(out), _stream())
         stats.update(sums=sums, counts=counts, out=out, triplet=st)
@@ -291,7 +323,7 @@ class HieraTriplet2Fn(torch.autograd.Function):
                 raise RuntimeError("seghiero_b200: backward through the fused loss can run only once")
             ctx.grad = None
             with torch.cuda.device(gx.device):
-                _lib.call("sh_scale_inplace", _p(gx), _dtype_code(gx), gx.numel(), _p(g), _stream())
+                _call("sh_scale_inplace", _p(gx), _dtype_code(gx), gx.numel(), _p(g), _stream())
         gemb = None
         if ctx.st is not None and ctx.needs_input_grad[1]:
             gemb = triplet_backward(ctx.emb, ctx.st, ctx.out[1:2], g)
@@ -347,9 +379,10 @@ class RMIHieraTriplet3Fn(torch.autograd.Function):
             nbytes = lib.sh_rmi3_workspace_bytes(b, hh, ww, cfg.n_fine, cfg.n_mid, cfg.n_high)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             out = torch.empty(4, dtype=torch.float32, device=dev)
-            _lib.call("sh_rmi3_forward", _p(x), _dtype_code(x), _p(lab), b, hh, ww, cfg.n_fine, cfg.n_mid, cfg.n_high,
-                      _p(tab), n_mh, cfg.lam, cfg.loss_weight, _p(ws), _stream())
-            _lib.call("sh_loss3_final", b, hh, ww, cfg.n_fine, cfg.n_mid, cfg.n_high, _p(ws), cfg.lam, _p(step_d),
+            _staged("sh_rmi3_forward", (1, 2, 4, 8), lambda st_bits: (
+                _p(x), _dtype_code(x), _p(lab), b, hh, ww, cfg.n_fine, cfg.n_mid, cfg.n_high, _p(tab), n_mh, cfg.lam,
+                cfg.loss_weight, _p(ws), st_bits, _stream()))
+            _call("sh_loss3_final", b, hh, ww, cfg.n_fine, cfg.n_mid, cfg.n_high, _p(ws), cfg.lam, _p(step_d),
                       cfg.total_steps, _p(st.trip) if st else None, _p(st.status) if st else None, cfg.loss_weight,
                       _p(out), _stream())
         stats.update(out=out, triplet=st, workspace=ws)
@@ -373,8 +406,9 @@ class RMIHieraTriplet3Fn(torch.autograd.Function):
             b, c, hh, ww = x.shape
             gx = torch.empty_like(x)
             with torch.cuda.device(x.device):
-                _lib.call("sh_rmi3_backward", _p(x), _dtype_code(x), _p(gx), b, hh, ww, cfg.n_fine, cfg.n_mid,
-                          cfg.n_high, _p(ctx.tab), ctx.n_mh, cfg.loss_weight, _p(ctx.ws), _p(g), _stream())
+                _staged("sh_rmi3_backward", (1, 2), lambda st_bits: (
+                    _p(x), _dtype_code(x), _p(gx), b, hh, ww, cfg.n_fine, cfg.n_mid, cfg.n_high, _p(ctx.tab), ctx.n_mh,
+                    cfg.loss_weight, _p(ctx.ws), _p(g), st_bits, _stream()))
         gemb = None
         if ctx.st is not None and ctx.needs_input_grad[1]:
             gemb = triplet_backward(ctx.emb, ctx.st, ctx.out[1:2], g)

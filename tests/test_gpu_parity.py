@@ -243,14 +243,16 @@ def test_three_level_flat_predictions(sb, golden):
     loss = mod(torch.tensor([0]), torch.zeros(1, 4, 2, 2).cuda(), None, x, torch.from_numpy(g["label"]).cuda())
     loss.backward()
     assert abs(float(loss) - float(g["loss"])) <= FP32_TOL * abs(float(g["loss"]))
-    assert rel(to_np(x.grad), g["dx"]) <= 1e-3      # rank-deficient regime: the reference itself is noisy
+    # rank-deficient regime (near-constant predictions): K and M^-1 amplify rounding ~1e4x; the oracle
+    # itself only reproduces the reference to 1e-4 here (tests/test_oracle_golden.py)
+    assert rel(to_np(x.grad), g["dx"]) <= 5e-3
 
 
 @pytest.mark.parametrize("case", [
     dict(b=2, h=37, w=50, labels="iid", step=0, lam=0.5, dtype=torch.float32),               # ragged, scalar path
     dict(b=1, h=48, w=132, labels="blob", step=100000, lam=1.0, dtype=torch.float32),        # 3 tiles wide, 3 tall
     dict(b=2, h=21, w=64, labels="blob", step=200000, lam=0.25, dtype=torch.float32),
-    dict(b=1, h=5, w=5, labels="iid", step=0, lam=0.5, dtype=torch.float32),                 # minimum size: all frame but 1
+    dict(b=1, h=5, w=5, labels="iid", step=0, lam=0.5, dtype=torch.float32, tol=5e-5),       # minimum size: 9 windows, M ~ alpha*I
     dict(b=1, h=40, w=72, labels="blob", step=100000, lam=0.5, dtype=torch.float16),
 ])
 def test_three_level_vs_oracle(sb, case):
@@ -271,7 +273,7 @@ def test_three_level_vs_oracle(sb, case):
                                  loss_weight=0.9)
     loss = mod(torch.tensor([case["step"]]).cuda(), ec, None, xc, lab.cuda())
     (loss * 1.5).backward()
-    tol = FP32_TOL if case["dtype"] == torch.float32 else BF16_TOL
+    tol = case.get("tol", FP32_TOL if case["dtype"] == torch.float32 else BF16_TOL)
     rmi_gpu = float(mod.last_stats["out"][2].item())
     assert abs(rmi_gpu - parts["rmi"]) <= tol * abs(parts["rmi"]), (rmi_gpu, parts["rmi"])
     assert abs(float(loss) - float(ref)) <= tol * abs(float(ref)), (float(loss), float(ref), parts)
@@ -350,11 +352,12 @@ def test_full_size_properties(sb):
         m1(torch.tensor([100000], device=dev), emb3[i:i + 1], None, x3[i:i + 1].detach(), lab3[i:i + 1])
         rmis.append(float(m1.last_stats["out"][2]))
     assert abs(rmi_batch - 0.5 * (rmis[0] + rmis[1])) <= 1e-5 * abs(rmi_batch)
-    # directional derivative check of the full-size gradient (fp32, central difference)
-    d = torch.randn_like(x3) * 1e-2
+    # directional derivative of the full-size gradient along sign(grad) (fp32 loss resolution ~1e-5,
+    # so the step must move the loss by ~1e-2)
+    d = torch.sign(x3.grad) * 2e-3
     with torch.no_grad():
         lp = mod(torch.tensor([100000], device=dev), emb3, None, x3 + d, lab3)
         lm = mod(torch.tensor([100000], device=dev), emb3, None, x3 - d, lab3)
     fd = (float(lp) - float(lm)) / 2
     an = float((x3.grad.double() * d.double()).sum())
-    assert abs(fd - an) <= 2e-2 * max(abs(an), 1e-6), (fd, an)
+    assert abs(fd - an) <= 2e-2 * abs(an), (fd, an)
