@@ -9,267 +9,338 @@
 
 namespace sh {
 
-__device__ __forceinline__ unsigned int load4_u8(const unsigned char* p, int nvalid, bool aligned) {
-  if (aligned && nvalid == 4) return *reinterpret_cast<const unsigned int*>(p);
-  unsigned int r = 0;
-  for (int k = 0; k < nvalid; ++k) r |= (unsigned int)p[k] << (8 * k);
-  return r;
-}
-
+// ---------------------------------------------------------------------------------------------
+// k3_pass2: grid (tiles_x, tiles_y, B), 512 threads, tile 64x32, rounds of 4 channels.
+// A thread owns a 4x2 pixel block for TWO of the round's channels in both phases:
+//   phase A: sigmoid/exp, BCE+CE gradient from the summaries (kept in registers), P -> plane
+//   phase B: 5x5 stencil over the plane, combine, store the gradient (128-bit, coalesced)
+// Planes are double buffered: one __syncthreads per round.
+// ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(kThreads, 1)
 k3_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hier3 h, Ws3 ws, float eps,
          float loss_weight, const float* __restrict__ gscale_ptr, int vec_ok) {
-  constexpr int TH = 16;
-  __shared__ __align__(16) float plane[(TH + 4) * kPitch];
-  __shared__ __align__(16) float wbuf[64];
-  __shared__ __align__(8) unsigned char labt[3 * (TH + 4) * kLabPitch];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int PX = kTH * kTW;
+  constexpr int kPlane = (kTH + 4) * kPitch;
+  float* planes = reinterpret_cast<float*>(smem_raw);        // [2][kNR][kPlane]
+  float* wbuf = planes + 2 * kNR * kPlane;                   // [2][kNR][64]
+  float* ivt = wbuf + 2 * kNR * 64;                          // [3][PX]  1/sum e^x per level
+  unsigned char* labt = reinterpret_cast<unsigned char*>(ivt + 3 * PX);   // [3][kTH+4][kLabPitch]
 
   const int C = h.nf + h.nm + h.nh;
-  const int b = blockIdx.z, y0 = blockIdx.y * TH, x0 = blockIdx.x * kTW;
+  const int b = blockIdx.z, y0 = blockIdx.y * kTH, x0 = blockIdx.x * kTW;
   const long HW = (long)H * W;
   const int tid = threadIdx.x;
-  const int ty = tid / kStrips, tx = (tid % kStrips) * 4;
-  const int y = y0 + ty, xg = x0 + tx;
   const unsigned char* lab8 = ws.lab8 + (long)b * HW;
   const unsigned char* flg = ws.flags + (long)b * HW;
   const float gscale = *gscale_ptr;
+  const T* xb = x + (long)b * C * HW;
+  T* gb = grad + (long)b * C * HW;
 
-  for (int e = tid; e < (TH + 4) * kPitch; e += 256) {
-    const int r = e / kPitch, j = e - r * kPitch;
-    const int yy = y0 - 2 + r, xx = x0 - 2 + j;
-    unsigned char f = 0xff, m = 0xff, g = 0xff;
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-      const int t = lab8[(long)yy * W + xx];
-      f = m = g = 0;
-      if (t != SH_IGNORE) { f = (unsigned char)t; m = (unsigned char)h.f2m[t]; g = (unsigned char)h.f2h[t]; }
-    }
-    labt[(0 * (TH + 4) + r) * kLabPitch + j] = f;
-    labt[(1 * (TH + 4) + r) * kLabPitch + j] = m;
-    labt[(2 * (TH + 4) + r) * kLabPitch + j] = g;
-  }
-
-  int tf[4], tm[4], thh[4];
-  bool inimg[4], interior[4];
-  unsigned int ulab[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
-  unsigned int nonuni[3] = {0u, 0u, 0u};
+  // thread -> (channel pair, 4x2 pixel block)
+  const int pair = tid >> 8, u = tid & 255, rp = u >> 4, st = u & 15;
+  const int ty = 2 * rp, tx = 4 * st;
+  const int xg = x0 + tx;
+  int nvalid = W - xg;
+  nvalid = nvalid > 4 ? 4 : (nvalid < 0 ? 0 : nvalid);
+  const bool st_al = vec_ok && ((W & 3) == 0);
+  bool row_ok[2];
+  long own_off[2];
+  unsigned int tf4[2], tm4[2], th4[2], hpf4[2], hpm4[2], ucode[3][2];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    inimg[k] = (y < H) && (xg + k < W);
-    int t = SH_IGNORE, fl = 0;
-    if (inimg[k]) { t = lab8[(long)y * W + xg + k]; fl = flg[(long)y * W + xg + k]; }
-    tf[k] = t;
-    tm[k] = t != SH_IGNORE ? h.f2m[t] : SH_IGNORE;
-    thh[k] = t != SH_IGNORE ? h.f2h[t] : SH_IGNORE;
-    interior[k] = (fl & kFlagInterior) != 0;
-    const int r3[3] = {t != SH_IGNORE ? t : 0, t != SH_IGNORE ? tm[k] : 0, t != SH_IGNORE ? thh[k] : 0};
+  for (int o = 0; o < 2; ++o) {
+    const int y = y0 + ty + o;
+    row_ok[o] = y < H && nvalid > 0;
+    own_off[o] = (long)y * W + xg;
+    tf4[o] = tm4[o] = th4[o] = 0xffffffffu;
+    hpf4[o] = hpm4[o] = 0;
 #pragma unroll
-    for (int l = 0; l < 3; ++l) {
-      if (interior[k]) {
-        if (fl & (kFlagUniF << l)) ulab[l] = (ulab[l] & ~(0xffu << (8 * k))) | ((unsigned int)r3[l] << (8 * k));
-        else nonuni[l] |= 1u << k;
+    for (int l = 0; l < 3; ++l) ucode[l][o] = 0xffffffffu;
+    if (row_ok[o]) {
+      tf4[o] = load4_u8(lab8 + own_off[o], nvalid, st_al) | (nvalid < 4 ? (0xffffffffu << (8 * nvalid)) : 0u);
+      const unsigned int fl4 = load4_u8(flg + own_off[o], nvalid, st_al);
+      hpf4[o] = load4_u8(ws.hold + ((size_t)(h.nm + h.nh) * B + b) * HW + own_off[o], nvalid, st_al);
+      hpm4[o] = load4_u8(ws.hold + ((size_t)(h.nm + h.nh + 1) * B + b) * HW + own_off[o], nvalid, st_al);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const unsigned int t = (tf4[o] >> (8 * k)) & 0xffu, fl = (fl4 >> (8 * k)) & 0xffu;
+        const unsigned int m = t != SH_IGNORE ? (unsigned)h.f2m[t] : 0xffu, g = t != SH_IGNORE ? (unsigned)h.f2h[t] : 0xffu;
+        tm4[o] = (tm4[o] & ~(0xffu << (8 * k))) | (m << (8 * k));
+        th4[o] = (th4[o] & ~(0xffu << (8 * k))) | (g << (8 * k));
+        const unsigned int r3[3] = {t != SH_IGNORE ? t : 0u, t != SH_IGNORE ? m : 0u, t != SH_IGNORE ? g : 0u};
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+          unsigned int code = 0xffu;
+          if (k < nvalid && (fl & kFlagInterior)) code = (fl & (kFlagUniF << l)) ? r3[l] : 0xfeu;
+          ucode[l][o] = (ucode[l][o] & ~(0xffu << (8 * k))) | (code << (8 * k));
+        }
       }
     }
   }
-  const bool row_ok = y < H;
-  int nvalid = row_ok ? W - xg : 0;
-  nvalid = nvalid > 4 ? 4 : (nvalid < 0 ? 0 : nvalid);
-  const long own_off = (long)y * W + xg;
-  const bool st_al = vec_ok && ((W & 3) == 0);
-  // summaries of pass 1
-  unsigned int hp_f = 0, hp_m = 0;
-  float iv[3][4];
-#pragma unroll
-  for (int l = 0; l < 3; ++l)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) iv[l][k] = 0.f;
-  if (nvalid > 0) {
-    hp_f = load4_u8(ws.hold + ((size_t)(h.nm + h.nh) * B + b) * HW + own_off, nvalid, st_al);
-    hp_m = load4_u8(ws.hold + ((size_t)(h.nm + h.nh + 1) * B + b) * HW + own_off, nvalid, st_al);
-    for (int l = 0; l < 3; ++l)
-      for (int k = 0; k < nvalid; ++k) iv[l][k] = ws.inv[((size_t)l * B + b) * HW + own_off + k];
+  load_label_tile(labt, kTH, lab8, H, W, y0, x0, h, tid, kThreads);
+  for (int i = tid; i < 3 * PX / 4; i += kThreads) {
+    const int l = i / (PX / 4), rem = i - l * (PX / 4), r = rem / kStrips, s4 = (rem % kStrips) * 4;
+    const int y = y0 + r, xx = x0 + s4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y < H && xx < W) {
+      const float* ip = ws.inv + ((size_t)l * B + b) * HW + (long)y * W + xx;
+      if (st_al && xx + 4 <= W) v = *reinterpret_cast<const float4*>(ip);
+      else { float t4[4] = {0.f, 0.f, 0.f, 0.f}; for (int k = 0; k < 4 && xx + k < W; ++k) t4[k] = ip[k]; v = make_float4(t4[0], t4[1], t4[2], t4[3]); }
+    }
+    *reinterpret_cast<float4*>(ivt + l * PX + r * kTW + s4) = v;
+  }
+  // halo slot (same position in every plane): rows 0,1 and kTH+2,kTH+3 of the plane, 2 columns either side
+  constexpr int nhalo = kPlane - kTH * kTW;   // 400
+  int h_sidx = -1;
+  long h_goff = -1;
+  bool h_valid = false;
+  if (tid < nhalo) {
+    int r, j;
+    if (tid < 4 * kPitch) { const int rr = tid / kPitch; r = rr < 2 ? rr : kTH + rr; j = tid % kPitch; }
+    else { const int e2 = tid - 4 * kPitch; r = 2 + (e2 >> 2); const int q = e2 & 3; j = q < 2 ? q : kTW + q; }
+    h_sidx = r * kPitch + j;
+    const int yy = y0 - 2 + r, xx = x0 - 2 + j;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) { h_goff = (long)yy * W + xx; h_valid = lab8[h_goff] != SH_IGNORE; }
   }
   __syncthreads();
   unsigned int pres[3] = {0u, 0u, 0u};
 #pragma unroll
   for (int l = 0; l < 3; ++l) {
-    if (nonuni[l]) {
-      for (int rr = 0; rr < 5; ++rr) {
-        const unsigned char* row = labt + ((l * (TH + 4)) + ty + rr) * kLabPitch + tx;
+    bool any_nu = false;
+#pragma unroll
+    for (int o = 0; o < 2; ++o)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) any_nu |= ((ucode[l][o] >> (8 * k)) & 0xffu) == 0xfeu;
+    if (any_nu) {
+      for (int rr = 0; rr < 6; ++rr) {
+        const unsigned char* row = labt + ((l * (kTH + 4)) + ty + rr) * kLabPitch + tx;
         for (int q = 0; q < 8; ++q) pres[l] |= 1u << (row[q] & 31);
       }
     }
   }
 
   const float nv = fmaxf((float)ws.counts[0], 1.0f);
-  const float wL[3] = {2.5f * loss_weight * gscale / (nv * (float)h.nf), 2.5f * loss_weight * gscale / (nv * (float)h.nm),
-                       2.5f * loss_weight * gscale / (nv * (float)h.nh)};
+  const float wF = 2.5f * loss_weight * gscale / (nv * (float)h.nf);
+  const float wM = 2.5f * loss_weight * gscale / (nv * (float)h.nm);
+  const float wH = 2.5f * loss_weight * gscale / (nv * (float)h.nh);
   const float wCE = loss_weight * gscale / ((float)B * (float)HW);
 
-  const T* xb = x + (long)b * C * HW;
-  T* gb = grad + (long)b * C * HW;
-  constexpr int nhalo = (TH + 4) * kPitch - TH * kTW;
-
-  float xv[4];
-  if (row_ok) load_n<T, 4>(xb, own_off, (long)y * W + W, vec_ok != 0, xv);
-  else { xv[0] = xv[1] = xv[2] = xv[3] = 0.f; }
-
-  for (int c = 0; c < C; ++c) {
-    const int lvl = c < h.nf ? 0 : (c < h.nf + h.nm ? 1 : 2);
-    const int cl = lvl == 0 ? c : (lvl == 1 ? c - h.nf : c - h.nf - h.nm);
-    const T* xc = xb + (long)c * HW;
-    float s[4], v[4], pk[4];
+  const int nrounds = (C + kNR - 1) / kNR;
+  float xv[2][2][4], hv[kNR];
+  auto prefetch = [&](int r) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      SigExp se = sig_exp(xv[k]);
-      s[k] = se.s; v[k] = se.v;
-      pk[k] = inimg[k] ? ((tf[k] != SH_IGNORE ? se.s : 0.f) + 1e-6f) : 0.f;
-    }
-    *reinterpret_cast<float2*>(plane + (ty + 2) * kPitch + tx + 2) = make_float2(pk[0], pk[1]);
-    *reinterpret_cast<float2*>(plane + (ty + 2) * kPitch + tx + 4) = make_float2(pk[2], pk[3]);
-    for (int e = tid; e < nhalo; e += 256) {
-      int r, j;
-      if (e < 4 * kPitch) { const int rr = e / kPitch; r = rr < 2 ? rr : TH + rr; j = e % kPitch; }
-      else { const int e2 = e - 4 * kPitch; r = 2 + (e2 >> 2); const int q = e2 & 3; j = q < 2 ? q : kTW + q; }
-      const int yy = y0 - 2 + r, xx = x0 - 2 + j;
-      float p = 0.f;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-        const bool valid = lab8[(long)yy * W + xx] != SH_IGNORE;
-        p = (valid ? sig_exp(to_f32<T>(xc[(long)yy * W + xx])).s : 0.f) + 1e-6f;
+    for (int jj = 0; jj < 2; ++jj) {
+      const int c = r * kNR + 2 * pair + jj;
+      if (c < C) {
+        const T* xc = xb + (long)c * HW;
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          if (row_ok[o]) load_n<T, 4>(xc, own_off[o], own_off[o] - xg + W, vec_ok != 0, xv[jj][o]);
+          else { xv[jj][o][0] = xv[jj][o][1] = xv[jj][o][2] = xv[jj][o][3] = 0.f; }
+        }
       }
-      plane[r * kPitch + j] = p;
     }
-    if (tid < 64) wbuf[tid] = ws.wts[((size_t)b * C + c) * 64 + tid];
-    if (c + 1 < C && row_ok) load_n<T, 4>(xc + HW, own_off, (long)y * W + W, vec_ok != 0, xv);
+#pragma unroll
+    for (int j = 0; j < kNR; ++j) {
+      const int c = r * kNR + j;
+      hv[j] = (c < C && h_goff >= 0) ? to_f32<T>(xb[(long)c * HW + h_goff]) : 0.f;
+    }
+  };
+
+  prefetch(0);
+  for (int r = 0; r < nrounds; ++r) {
+    const int buf = r & 1;
+    float g0[2][2][4];
+    // ======================= phase A =======================
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      const int c = r * kNR + 2 * pair + jj;
+      if (c >= C) break;
+      const int lvl = c < h.nf ? 0 : (c < h.nf + h.nm ? 1 : 2);
+      const int cl = lvl == 0 ? c : (lvl == 1 ? c - h.nf : c - h.nf - h.nm);
+      float* plane = planes + (buf * kNR + 2 * pair + jj) * kPlane;
+      const int mid = lvl == 0 ? h.f2m[cl] : (lvl == 1 ? cl : -1);
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        float s[4], v[4], pk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const SigExp se = sig_exp(xv[jj][o][k]);
+          s[k] = se.s; v[k] = se.v;
+          const bool valid = ((tf4[o] >> (8 * k)) & 0xffu) != SH_IGNORE;
+          pk[k] = (row_ok[o] && k < nvalid) ? ((valid ? se.s : 0.f) + 1e-6f) : 0.f;
+        }
+        *reinterpret_cast<float2*>(plane + (ty + o + 2) * kPitch + tx + 2) = make_float2(pk[0], pk[1]);
+        *reinterpret_cast<float2*>(plane + (ty + o + 2) * kPitch + tx + 4) = make_float2(pk[2], pk[3]);
+        // tree BCE + CE gradient of this channel at these 4 pixels
+        unsigned int hm = 0, hh_own = 0;
+        if (row_ok[o]) {
+          if (mid >= 0) hm = load4_u8(ws.hold + ((size_t)mid * B + b) * HW + own_off[o], nvalid, st_al);
+          if (lvl == 2) hh_own = load4_u8(ws.hold + ((size_t)(h.nm + cl) * B + b) * HW + own_off[o], nvalid, st_al);
+        }
+        float dneg[4] = {0.f, 0.f, 0.f, 0.f}, dpos[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const unsigned int t = (tf4[o] >> (8 * k)) & 0xffu;
+          if (t == SH_IGNORE) continue;
+          const unsigned int tmk = (tm4[o] >> (8 * k)) & 0xffu, thk = (th4[o] >> (8 * k)) & 0xffu;
+          const unsigned int hpf = (hpf4[o] >> (8 * k)) & 0xffu, hpm = (hpm4[o] >> (8 * k)) & 0xffu;
+          const unsigned int hmk = (hm >> (8 * k)) & 0xffu;
+          if (lvl == 0) {
+            if ((unsigned)cl == t) { if (hpf == (unsigned)c) dpos[k] += wF; }
+            else dneg[k] += wF;
+            if ((unsigned)mid != tmk && hmk == (unsigned)c) dneg[k] += wM;
+          } else if (lvl == 1) {
+            if ((unsigned)cl == tmk) {
+              if (hpf == (unsigned)c) dpos[k] += wF;
+              if (hpm == (unsigned)c) dpos[k] += wM;
+            } else if (hmk == (unsigned)c) dneg[k] += wM;
+          } else {
+            if (hpm == (unsigned)c) dpos[k] += wM;
+            if ((unsigned)cl == thk) dpos[k] += wH;
+            else if (((hh_own >> (8 * k)) & 0xffu) == (unsigned)c) dneg[k] += wH;
+          }
+        }
+        if (lvl != 2 && row_ok[o]) {   // high-level negative terms routed down to this channel
+          for (int q = h.mh_ptr[mid]; q < h.mh_ptr[mid + 1]; ++q) {
+            const int hi = h.mh_idx[q];
+            const unsigned int hh = load4_u8(ws.hold + ((size_t)(h.nm + hi) * B + b) * HW + own_off[o], nvalid, st_al);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const unsigned int t = (tf4[o] >> (8 * k)) & 0xffu, thk = (th4[o] >> (8 * k)) & 0xffu;
+              if (t != SH_IGNORE && (unsigned)hi != thk && ((hh >> (8 * k)) & 0xffu) == (unsigned)c) dneg[k] += wH;
+            }
+          }
+        }
+        const float4 iv4 = *reinterpret_cast<const float4*>(ivt + lvl * PX + (ty + o) * kTW + tx);
+        const float ivk[4] = {iv4.x, iv4.y, iv4.z, iv4.w};
+        const unsigned int tg4 = lvl == 0 ? tf4[o] : (lvl == 1 ? tm4[o] : th4[o]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float q1 = 1.0f - s[k];
+          float ds = 0.f;
+          if (dneg[k] != 0.f) ds += dneg[k] * rcp(q1 + eps);
+          if (dpos[k] != 0.f) ds -= dpos[k] * rcp(s[k] + eps);
+          const bool valid = ((tf4[o] >> (8 * k)) & 0xffu) != SH_IGNORE;
+          const float ce = valid ? wCE * (v[k] * ivk[k] - (((tg4 >> (8 * k)) & 0xffu) == (unsigned)cl ? 1.f : 0.f)) : 0.f;
+          g0[jj][o][k] = ds * (q1 * s[k]) + ce;
+        }
+      }
+    }
+    // halo of the 4 planes + stencil weights of the round
+#pragma unroll
+    for (int j = 0; j < kNR; ++j) {
+      if (r * kNR + j < C && h_sidx >= 0)
+        planes[(buf * kNR + j) * kPlane + h_sidx] = h_goff >= 0 ? ((h_valid ? sig_exp(hv[j]).s : 0.f) + 1e-6f) : 0.f;
+    }
+    if (tid < kNR * 64) {
+      const int j = tid >> 6, c = r * kNR + j;
+      if (c < C) wbuf[(buf * kNR + j) * 64 + (tid & 63)] = ws.wts[((size_t)b * C + c) * 64 + (tid & 63)];
+    }
+    if (r + 1 < nrounds) prefetch(r + 1);
     __syncthreads();
 
-    // ---- RMI gradient wrt P: 5x5 stencil -------------------------------------------------------
-    float dP[4] = {0.f, 0.f, 0.f, 0.f};
-    {
+    // ======================= phase B =======================
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      const int c = r * kNR + 2 * pair + jj;
+      if (c >= C) break;
+      const int lvl = c < h.nf ? 0 : (c < h.nf + h.nm ? 1 : 2);
+      const int cl = lvl == 0 ? c : (lvl == 1 ? c - h.nf : c - h.nf - h.nm);
+      const float* plane = planes + (buf * kNR + 2 * pair + jj) * kPlane;
+      const float* wb = wbuf + (buf * kNR + 2 * pair + jj) * 64;
       float w1[25];
 #pragma unroll
       for (int q = 0; q < 6; ++q) {
-        const float4 t4 = *reinterpret_cast<const float4*>(wbuf + 4 * q);
+        const float4 t4 = *reinterpret_cast<const float4*>(wb + 4 * q);
         w1[4 * q] = t4.x; w1[4 * q + 1] = t4.y; w1[4 * q + 2] = t4.z; w1[4 * q + 3] = t4.w;
       }
-      w1[24] = wbuf[24];
+      w1[24] = wb[24];
+      float dP[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      float pc[2][4];
 #pragma unroll
-      for (int rr = 0; rr < 5; ++rr) {
-        const float4* pr = reinterpret_cast<const float4*>(plane + (ty + rr) * kPitch + tx);
-        const float4 a = pr[0], bq = pr[1];
+      for (int rr = 0; rr < 6; ++rr) {      // plane rows ty+rr  <->  image rows y0+ty+rr-2
+        const float4* p4 = reinterpret_cast<const float4*>(plane + (ty + rr) * kPitch + tx);
+        const float4 a = p4[0], bq = p4[1];
         const float w[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
-        for (int dx = 0; dx < 5; ++dx)
+        for (int o = 0; o < 2; ++o) {
+          const int dyi = rr - o;            // = dy + 2
+          if (dyi < 0 || dyi > 4) continue;
+          if (dyi == 2) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) dP[k] = fmaf(w1[rr * 5 + dx], w[k + dx], dP[k]);
+            for (int k = 0; k < 4; ++k) pc[o][k] = w[k + 2];
+          }
+#pragma unroll
+          for (int dx = 0; dx < 5; ++dx)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dP[o][k] = fmaf(w1[dyi * 5 + dx], w[k + dx], dP[o][k]);
+        }
       }
-      const float w2full = wbuf[50];
-      const unsigned int ul = ulab[lvl];
+      const float w2full = wb[50];
+      const unsigned int pr = lvl == 0 ? pres[0] : (lvl == 1 ? pres[1] : pres[2]);
+      const bool want = (pr >> (cl & 31)) & 1u;
+      float add[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      if (want) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (((ul >> (8 * k)) & 0xffu) == (unsigned int)cl) dP[k] += w2full;
-      if (nonuni[lvl] && ((pres[lvl] >> (cl & 31)) & 1u)) {
-        float add[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int rr = 0; rr < 5; ++rr) {
+        for (int rr = 0; rr < 6; ++rr) {
           const unsigned int* row = reinterpret_cast<const unsigned int*>(
-              labt + ((lvl * (TH + 4)) + ty + rr) * kLabPitch + tx);
+              labt + ((lvl * (kTH + 4)) + ty + rr) * kLabPitch + tx);
           const unsigned long long wbits = (unsigned long long)row[0] | ((unsigned long long)row[1] << 32);
           float mt[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) mt[q] = (byte_of(wbits, q) == (unsigned int)cl) ? 1.f : 0.f;
 #pragma unroll
-          for (int dx = 0; dx < 5; ++dx) {
-            const float w2 = wbuf[25 + rr * 5 + dx];
+          for (int o = 0; o < 2; ++o) {
+            const int dyi = rr - o;
+            if (dyi < 0 || dyi > 4) continue;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) add[k] = fmaf(w2, mt[k + dx], add[k]);
+            for (int dx = 0; dx < 5; ++dx) {
+              const float w2 = wb[25 + dyi * 5 + dx];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) add[o][k] = fmaf(w2, mt[k + dx], add[o][k]);
+            }
           }
         }
+      }
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if ((nonuni[lvl] >> k) & 1u) dP[k] += add[k];
+      for (int o = 0; o < 2; ++o) {
+        const unsigned int uc = lvl == 0 ? ucode[0][o] : (lvl == 1 ? ucode[1][o] : ucode[2][o]);
+        float g[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const unsigned int code = (uc >> (8 * k)) & 0xffu;
+          float d = dP[o][k];
+          if (code == (unsigned int)cl) d += w2full;
+          else if (code == 0xfeu) d += add[o][k];
+          const bool valid = ((tf4[o] >> (8 * k)) & 0xffu) != SH_IGNORE;
+          const float s = pc[o][k] - 1e-6f;            // valid pixels: P = s + 1e-6
+          const float q = (valid && code != 0xffu) ? s * (1.0f - s) * gscale : 0.f;
+          g[k] = fmaf(q, d, g0[jj][o][k]);
+        }
+        if (row_ok[o]) store_n<T, 4>(gb + (long)c * HW, own_off[o], own_off[o] - xg + W, vec_ok != 0, g);
       }
     }
-
-    // ---- tree BCE + CE gradient from the summaries ----------------------------------------------
-    float g[4];
-    {
-      unsigned int hm = 0;       // holder of MCMBc for this channel's mid
-      int mid = -1;
-      if (lvl == 0) mid = h.f2m[cl]; else if (lvl == 1) mid = cl;
-      if (mid >= 0 && nvalid > 0) hm = load4_u8(ws.hold + ((size_t)mid * B + b) * HW + own_off, nvalid, st_al);
-      float dneg[4] = {0.f, 0.f, 0.f, 0.f}, dpos[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (tf[k] == SH_IGNORE) continue;
-        const unsigned int hpf = (hp_f >> (8 * k)) & 0xffu, hpm = (hp_m >> (8 * k)) & 0xffu;
-        if (lvl == 0) {
-          if (cl == tf[k]) { if (hpf == (unsigned int)c) dpos[k] += wL[0]; }
-          else dneg[k] += wL[0];
-          if (mid != tm[k] && ((hm >> (8 * k)) & 0xffu) == (unsigned int)c) dneg[k] += wL[1];
-        } else if (lvl == 1) {
-          if (cl == tm[k]) {
-            if (hpf == (unsigned int)c) dpos[k] += wL[0];
-            if (hpm == (unsigned int)c) dpos[k] += wL[1];
-          } else if (((hm >> (8 * k)) & 0xffu) == (unsigned int)c) dneg[k] += wL[1];
-        } else {
-          if (hpm == (unsigned int)c) dpos[k] += wL[1];
-          if (cl == thh[k]) dpos[k] += wL[2];
-        }
-      }
-      // high-level negative terms routed to this channel
-      if (lvl == 2) {
-        if (nvalid > 0) {
-          const unsigned int hh = load4_u8(ws.hold + ((size_t)(h.nm + cl) * B + b) * HW + own_off, nvalid, st_al);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (tf[k] != SH_IGNORE && cl != thh[k] && ((hh >> (8 * k)) & 0xffu) == (unsigned int)c) dneg[k] += wL[2];
-        }
-      } else if (nvalid > 0) {
-        for (int q = h.mh_ptr[mid]; q < h.mh_ptr[mid + 1]; ++q) {
-          const int hi = h.mh_idx[q];
-          const unsigned int hh = load4_u8(ws.hold + ((size_t)(h.nm + hi) * B + b) * HW + own_off, nvalid, st_al);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (tf[k] != SH_IGNORE && hi != thh[k] && ((hh >> (8 * k)) & 0xffu) == (unsigned int)c) dneg[k] += wL[2];
-        }
-      }
-      const int tgt_sel = lvl;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float q1 = 1.0f - s[k];
-        float ds = 0.f;
-        if (dneg[k] != 0.f) ds += dneg[k] * rcp(q1 + eps);
-        if (dpos[k] != 0.f) ds -= dpos[k] * rcp(s[k] + eps);
-        const bool valid = tf[k] != SH_IGNORE;
-        if (valid && interior[k]) ds += dP[k] * gscale;
-        float ce = 0.f;
-        if (valid) {
-          const int tgt = tgt_sel == 0 ? tf[k] : (tgt_sel == 1 ? tm[k] : thh[k]);
-          ce = wCE * (v[k] * iv[lvl][k] - (cl == tgt ? 1.f : 0.f));
-        }
-        g[k] = ds * (q1 * s[k]) + ce;
-      }
-    }
-    if (row_ok) store_n<T, 4>(gb + (long)c * HW, own_off, (long)y * W + W, vec_ok != 0, g);
-    __syncthreads();
   }
 }
 
 // grid (B*C, nseg), block 256: threads stride over the frame pixels of one (b, c) plane
 template <typename T>
-__global__ void __launch_bounds__(256) k3_frame2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W,
-                                                 Hier3 h, Ws3 ws, const float* __restrict__ gscale_ptr) {
+__global__ void __launch_bounds__(256) k3_frame2(T* __restrict__ grad, int B, int H, int W, Hier3 h, Ws3 ws,
+                                                 const float* __restrict__ bandR, const float* __restrict__ bandC,
+                                                 const float* __restrict__ gscale_ptr) {
   __shared__ float fw[25 * 50];
   const int C = h.nf + h.nm + h.nh;
   const int bc = blockIdx.x, b = bc / C, c = bc % C;
   const int lvl = c < h.nf ? 0 : (c < h.nf + h.nm ? 1 : 2);
   const int cl = lvl == 0 ? c : (lvl == 1 ? c - h.nf : c - h.nf - h.nm);
-  const int* lmap = lvl == 0 ? nullptr : (lvl == 1 ? h.f2m : h.f2h);
   const long HW = (long)H * W;
-  const T* xc = x + ((long)b * C + c) * HW;
+  BandView bv;
+  bv.bandR = bandR + (size_t)bc * 8 * W; bv.bandC = bandC + (size_t)bc * 8 * H;
+  bv.lab8 = ws.lab8 + (long)b * HW; bv.lmap = lvl == 0 ? nullptr : (lvl == 1 ? h.f2m : h.f2h);
+  bv.H = H; bv.W = W;
   T* gc = grad + ((long)b * C + c) * HW;
-  const unsigned char* lab8 = ws.lab8 + (long)b * HW;
   const float gscale = *gscale_ptr;
   for (int i = threadIdx.x; i < 25 * 50; i += 256) fw[i] = ws.fwts[(size_t)bc * 25 * 50 + i];
   __syncthreads();
@@ -280,8 +351,7 @@ __global__ void __launch_bounds__(256) k3_frame2(const T* __restrict__ x, T* __r
     int yy, xx;
     if (idx < 4 * W) { const int r = idx / W; yy = r < 2 ? r : H - 4 + r; xx = idx - r * W; }
     else { const int i2 = idx - 4 * W; const int q = i2 / (H - 4); xx = q < 2 ? q : W - 4 + q; yy = 2 + (i2 - q * (H - 4)); }
-    const int tr = lab8[(long)yy * W + xx];
-    if (tr == SH_IGNORE) continue;   // dP/ds = valid
+    if (bv.lab8[(long)yy * W + xx] == SH_IGNORE) continue;   // dP/ds = valid
     const float* w = fw + (axis_class(yy, H) * 5 + axis_class(xx, W)) * 50;
     float dP = 0.f;
 #pragma unroll
@@ -290,33 +360,39 @@ __global__ void __launch_bounds__(256) k3_frame2(const T* __restrict__ x, T* __r
       for (int dx = -2; dx <= 2; ++dx) {
         const int y2 = yy + dy, x2 = xx + dx;
         if (y2 < 0 || y2 >= H || x2 < 0 || x2 >= W) continue;
-        const int tn = lab8[(long)y2 * W + x2];
-        const bool vn = tn != SH_IGNORE;
-        const float pn = (vn ? sig_exp(to_f32<T>(xc[(long)y2 * W + x2])).s : 0.f) + 1e-6f;
-        const int rl_n = vn ? (lmap ? lmap[tn] : tn) : 0;
         const int t = (dy + 2) * 5 + dx + 2;
-        dP = fmaf(w[t], pn, dP);
-        if (rl_n == cl) dP += w[25 + t];
+        dP = fmaf(w[t], bv.P(y2, x2), dP);
+        if (bv.L(y2, x2) == cl) dP += w[25 + t];
       }
     }
-    const float s = sig_exp(to_f32<T>(xc[(long)yy * W + xx])).s;
+    const float s = bv.P(yy, xx) - 1e-6f;
     const float add = dP * gscale * s * (1.0f - s);
     gc[(long)yy * W + xx] = from_f32<T>(to_f32<T>(gc[(long)yy * W + xx]) + add);
   }
 }
 
+static size_t pass2_smem_bytes() {
+  size_t s = (size_t)2 * kNR * (kTH + 4) * kPitch * 4 + 2 * kNR * 64 * 4 + 3 * kTH * kTW * 4 +
+             3 * (kTH + 4) * kLabPitch;
+  return (s + 15) & ~(size_t)15;
+}
+
 template <typename T>
-static int run_backward3(const void* x, void* grad, int B, int H, int W, const Hier3& h, const Ws3& ws, float eps,
-                         float lw, const float* gscale, int stages, cudaStream_t st) {
+static int run_backward3(const void* x, void* grad, int B, int H, int W, const Hier3& h, const Ws3& ws,
+                         const float* bandR, const float* bandC, float eps, float lw, const float* gscale, int stages,
+                         cudaStream_t st) {
   const int C = h.nf + h.nm + h.nh;
   const bool vec_ok = ((W & 3) == 0) && ((uintptr_t)x % (4 * sizeof(T)) == 0) && ((uintptr_t)grad % (4 * sizeof(T)) == 0);
-  dim3 g2((W + kTW - 1) / kTW, (H + 15) / 16, B);
   if (stages & 1) {
-    k3_pass2<T><<<g2, 256, 0, st>>>((const T*)x, (T*)grad, B, H, W, h, ws, eps, lw, gscale, vec_ok ? 1 : 0);
+    const size_t smem = pass2_smem_bytes();
+    auto kern = k3_pass2<T>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 g2(ws.tiles_x, ws.tiles_y, B);
+    kern<<<g2, kThreads, smem, st>>>((const T*)x, (T*)grad, B, H, W, h, ws, eps, lw, gscale, vec_ok ? 1 : 0);
     SH_CHECK_LAUNCH();
   }
   if (stages & 2) {
-    k3_frame2<T><<<dim3(B * C, ws.nseg), 256, 0, st>>>((const T*)x, (T*)grad, B, H, W, h, ws, gscale);
+    k3_frame2<T><<<dim3(B * C, ws.nseg), 256, 0, st>>>((T*)grad, B, H, W, h, ws, bandR, bandC, gscale);
     SH_CHECK_LAUNCH();
   }
   return SH_OK;
@@ -329,14 +405,16 @@ extern "C" {
 int sh_rmi3_backward(const void* logits, int dtype, void* grad, int B, int H, int W, int nf, int nm, int nh,
                      const int* hier_tab, int n_mh, float loss_weight, void* workspace, const float* grad_out,
                      int stages, void* stream) {
-  if (B <= 0 || H < 5 || W < 5 || nf + nm + nh > 255) return SH_ERR_BAD_ARG;
+  if (B <= 0 || H < 8 || W < 8 || nf + nm + nh > 254) return SH_ERR_BAD_ARG;
   sh::Ws3 ws = sh::ws3_layout(workspace, B, H, W, nf, nm, nh);
+  const float* bandR = (const float*)((unsigned char*)workspace + ws.bytes);
+  const float* bandC = bandR + (size_t)B * (nf + nm + nh) * 8 * W;
   sh::Hier3 h = sh::hier3_from_tab(hier_tab, nf, nm, nh, n_mh);
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case SH_DT_F32: return sh::run_backward3<float>(logits, grad, B, H, W, h, ws, 1e-6f, loss_weight, grad_out, stages, st);
-    case SH_DT_BF16: return sh::run_backward3<__nv_bfloat16>(logits, grad, B, H, W, h, ws, 1e-6f, loss_weight, grad_out, stages, st);
-    case SH_DT_F16: return sh::run_backward3<__half>(logits, grad, B, H, W, h, ws, 1e-6f, loss_weight, grad_out, stages, st);
+    case SH_DT_F32: return sh::run_backward3<float>(logits, grad, B, H, W, h, ws, bandR, bandC, 1e-6f, loss_weight, grad_out, stages, st);
+    case SH_DT_BF16: return sh::run_backward3<__nv_bfloat16>(logits, grad, B, H, W, h, ws, bandR, bandC, 1e-6f, loss_weight, grad_out, stages, st);
+    case SH_DT_F16: return sh::run_backward3<__half>(logits, grad, B, H, W, h, ws, bandR, bandC, 1e-6f, loss_weight, grad_out, stages, st);
   }
   return SH_ERR_UNSUPPORTED;
 }

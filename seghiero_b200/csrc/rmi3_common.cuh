@@ -8,33 +8,56 @@
 // valid for them: 0,1 = first two rows, 2 = middle, 3,4 = last two rows.  The
 // (2,2) class (the interior) is accumulated by the streaming kernels as 25/13 "taps";
 // the 24 border classes are accumulated by the small frame kernels.
+//
+// Precision: the reference accumulates the moments in float64.  Here every tap is
+// split into a large common part and a small difference part,
+//     P[r] P[r+d] = P[r]^2 + P[r] (P[r+d] - P[r]),
+// the common parts (sum P^2, sum P over a class region) are carried in float64 from
+// the warp level upwards, the difference parts in float32 (their rounding error
+// scales with the LOCAL variation of P, which is what the small eigenvalues of the
+// 9x9 matrices are made of).  All 9x9 algebra is float64.
 #pragma once
 #include "common.cuh"
 
 namespace sh {
 
-constexpr int kTW = 64;           // tile width (pixels); one thread owns 4 consecutive pixels
-constexpr int kStrips = kTW / 4;  // 16 strips per tile row
-constexpr int kPitch = kTW + 4;   // plane pitch: cols x0-2 .. x0+TW+1
-constexpr int kLabPitch = kTW + 8;  // label tile pitch (bytes), cols x0-2 .. (8-byte windows stay in bounds)
-constexpr int kNPart = 56;        // per (tile, channel) partial: see PartIdx
-constexpr int kNTap = 25;
-constexpr int kNHalf = 13;
+constexpr int kTW = 64;             // tile width (pixels)
+constexpr int kTH = 32;             // tile height of the streaming kernels
+constexpr int kStrips = kTW / 4;    // 16 four-pixel strips per tile row
+constexpr int kPitch = kTW + 4;     // plane pitch: cols x0-2 .. x0+TW+1
+constexpr int kLabPitch = kTW + 8;  // label tile pitch (bytes); 8-byte windows stay in bounds
+constexpr int kNR = 4;              // channels per round
+constexpr int kThreads = 512;       // CTA size of k3_pass1 / k3_pass2
+constexpr int kRec = 64;            // floats per (tile, channel) partial record
 
-// layout of one per-(tile,channel) partial record (floats)
-enum PartIdx {
-  kPP = 0,        // [13] interior taps of P*P, half plane
-  kLPFull = 13,   // sum of P over label-uniform interior anchors of this class (all 25 lp taps)
-  kLLFull = 14,   // count of label-uniform interior anchors of this class   (all ll taps)
-  kLPS = 15,      // [25] lp taps from non-uniform interior anchors
-  kLLS = 40,      // [13] ll taps from non-uniform interior anchors (half plane)
+// layout of one per-(tile,channel) partial record (float slots)
+enum RecIdx {
+  kD = 0,        // [12] difference taps  sum a P[r] (P[r+d] - P[r]),  d in half plane \ {0}  (order: half_tap_index-1)
+  kLLFull = 12,  // count of label-uniform interior anchors of this class
+  kT0 = 16,      // double: sum a P[r]^2
+  kLPFull = 18,  // double: sum of P over label-uniform interior anchors of this class
+  kLPS = 20,     // [25] lp taps from non-uniform interior anchors
+  kLLS = 45,     // [13] ll taps from non-uniform interior anchors (half plane)
+};
+
+// per-class record of the frame kernels (float slots, kFrameRec per class)
+constexpr int kFrameRec = 80;
+enum FrameIdx {
+  kFT0 = 0,     // double: sum P[r]^2 over the class
+  kFLP0 = 2,    // double: sum P[r] L[r]
+  kFD = 4,      // [25] sum P[r] (P[r+d] - P[r])
+  kFDL = 29,    // [25] sum P[r] (L[r+d] - L[r])
+  kFLL = 54,    // [25] sum L[r] L[r+d]
 };
 
 // flags byte per pixel (from k3_prep)
 constexpr int kFlagInterior = 1;
 constexpr int kFlagUniF = 2;
-constexpr int kFlagUniM = 4;
-constexpr int kFlagUniH = 8;
+
+// channel processing order entry (pass 1): kind 0/1/2 = fine/mid/high
+struct OrderEntry {
+  unsigned char kind, cl, flags, pad;   // flags: bit0 reset running max, bit1 flush the level's log product
+};
 
 struct Hier3 {
   int nf, nm, nh;
@@ -43,6 +66,7 @@ struct Hier3 {
   const int* mh_ptr;          // [nm+1]  CSR: highs h with m in Ms(h)
   const int* mh_idx;
   const unsigned int* hsmask; // [nm] bit h set iff h in Hs(m)
+  const unsigned int* order;  // [C] packed OrderEntry: kind | cl<<8 | flags<<16
 };
 
 __host__ __device__ inline int half_tap_index(int dy, int dx) {
@@ -66,32 +90,22 @@ struct Ws3 {
   unsigned char* flags;        // [B*HW]
   unsigned char* hold;         // [(nm+nh+2)][B*HW]
   float* inv;                  // [3][B*HW]   1/sum_c e^x per level
-  float* part1;                // [B*ntiles][C][kNPart]
+  float* part1;                // [B*ntiles][C][kRec]
   float* bcepart;              // [B*ntiles][8]
   double* sums;                // [8]
-  float* frameT;               // [nseg][B*C][25 classes][75]
+  float* frameT;               // [nseg][B*C][25 classes][kFrameRec]
   double* rbc;                 // [B*C]
   float* wts;                  // [B*C][64]: W1[25], W2[25], W2full at 50
   float* fwts;                 // [B*C][25 classes][50]
   size_t bytes;
-  int tiles_x, tiles_y, th, nseg;
+  int tiles_x, tiles_y, nseg;
 };
 
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-// Tile height: as tall as the per-pixel streaming state of pass 1 allows (see k3_pass1).
-inline int pick_tile_rows(int nm, int nh) {
-  for (int th = 16; th >= 2; th >>= 1) {
-    size_t px = (size_t)th * kTW;
-    size_t state = (size_t)(nm + nh) * px * 5;
-    if (state <= 96 * 1024) return th;
-  }
-  return 2;
-}
-
 // frame runs are split into segments so that long image edges spread over more CTAs
 inline int frame_segments(int H, int W) {
-  int n = ((H > W ? H : W) + 511) / 512;
+  int n = ((H > W ? H : W) + 255) / 256;
   return n < 1 ? 1 : (n > 8 ? 8 : n);
 }
 
@@ -99,9 +113,8 @@ inline Ws3 ws3_layout(void* base, int B, int H, int W, int nf, int nm, int nh) {
   Ws3 w;
   const size_t n = (size_t)B * H * W;
   const int C = nf + nm + nh;
-  w.th = pick_tile_rows(nm, nh);
   w.tiles_x = (W + kTW - 1) / kTW;
-  w.tiles_y = (H + w.th - 1) / w.th;
+  w.tiles_y = (H + kTH - 1) / kTH;
   const size_t ntiles = (size_t)w.tiles_x * w.tiles_y * B;
   size_t off = 0;
   unsigned char* p = (unsigned char*)base;
@@ -112,10 +125,10 @@ inline Ws3 ws3_layout(void* base, int B, int H, int W, int nf, int nm, int nh) {
   w.flags = take(n);
   w.hold = take((size_t)(nm + nh + 2) * n);
   w.inv = (float*)take(3 * n * 4);
-  w.part1 = (float*)take(ntiles * C * kNPart * 4);
+  w.part1 = (float*)take(ntiles * C * kRec * 4);
   w.bcepart = (float*)take(ntiles * 8 * 4);
   w.nseg = frame_segments(H, W);
-  w.frameT = (float*)take((size_t)w.nseg * B * C * 25 * 75 * 4);
+  w.frameT = (float*)take((size_t)w.nseg * B * C * 25 * kFrameRec * 4);
   w.rbc = (double*)take((size_t)B * C * 8);
   w.wts = (float*)take((size_t)B * C * 64 * 4);
   w.fwts = (float*)take((size_t)B * C * 25 * 50 * 4);
@@ -123,6 +136,7 @@ inline Ws3 ws3_layout(void* base, int B, int H, int W, int nf, int nm, int nh) {
   return w;
 }
 
+// hier_tab (device int32): [f2m nf][f2h nf][mh_ptr nm+1][mh_idx n_mh][hsmask nm][order C]
 inline Hier3 hier3_from_tab(const int* tab, int nf, int nm, int nh, int n_mh) {
   Hier3 h;
   h.nf = nf; h.nm = nm; h.nh = nh;
@@ -131,10 +145,77 @@ inline Hier3 hier3_from_tab(const int* tab, int nf, int nm, int nh, int n_mh) {
   h.mh_ptr = h.f2h + nf;
   h.mh_idx = h.mh_ptr + nm + 1;
   h.hsmask = (const unsigned int*)(h.mh_idx + n_mh);
+  h.order = h.hsmask + nm;
   return h;
 }
 
 // byte k of a 64-bit little-endian window
 __device__ __forceinline__ unsigned int byte_of(unsigned long long w, int k) { return (unsigned int)(w >> (8 * k)) & 0xffu; }
+
+__device__ __forceinline__ unsigned int load4_u8(const unsigned char* p, int nvalid, bool aligned) {
+  if (aligned && nvalid == 4) return *reinterpret_cast<const unsigned int*>(p);
+  unsigned int r = 0;
+  for (int k = 0; k < nvalid; ++k) r |= (unsigned int)p[k] << (8 * k);
+  return r;
+}
+__device__ __forceinline__ void store4_u8(unsigned char* p, unsigned int v, int nvalid, bool aligned) {
+  if (aligned && nvalid == 4) {
+    *reinterpret_cast<unsigned int*>(p) = v;
+  } else {
+    for (int k = 0; k < nvalid; ++k) p[k] = (unsigned char)(v >> (8 * k));
+  }
+}
+
+// 16 values per lane -> every even lane holds the warp total of element
+// e(lane) = 8*bit4 + 4*bit3 + 2*bit2 + bit1 in the return value (61 instructions instead of 160).
+__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int n = 8, off = 16; n >= 1; n >>= 1, off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float send = up ? v[i] : v[i + n];
+      const float keep = up ? v[i + n] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+__device__ __forceinline__ int reduce16_slot(int lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
+// P and RMI label of a pixel that is known to lie in a 4-pixel border band (see k3_band)
+struct BandView {
+  const float* bandR; const float* bandC; const unsigned char* lab8; const int* lmap; int H, W;
+  __device__ __forceinline__ float P(int yy, int xx) const {
+    if (yy < 4) return bandR[(size_t)yy * W + xx];
+    if (yy >= H - 4) return bandR[(size_t)(yy - (H - 8)) * W + xx];
+    if (xx < 4) return bandC[(size_t)xx * H + yy];
+    return bandC[(size_t)(xx - (W - 8)) * H + yy];
+  }
+  __device__ __forceinline__ int L(int yy, int xx) const {
+    const int t = lab8[(long)yy * W + xx];
+    return t == SH_IGNORE ? 0 : (lmap ? lmap[t] : t);
+  }
+};
+
+// label tile (3 levels, halo 2) from the uint8 labels: rows y0-2 .. y0+rows+1, cols x0-2 .. x0+65
+__device__ __forceinline__ void load_label_tile(unsigned char* labt, int rows, const unsigned char* lab8, int H, int W,
+                                                int y0, int x0, const Hier3& h, int tid, int nthreads) {
+  for (int e = tid; e < (rows + 4) * kPitch; e += nthreads) {
+    const int r = e / kPitch, j = e - r * kPitch;
+    const int yy = y0 - 2 + r, xx = x0 - 2 + j;
+    unsigned char f = 0xff, m = 0xff, g = 0xff;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      const int t = lab8[(long)yy * W + xx];
+      f = m = g = 0;   // void pixels are one-hot of class 0 at every level inside RMI
+      if (t != SH_IGNORE) { f = (unsigned char)t; m = (unsigned char)h.f2m[t]; g = (unsigned char)h.f2h[t]; }
+    }
+    labt[(0 * (rows + 4) + r) * kLabPitch + j] = f;
+    labt[(1 * (rows + 4) + r) * kLabPitch + j] = m;
+    labt[(2 * (rows + 4) + r) * kLabPitch + j] = g;
+  }
+}
 
 }  // namespace sh

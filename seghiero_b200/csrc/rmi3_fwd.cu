@@ -2,6 +2,7 @@
 //   k3_prep     labels int64 -> uint8 + per-pixel flags (interior / label-uniform 5x5 per level)
 //   k3_pass1    ONE streaming read of the logits: tree BCE + CE sums, per-pixel
 //               summaries for the backward pass, RMI interior taps per (tile, channel)
+//   k3_band     P = sigmoid*valid + 1e-6 of the 4-pixel image border bands (feeds the frame kernels)
 //   k3_frame1   RMI taps of the 2-pixel image frame, per border class
 //   k3_finalize per (b,c): fp64 reduction, 9x9 algebra (inverse, Schur, log-det),
 //               analytic adjoints -> 5x5 stencil weights for the backward pass
@@ -12,7 +13,7 @@
 namespace sh {
 
 // ---------------------------------------------------------------------------------------------
-// k3_prep
+// k3_prep: tile 64x16, 256 threads, one thread = 4 consecutive pixels
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k3_prep(const long long* __restrict__ label, int B, int H, int W, Hier3 h,
                                                unsigned char* __restrict__ lab8, unsigned char* __restrict__ flags,
@@ -38,216 +39,321 @@ __global__ void __launch_bounds__(256) k3_prep(const long long* __restrict__ lab
   }
   __syncthreads();
   const int ty = threadIdx.x / kStrips, tx = (threadIdx.x % kStrips) * 4;
-  const int y = y0 + ty;
+  const int y = y0 + ty, xg = x0 + tx;
   long long nv = 0;
-  if (y < H) {
-    for (int k = 0; k < 4; ++k) {
-      const int x = x0 + tx + k;
-      if (x >= W) break;
+  if (y < H && xg < W) {
+    unsigned int fl4 = 0, lab4 = 0xffffffffu;
+    unsigned int uni[3] = {0xfu, 0xfu, 0xfu};   // bit k: 5x5 neighbourhood of pixel k uniform at this level
+#pragma unroll
+    for (int lvl = 0; lvl < 3; ++lvl) {
+      const unsigned int* c2 = reinterpret_cast<const unsigned int*>(&rl[lvl][ty + 2][tx]);
+      const unsigned long long ctr = (unsigned long long)c2[0] | ((unsigned long long)c2[1] << 32);
+#pragma unroll
+      for (int rr = 0; rr < 5; ++rr) {
+        const unsigned int* rp = reinterpret_cast<const unsigned int*>(&rl[lvl][ty + rr][tx]);
+        const unsigned long long w = (unsigned long long)rp[0] | ((unsigned long long)rp[1] << 32);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const unsigned long long pat = (unsigned long long)byte_of(ctr, k + 2) * 0x0101010101ULL;
+          if (((w >> (8 * k)) & 0xffffffffffULL) != pat) uni[lvl] &= ~(1u << k);
+        }
+      }
+    }
+    const int nvalid = min(4, W - xg);
+    for (int k = 0; k < nvalid; ++k) {
+      const int x = xg + k;
       const long long t = lb[(long)y * W + x];
       const bool valid = (t != SH_IGNORE);
       nv += valid;
-      unsigned char fl = 0;
+      unsigned int fl = 0;
       if (y >= 2 && y < H - 2 && x >= 2 && x < W - 2) {
         fl = kFlagInterior;
 #pragma unroll
-        for (int lvl = 0; lvl < 3; ++lvl) {
-          const unsigned char ctr = rl[lvl][ty + 2][tx + k + 2];
-          bool uni = true;
-#pragma unroll
-          for (int dy = 0; dy < 5; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < 5; ++dx) uni &= (rl[lvl][ty + dy][tx + k + dx] == ctr);
-          if (uni) fl |= (kFlagUniF << lvl);
-        }
+        for (int lvl = 0; lvl < 3; ++lvl)
+          if ((uni[lvl] >> k) & 1u) fl |= (kFlagUniF << lvl);
       }
-      lab8[(long)b * H * W + (long)y * W + x] = (valid && t >= 0 && t < h.nf) ? (unsigned char)t : SH_IGNORE;
-      flags[(long)b * H * W + (long)y * W + x] = fl;
+      const unsigned int l8 = (valid && t >= 0 && t < h.nf) ? (unsigned int)t : SH_IGNORE;
+      lab4 = (lab4 & ~(0xffu << (8 * k))) | (l8 << (8 * k));
+      fl4 |= fl << (8 * k);
     }
+    const bool al = (W & 3) == 0;
+    const long off = (long)b * H * W + (long)y * W + xg;
+    store4_u8(lab8 + off, lab4, nvalid, al);
+    store4_u8(flags + off, fl4, nvalid, al);
   }
   nv = warp_sum(nv);
   if ((threadIdx.x & 31) == 0 && nv) atomicAdd(counts, (unsigned long long)nv);
   if (bad) atomicOr((unsigned int*)(counts + 2), 1u);
 }
 
-// 16 values per lane -> every even lane holds the warp total of element
-// e(lane) = 8*bit4 + 4*bit3 + 2*bit2 + bit1 in the return value (61 instructions instead of 160).
-__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
+// Slow path of k3_pass1 (kept out of line so that its registers do not burden the streaming loop):
+// lp / ll taps of the interior anchors of one 4x4 block whose 5x5 label neighbourhood is NOT uniform.
+// All lanes of the warp must call it (warp-level reductions); lanes with want == false add zeros.
+__device__ __noinline__ void pass1_slow_path(const float* plane, const unsigned char* labl, unsigned int u0,
+                                             unsigned int u1, unsigned int u2, unsigned int u3, int br, int bs,
+                                             int cl, bool want, int lane, float* sp) {
+  float sl[48];   // [0,25) lp taps, [25,38) ll half-plane taps, rest padding
 #pragma unroll
-  for (int n = 8, off = 16; n >= 1; n >>= 1, off >>= 1) {
-    const bool up = (lane & off) != 0;
+  for (int i = 0; i < 48; ++i) sl[i] = 0.f;
+  if (want) {
+    const unsigned int ub4[4] = {u0, u1, u2, u3};
+    float bk[4][4], lk[4][4];
 #pragma unroll
-    for (int i = 0; i < n; ++i) {
-      const float send = up ? v[i] : v[i + n];
-      const float keep = up ? v[i + n] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    for (int i = 0; i < 4; ++i) {
+      const float* prow = plane + (4 * br + i) * kPitch + 4 * bs + 2;
+      const unsigned char* crow = labl + (4 * br + i + 2) * kLabPitch + 4 * bs + 2;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool nu = ((ub4[i] >> (8 * k)) & 0xffu) == 0xfeu;
+        bk[i][k] = nu ? prow[k] : 0.f;
+        lk[i][k] = (nu && crow[k] == cl) ? 1.f : 0.f;
+      }
     }
-  }
-  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
-__device__ __forceinline__ int reduce16_slot(int lane) {
-  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-}
-
-__device__ __forceinline__ void store4_u8(unsigned char* p, const unsigned char (&v)[4], int nvalid, bool aligned) {
-  if (aligned && nvalid == 4) {
-    *reinterpret_cast<unsigned int*>(p) = v[0] | (v[1] << 8) | (v[2] << 16) | ((unsigned int)v[3] << 24);
-  } else {
-    for (int k = 0; k < nvalid; ++k) p[k] = v[k];
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// k3_pass1: grid (tiles_x, tiles_y, B), block th*16 threads, one thread = 4 consecutive pixels.
-// ---------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256, 2)
-k3_pass1(const T* __restrict__ x, int B, int H, int W, Hier3 h, Ws3 ws, float eps, int vec_ok) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int th = blockDim.x / kStrips;
-  const int PX = th * kTW;
-  const int C = h.nf + h.nm + h.nh;
-  float* plane = reinterpret_cast<float*>(smem_raw);                 // [(th+2)][kPitch]
-  float* maxA = plane + (th + 2) * kPitch;                           // [nm][PX]
-  float* maxB = maxA + (size_t)h.nm * PX;                            // [nh][PX]
-  float* chacc = maxB + (size_t)h.nh * PX;                           // [64]
-  unsigned char* holdA = reinterpret_cast<unsigned char*>(chacc + 64);  // [nm][PX]
-  unsigned char* holdB = holdA + (size_t)h.nm * PX;                  // [nh][PX]
-  unsigned char* labt = holdB + (size_t)h.nh * PX;                   // [3][(th+4)][kLabPitch]
-
-  const int b = blockIdx.z, y0 = blockIdx.y * th, x0 = blockIdx.x * kTW;
-  const long HW = (long)H * W;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int ty = tid / kStrips, tx = (tid % kStrips) * 4;
-  const int y = y0 + ty, xg = x0 + tx;
-  const long tile_id = ((long)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-  const unsigned char* lab8 = ws.lab8 + (long)b * HW;
-  const unsigned char* flg = ws.flags + (long)b * HW;
-
-  // ---- label tile (3 levels, halo 2) ------------------------------------------------------------
-  for (int e = tid; e < (th + 4) * kPitch; e += blockDim.x) {
-    const int r = e / kPitch, j = e - r * kPitch;
-    const int yy = y0 - 2 + r, xx = x0 - 2 + j;
-    unsigned char f = 0xff, m = 0xff, g = 0xff;
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-      const int t = lab8[(long)yy * W + xx];
-      f = m = g = 0;
-      if (t != SH_IGNORE) { f = (unsigned char)t; m = (unsigned char)h.f2m[t]; g = (unsigned char)h.f2h[t]; }
-    }
-    labt[(0 * (th + 4) + r) * kLabPitch + j] = f;
-    labt[(1 * (th + 4) + r) * kLabPitch + j] = m;
-    labt[(2 * (th + 4) + r) * kLabPitch + j] = g;
-  }
-  // ---- per-pixel label state ----------------------------------------------------------------------
-  int tf[4], tm[4], thh[4];
-  unsigned int hsm[4];
-  bool inimg[4], interior[4];
-  unsigned int ulab[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};  // byte k: class if (interior & uniform) else 0xff
-  unsigned int nonuni[3] = {0u, 0u, 0u};                           // bit k: interior & !uniform
-  unsigned int rlab[3] = {0u, 0u, 0u};                             // byte k: RMI label (void -> 0)
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    inimg[k] = (y < H) && (xg + k < W);
-    int t = SH_IGNORE, fl = 0;
-    if (inimg[k]) { t = lab8[(long)y * W + xg + k]; fl = flg[(long)y * W + xg + k]; }
-    tf[k] = t;
-    tm[k] = t != SH_IGNORE ? h.f2m[t] : SH_IGNORE;
-    thh[k] = t != SH_IGNORE ? h.f2h[t] : SH_IGNORE;
-    hsm[k] = t != SH_IGNORE ? h.hsmask[tm[k]] : 0u;
-    interior[k] = (fl & kFlagInterior) != 0;
-    const int r3[3] = {t != SH_IGNORE ? t : 0, t != SH_IGNORE ? tm[k] : 0, t != SH_IGNORE ? thh[k] : 0};
+    for (int R = 0; R < 8; ++R) {    // label rows 4br-2 .. 4br+5 of the tile
+      const unsigned int* row = reinterpret_cast<const unsigned int*>(labl + (4 * br + R) * kLabPitch + 4 * bs);
+      const unsigned long long wbits = (unsigned long long)row[0] | ((unsigned long long)row[1] << 32);
+      float mt[8];
 #pragma unroll
-    for (int l = 0; l < 3; ++l) {
-      rlab[l] |= (unsigned int)r3[l] << (8 * k);
-      if (interior[k]) {
-        if (fl & (kFlagUniF << l)) ulab[l] = (ulab[l] & ~(0xffu << (8 * k))) | ((unsigned int)r3[l] << (8 * k));
-        else nonuni[l] |= 1u << k;
+      for (int q = 0; q < 8; ++q) mt[q] = (byte_of(wbits, q) == (unsigned int)cl) ? 1.f : 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = R - i;        // dy + 2
+        if (rr < 0 || rr > 4) continue;
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            sl[rr * 5 + dx] = fmaf(bk[i][k], mt[k + dx], sl[rr * 5 + dx]);
+            if (rr > 2 || (rr == 2 && dx >= 2)) {
+              const int hi = rr == 2 ? dx - 2 : 3 + (rr - 3) * 5 + dx;
+              sl[25 + hi] = fmaf(lk[i][k], mt[k + dx], sl[25 + hi]);
+            }
+          }
+        }
       }
     }
   }
-  for (int i = tid; i < h.nm * PX; i += blockDim.x) { maxA[i] = -1.f; holdA[i] = 0; }
-  for (int i = tid; i < h.nh * PX; i += blockDim.x) { maxB[i] = -1.f; holdB[i] = 0; }
+#pragma unroll
+  for (int base = 0; base < 48; base += 16) {
+    const float t2 = warp_reduce16(*reinterpret_cast<float(*)[16]>(sl + base), lane);
+    if ((lane & 1) == 0) {
+      const int idx = base + reduce16_slot(lane);
+      if (idx < 38 && t2 != 0.f) atomicAdd(sp + idx, t2);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k3_pass1: grid (tiles_x, tiles_y, B), 512 threads, tile 64x32.
+//   phase A (thread = 4 consecutive pixels, all channels): sigmoid/exp, tree BCE + CE streaming
+//            (channels visited in tree order so running maxima stay in registers), P -> plane
+//   phase B (thread = one 4x4 block of ONE of the round's 4 channel planes): interior taps
+// Planes are double buffered: one __syncthreads per round of 4 channels.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+k3_pass1(const T* __restrict__ x, int B, int H, int W, Hier3 h, Ws3 ws, float eps, int vec_ok) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int PX = kTH * kTW;
+  constexpr int kPlane = (kTH + 2) * kPitch;
+  const int C = h.nf + h.nm + h.nh;
+  float* planes = reinterpret_cast<float*>(smem_raw);                    // [2][kNR][kPlane]
+  float* red = planes + 2 * kNR * kPlane;                                // [2][kNR][4 warps][20]
+  float* slow = red + 2 * kNR * 4 * 20;                                  // [2][kNR][40]
+  float* maxB = slow + 2 * kNR * 40;                                     // [nh][PX]
+  unsigned char* holdB = reinterpret_cast<unsigned char*>(maxB + (size_t)h.nh * PX);  // [nh][PX]
+  unsigned char* U = holdB + (size_t)h.nh * PX;                          // [3][kTH][kTW]
+  unsigned char* labt = U + 3 * PX;                                      // [3][kTH+4][kLabPitch]
+
+  const int b = blockIdx.z, y0 = blockIdx.y * kTH, x0 = blockIdx.x * kTW;
+  const long HW = (long)H * W;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const long tile_id = ((long)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const unsigned char* lab8 = ws.lab8 + (long)b * HW;
+  const unsigned char* flg = ws.flags + (long)b * HW;
+  const T* xb = x + (long)b * C * HW;
+
+  // ---- phase-A role: own 4 pixels -------------------------------------------------------------------
+  const int ty = tid / kStrips, tx = (tid % kStrips) * 4;
+  const int y = y0 + ty, xg = x0 + tx;
+  const int px0 = ty * kTW + tx;
+  const bool row_ok = y < H;
+  const long own_off = (long)y * W + xg;
+  int nvalid = row_ok ? W - xg : 0;
+  nvalid = nvalid > 4 ? 4 : (nvalid < 0 ? 0 : nvalid);
+  const bool st_al = vec_ok && ((W & 3) == 0);
+
+  load_label_tile(labt, kTH, lab8, H, W, y0, x0, h, tid, kThreads);
+  int tf[4], tm[4], thh[4];
+  unsigned int hsm[4];
+  {
+    unsigned int u4[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int t = SH_IGNORE, fl = 0;
+      if (k < nvalid) { t = lab8[own_off + k]; fl = flg[own_off + k]; }
+      tf[k] = t;
+      tm[k] = t != SH_IGNORE ? h.f2m[t] : SH_IGNORE;
+      thh[k] = t != SH_IGNORE ? h.f2h[t] : SH_IGNORE;
+      hsm[k] = t != SH_IGNORE ? h.hsmask[tm[k]] : 0u;
+      const unsigned int r3[3] = {t != SH_IGNORE ? (unsigned)t : 0u, t != SH_IGNORE ? (unsigned)tm[k] : 0u,
+                                  t != SH_IGNORE ? (unsigned)thh[k] : 0u};
+#pragma unroll
+      for (int l = 0; l < 3; ++l) {
+        unsigned int code = 0xffu;                                   // not an interior anchor
+        if (fl & kFlagInterior) code = (fl & (kFlagUniF << l)) ? r3[l] : 0xfeu;
+        u4[l] = (u4[l] & ~(0xffu << (8 * k))) | (code << (8 * k));
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < 3; ++l) *reinterpret_cast<unsigned int*>(U + l * PX + px0) = u4[l];
+  }
+  for (int i = tid; i < h.nh * PX; i += kThreads) { maxB[i] = -1.f; holdB[i] = 0; }
+  for (int i = tid; i < 2 * kNR * 40; i += kThreads) slow[i] = 0.f;
+  // halo slot of this thread (same position in every plane)
+  constexpr int nhalo = kPlane - kTH * kTW;   // 264
+  int h_sidx = -1;
+  long h_goff = -1;
+  bool h_valid = false;
+  if (tid < nhalo) {
+    int r, j;
+    if (tid < 2 * kPitch) { r = kTH + tid / kPitch; j = tid % kPitch; }
+    else { const int e2 = tid - 2 * kPitch; r = e2 >> 2; const int q = e2 & 3; j = q < 2 ? q : kTW + q; }
+    h_sidx = r * kPitch + j;
+    const int yy = y0 + r, xx = x0 - 2 + j;
+    if (yy < H && xx >= 0 && xx < W) { h_goff = (long)yy * W + xx; h_valid = lab8[h_goff] != SH_IGNORE; }
+  }
   __syncthreads();
-  // bloom filter of the labels in this strip's 5x8 window (only if some pixel needs the slow path)
+
+  // ---- phase-B role: one 4x4 block of plane g ------------------------------------------------------
+  const int g = tid >> 7, u = tid & 127, br = u >> 4, bs = u & 15;
+  unsigned int ub[3][4];        // U codes of the block rows, per level
   unsigned int pres[3] = {0u, 0u, 0u};
 #pragma unroll
   for (int l = 0; l < 3; ++l) {
-    if (nonuni[l]) {
-      for (int rr = 0; rr < 5; ++rr) {
-        const unsigned char* row = labt + ((l * (th + 4)) + ty + rr) * kLabPitch + tx;
+    bool any_nu = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ub[l][i] = *reinterpret_cast<const unsigned int*>(U + l * PX + (4 * br + i) * kTW + 4 * bs);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) any_nu |= ((ub[l][i] >> (8 * k)) & 0xffu) == 0xfeu;
+    }
+    if (any_nu) {
+      for (int rr = 0; rr < 8; ++rr) {
+        const unsigned char* row = labt + ((l * (kTH + 4)) + 4 * br + rr) * kLabPitch + 4 * bs;
         for (int q = 0; q < 8; ++q) pres[l] |= 1u << (row[q] & 31);
       }
     }
   }
 
-  // ---- streaming state --------------------------------------------------------------------------
-  float sumv[3][4], vt[3][4], a_t[4], b_t[4], c_t[4], min_c[4], prod[4];
-  int hold_minc[4];
-  float lacc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // BCE fine/mid/high, CE fine/mid/high
+  // ---- streaming state (phase-A role) ----------------------------------------------------------------
+  float sumvF[4], sumvM[4], sumvH[4], prodF[4], prodM[4], prodH[4], a_t[4], b_t[4], c_t[4], min_c[4], runmax[4];
+  unsigned int runhold = 0, hold_minc = 0;
+  float lacc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // BCE fine/mid/high, CE fine/mid/high
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-#pragma unroll
-    for (int l = 0; l < 3; ++l) { sumv[l][k] = 0.f; vt[l][k] = 1.f; }
-    a_t[k] = b_t[k] = c_t[k] = 1.f; min_c[k] = 3.0e38f; hold_minc[k] = 0; prod[k] = 1.f;
+    sumvF[k] = sumvM[k] = sumvH[k] = 0.f;
+    prodF[k] = prodM[k] = prodH[k] = 1.f;
+    a_t[k] = b_t[k] = c_t[k] = 1.f;
+    min_c[k] = 3.0e38f;
+    runmax[k] = -1.f;
   }
-  const int px0 = ty * kTW + tx;
-  const T* xb = x + (long)b * C * HW;
-  const long own_off = (long)y * W + xg;
-  const bool row_ok = y < H;
-  const int nhalo = (th + 2) * kPitch - th * kTW;
-  const bool st_al = vec_ok && ((W & 3) == 0);
 
-  float xv[4];
-  if (row_ok) load_n<T, 4>(xb, own_off, (long)y * W + W, vec_ok != 0, xv);
-  else { xv[0] = xv[1] = xv[2] = xv[3] = 0.f; }
+  const int nrounds = (C + kNR - 1) / kNR;
+  float xv[kNR][4], hv[kNR];
+  auto chan_of = [&](unsigned int oe) {
+    const int kind = oe & 0xff, cl = (oe >> 8) & 0xff;
+    return kind == 0 ? cl : (kind == 1 ? h.nf + cl : h.nf + h.nm + cl);
+  };
+  auto prefetch = [&](int r) {
+#pragma unroll
+    for (int j = 0; j < kNR; ++j) {
+      const int ci = r * kNR + j;
+      if (ci < C) {
+        const T* xc = xb + (long)chan_of(h.order[ci]) * HW;
+        if (row_ok) load_n<T, 4>(xc, own_off, (long)y * W + W, vec_ok != 0, xv[j]);
+        else { xv[j][0] = xv[j][1] = xv[j][2] = xv[j][3] = 0.f; }
+        hv[j] = h_goff >= 0 ? to_f32<T>(xc[h_goff]) : 0.f;
+      }
+    }
+  };
+  auto flush = [&](int r) {
+    // combine the 4 warps of every plane of round r and write the per-(tile, channel) records
+    const int buf = r & 1;
+    if (tid < kNR * 16) {
+      const int j = tid >> 4, k = tid & 15, ci = r * kNR + j;
+      if (ci < C && k < 13) {
+        const float* rp = red + ((buf * kNR + j) * 4) * 20 + k;
+        ws.part1[((size_t)tile_id * C + chan_of(h.order[ci])) * kRec + k] = rp[0] + rp[20] + rp[40] + rp[60];
+      }
+    } else if (tid < kNR * 16 + 2 * kNR) {
+      const int q = tid - kNR * 16, j = q >> 1, which = q & 1, ci = r * kNR + j;
+      if (ci < C) {
+        const double* rp = reinterpret_cast<const double*>(red + ((buf * kNR + j) * 4) * 20 + 16) + which;
+        const double v = rp[0] + rp[10] + rp[20] + rp[30];
+        *reinterpret_cast<double*>(ws.part1 + ((size_t)tile_id * C + chan_of(h.order[ci])) * kRec + kT0 + 2 * which) = v;
+      }
+    } else if (tid >= 128 && tid < 128 + kNR * 40) {
+      const int q = tid - 128, j = q / 40, k = q % 40, ci = r * kNR + j;
+      if (ci < C && k < 38) {
+        float* sp = slow + (buf * kNR + j) * 40 + k;
+        ws.part1[((size_t)tile_id * C + chan_of(h.order[ci])) * kRec + kLPS + k] = *sp;
+        *sp = 0.f;
+      }
+    }
+  };
 
-  for (int c = 0; c < C; ++c) {
-    const int lvl = c < h.nf ? 0 : (c < h.nf + h.nm ? 1 : 2);
-    const int cl = lvl == 0 ? c : (lvl == 1 ? c - h.nf : c - h.nf - h.nm);
-    const T* xc = xb + (long)c * HW;
-    // ---------------- phase A: sigmoid/exp, BCE/CE streaming, park P in the plane ---------------
-    float pk[4];
-    {
-      float s[4], v[4];
+  prefetch(0);
+  for (int r = 0; r < nrounds; ++r) {
+    const int buf = r & 1;
+    // ======================= phase A =======================
+#pragma unroll
+    for (int j = 0; j < kNR; ++j) {
+      const int ci = r * kNR + j;
+      if (ci >= C) break;
+      const unsigned int oe = h.order[ci];
+      const int kind = oe & 0xff, cl = (oe >> 8) & 0xff, fl = (oe >> 16) & 0xff;
+      float* plane = planes + (buf * kNR + j) * kPlane;
+      float s[4], v[4], pk[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        SigExp se = sig_exp(xv[k]);
+        const SigExp se = sig_exp(xv[j][k]);
         s[k] = se.s; v[k] = se.v;
-        pk[k] = inimg[k] ? ((tf[k] != SH_IGNORE ? se.s : 0.f) + 1e-6f) : 0.f;
+        pk[k] = k < nvalid ? ((tf[k] != SH_IGNORE ? se.s : 0.f) + 1e-6f) : 0.f;
       }
       *reinterpret_cast<float2*>(plane + ty * kPitch + tx + 2) = make_float2(pk[0], pk[1]);
       *reinterpret_cast<float2*>(plane + ty * kPitch + tx + 4) = make_float2(pk[2], pk[3]);
-      if (lvl == 0) {
-        const int m = h.f2m[cl];
-        float4 cur = *reinterpret_cast<float4*>(maxA + (size_t)m * PX + px0);
-        unsigned int hd = *reinterpret_cast<unsigned int*>(holdA + (size_t)m * PX + px0);
-        float curv[4] = {cur.x, cur.y, cur.z, cur.w};
+      if (h_sidx >= 0) plane[h_sidx] = h_goff >= 0 ? ((h_valid ? sig_exp(hv[j]).s : 0.f) + 1e-6f) : 0.f;
+      if (fl & 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) runmax[k] = -1.f;
+        runhold = 0;
+      }
+      if (kind == 0) {
+        const unsigned int c = cl;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          sumv[0][k] += v[k];
-          if (cl == tf[k]) { a_t[k] = s[k]; vt[0][k] = v[k]; }
-          else prod[k] *= (1.0f - s[k]) + eps;
-          if (s[k] > curv[k]) { curv[k] = s[k]; hd = (hd & ~(0xffu << (8 * k))) | ((unsigned int)c << (8 * k)); }
+          sumvF[k] += v[k];
+          if (cl == tf[k]) { a_t[k] = s[k]; lacc[3] -= fast_log(v[k]); }
+          else prodF[k] *= (1.0f - s[k]) + eps;
+          if (s[k] > runmax[k]) { runmax[k] = s[k]; runhold = (runhold & ~(0xffu << (8 * k))) | (c << (8 * k)); }
         }
-        *reinterpret_cast<float4*>(maxA + (size_t)m * PX + px0) = make_float4(curv[0], curv[1], curv[2], curv[3]);
-        *reinterpret_cast<unsigned int*>(holdA + (size_t)m * PX + px0) = hd;
-        if ((cl & 3) == 3 || cl == h.nf - 1) {
+        if (fl & 2) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) { if (tf[k] != SH_IGNORE) lacc[0] -= fast_log(prod[k]); prod[k] = 1.f; }
+          for (int k = 0; k < 4; ++k) { if (tf[k] != SH_IGNORE) lacc[0] -= fast_log(prodF[k]); prodF[k] = 1.f; }
         }
-      } else if (lvl == 1) {
-        float4 cur = *reinterpret_cast<float4*>(maxA + (size_t)cl * PX + px0);
-        unsigned int hd = *reinterpret_cast<unsigned int*>(holdA + (size_t)cl * PX + px0);
-        float curv[4] = {cur.x, cur.y, cur.z, cur.w};
-        unsigned char hv[4];
+      } else if (kind == 1) {
+        const unsigned int c = h.nf + cl;
+        float cur[4];
+        unsigned int hd = runhold;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          sumv[1][k] += v[k];
-          int holder = (hd >> (8 * k)) & 0xff;
-          if (s[k] > curv[k]) { curv[k] = s[k]; holder = c; }   // fine max wins ties
-          hv[k] = (unsigned char)holder;
-          if (cl == tm[k]) { b_t[k] = s[k]; vt[1][k] = v[k]; }
-          else prod[k] *= (1.0f - curv[k]) + eps;
+          sumvM[k] += v[k];
+          cur[k] = runmax[k];
+          if (s[k] > cur[k]) { cur[k] = s[k]; hd = (hd & ~(0xffu << (8 * k))) | (c << (8 * k)); }   // fine max wins ties
+          if (cl == tm[k]) { b_t[k] = s[k]; lacc[4] -= fast_log(v[k]); }
+          else prodM[k] *= (1.0f - cur[k]) + eps;
         }
         for (int q = h.mh_ptr[cl]; q < h.mh_ptr[cl + 1]; ++q) {
           const int hh = h.mh_idx[q];
@@ -256,273 +362,258 @@ k3_pass1(const T* __restrict__ x, int B, int H, int W, Hier3 h, Ws3 ws, float ep
           float cbv[4] = {cb.x, cb.y, cb.z, cb.w};
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            if (curv[k] > cbv[k]) { cbv[k] = curv[k]; hb = (hb & ~(0xffu << (8 * k))) | ((unsigned int)hv[k] << (8 * k)); }
+            if (cur[k] > cbv[k]) { cbv[k] = cur[k]; hb = (hb & ~(0xffu << (8 * k))) | (hd & (0xffu << (8 * k))); }
           *reinterpret_cast<float4*>(maxB + (size_t)hh * PX + px0) = make_float4(cbv[0], cbv[1], cbv[2], cbv[3]);
           *reinterpret_cast<unsigned int*>(holdB + (size_t)hh * PX + px0) = hb;
         }
-        if (row_ok) {
-          int nvalid = W - xg; nvalid = nvalid > 4 ? 4 : nvalid;
-          if (nvalid > 0) store4_u8(ws.hold + ((size_t)cl * B + b) * HW + own_off, hv, nvalid, st_al);
-        }
-        if ((cl & 3) == 3 || cl == h.nm - 1) {
+        if (nvalid > 0) store4_u8(ws.hold + ((size_t)cl * B + b) * HW + own_off, hd, nvalid, st_al);
+        if (fl & 2) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) { if (tf[k] != SH_IGNORE) lacc[1] -= fast_log(prod[k]); prod[k] = 1.f; }
+          for (int k = 0; k < 4; ++k) { if (tf[k] != SH_IGNORE) lacc[1] -= fast_log(prodM[k]); prodM[k] = 1.f; }
         }
       } else {
-        float4 cur = *reinterpret_cast<float4*>(maxB + (size_t)cl * PX + px0);
-        unsigned int hd = *reinterpret_cast<unsigned int*>(holdB + (size_t)cl * PX + px0);
-        float curv[4] = {cur.x, cur.y, cur.z, cur.w};
-        unsigned char hv[4];
+        const unsigned int c = h.nf + h.nm + cl;
+        const float4 cb = *reinterpret_cast<const float4*>(maxB + (size_t)cl * PX + px0);
+        unsigned int hd = *reinterpret_cast<const unsigned int*>(holdB + (size_t)cl * PX + px0);
+        float cur[4] = {cb.x, cb.y, cb.z, cb.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          sumv[2][k] += v[k];
-          int holder = (hd >> (8 * k)) & 0xff;
-          if (s[k] > curv[k]) { curv[k] = s[k]; holder = c; }   // mid max wins ties
-          hv[k] = (unsigned char)holder;
-          if (cl == thh[k]) { c_t[k] = s[k]; vt[2][k] = v[k]; }
-          else prod[k] *= (1.0f - curv[k]) + eps;
-          if ((hsm[k] >> cl) & 1u) { if (s[k] < min_c[k]) { min_c[k] = s[k]; hold_minc[k] = c; } }
+          sumvH[k] += v[k];
+          if (s[k] > cur[k]) { cur[k] = s[k]; hd = (hd & ~(0xffu << (8 * k))) | (c << (8 * k)); }   // mid max wins ties
+          if (cl == thh[k]) { c_t[k] = s[k]; lacc[5] -= fast_log(v[k]); }
+          else prodH[k] *= (1.0f - cur[k]) + eps;
+          if (((hsm[k] >> cl) & 1u) && s[k] < min_c[k]) {
+            min_c[k] = s[k];
+            hold_minc = (hold_minc & ~(0xffu << (8 * k))) | (c << (8 * k));
+          }
         }
-        if (row_ok) {
-          int nvalid = W - xg; nvalid = nvalid > 4 ? 4 : nvalid;
-          if (nvalid > 0) store4_u8(ws.hold + ((size_t)(h.nm + cl) * B + b) * HW + own_off, hv, nvalid, st_al);
-        }
-        if ((cl & 3) == 3 || cl == h.nh - 1) {
+        if (nvalid > 0) store4_u8(ws.hold + ((size_t)(h.nm + cl) * B + b) * HW + own_off, hd, nvalid, st_al);
+        if (fl & 2) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) { if (tf[k] != SH_IGNORE) lacc[2] -= fast_log(prod[k]); prod[k] = 1.f; }
+          for (int k = 0; k < 4; ++k) { if (tf[k] != SH_IGNORE) lacc[2] -= fast_log(prodH[k]); prodH[k] = 1.f; }
         }
       }
     }
-    // halo of the plane: 2 rows below, 2 columns either side
-    for (int e = tid; e < nhalo; e += blockDim.x) {
-      int r, j;
-      if (e < 2 * kPitch) { r = th + e / kPitch; j = e % kPitch; }
-      else { const int e2 = e - 2 * kPitch; r = e2 >> 2; const int q = e2 & 3; j = q < 2 ? q : kTW + q; }
-      const int yy = y0 + r, xx = x0 - 2 + j;
-      float p = 0.f;
-      if (yy < H && xx >= 0 && xx < W) {
-        const bool valid = lab8[(long)yy * W + xx] != SH_IGNORE;
-        p = (valid ? sig_exp(to_f32<T>(xc[(long)yy * W + xx])).s : 0.f) + 1e-6f;
-      }
-      plane[r * kPitch + j] = p;
-    }
-    if (tid < kNPart) chacc[tid] = 0.f;
-    // prefetch next channel's own pixels
-    if (c + 1 < C && row_ok) load_n<T, 4>(xc + HW, own_off, (long)y * W + W, vec_ok != 0, xv);
+    if (r + 1 < nrounds) prefetch(r + 1);
     __syncthreads();
+    if (r > 0) flush(r - 1);
 
-    // ---------------- phase B: interior taps -----------------------------------------------------
-    {
-      float acc[16];
+    // ======================= phase B =======================
+    const int ci = r * kNR + g;
+    if (ci < C) {
+      const unsigned int oe = h.order[ci];
+      const int lvl = oe & 0xff, cl = (oe >> 8) & 0xff;
+      const float* plane = planes + (buf * kNR + g) * kPlane;
+      float acc[16];          // [0..11] difference taps, [12] count of uniform anchors, rest 0
 #pragma unroll
       for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-      float w0[8], w1[8], w2[8];
-      {
-        const float4* p0 = reinterpret_cast<const float4*>(plane + (ty + 0) * kPitch + tx);
-        const float4* p1 = reinterpret_cast<const float4*>(plane + (ty + 1) * kPitch + tx);
-        const float4* p2 = reinterpret_cast<const float4*>(plane + (ty + 2) * kPitch + tx);
-        float4 a = p0[0], bq = p0[1]; w0[0]=a.x; w0[1]=a.y; w0[2]=a.z; w0[3]=a.w; w0[4]=bq.x; w0[5]=bq.y; w0[6]=bq.z; w0[7]=bq.w;
-        a = p1[0]; bq = p1[1]; w1[0]=a.x; w1[1]=a.y; w1[2]=a.z; w1[3]=a.w; w1[4]=bq.x; w1[5]=bq.y; w1[6]=bq.z; w1[7]=bq.w;
-        a = p2[0]; bq = p2[1]; w2[0]=a.x; w2[1]=a.y; w2[2]=a.z; w2[3]=a.w; w2[4]=bq.x; w2[5]=bq.y; w2[6]=bq.z; w2[7]=bq.w;
+      float t0 = 0.f, lpf = 0.f;
+      float w[6][8];
+#pragma unroll
+      for (int rr = 0; rr < 6; ++rr) {
+        const float4* p4 = reinterpret_cast<const float4*>(plane + (4 * br + rr) * kPitch + 4 * bs);
+        const float4 a = p4[0], bq = p4[1];
+        w[rr][0] = a.x; w[rr][1] = a.y; w[rr][2] = a.z; w[rr][3] = a.w;
+        w[rr][4] = bq.x; w[rr][5] = bq.y; w[rr][6] = bq.z; w[rr][7] = bq.w;
       }
-      const unsigned int ul = ulab[lvl];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float a = interior[k] ? pk[k] : 0.f;
+      for (int i = 0; i < 4; ++i) {
+        const unsigned int ui = lvl == 0 ? ub[0][i] : (lvl == 1 ? ub[1][i] : ub[2][i]);
 #pragma unroll
-        for (int dx = 0; dx <= 2; ++dx) acc[dx] = fmaf(a, w0[k + 2 + dx], acc[dx]);
+        for (int k = 0; k < 4; ++k) {
+          const unsigned int code = (ui >> (8 * k)) & 0xffu;
+          const float p = w[i][k + 2];
+          const float a = code != 0xffu ? p : 0.f;
+          t0 = fmaf(a, p, t0);
+          acc[0] = fmaf(a, w[i][k + 3] - p, acc[0]);
+          acc[1] = fmaf(a, w[i][k + 4] - p, acc[1]);
 #pragma unroll
-        for (int dx = -2; dx <= 2; ++dx) {
-          acc[3 + dx + 2] = fmaf(a, w1[k + 2 + dx], acc[3 + dx + 2]);
-          acc[8 + dx + 2] = fmaf(a, w2[k + 2 + dx], acc[8 + dx + 2]);
+          for (int dx = 0; dx < 5; ++dx) {
+            acc[2 + dx] = fmaf(a, w[i + 1][k + dx] - p, acc[2 + dx]);
+            acc[7 + dx] = fmaf(a, w[i + 2][k + dx] - p, acc[7 + dx]);
+          }
+          const bool hit = code == (unsigned int)cl;
+          lpf += hit ? p : 0.f;
+          acc[12] += hit ? 1.f : 0.f;
         }
-        const bool hit = ((ul >> (8 * k)) & 0xffu) == (unsigned int)cl;
-        acc[kLPFull] += hit ? pk[k] : 0.f;
-        acc[kLLFull] += hit ? 1.f : 0.f;
       }
+      // warp totals: 13 floats through the transposed reduction, the two big sums in double
+      float* rp = red + ((buf * kNR + g) * 4 + ((tid >> 5) & 3)) * 20;
       const float tot = warp_reduce16(acc, lane);
       if ((lane & 1) == 0) {
         const int slot = reduce16_slot(lane);
-        if (slot < 15 && tot != 0.f) atomicAdd(&chacc[slot], tot);
+        if (slot < 13) rp[slot] = tot;
+      }
+      const double t0d = warp_sum((double)t0), lpd = warp_sum((double)lpf);
+      if (lane == 0) {
+        reinterpret_cast<double*>(rp + 16)[0] = t0d;
+        reinterpret_cast<double*>(rp + 16)[1] = lpd;
       }
       // slow path: anchors whose 5x5 label neighbourhood is not uniform at this level
-      const bool want = nonuni[lvl] && ((pres[lvl] >> (cl & 31)) & 1u);
+      const unsigned int pr = lvl == 0 ? pres[0] : (lvl == 1 ? pres[1] : pres[2]);
+      const bool want = (pr >> (cl & 31)) & 1u;
       if (__any_sync(0xffffffffu, want)) {
-        float sl[48];  // [0,25) lp taps, [25,38) ll half-plane taps, rest padding
-#pragma unroll
-        for (int i = 0; i < 48; ++i) sl[i] = 0.f;
-        if (want) {
-          float bk[4], lk[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const bool nu = (nonuni[lvl] >> k) & 1u;
-            bk[k] = nu ? pk[k] : 0.f;
-            lk[k] = (nu && ((rlab[lvl] >> (8 * k)) & 0xffu) == (unsigned int)cl) ? 1.f : 0.f;
-          }
-#pragma unroll
-          for (int rr = 0; rr < 5; ++rr) {
-            const unsigned int* row = reinterpret_cast<const unsigned int*>(
-                labt + ((lvl * (th + 4)) + ty + rr) * kLabPitch + tx);
-            const unsigned long long wbits = (unsigned long long)row[0] | ((unsigned long long)row[1] << 32);
-            float mt[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) mt[q] = (byte_of(wbits, q) == (unsigned int)cl) ? 1.f : 0.f;
-#pragma unroll
-            for (int dx = -2; dx <= 2; ++dx) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                sl[rr * 5 + dx + 2] = fmaf(bk[k], mt[k + 2 + dx], sl[rr * 5 + dx + 2]);
-                if (rr > 2 || (rr == 2 && dx >= 0)) {
-                  const int hi = rr == 2 ? dx : 3 + (rr - 3) * 5 + (dx + 2);
-                  sl[25 + hi] = fmaf(lk[k], mt[k + 2 + dx], sl[25 + hi]);
-                }
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int base = 0; base < 48; base += 16) {
-          const float t2 = warp_reduce16(*reinterpret_cast<float(*)[16]>(sl + base), lane);
-          if ((lane & 1) == 0) {
-            const int idx = base + reduce16_slot(lane);
-            if (idx < 38 && t2 != 0.f) atomicAdd(&chacc[kLPS + idx], t2);
-          }
-        }
-      }
-    }
-    __syncthreads();
-    if (tid < kNPart) ws.part1[((size_t)tile_id * C + c) * kNPart + tid] = chacc[tid];
-  }
-
-  // ---- per-pixel epilogue: positive terms, CE, summaries ----------------------------------------
-  {
-    unsigned char hp_f[4], hp_m[4];
-    float iv[3][4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      hp_f[k] = 0; hp_m[k] = 0;
-#pragma unroll
-      for (int l = 0; l < 3; ++l) iv[l][k] = rcp(sumv[l][k]);
-      if (tf[k] != SH_IGNORE) {
-        const bool a_holds = a_t[k] <= b_t[k];                 // fine wins ties (rmi...py:421-425)
-        const float mcla = a_holds ? a_t[k] : b_t[k];
-        hp_f[k] = (unsigned char)(a_holds ? tf[k] : h.nf + tm[k]);
-        const bool c_holds = min_c[k] <= b_t[k];               // high wins ties (rmi...py:439-440)
-        const float mclb = c_holds ? min_c[k] : b_t[k];
-        hp_m[k] = (unsigned char)(c_holds ? hold_minc[k] : h.nf + tm[k]);
-        lacc[0] -= fast_log(mcla + eps);
-        lacc[1] -= fast_log(mclb + eps);
-        lacc[2] -= fast_log(c_t[k] + eps);
-#pragma unroll
-        for (int l = 0; l < 3; ++l) lacc[3 + l] += fast_log(sumv[l][k]) - fast_log(vt[l][k]);
-      }
-    }
-    if (row_ok) {
-      int nvalid = W - xg; nvalid = nvalid > 4 ? 4 : nvalid;
-      if (nvalid > 0) {
-        store4_u8(ws.hold + ((size_t)(h.nm + h.nh) * B + b) * HW + own_off, hp_f, nvalid, st_al);
-        store4_u8(ws.hold + ((size_t)(h.nm + h.nh + 1) * B + b) * HW + own_off, hp_m, nvalid, st_al);
-        for (int l = 0; l < 3; ++l)
-          for (int k = 0; k < nvalid; ++k) ws.inv[((size_t)l * B + b) * HW + own_off + k] = iv[l][k];
+        const unsigned int u0 = lvl == 0 ? ub[0][0] : (lvl == 1 ? ub[1][0] : ub[2][0]);
+        const unsigned int u1 = lvl == 0 ? ub[0][1] : (lvl == 1 ? ub[1][1] : ub[2][1]);
+        const unsigned int u2 = lvl == 0 ? ub[0][2] : (lvl == 1 ? ub[1][2] : ub[2][2]);
+        const unsigned int u3 = lvl == 0 ? ub[0][3] : (lvl == 1 ? ub[1][3] : ub[2][3]);
+        pass1_slow_path(plane, labt + (lvl * (kTH + 4)) * kLabPitch, u0, u1, u2, u3, br, bs, cl, want, lane,
+                        slow + (buf * kNR + g) * 40);
       }
     }
   }
   __syncthreads();
-  float* red = plane;  // reuse (needs 6 * nwarps floats)
-  const float r = block_sum_k<6>(lacc, red);
-  if (tid < 6) ws.bcepart[(size_t)tile_id * 8 + tid] = r;
+  flush(nrounds - 1);
+
+  // ---- per-pixel epilogue: positive terms, CE, summaries ----------------------------------------
+  {
+    unsigned int hp_f = 0, hp_m = 0;
+    float iv[3][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      iv[0][k] = rcp(sumvF[k]); iv[1][k] = rcp(sumvM[k]); iv[2][k] = rcp(sumvH[k]);
+      if (tf[k] != SH_IGNORE) {
+        const bool a_holds = a_t[k] <= b_t[k];                 // fine wins ties (rmi...py:421-425)
+        const float mcla = a_holds ? a_t[k] : b_t[k];
+        hp_f |= (unsigned int)(a_holds ? tf[k] : h.nf + tm[k]) << (8 * k);
+        const bool c_holds = min_c[k] <= b_t[k];               // high wins ties (rmi...py:439-440)
+        const float mclb = c_holds ? min_c[k] : b_t[k];
+        hp_m |= (c_holds ? ((hold_minc >> (8 * k)) & 0xffu) : (unsigned int)(h.nf + tm[k])) << (8 * k);
+        lacc[0] -= fast_log(mcla + eps);
+        lacc[1] -= fast_log(mclb + eps);
+        lacc[2] -= fast_log(c_t[k] + eps);
+        lacc[3] += fast_log(sumvF[k]);
+        lacc[4] += fast_log(sumvM[k]);
+        lacc[5] += fast_log(sumvH[k]);
+      }
+    }
+    if (nvalid > 0) {
+      store4_u8(ws.hold + ((size_t)(h.nm + h.nh) * B + b) * HW + own_off, hp_f, nvalid, st_al);
+      store4_u8(ws.hold + ((size_t)(h.nm + h.nh + 1) * B + b) * HW + own_off, hp_m, nvalid, st_al);
+#pragma unroll
+      for (int l = 0; l < 3; ++l) {
+        float* ip = ws.inv + ((size_t)l * B + b) * HW + own_off;
+        if (st_al && nvalid == 4) *reinterpret_cast<float4*>(ip) = make_float4(iv[l][0], iv[l][1], iv[l][2], iv[l][3]);
+        else for (int k = 0; k < nvalid; ++k) ip[k] = iv[l][k];
+      }
+    }
+  }
+  __syncthreads();
+  const float r6 = block_sum_k<6>(lacc, planes);   // planes are free now (needs 6 * 16 floats)
+  if (tid < 6) ws.bcepart[(size_t)tile_id * 8 + tid] = r6;
   else if (tid < 8) ws.bcepart[(size_t)tile_id * 8 + tid] = 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k3_band: P of the 4-pixel border bands of every (b, c) plane.
+//   bandR[bc][q][x]  q = 0..3 -> rows 0..3, q = 4..7 -> rows H-4..H-1
+//   bandC[bc][q][y]  q = 0..3 -> cols 0..3, q = 4..7 -> cols W-4..W-1
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k3_band(const T* __restrict__ x, int B, int C, int H, int W,
+                                               const unsigned char* __restrict__ lab8_all, float* __restrict__ bandR,
+                                               float* __restrict__ bandC) {
+  const int bc = blockIdx.x, b = bc / C;
+  const long HW = (long)H * W;
+  const T* xc = x + (long)bc * HW;
+  const unsigned char* lab8 = lab8_all + (long)b * HW;
+  const int n = 8 * W + 8 * H;
+  for (int i = blockIdx.y * 256 + threadIdx.x; i < n; i += gridDim.y * 256) {
+    int yy, xx;
+    float* dst;
+    if (i < 8 * W) { const int q = i / W; xx = i - q * W; yy = q < 4 ? q : H - 8 + q; dst = bandR + ((size_t)bc * 8 + q) * W + xx; }
+    else { const int i2 = i - 8 * W; const int q = i2 / H; yy = i2 - q * H; xx = q < 4 ? q : W - 8 + q; dst = bandC + ((size_t)bc * 8 + q) * H + yy; }
+    const long off = (long)yy * W + xx;
+    const bool valid = lab8[off] != SH_IGNORE;
+    *dst = (valid ? sig_exp(to_f32<T>(xc[off])).s : 0.f) + 1e-6f;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
 // k3_frame1: taps of the image frame.  grid (B*C, nseg), block 256 = 8 warps; warp w owns run w
 // (rows 0,1,H-2,H-1 x middle columns; columns 0,1,W-2,W-1 x middle rows); warp 0 of segment 0
-// then does the 16 corner pixels.  Output: frameT[seg][b*C+c][class][75] = pp[25] lp[25] ll[25].
+// then does the 16 corner pixels.  Output: frameT[seg][b*C+c][class][kFrameRec].
 // ---------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ void frame_pixel_taps(const T* __restrict__ xc, const unsigned char* __restrict__ lab8,
-                                                 const int* __restrict__ lmap, int cl, int H, int W, int y, int x,
+__device__ __forceinline__ void frame_pixel_taps(const BandView& bv, int cl, int y, int x, double& t0, double& lp0,
                                                  float (&acc)[75]) {
-  const int tr = lab8[(long)y * W + x];
-  const bool vr = tr != SH_IGNORE;
-  const float pr = (vr ? sig_exp(to_f32<T>(xc[(long)y * W + x])).s : 0.f) + 1e-6f;
-  const int rl_r = vr ? (lmap ? lmap[tr] : tr) : 0;
-  const float lr = rl_r == cl ? 1.f : 0.f;
+  const float pr = bv.P(y, x);
+  const float lr = bv.L(y, x) == cl ? 1.f : 0.f;
+  t0 += (double)pr * (double)pr;
+  lp0 += (double)(pr * lr);
 #pragma unroll
   for (int dy = -2; dy <= 2; ++dy) {
 #pragma unroll
     for (int dx = -2; dx <= 2; ++dx) {
       const int yy = y + dy, xx = x + dx;
-      float pn = 0.f, ln = 0.f;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-        const int tn = lab8[(long)yy * W + xx];
-        const bool vn = tn != SH_IGNORE;
-        pn = (vn ? sig_exp(to_f32<T>(xc[(long)yy * W + xx])).s : 0.f) + 1e-6f;
-        const int rl_n = vn ? (lmap ? lmap[tn] : tn) : 0;
-        ln = rl_n == cl ? 1.f : 0.f;
-      }
+      if (yy < 0 || yy >= bv.H || xx < 0 || xx >= bv.W) continue;   // such taps have no valid window
+      const float pn = bv.P(yy, xx);
+      const float ln = bv.L(yy, xx) == cl ? 1.f : 0.f;
       const int t = (dy + 2) * 5 + dx + 2;
-      acc[t] = fmaf(pr, pn, acc[t]);
-      acc[25 + t] = fmaf(pr, ln, acc[25 + t]);
+      acc[t] = fmaf(pr, pn - pr, acc[t]);
+      acc[25 + t] = fmaf(pr, ln - lr, acc[25 + t]);
       acc[50 + t] = fmaf(lr, ln, acc[50 + t]);
     }
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) k3_frame1(const T* __restrict__ x, int B, int H, int W, Hier3 h, Ws3 ws) {
+__global__ void __launch_bounds__(256) k3_frame1(int B, int H, int W, Hier3 h, Ws3 ws, const float* __restrict__ bandR,
+                                                 const float* __restrict__ bandC) {
   const int C = h.nf + h.nm + h.nh;
   const int bc = blockIdx.x, b = bc / C, c = bc % C;
   const int seg = blockIdx.y, nseg = gridDim.y;
   const int lvl = c < h.nf ? 0 : (c < h.nf + h.nm ? 1 : 2);
   const int cl = lvl == 0 ? c : (lvl == 1 ? c - h.nf : c - h.nf - h.nm);
-  const int* lmap = lvl == 0 ? nullptr : (lvl == 1 ? h.f2m : h.f2h);
-  const long HW = (long)H * W;
-  const T* xc = x + ((long)b * C + c) * HW;
-  const unsigned char* lab8 = ws.lab8 + (long)b * HW;
+  BandView bv;
+  bv.bandR = bandR + (size_t)bc * 8 * W; bv.bandC = bandC + (size_t)bc * 8 * H;
+  bv.lab8 = ws.lab8 + (long)b * H * W; bv.lmap = lvl == 0 ? nullptr : (lvl == 1 ? h.f2m : h.f2h);
+  bv.H = H; bv.W = W;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* out = ws.frameT + ((size_t)seg * B * C + bc) * 25 * 75;
+  float* out = ws.frameT + ((size_t)seg * B * C + bc) * 25 * kFrameRec;
 
   float acc[75];
 #pragma unroll
   for (int i = 0; i < 75; ++i) acc[i] = 0.f;
+  double t0 = 0.0, lp0 = 0.0;
   const bool is_row = warp < 4;
   const int line = (warp & 3) < 2 ? (warp & 3) : (is_row ? H : W) - 4 + (warp & 3);  // 0,1,n-2,n-1
   const int len = (is_row ? W : H) - 4;
   const int per = (len + nseg - 1) / nseg;
   const int lo = 2 + seg * per, hi = min(2 + len, lo + per);
-  for (int i = lo + lane; i < hi; i += 32) {
-    const int yy = is_row ? line : i, xx = is_row ? i : line;
-    frame_pixel_taps<T>(xc, lab8, lmap, cl, H, W, yy, xx, acc);
-  }
+  for (int i = lo + lane; i < hi; i += 32)
+    frame_pixel_taps(bv, cl, is_row ? line : i, is_row ? i : line, t0, lp0, acc);
   const int kline = (warp & 3) < 2 ? (warp & 3) : 1 + (warp & 3);  // class 0,1,3,4
   const int cls = is_row ? kline * 5 + 2 : 2 * 5 + kline;
+  float* oc = out + cls * kFrameRec;
 #pragma unroll
   for (int i = 0; i < 75; ++i) {
     const float r = warp_sum(acc[i]);
-    if (lane == 0) out[cls * 75 + i] = r;
+    if (lane == 0) oc[kFD + i] = r;
   }
+  t0 = warp_sum(t0); lp0 = warp_sum(lp0);
+  if (lane == 0) { reinterpret_cast<double*>(oc)[0] = t0; reinterpret_cast<double*>(oc)[1] = lp0; }
   if (warp == 0) {
     // corners: one lane per pixel, each its own class
 #pragma unroll
     for (int i = 0; i < 75; ++i) acc[i] = 0.f;
+    t0 = 0.0; lp0 = 0.0;
     const int ky = (lane >> 2) & 3, kx = lane & 3;
     const int cy = ky < 2 ? ky : ky + 1, cx = kx < 2 ? kx : kx + 1;  // classes 0,1,3,4
-    if (lane < 16 && seg == 0) {
-      const int yy = ky < 2 ? ky : H - 4 + ky, xx = kx < 2 ? kx : W - 4 + kx;
-      frame_pixel_taps<T>(xc, lab8, lmap, cl, H, W, yy, xx, acc);
-    }
+    if (lane < 16 && seg == 0)
+      frame_pixel_taps(bv, cl, ky < 2 ? ky : H - 4 + ky, kx < 2 ? kx : W - 4 + kx, t0, lp0, acc);
     if (lane < 16) {
-      for (int i = 0; i < 75; ++i) out[(cy * 5 + cx) * 75 + i] = acc[i];
+      float* o2 = out + (cy * 5 + cx) * kFrameRec;
+      reinterpret_cast<double*>(o2)[0] = t0; reinterpret_cast<double*>(o2)[1] = lp0;
+      for (int i = 0; i < 75; ++i) o2[kFD + i] = acc[i];
     }
     if (lane == 16) {
-      for (int i = 0; i < 75; ++i) out[(2 * 5 + 2) * 75 + i] = 0.f;  // interior class unused
+      float* o2 = out + (2 * 5 + 2) * kFrameRec;
+      for (int i = 0; i < kFrameRec; ++i) o2[i] = 0.f;   // interior class unused
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// k3_finalize: one CTA (64 threads) per (b, c).
+// k3_finalize: one CTA (256 threads) per (b, c).
 // ---------------------------------------------------------------------------------------------
 __device__ void gj_inverse9(double* A, double* Inv, double* piv, double* fac, int lane) {
   for (int e = lane; e < 81; e += 32) Inv[e] = (e / 9 == e % 9) ? 1.0 : 0.0;
@@ -558,27 +649,44 @@ __device__ void mm9(const double* X, bool xt, const double* Y, bool yt, double* 
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(64) k3_finalize(int B, int C, long tiles_per_img, int nseg, Ws3 ws, double scale) {
-  __shared__ double part[kNPart];
-  __shared__ double fr[25 * 75];
+__global__ void __launch_bounds__(256) k3_finalize(int B, int C, long tiles_per_img, int nseg, Ws3 ws, double scale) {
+  __shared__ double part4[4][kRec];
+  __shared__ double part[kRec];
+  __shared__ double fr[25 * kFrameRec];
   __shared__ double Spp[81], Slp[81], Sll[81], K[81], T1[81], M[81], Wm[81], U[81], Gpp[81], tmp[81];
   __shared__ double piv[9], fac[9];
   const int bc = blockIdx.x, b = bc / C, c = bc % C;
   const int tid = threadIdx.x;
-  if (tid < kNPart) {
+  {
+    // 4 slices x 64 record slots; slots kT0 .. kT0+3 hold two doubles
+    const int k = tid & 63, sl = tid >> 6;
+    const bool is_dbl = k >= kT0 && k < kT0 + 4;
     double a = 0.0;
-    const float* p = ws.part1 + ((size_t)b * tiles_per_img * C + c) * kNPart + tid;
-    for (long t = 0; t < tiles_per_img; ++t) a += (double)p[(size_t)t * C * kNPart];
-    part[tid] = a;
+    const float* p = ws.part1 + ((size_t)b * tiles_per_img * C + c) * kRec;
+    if (!is_dbl) {
+      for (long t = sl; t < tiles_per_img; t += 4) a += (double)p[(size_t)t * C * kRec + k];
+    } else if ((k & 1) == 0) {
+      for (long t = sl; t < tiles_per_img; t += 4) a += *reinterpret_cast<const double*>(p + (size_t)t * C * kRec + k);
+    }
+    part4[sl][k] = a;
   }
-  for (int e = tid; e < 25 * 75; e += 64) {
+  for (int e = tid; e < 25 * kFrameRec; e += 256) {
+    const int k = e % kFrameRec;
     double a = 0.0;
-    for (int s = 0; s < nseg; ++s) a += (double)ws.frameT[((size_t)s * B * C + bc) * 25 * 75 + e];
+    if (k < 4) {
+      if ((k & 1) == 0)
+        for (int s = 0; s < nseg; ++s)
+          a += *reinterpret_cast<const double*>(ws.frameT + ((size_t)s * B * C + bc) * 25 * kFrameRec + e);
+    } else {
+      for (int s = 0; s < nseg; ++s) a += (double)ws.frameT[((size_t)s * B * C + bc) * 25 * kFrameRec + e];
+    }
     fr[e] = a;
   }
   __syncthreads();
+  if (tid < kRec) part[tid] = part4[0][tid] + part4[1][tid] + part4[2][tid] + part4[3][tid];
+  __syncthreads();
   // assemble
-  for (int e = tid; e < 81; e += 64) {
+  for (int e = tid; e < 81; e += 256) {
     const int i = e / 9, j = e % 9;
     const int yi = i / 3, xi = i % 3, yj = j / 3, xj = j % 3;
     const int dy = yi - yj, dx = xi - xj;
@@ -588,18 +696,20 @@ __global__ void __launch_bounds__(64) k3_finalize(int B, int C, long tiles_per_i
       for (int kx = 0; kx < 5; ++kx) {
         if (ky == 2 && kx == 2) continue;
         if (!offset_valid(ky, yj) || !offset_valid(kx, xj)) continue;
-        const double* f = fr + (ky * 5 + kx) * 75;
-        fpp += f[t]; flp += f[25 + t]; fll += f[50 + t];
+        const double* f = fr + (ky * 5 + kx) * kFrameRec;
+        fpp += f[kFT0] + f[kFD + t];
+        flp += f[kFLP0] + f[kFDL + t];
+        fll += f[kFLL + t];
       }
     Slp[e] = part[kLPFull] + part[kLPS + t] + flp;
     if (in_half_plane(dy, dx)) {
       const int ht = half_tap_index(dy, dx);
-      Spp[e] = part[kPP + ht] + fpp;
+      Spp[e] = part[kT0] + (ht > 0 ? part[kD + ht - 1] : 0.0) + fpp;
       Sll[e] = part[kLLFull] + part[kLLS + ht] + fll;
     }
   }
   __syncthreads();
-  for (int e = tid; e < 81; e += 64) {
+  for (int e = tid; e < 81; e += 256) {
     const int i = e / 9, j = e % 9;
     const int dy = i / 3 - j / 3, dx = i % 3 - j % 3;
     if (!in_half_plane(dy, dx)) { Spp[e] = Spp[j * 9 + i]; Sll[e] = Sll[j * 9 + i]; }
@@ -623,8 +733,7 @@ __global__ void __launch_bounds__(64) k3_finalize(int B, int C, long tiles_per_i
       ws.rbc[bc] = r;                              // = 0.5 * log_det_by_cholesky(M)
     }
     mm9(Wm, false, T1, false, U, lane);            // U = W Slp K ;  G_lp = -U
-    mm9(T1, true, U, false, Gpp, lane);            // G_pp = 0.5 * T1^T U
-    // stencil weights
+    mm9(T1, true, U, false, Gpp, lane);            // 2 * G_pp = T1^T U
     float* wout = ws.wts + (size_t)bc * 64;
     float* fout = ws.fwts + (size_t)bc * 25 * 50;
     if (lane < 25) {
@@ -633,15 +742,17 @@ __global__ void __launch_bounds__(64) k3_finalize(int B, int C, long tiles_per_i
         const int i = e / 9, j = e % 9;
         if (tap_index(i / 3 - j / 3, i % 3 - j % 3) == lane) { w1 += Gpp[e]; w2 -= U[e]; }
       }
-      wout[lane] = (float)(scale * w1);            // 2 * (0.5 * T1^T U) * scale
+      wout[lane] = (float)(scale * w1);
       wout[25 + lane] = (float)(scale * w2);
       tmp[lane] = scale * w2;
+      tmp[32 + lane] = scale * w1;
     }
     __syncwarp();
     if (lane == 0) {
-      double s = 0.0;
-      for (int t = 0; t < 25; ++t) s += tmp[t];
-      wout[50] = (float)s;
+      double s2 = 0.0, s1 = 0.0;
+      for (int t = 0; t < 25; ++t) { s2 += tmp[t]; s1 += tmp[32 + t]; }
+      wout[50] = (float)s2;      // sum of the lp weights: label-uniform pixels
+      wout[51] = (float)s1;      // sum of the pp weights: difference form of the stencil
     }
     for (int q = lane; q < 25 * 25; q += 32) {
       const int cls = q / 25, t = q % 25, ky = cls / 5, kx = cls % 5;
@@ -698,26 +809,31 @@ __global__ void __launch_bounds__(256) k3_loss(int B, int C, int nf, int nm, int
   }
 }
 
+// one CTA per output k: out[k] = sum_i part[i][k] in double, fixed order
 __global__ void __launch_bounds__(256) k_reduce_partials3(const float* __restrict__ part, long n, int K,
                                                           double* __restrict__ out) {
   __shared__ double sm[256];
-  for (int k = 0; k < K; ++k) {
-    double a = 0.0;
-    for (long i = threadIdx.x; i < n; i += 256) a += (double)part[(size_t)i * K + k];
-    sm[threadIdx.x] = a;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-      if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) out[k] = sm[0];
+  const int k = blockIdx.x;
+  double a = 0.0;
+  for (long i = threadIdx.x; i < n; i += 256) a += (double)part[(size_t)i * K + k];
+  sm[threadIdx.x] = a;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
     __syncthreads();
   }
+  if (threadIdx.x == 0) out[k] = sm[0];
+}
+
+static size_t pass1_smem_bytes(int nh) {
+  size_t s = (size_t)2 * kNR * (kTH + 2) * kPitch * 4 + 2 * kNR * 4 * 20 * 4 + 2 * kNR * 40 * 4;
+  s += (size_t)nh * kTH * kTW * 5 + 3 * kTH * kTW + 3 * (kTH + 4) * kLabPitch;
+  return (s + 15) & ~(size_t)15;
 }
 
 template <typename T>
 static int run_forward3(const void* x, const long long* label, int B, int H, int W, const Hier3& h, const Ws3& ws,
-                        float eps, double scale, int stages, cudaStream_t st) {
+                        float* bandR, float* bandC, float eps, double scale, int stages, cudaStream_t st) {
   const int C = h.nf + h.nm + h.nh;
   if (stages & 1) {
     cudaError_t e = cudaMemsetAsync(ws.counts, 0, 4 * sizeof(unsigned long long), st);
@@ -726,28 +842,27 @@ static int run_forward3(const void* x, const long long* label, int B, int H, int
     k3_prep<<<gp, 256, 0, st>>>(label, B, H, W, h, ws.lab8, ws.flags, ws.counts);
     SH_CHECK_LAUNCH();
   }
-  const int th = ws.th, PX = th * kTW;
-  size_t smem = (size_t)(th + 2) * kPitch * 4 + (size_t)(h.nm + h.nh) * PX * 5 + 64 * 4 + 3 * (size_t)(th + 4) * kLabPitch;
-  smem = (smem + 15) & ~(size_t)15;
-  if (smem > 227 * 1024) return SH_ERR_UNSUPPORTED;
-  const bool vec_ok = ((W & 3) == 0) && ((uintptr_t)x % (4 * sizeof(T)) == 0);
-  auto kern = k3_pass1<T>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  dim3 g1(ws.tiles_x, ws.tiles_y, B);
   if (stages & 2) {
-    kern<<<g1, th * kStrips, smem, st>>>((const T*)x, B, H, W, h, ws, eps, vec_ok ? 1 : 0);
+    const size_t smem = pass1_smem_bytes(h.nh);
+    if (smem > 227 * 1024) return SH_ERR_UNSUPPORTED;
+    const bool vec_ok = ((W & 3) == 0) && ((uintptr_t)x % (4 * sizeof(T)) == 0);
+    auto kern = k3_pass1<T>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 g1(ws.tiles_x, ws.tiles_y, B);
+    kern<<<g1, kThreads, smem, st>>>((const T*)x, B, H, W, h, ws, eps, vec_ok ? 1 : 0);
     SH_CHECK_LAUNCH();
   }
-  const int nseg = ws.nseg;
   if (stages & 4) {
-    k3_frame1<T><<<dim3(B * C, nseg), 256, 0, st>>>((const T*)x, B, H, W, h, ws);
+    k3_band<T><<<dim3(B * C, 4), 256, 0, st>>>((const T*)x, B, C, H, W, ws.lab8, bandR, bandC);
+    SH_CHECK_LAUNCH();
+    k3_frame1<<<dim3(B * C, ws.nseg), 256, 0, st>>>(B, H, W, h, ws, bandR, bandC);
     SH_CHECK_LAUNCH();
   }
   if (stages & 8) {
     const long ntiles = (long)ws.tiles_x * ws.tiles_y * B;
-    k_reduce_partials3<<<1, 256, 0, st>>>(ws.bcepart, ntiles, 8, ws.sums);
+    k_reduce_partials3<<<6, 256, 0, st>>>(ws.bcepart, ntiles, 8, ws.sums);
     SH_CHECK_LAUNCH();
-    k3_finalize<<<B * C, 64, 0, st>>>(B, C, (long)ws.tiles_x * ws.tiles_y, nseg, ws, scale);
+    k3_finalize<<<B * C, 256, 0, st>>>(B, C, (long)ws.tiles_x * ws.tiles_y, ws.nseg, ws, scale);
     SH_CHECK_LAUNCH();
   }
   return SH_OK;
@@ -757,8 +872,10 @@ static int run_forward3(const void* x, const long long* label, int B, int H, int
 
 extern "C" {
 
+// workspace = Ws3 fields, then bandR [B*C][8][W] and bandC [B*C][8][H] floats
 size_t sh_rmi3_workspace_bytes(int B, int H, int W, int nf, int nm, int nh) {
-  return sh::ws3_layout(nullptr, B, H, W, nf, nm, nh).bytes;
+  const size_t base = sh::ws3_layout(nullptr, B, H, W, nf, nm, nh).bytes;
+  return base + sh::align256((size_t)B * (nf + nm + nh) * 8 * ((size_t)W + H) * 4);
 }
 
 // Byte offsets of the workspace fields (diagnostics / tests):
@@ -770,20 +887,22 @@ int sh_rmi3_workspace_offsets(int B, int H, int W, int nf, int nm, int nh, size_
   return SH_OK;
 }
 
-// hier_tab (device int32): [f2m nf][f2h nf][mh_ptr nm+1][mh_idx n_mh][hsmask nm]
+// hier_tab (device int32): [f2m nf][f2h nf][mh_ptr nm+1][mh_idx n_mh][hsmask nm][order C]
 int sh_rmi3_forward(const void* logits, int dtype, const long long* label, int B, int H, int W, int nf, int nm, int nh,
                     const int* hier_tab, int n_mh, float lam, float loss_weight, void* workspace, int stages,
                     void* stream) {
-  if (B <= 0 || H < 5 || W < 5 || nf <= 0 || nm <= 0 || nh <= 0 || nf + nm + nh > 255 || nh > 32)
+  if (B <= 0 || H < 8 || W < 8 || nf <= 0 || nm <= 0 || nh <= 0 || nf + nm + nh > 254 || nh > 32)
     return SH_ERR_BAD_ARG;
   sh::Ws3 ws = sh::ws3_layout(workspace, B, H, W, nf, nm, nh);
+  float* bandR = (float*)((unsigned char*)workspace + ws.bytes);
+  float* bandC = bandR + (size_t)B * (nf + nm + nh) * 8 * W;
   sh::Hier3 h = sh::hier3_from_tab(hier_tab, nf, nm, nh, n_mh);
   const double scale = (double)lam * (double)loss_weight / (9.0 * B);
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case SH_DT_F32: return sh::run_forward3<float>(logits, label, B, H, W, h, ws, 1e-6f, scale, stages, st);
-    case SH_DT_BF16: return sh::run_forward3<__nv_bfloat16>(logits, label, B, H, W, h, ws, 1e-6f, scale, stages, st);
-    case SH_DT_F16: return sh::run_forward3<__half>(logits, label, B, H, W, h, ws, 1e-6f, scale, stages, st);
+    case SH_DT_F32: return sh::run_forward3<float>(logits, label, B, H, W, h, ws, bandR, bandC, 1e-6f, scale, stages, st);
+    case SH_DT_BF16: return sh::run_forward3<__nv_bfloat16>(logits, label, B, H, W, h, ws, bandR, bandC, 1e-6f, scale, stages, st);
+    case SH_DT_F16: return sh::run_forward3<__half>(logits, label, B, H, W, h, ws, bandR, bandC, 1e-6f, scale, stages, st);
   }
   return SH_ERR_UNSUPPORTED;
 }

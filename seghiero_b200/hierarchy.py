@@ -56,8 +56,8 @@ def three_level_tables(n_fine: int, n_mid: int, n_high: int, fine_to_mid, fine_t
         raise ValueError("fine_to_high holds ids outside [0, n_high) (uninitialised map?)")
     if n_high > 32:
         raise ValueError("n_high > 32 is not supported")
-    if n_fine + n_mid + n_high > 255:
-        raise ValueError("more than 255 channels are not supported")
+    if n_fine + n_mid + n_high > 254:
+        raise ValueError("more than 254 channels are not supported")
     # Ms(h) = {f2m[f] : f2h[f]==h};  mh list of mid m = highs whose Ms contains m
     mh = [sorted({int(f2h[f]) for f in range(n_fine) if f2m[f] == m}) for m in range(n_mid)]
     mh_ptr = np.zeros(n_mid + 1, dtype=np.int32)
@@ -69,8 +69,35 @@ def three_level_tables(n_fine: int, n_mid: int, n_high: int, fine_to_mid, fine_t
         for h in mh[m]:                                   # Hs(m) = {f2h[f] : f in F(m)} -- the same set
             hsmask[m] |= np.uint32(1) << np.uint32(h)
     blob = np.concatenate([f2m.astype(np.int32), f2h.astype(np.int32), mh_ptr,
-                           np.array(mh_idx, dtype=np.int32), hsmask.view(np.int32)]).astype(np.int32)
+                           np.array(mh_idx, dtype=np.int32), hsmask.view(np.int32),
+                           tree_order(n_fine, n_mid, n_high, f2m)]).astype(np.int32)
     return blob, len(mh_idx)
+
+
+def tree_order(n_fine: int, n_mid: int, n_high: int, f2m) -> np.ndarray:
+    """Channel visiting order of the forward pass: for every mid m its fine children (ascending), then
+    the mid channel itself; the high channels last.  The running max over a mid's children then lives
+    in registers.  Entry = kind | class << 8 | flags << 16 with kind 0/1/2 = fine/mid/high,
+    flags bit0 = reset the running max (first entry of a mid group), bit1 = flush the level's product
+    of (1 - s + eps) factors into a log (every 4th entry of a level and its last one)."""
+    entries = []
+    for m in range(n_mid):
+        first = True
+        for f in range(n_fine):
+            if int(f2m[f]) == m:
+                entries.append([0, f, 1 if first else 0])
+                first = False
+        entries.append([1, m, 1 if first else 0])
+    for hh in range(n_high):
+        entries.append([2, hh, 0])
+    seen = [0, 0, 0]
+    total = [n_fine, n_mid, n_high]
+    for e in entries:
+        seen[e[0]] += 1
+        if seen[e[0]] % 4 == 0 or seen[e[0]] == total[e[0]]:
+            e[2] |= 2
+    assert len(entries) == n_fine + n_mid + n_high
+    return np.array([k | (c << 8) | (fl << 16) for k, c, fl in entries], dtype=np.int32)
 
 
 def triplet_tables_hierarchy(hiera_map: Sequence[int], hiera_index: Sequence[Sequence[int]]):

@@ -362,8 +362,8 @@ class RMIHieraTriplet3Fn(torch.autograd.Function):
             raise ValueError(f"cls_score has {c} channels, expected {cfg.n_fine + cfg.n_mid + cfg.n_high}")
         if tuple(lab.shape) != (b, hh, ww):
             raise ValueError("label must be [B,H,W] matching cls_score")
-        if hh < 5 or ww < 5:
-            raise ValueError("the RMI term needs H, W >= 5")
+        if hh < 8 or ww < 8:
+            raise ValueError("the CUDA RMI path needs H, W >= 8 (the reference needs >= 3)")
         key = ("h3", cfg.n_fine, cfg.n_mid, cfg.n_high, cfg.fine_to_mid, cfg.fine_to_high)
         tab, n_mh = device_table(key, lambda: H.three_level_tables(cfg.n_fine, cfg.n_mid, cfg.n_high,
                                                                    cfg.fine_to_mid, cfg.fine_to_high), dev)
