@@ -233,6 +233,65 @@ __device__ __forceinline__ void store_n(T* base, long idx, long limit, bool vec_
   }
 }
 
+// ---- asynchronous global -> shared copies (LDGSTS): prefetch without holding registers -------------
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// 4 consecutive elements of T staged by cp.async into a 16-byte slot -> fp32
+template <typename T>
+__device__ __forceinline__ void cp_async_vec4(void* slot, const T* g) {
+  if (sizeof(T) == 4) cp_async_16(slot, g); else cp_async_8(slot, g);
+}
+template <typename T>
+__device__ __forceinline__ void staged_vec4(const void* slot, float (&o)[4]);
+template <>
+__device__ __forceinline__ void staged_vec4<float>(const void* slot, float (&o)[4]) {
+  const float4 v = *reinterpret_cast<const float4*>(slot);
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+template <>
+__device__ __forceinline__ void staged_vec4<__nv_bfloat16>(const void* slot, float (&o)[4]) {
+  const uint2 v = *reinterpret_cast<const uint2*>(slot);
+  o[0] = __uint_as_float(v.x << 16); o[1] = __uint_as_float(v.x & 0xffff0000u);
+  o[2] = __uint_as_float(v.y << 16); o[3] = __uint_as_float(v.y & 0xffff0000u);
+}
+template <>
+__device__ __forceinline__ void staged_vec4<__half>(const void* slot, float (&o)[4]) {
+  const uint2 v = *reinterpret_cast<const uint2*>(slot);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+// one element of T staged as the aligned 4-byte word that contains it
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(void* slot, const T* base, long idx) {
+  if (sizeof(T) == 4) cp_async_4(slot, base + idx); else cp_async_4(slot, base + (idx & ~1L));
+}
+template <typename T>
+__device__ __forceinline__ float staged_elem(const void* slot, long idx);
+template <>
+__device__ __forceinline__ float staged_elem<float>(const void* slot, long) { return *reinterpret_cast<const float*>(slot); }
+template <>
+__device__ __forceinline__ float staged_elem<__nv_bfloat16>(const void* slot, long idx) {
+  const unsigned int w = *reinterpret_cast<const unsigned int*>(slot);
+  return __uint_as_float((idx & 1) ? (w & 0xffff0000u) : (w << 16));
+}
+template <>
+__device__ __forceinline__ float staged_elem<__half>(const void* slot, long idx) {
+  const unsigned int w = *reinterpret_cast<const unsigned int*>(slot);
+  const __half2 h2 = *reinterpret_cast<const __half2*>(&w);
+  return (idx & 1) ? __high2float(h2) : __low2float(h2);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -17,8 +17,8 @@ namespace sh {
 // Planes are double buffered: one __syncthreads per round.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(kThreads, 1)
-k3_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hier3 h, Ws3 ws, float eps,
+__global__ void __launch_bounds__(kThreads, 512 / kThreads)
+k3_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hier3 hg, Ws3 ws, float eps,
          float loss_weight, const float* __restrict__ gscale_ptr, int vec_ok) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int PX = kTH * kTW;
@@ -27,11 +27,15 @@ k3_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hie
   float* wbuf = planes + 2 * kNR * kPlane;                   // [2][kNR][64]
   float* ivt = wbuf + 2 * kNR * 64;                          // [3][PX]  1/sum e^x per level
   unsigned char* labt = reinterpret_cast<unsigned char*>(ivt + 3 * PX);   // [3][kTH+4][kLabPitch]
+  int* htab = reinterpret_cast<int*>(labt + 3 * (kTH + 4) * kLabPitch);   // hierarchy tables (6 KB)
+  uint4* xstage = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(htab) + 6144);   // [4][kThreads] raw logits
 
+  const int tid = threadIdx.x;
+  const Hier3 h = stage_hier(hg, htab, tid, kThreads);
+  __syncthreads();
   const int C = h.nf + h.nm + h.nh;
   const int b = blockIdx.z, y0 = blockIdx.y * kTH, x0 = blockIdx.x * kTW;
   const long HW = (long)H * W;
-  const int tid = threadIdx.x;
   const unsigned char* lab8 = ws.lab8 + (long)b * HW;
   const unsigned char* flg = ws.flags + (long)b * HW;
   const float gscale = *gscale_ptr;
@@ -39,7 +43,7 @@ k3_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hie
   T* gb = grad + (long)b * C * HW;
 
   // thread -> (channel pair, 4x2 pixel block)
-  const int pair = tid >> 8, u = tid & 255, rp = u >> 4, st = u & 15;
+  const int pair = tid / (kThreads / 2), u = tid % (kThreads / 2), rp = u >> 4, st = u & 15;
   const int ty = 2 * rp, tx = 4 * st;
   const int xg = x0 + tx;
   int nvalid = W - xg;
@@ -90,18 +94,24 @@ k3_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hie
     }
     *reinterpret_cast<float4*>(ivt + l * PX + r * kTW + s4) = v;
   }
-  // halo slot (same position in every plane): rows 0,1 and kTH+2,kTH+3 of the plane, 2 columns either side
-  constexpr int nhalo = kPlane - kTH * kTW;   // 400
-  int h_sidx = -1;
-  long h_goff = -1;
-  bool h_valid = false;
-  if (tid < nhalo) {
-    int r, j;
-    if (tid < 4 * kPitch) { const int rr = tid / kPitch; r = rr < 2 ? rr : kTH + rr; j = tid % kPitch; }
-    else { const int e2 = tid - 4 * kPitch; r = 2 + (e2 >> 2); const int q = e2 & 3; j = q < 2 ? q : kTW + q; }
-    h_sidx = r * kPitch + j;
-    const int yy = y0 - 2 + r, xx = x0 - 2 + j;
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W) { h_goff = (long)yy * W + xx; h_valid = lab8[h_goff] != SH_IGNORE; }
+  // halo slots (same positions in every plane): rows 0,1 and kTH+2,kTH+3 of the plane, 2 columns either side
+  constexpr int nhalo = kPlane - kTH * kTW;
+  constexpr int kHS = (nhalo + kThreads - 1) / kThreads;
+  int h_sidx[kHS];
+  long h_goff[kHS];
+  bool h_valid[kHS];
+#pragma unroll
+  for (int q = 0; q < kHS; ++q) {
+    const int e = tid + q * kThreads;
+    h_sidx[q] = -1; h_goff[q] = -1; h_valid[q] = false;
+    if (e < nhalo) {
+      int r, j;
+      if (e < 4 * kPitch) { const int rr = e / kPitch; r = rr < 2 ? rr : kTH + rr; j = e % kPitch; }
+      else { const int e2 = e - 4 * kPitch; r = 2 + (e2 >> 2); const int qq = e2 & 3; j = qq < 2 ? qq : kTW + qq; }
+      h_sidx[q] = r * kPitch + j;
+      const int yy = y0 - 2 + r, xx = x0 - 2 + j;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) { h_goff[q] = (long)yy * W + xx; h_valid[q] = lab8[h_goff[q]] != SH_IGNORE; }
+    }
   }
   __syncthreads();
   unsigned int pres[3] = {0u, 0u, 0u};
@@ -114,10 +124,21 @@ k3_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hie
       for (int k = 0; k < 4; ++k) any_nu |= ((ucode[l][o] >> (8 * k)) & 0xffu) == 0xfeu;
     if (any_nu) {
       for (int rr = 0; rr < 6; ++rr) {
-        const unsigned char* row = labt + ((l * (kTH + 4)) + ty + rr) * kLabPitch + tx;
-        for (int q = 0; q < 8; ++q) pres[l] |= 1u << (row[q] & 31);
+        const unsigned int* row = reinterpret_cast<const unsigned int*>(labt + ((l * (kTH + 4)) + ty + rr) * kLabPitch + tx);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const unsigned int wd = row[q];
+          pres[l] |= (1u << (wd & 31)) | (1u << ((wd >> 8) & 31)) | (1u << ((wd >> 16) & 31)) | (1u << ((wd >> 24) & 31));
+        }
       }
     }
+  }
+  // byte masks used by the gradient logic (0xff per pixel byte where the condition holds)
+  unsigned int valid4[2], cth4[2];
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    valid4[o] = __vcmpne4(tf4[o], 0xffffffffu);
+    cth4[o] = ((th4[o] & valid4[o]) + (unsigned int)(h.nf + h.nm) * 0x01010101u) | ~valid4[o];   // channel of the high target
   }
 
   const float nv = fmaxf((float)ws.counts[0], 1.0f);
@@ -127,7 +148,13 @@ k3_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hie
   const float wCE = loss_weight * gscale / ((float)B * (float)HW);
 
   const int nrounds = (C + kNR - 1) / kNR;
-  float xv[2][2][4], hv[kNR];
+  float4* gstage = reinterpret_cast<float4*>(xstage + 4 * kThreads);                        // [4][kThreads] BCE+CE gradient
+  unsigned int* hstage = reinterpret_cast<unsigned int*>(gstage + 4 * kThreads);            // [kNR][kHS][kThreads]
+  // next round's logits travel global -> shared with cp.async; ragged strips load synchronously on use
+  bool fast_own[2];
+#pragma unroll
+  for (int o = 0; o < 2; ++o) fast_own[o] = vec_ok && row_ok[o] && nvalid == 4;
+  const bool halo_async_ok = sizeof(T) == 4 || vec_ok;
   auto prefetch = [&](int r) {
 #pragma unroll
     for (int jj = 0; jj < 2; ++jj) {
@@ -135,25 +162,27 @@ k3_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hie
       if (c < C) {
         const T* xc = xb + (long)c * HW;
 #pragma unroll
-        for (int o = 0; o < 2; ++o) {
-          if (row_ok[o]) load_n<T, 4>(xc, own_off[o], own_off[o] - xg + W, vec_ok != 0, xv[jj][o]);
-          else { xv[jj][o][0] = xv[jj][o][1] = xv[jj][o][2] = xv[jj][o][3] = 0.f; }
-        }
+        for (int o = 0; o < 2; ++o)
+          if (fast_own[o]) cp_async_vec4<T>(xstage + (jj * 2 + o) * kThreads + tid, xc + own_off[o]);
       }
     }
 #pragma unroll
     for (int j = 0; j < kNR; ++j) {
       const int c = r * kNR + j;
-      hv[j] = (c < C && h_goff >= 0) ? to_f32<T>(xb[(long)c * HW + h_goff]) : 0.f;
+#pragma unroll
+      for (int q = 0; q < kHS; ++q)
+        if (c < C && h_goff[q] >= 0 && halo_async_ok)
+          cp_async_elem<T>(hstage + (j * kHS + q) * kThreads + tid, xb + (long)c * HW, h_goff[q]);
     }
+    cp_async_commit();
   };
 
   prefetch(0);
   for (int r = 0; r < nrounds; ++r) {
     const int buf = r & 1;
-    float g0[2][2][4];
     // ======================= phase A =======================
-#pragma unroll
+    cp_async_wait_all();
+#pragma unroll 1     // rolled on purpose: the fully unrolled body overflows the instruction cache
     for (int jj = 0; jj < 2; ++jj) {
       const int c = r * kNR + 2 * pair + jj;
       if (c >= C) break;
@@ -163,86 +192,101 @@ k3_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hie
       const int mid = lvl == 0 ? h.f2m[cl] : (lvl == 1 ? cl : -1);
 #pragma unroll
       for (int o = 0; o < 2; ++o) {
-        float s[4], v[4], pk[4];
+        float s[4], v[4], pk[4], xv[4];
+        if (fast_own[o]) staged_vec4<T>(xstage + (jj * 2 + o) * kThreads + tid, xv);
+        else if (row_ok[o]) load_n<T, 4>(xb + (long)c * HW, own_off[o], own_off[o] - xg + W, vec_ok != 0, xv);
+        else { xv[0] = xv[1] = xv[2] = xv[3] = 0.f; }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const SigExp se = sig_exp(xv[jj][o][k]);
+          const SigExp se = sig_exp(xv[k]);
           s[k] = se.s; v[k] = se.v;
           const bool valid = ((tf4[o] >> (8 * k)) & 0xffu) != SH_IGNORE;
           pk[k] = (row_ok[o] && k < nvalid) ? ((valid ? se.s : 0.f) + 1e-6f) : 0.f;
         }
         *reinterpret_cast<float2*>(plane + (ty + o + 2) * kPitch + tx + 2) = make_float2(pk[0], pk[1]);
         *reinterpret_cast<float2*>(plane + (ty + o + 2) * kPitch + tx + 4) = make_float2(pk[2], pk[3]);
-        // tree BCE + CE gradient of this channel at these 4 pixels
-        unsigned int hm = 0, hh_own = 0;
+        // tree BCE + CE gradient of this channel at these 4 pixels, with per-byte SIMD masks:
+        //   negative terms: own fine term (f != tf), mid-level term held by this channel (m != tm),
+        //                   high-level term(s) held by this channel (h != th)
+        //   positive terms: this channel holds min(A_tf, B_tm) / min(C_h.., B_tm) / is the high target
+        float g0[4];
+        const unsigned int cc = (unsigned int)c * 0x01010101u;
+        const unsigned int v4 = valid4[o];
+        unsigned int negO = 0, negM = 0, negH = 0, posH = 0;
+        float extra[4] = {0.f, 0.f, 0.f, 0.f};
+        if (lvl == 0) negO = __vcmpne4(tf4[o], cc) & v4;
         if (row_ok[o]) {
-          if (mid >= 0) hm = load4_u8(ws.hold + ((size_t)mid * B + b) * HW + own_off[o], nvalid, st_al);
-          if (lvl == 2) hh_own = load4_u8(ws.hold + ((size_t)(h.nm + cl) * B + b) * HW + own_off[o], nvalid, st_al);
-        }
-        float dneg[4] = {0.f, 0.f, 0.f, 0.f}, dpos[4] = {0.f, 0.f, 0.f, 0.f};
+          if (lvl != 2) {
+            const unsigned int hm = load4_u8(ws.hold + ((size_t)mid * B + b) * HW + own_off[o], nvalid, st_al);
+            negM = __vcmpeq4(hm, cc) & __vcmpne4(tm4[o], (unsigned int)mid * 0x01010101u) & v4;
+            const int q0 = h.mh_ptr[mid], q1e = h.mh_ptr[mid + 1];
+            for (int q = q0; q < q1e; ++q) {
+              const int hi = h.mh_idx[q];
+              const unsigned int hh = load4_u8(ws.hold + ((size_t)(h.nm + hi) * B + b) * HW + own_off[o], nvalid, st_al);
+              const unsigned int m4 = __vcmpeq4(hh, cc) & __vcmpne4(th4[o], (unsigned int)hi * 0x01010101u) & v4;
+              if (q == q0) negH = m4;
+              else {       // a mid that feeds several highs (non-tree maps): keep the multiplicity
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const unsigned int t = (tf4[o] >> (8 * k)) & 0xffu;
-          if (t == SH_IGNORE) continue;
-          const unsigned int tmk = (tm4[o] >> (8 * k)) & 0xffu, thk = (th4[o] >> (8 * k)) & 0xffu;
-          const unsigned int hpf = (hpf4[o] >> (8 * k)) & 0xffu, hpm = (hpm4[o] >> (8 * k)) & 0xffu;
-          const unsigned int hmk = (hm >> (8 * k)) & 0xffu;
-          if (lvl == 0) {
-            if ((unsigned)cl == t) { if (hpf == (unsigned)c) dpos[k] += wF; }
-            else dneg[k] += wF;
-            if ((unsigned)mid != tmk && hmk == (unsigned)c) dneg[k] += wM;
-          } else if (lvl == 1) {
-            if ((unsigned)cl == tmk) {
-              if (hpf == (unsigned)c) dpos[k] += wF;
-              if (hpm == (unsigned)c) dpos[k] += wM;
-            } else if (hmk == (unsigned)c) dneg[k] += wM;
-          } else {
-            if (hpm == (unsigned)c) dpos[k] += wM;
-            if ((unsigned)cl == thk) dpos[k] += wH;
-            else if (((hh_own >> (8 * k)) & 0xffu) == (unsigned)c) dneg[k] += wH;
-          }
-        }
-        if (lvl != 2 && row_ok[o]) {   // high-level negative terms routed down to this channel
-          for (int q = h.mh_ptr[mid]; q < h.mh_ptr[mid + 1]; ++q) {
-            const int hi = h.mh_idx[q];
-            const unsigned int hh = load4_u8(ws.hold + ((size_t)(h.nm + hi) * B + b) * HW + own_off[o], nvalid, st_al);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const unsigned int t = (tf4[o] >> (8 * k)) & 0xffu, thk = (th4[o] >> (8 * k)) & 0xffu;
-              if (t != SH_IGNORE && (unsigned)hi != thk && ((hh >> (8 * k)) & 0xffu) == (unsigned)c) dneg[k] += wH;
+                for (int k = 0; k < 4; ++k) extra[k] += (m4 >> (8 * k)) & 1u ? wH : 0.f;
+              }
             }
+          } else {
+            const unsigned int hh = load4_u8(ws.hold + ((size_t)(h.nm + cl) * B + b) * HW + own_off[o], nvalid, st_al);
+            posH = __vcmpeq4(cth4[o], cc) & v4;
+            negH = __vcmpeq4(hh, cc) & ~posH & v4;
           }
         }
+        const unsigned int posF = __vcmpeq4(hpf4[o], cc) & v4, posM = __vcmpeq4(hpm4[o], cc) & v4;
+        const unsigned int pos_any = posF | posM | posH;
         const float4 iv4 = *reinterpret_cast<const float4*>(ivt + lvl * PX + (ty + o) * kTW + tx);
         const float ivk[4] = {iv4.x, iv4.y, iv4.z, iv4.w};
-        const unsigned int tg4 = lvl == 0 ? tf4[o] : (lvl == 1 ? tm4[o] : th4[o]);
+        const unsigned int tgt4 = __vcmpeq4(lvl == 0 ? tf4[o] : (lvl == 1 ? tm4[o] : th4[o]), (unsigned int)cl * 0x01010101u) & v4;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
+          const unsigned int bit = 1u << (8 * k);
           const float q1 = 1.0f - s[k];
-          float ds = 0.f;
-          if (dneg[k] != 0.f) ds += dneg[k] * rcp(q1 + eps);
-          if (dpos[k] != 0.f) ds -= dpos[k] * rcp(s[k] + eps);
-          const bool valid = ((tf4[o] >> (8 * k)) & 0xffu) != SH_IGNORE;
-          const float ce = valid ? wCE * (v[k] * ivk[k] - (((tg4 >> (8 * k)) & 0xffu) == (unsigned)cl ? 1.f : 0.f)) : 0.f;
-          g0[jj][o][k] = ds * (q1 * s[k]) + ce;
+          float dneg = extra[k];
+          dneg += (negO & bit) ? wF : 0.f;
+          dneg += (negM & bit) ? wM : 0.f;
+          dneg += (negH & bit) ? wH : 0.f;
+          float ds = dneg * rcp(q1 + eps);
+          if (pos_any & bit) {
+            float dpos = (posF & bit) ? wF : 0.f;
+            dpos += (posM & bit) ? wM : 0.f;
+            dpos += (posH & bit) ? wH : 0.f;
+            ds -= dpos * rcp(s[k] + eps);
+          }
+          float ce = v[k] * ivk[k] - ((tgt4 & bit) ? 1.f : 0.f);
+          ce = (v4 & bit) ? wCE * ce : 0.f;
+          g0[k] = fmaf(ds, q1 * s[k], ce);
         }
+        gstage[(jj * 2 + o) * kThreads + tid] = make_float4(g0[0], g0[1], g0[2], g0[3]);
       }
     }
     // halo of the 4 planes + stencil weights of the round
 #pragma unroll
     for (int j = 0; j < kNR; ++j) {
-      if (r * kNR + j < C && h_sidx >= 0)
-        planes[(buf * kNR + j) * kPlane + h_sidx] = h_goff >= 0 ? ((h_valid ? sig_exp(hv[j]).s : 0.f) + 1e-6f) : 0.f;
+#pragma unroll
+      for (int q = 0; q < kHS; ++q)
+        if (r * kNR + j < C && h_sidx[q] >= 0) {
+          float p = 0.f;
+          if (h_goff[q] >= 0) {
+            const float hx = halo_async_ok ? staged_elem<T>(hstage + (j * kHS + q) * kThreads + tid, h_goff[q])
+                                           : to_f32<T>(xb[(long)(r * kNR + j) * HW + h_goff[q]]);
+            p = (h_valid[q] ? sig_exp(hx).s : 0.f) + 1e-6f;
+          }
+          planes[(buf * kNR + j) * kPlane + h_sidx[q]] = p;
+        }
     }
-    if (tid < kNR * 64) {
-      const int j = tid >> 6, c = r * kNR + j;
-      if (c < C) wbuf[(buf * kNR + j) * 64 + (tid & 63)] = ws.wts[((size_t)b * C + c) * 64 + (tid & 63)];
+    for (int q = tid; q < kNR * 64; q += kThreads) {
+      const int j = q >> 6, c = r * kNR + j;
+      if (c < C) wbuf[(buf * kNR + j) * 64 + (q & 63)] = ws.wts[((size_t)b * C + c) * 64 + (q & 63)];
     }
     if (r + 1 < nrounds) prefetch(r + 1);
     __syncthreads();
 
     // ======================= phase B =======================
-#pragma unroll
+#pragma unroll 1
     for (int jj = 0; jj < 2; ++jj) {
       const int c = r * kNR + 2 * pair + jj;
       if (c >= C) break;
@@ -308,6 +352,8 @@ k3_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hie
       for (int o = 0; o < 2; ++o) {
         const unsigned int uc = lvl == 0 ? ucode[0][o] : (lvl == 1 ? ucode[1][o] : ucode[2][o]);
         float g[4];
+        const float4 g4 = gstage[(jj * 2 + o) * kThreads + tid];
+        const float g0[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const unsigned int code = (uc >> (8 * k)) & 0xffu;
@@ -317,7 +363,7 @@ k3_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hie
           const bool valid = ((tf4[o] >> (8 * k)) & 0xffu) != SH_IGNORE;
           const float s = pc[o][k] - 1e-6f;            // valid pixels: P = s + 1e-6
           const float q = (valid && code != 0xffu) ? s * (1.0f - s) * gscale : 0.f;
-          g[k] = fmaf(q, d, g0[jj][o][k]);
+          g[k] = fmaf(q, d, g0[k]);
         }
         if (row_ok[o]) store_n<T, 4>(gb + (long)c * HW, own_off[o], own_off[o] - xg + W, vec_ok != 0, g);
       }
@@ -373,7 +419,10 @@ __global__ void __launch_bounds__(256) k3_frame2(T* __restrict__ grad, int B, in
 
 static size_t pass2_smem_bytes() {
   size_t s = (size_t)2 * kNR * (kTH + 4) * kPitch * 4 + 2 * kNR * 64 * 4 + 3 * kTH * kTW * 4 +
-             3 * (kTH + 4) * kLabPitch;
+             3 * (kTH + 4) * kLabPitch + 6144 /* hierarchy tables */;
+  s = (s + 15) & ~(size_t)15;
+  constexpr int kHS = ((kTH + 4) * kPitch - kTH * kTW + kThreads - 1) / kThreads;
+  s += (size_t)2 * 4 * kThreads * 16 + (size_t)kNR * kHS * kThreads * 4;   // cp.async staging + parked BCE gradient
   return (s + 15) & ~(size_t)15;
 }
 

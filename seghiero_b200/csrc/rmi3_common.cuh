@@ -22,12 +22,14 @@
 namespace sh {
 
 constexpr int kTW = 64;             // tile width (pixels)
-constexpr int kTH = 32;             // tile height of the streaming kernels
+constexpr int kTH = 16;             // tile height of the streaming kernels
 constexpr int kStrips = kTW / 4;    // 16 four-pixel strips per tile row
 constexpr int kPitch = kTW + 4;     // plane pitch: cols x0-2 .. x0+TW+1
 constexpr int kLabPitch = kTW + 8;  // label tile pitch (bytes); 8-byte windows stay in bounds
 constexpr int kNR = 4;              // channels per round
-constexpr int kThreads = 512;       // CTA size of k3_pass1 / k3_pass2
+constexpr int kThreads = 16 * kTH;  // CTA size of k3_pass1 / k3_pass2 (one thread per 4-pixel strip)
+constexpr int kGroup = kThreads / kNR;      // threads that share one channel plane in phase B of pass 1
+constexpr int kGroupWarps = kGroup / 32;
 constexpr int kRec = 64;            // floats per (tile, channel) partial record
 
 // layout of one per-(tile,channel) partial record (float slots)
@@ -67,6 +69,8 @@ struct Hier3 {
   const int* mh_idx;
   const unsigned int* hsmask; // [nm] bit h set iff h in Hs(m)
   const unsigned int* order;  // [C] packed OrderEntry: kind | cl<<8 | flags<<16
+  const int* tab;             // the whole int32 blob the pointers above point into
+  int n_mh, tab_len;
 };
 
 __host__ __device__ inline int half_tap_index(int dy, int dx) {
@@ -137,9 +141,11 @@ inline Ws3 ws3_layout(void* base, int B, int H, int W, int nf, int nm, int nh) {
 }
 
 // hier_tab (device int32): [f2m nf][f2h nf][mh_ptr nm+1][mh_idx n_mh][hsmask nm][order C]
-inline Hier3 hier3_from_tab(const int* tab, int nf, int nm, int nh, int n_mh) {
+__host__ __device__ inline Hier3 hier3_from_tab(const int* tab, int nf, int nm, int nh, int n_mh) {
   Hier3 h;
   h.nf = nf; h.nm = nm; h.nh = nh;
+  h.tab = tab; h.n_mh = n_mh;
+  h.tab_len = 2 * nf + (nm + 1) + n_mh + nm + (nf + nm + nh);
   h.f2m = tab;
   h.f2h = h.f2m + nf;
   h.mh_ptr = h.f2h + nf;
@@ -199,6 +205,13 @@ struct BandView {
     return t == SH_IGNORE ? 0 : (lmap ? lmap[t] : t);
   }
 };
+
+// Copy the hierarchy tables into shared memory (they are read once per channel by every thread) and
+// return a view that points into the copy.  Caller must __syncthreads() before using it.
+__device__ __forceinline__ Hier3 stage_hier(const Hier3& h, int* dst, int tid, int nthreads) {
+  for (int i = tid; i < h.tab_len; i += nthreads) dst[i] = h.tab[i];
+  return hier3_from_tab(dst, h.nf, h.nm, h.nh, h.n_mh);
+}
 
 // label tile (3 levels, halo 2) from the uint8 labels: rows y0-2 .. y0+rows+1, cols x0-2 .. x0+65
 __device__ __forceinline__ void load_label_tile(unsigned char* labt, int rows, const unsigned char* lab8, int H, int W,

@@ -89,6 +89,8 @@ __global__ void __launch_bounds__(256) k3_prep(const long long* __restrict__ lab
 // Slow path of k3_pass1 (kept out of line so that its registers do not burden the streaming loop):
 // lp / ll taps of the interior anchors of one 4x4 block whose 5x5 label neighbourhood is NOT uniform.
 // All lanes of the warp must call it (warp-level reductions); lanes with want == false add zeros.
+// (A tap-per-lane redistribution over the lanes that have work was measured slower: label-byte gathers
+// with 38 different offsets serialise in the shared-memory banks.)
 __device__ __noinline__ void pass1_slow_path(const float* plane, const unsigned char* labl, unsigned int u0,
                                              unsigned int u1, unsigned int u2, unsigned int u3, int br, int bs,
                                              int cl, bool want, int lane, float* sp) {
@@ -152,19 +154,24 @@ __device__ __noinline__ void pass1_slow_path(const float* plane, const unsigned 
 // Planes are double buffered: one __syncthreads per round of 4 channels.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(kThreads, 1)
-k3_pass1(const T* __restrict__ x, int B, int H, int W, Hier3 h, Ws3 ws, float eps, int vec_ok) {
+__global__ void __launch_bounds__(kThreads, 512 / kThreads)
+k3_pass1(const T* __restrict__ x, int B, int H, int W, Hier3 hg, Ws3 ws, float eps, int vec_ok) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int PX = kTH * kTW;
   constexpr int kPlane = (kTH + 2) * kPitch;
-  const int C = h.nf + h.nm + h.nh;
+  const int C = hg.nf + hg.nm + hg.nh;
   float* planes = reinterpret_cast<float*>(smem_raw);                    // [2][kNR][kPlane]
-  float* red = planes + 2 * kNR * kPlane;                                // [2][kNR][4 warps][20]
-  float* slow = red + 2 * kNR * 4 * 20;                                  // [2][kNR][40]
+  float* red = planes + 2 * kNR * kPlane;                                // [2][kNR][kGroupWarps][20]
+  float* slow = red + 2 * kNR * kGroupWarps * 20;                        // [2][kNR][40]
   float* maxB = slow + 2 * kNR * 40;                                     // [nh][PX]
-  unsigned char* holdB = reinterpret_cast<unsigned char*>(maxB + (size_t)h.nh * PX);  // [nh][PX]
-  unsigned char* U = holdB + (size_t)h.nh * PX;                          // [3][kTH][kTW]
+  unsigned char* holdB = reinterpret_cast<unsigned char*>(maxB + (size_t)hg.nh * PX);  // [nh][PX]
+  unsigned char* U = holdB + (size_t)hg.nh * PX;                         // [3][kTH][kTW]
   unsigned char* labt = U + 3 * PX;                                      // [3][kTH+4][kLabPitch]
+  int* htab = reinterpret_cast<int*>(labt + 3 * (kTH + 4) * kLabPitch);  // hierarchy tables (6 KB)
+  uint4* xstage = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(htab) + 6144);   // [kNR][kThreads] raw logits
+  unsigned int* hstage = reinterpret_cast<unsigned int*>(xstage + kNR * kThreads);           // [kNR][kThreads] halo logits
+  const Hier3 h = stage_hier(hg, htab, threadIdx.x, kThreads);
+  __syncthreads();
 
   const int b = blockIdx.z, y0 = blockIdx.y * kTH, x0 = blockIdx.x * kTW;
   const long HW = (long)H * W;
@@ -227,7 +234,7 @@ k3_pass1(const T* __restrict__ x, int B, int H, int W, Hier3 h, Ws3 ws, float ep
   __syncthreads();
 
   // ---- phase-B role: one 4x4 block of plane g ------------------------------------------------------
-  const int g = tid >> 7, u = tid & 127, br = u >> 4, bs = u & 15;
+  const int g = tid / kGroup, u = tid % kGroup, br = u >> 4, bs = u & 15;
   unsigned int ub[3][4];        // U codes of the block rows, per level
   unsigned int pres[3] = {0u, 0u, 0u};
 #pragma unroll
@@ -241,15 +248,19 @@ k3_pass1(const T* __restrict__ x, int B, int H, int W, Hier3 h, Ws3 ws, float ep
     }
     if (any_nu) {
       for (int rr = 0; rr < 8; ++rr) {
-        const unsigned char* row = labt + ((l * (kTH + 4)) + 4 * br + rr) * kLabPitch + 4 * bs;
-        for (int q = 0; q < 8; ++q) pres[l] |= 1u << (row[q] & 31);
+        const unsigned int* row = reinterpret_cast<const unsigned int*>(labt + ((l * (kTH + 4)) + 4 * br + rr) * kLabPitch + 4 * bs);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const unsigned int wd = row[q];
+          pres[l] |= (1u << (wd & 31)) | (1u << ((wd >> 8) & 31)) | (1u << ((wd >> 16) & 31)) | (1u << ((wd >> 24) & 31));
+        }
       }
     }
   }
 
   // ---- streaming state (phase-A role) ----------------------------------------------------------------
-  float sumvF[4], sumvM[4], sumvH[4], prodF[4], prodM[4], prodH[4], a_t[4], b_t[4], c_t[4], min_c[4], runmax[4];
-  unsigned int runhold = 0, hold_minc = 0;
+  float sumvF[4], sumvM[4], sumvH[4], prodF[4], prodM[4], prodH[4], a_t[4], b_t[4], c_t[4], min_c[4], runmax[4], validf[4];
+  unsigned int runhold[4] = {0u, 0u, 0u, 0u}, hold_minc = 0;
   float lacc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // BCE fine/mid/high, CE fine/mid/high
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -258,10 +269,14 @@ k3_pass1(const T* __restrict__ x, int B, int H, int W, Hier3 h, Ws3 ws, float ep
     a_t[k] = b_t[k] = c_t[k] = 1.f;
     min_c[k] = 3.0e38f;
     runmax[k] = -1.f;
+    validf[k] = tf[k] != SH_IGNORE ? 1.f : 0.f;
   }
 
   const int nrounds = (C + kNR - 1) / kNR;
-  float xv[kNR][4], hv[kNR];
+  // next round's logits travel global -> shared with cp.async (no registers held across phase B);
+  // ragged / unaligned strips fall back to synchronous loads when they are consumed
+  const bool fast_own = vec_ok && row_ok && nvalid == 4;
+  const bool halo_async = h_goff >= 0 && (sizeof(T) == 4 || vec_ok);
   auto chan_of = [&](unsigned int oe) {
     const int kind = oe & 0xff, cl = (oe >> 8) & 0xff;
     return kind == 0 ? cl : (kind == 1 ? h.nf + cl : h.nf + h.nm + cl);
@@ -272,33 +287,33 @@ k3_pass1(const T* __restrict__ x, int B, int H, int W, Hier3 h, Ws3 ws, float ep
       const int ci = r * kNR + j;
       if (ci < C) {
         const T* xc = xb + (long)chan_of(h.order[ci]) * HW;
-        if (row_ok) load_n<T, 4>(xc, own_off, (long)y * W + W, vec_ok != 0, xv[j]);
-        else { xv[j][0] = xv[j][1] = xv[j][2] = xv[j][3] = 0.f; }
-        hv[j] = h_goff >= 0 ? to_f32<T>(xc[h_goff]) : 0.f;
+        if (fast_own) cp_async_vec4<T>(xstage + j * kThreads + tid, xc + own_off);
+        if (halo_async) cp_async_elem<T>(hstage + j * kThreads + tid, xc, h_goff);
       }
     }
+    cp_async_commit();
   };
   auto flush = [&](int r) {
-    // combine the 4 warps of every plane of round r and write the per-(tile, channel) records
+    // combine the warps of every plane of round r and write the per-(tile, channel) records
     const int buf = r & 1;
-    if (tid < kNR * 16) {
-      const int j = tid >> 4, k = tid & 15, ci = r * kNR + j;
-      if (ci < C && k < 13) {
-        const float* rp = red + ((buf * kNR + j) * 4) * 20 + k;
-        ws.part1[((size_t)tile_id * C + chan_of(h.order[ci])) * kRec + k] = rp[0] + rp[20] + rp[40] + rp[60];
-      }
-    } else if (tid < kNR * 16 + 2 * kNR) {
-      const int q = tid - kNR * 16, j = q >> 1, which = q & 1, ci = r * kNR + j;
-      if (ci < C) {
-        const double* rp = reinterpret_cast<const double*>(red + ((buf * kNR + j) * 4) * 20 + 16) + which;
-        const double v = rp[0] + rp[10] + rp[20] + rp[30];
-        *reinterpret_cast<double*>(ws.part1 + ((size_t)tile_id * C + chan_of(h.order[ci])) * kRec + kT0 + 2 * which) = v;
-      }
-    } else if (tid >= 128 && tid < 128 + kNR * 40) {
-      const int q = tid - 128, j = q / 40, k = q % 40, ci = r * kNR + j;
-      if (ci < C && k < 38) {
-        float* sp = slow + (buf * kNR + j) * 40 + k;
-        ws.part1[((size_t)tile_id * C + chan_of(h.order[ci])) * kRec + kLPS + k] = *sp;
+    for (int q = tid; q < kNR * 56; q += kThreads) {
+      const int j = q / 56, k = q % 56, ci = r * kNR + j;
+      if (ci >= C) continue;
+      float* rec = ws.part1 + ((size_t)tile_id * C + chan_of(h.order[ci])) * kRec;
+      const float* rp = red + ((buf * kNR + j) * kGroupWarps) * 20;
+      if (k < 13) {
+        float a = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < kGroupWarps; ++wq) a += rp[wq * 20 + k];
+        rec[k] = a;
+      } else if (k < 15) {
+        double a = 0.0;
+#pragma unroll
+        for (int wq = 0; wq < kGroupWarps; ++wq) a += reinterpret_cast<const double*>(rp + wq * 20 + 16)[k - 13];
+        *reinterpret_cast<double*>(rec + kT0 + 2 * (k - 13)) = a;
+      } else if (k < 15 + 38) {
+        float* sp = slow + (buf * kNR + j) * 40 + (k - 15);
+        rec[kLPS + (k - 15)] = *sp;
         *sp = 0.f;
       }
     }
@@ -308,27 +323,38 @@ k3_pass1(const T* __restrict__ x, int B, int H, int W, Hier3 h, Ws3 ws, float ep
   for (int r = 0; r < nrounds; ++r) {
     const int buf = r & 1;
     // ======================= phase A =======================
-#pragma unroll
+    cp_async_wait_all();
+#pragma unroll 1     // keep the round body small: the kernel is instruction-cache bound when fully unrolled
     for (int j = 0; j < kNR; ++j) {
       const int ci = r * kNR + j;
       if (ci >= C) break;
       const unsigned int oe = h.order[ci];
       const int kind = oe & 0xff, cl = (oe >> 8) & 0xff, fl = (oe >> 16) & 0xff;
       float* plane = planes + (buf * kNR + j) * kPlane;
-      float s[4], v[4], pk[4];
+      float s[4], v[4], pk[4], xv[4];
+      if (fast_own) staged_vec4<T>(xstage + j * kThreads + tid, xv);
+      else if (row_ok) load_n<T, 4>(xb + (long)chan_of(oe) * HW, own_off, (long)y * W + W, vec_ok != 0, xv);
+      else { xv[0] = xv[1] = xv[2] = xv[3] = 0.f; }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const SigExp se = sig_exp(xv[j][k]);
+        const SigExp se = sig_exp(xv[k]);
         s[k] = se.s; v[k] = se.v;
-        pk[k] = k < nvalid ? ((tf[k] != SH_IGNORE ? se.s : 0.f) + 1e-6f) : 0.f;
+        pk[k] = fmaf(se.s, validf[k], 1e-6f);      // literally probs * valid + 1e-6 (rmi...py:487)
       }
       *reinterpret_cast<float2*>(plane + ty * kPitch + tx + 2) = make_float2(pk[0], pk[1]);
       *reinterpret_cast<float2*>(plane + ty * kPitch + tx + 4) = make_float2(pk[2], pk[3]);
-      if (h_sidx >= 0) plane[h_sidx] = h_goff >= 0 ? ((h_valid ? sig_exp(hv[j]).s : 0.f) + 1e-6f) : 0.f;
+      if (h_sidx >= 0) {
+        float p = 0.f;
+        if (h_goff >= 0) {
+          const float hx = halo_async ? staged_elem<T>(hstage + j * kThreads + tid, h_goff)
+                                      : to_f32<T>(xb[(long)chan_of(oe) * HW + h_goff]);
+          p = (h_valid ? sig_exp(hx).s : 0.f) + 1e-6f;
+        }
+        plane[h_sidx] = p;
+      }
       if (fl & 1) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) runmax[k] = -1.f;
-        runhold = 0;
+        for (int k = 0; k < 4; ++k) { runmax[k] = -1.f; runhold[k] = 0u; }
       }
       if (kind == 0) {
         const unsigned int c = cl;
@@ -337,7 +363,7 @@ k3_pass1(const T* __restrict__ x, int B, int H, int W, Hier3 h, Ws3 ws, float ep
           sumvF[k] += v[k];
           if (cl == tf[k]) { a_t[k] = s[k]; lacc[3] -= fast_log(v[k]); }
           else prodF[k] *= (1.0f - s[k]) + eps;
-          if (s[k] > runmax[k]) { runmax[k] = s[k]; runhold = (runhold & ~(0xffu << (8 * k))) | (c << (8 * k)); }
+          if (s[k] > runmax[k]) { runmax[k] = s[k]; runhold[k] = c; }
         }
         if (fl & 2) {
 #pragma unroll
@@ -346,12 +372,14 @@ k3_pass1(const T* __restrict__ x, int B, int H, int W, Hier3 h, Ws3 ws, float ep
       } else if (kind == 1) {
         const unsigned int c = h.nf + cl;
         float cur[4];
-        unsigned int hd = runhold;
+        unsigned int hd = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           sumvM[k] += v[k];
           cur[k] = runmax[k];
-          if (s[k] > cur[k]) { cur[k] = s[k]; hd = (hd & ~(0xffu << (8 * k))) | (c << (8 * k)); }   // fine max wins ties
+          unsigned int hk = runhold[k];
+          if (s[k] > cur[k]) { cur[k] = s[k]; hk = c; }   // fine max wins ties
+          hd |= hk << (8 * k);
           if (cl == tm[k]) { b_t[k] = s[k]; lacc[4] -= fast_log(v[k]); }
           else prodM[k] *= (1.0f - cur[k]) + eps;
         }
@@ -438,7 +466,7 @@ k3_pass1(const T* __restrict__ x, int B, int H, int W, Hier3 h, Ws3 ws, float ep
         }
       }
       // warp totals: 13 floats through the transposed reduction, the two big sums in double
-      float* rp = red + ((buf * kNR + g) * 4 + ((tid >> 5) & 3)) * 20;
+      float* rp = red + ((buf * kNR + g) * kGroupWarps + ((tid >> 5) % kGroupWarps)) * 20;
       const float tot = warp_reduce16(acc, lane);
       if ((lane & 1) == 0) {
         const int slot = reduce16_slot(lane);
@@ -826,8 +854,10 @@ __global__ void __launch_bounds__(256) k_reduce_partials3(const float* __restric
 }
 
 static size_t pass1_smem_bytes(int nh) {
-  size_t s = (size_t)2 * kNR * (kTH + 2) * kPitch * 4 + 2 * kNR * 4 * 20 * 4 + 2 * kNR * 40 * 4;
-  s += (size_t)nh * kTH * kTW * 5 + 3 * kTH * kTW + 3 * (kTH + 4) * kLabPitch;
+  size_t s = (size_t)2 * kNR * (kTH + 2) * kPitch * 4 + 2 * kNR * kGroupWarps * 20 * 4 + 2 * kNR * 40 * 4;
+  s += (size_t)nh * kTH * kTW * 5 + 3 * kTH * kTW + 3 * (kTH + 4) * kLabPitch + 6144 /* hierarchy tables */;
+  s = (s + 15) & ~(size_t)15;
+  s += (size_t)kNR * kThreads * (16 + 4);   // cp.async staging of the next round's logits
   return (s + 15) & ~(size_t)15;
 }
 
