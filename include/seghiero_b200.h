@@ -79,13 +79,20 @@ size_t sh_rmi3_workspace_bytes(int B, int H, int W, int nf, int nm, int nh);
  * hold, inv, part1, bcepart, frameT, rbc, wts, fwts. */
 int sh_rmi3_workspace_offsets(int B, int H, int W, int nf, int nm, int nh, size_t* out);
 
+/* 1 when the warp-specialised kernels (csrc/rmi3_fast.cuh) will run this problem: tree-shaped maps
+ * (fast_tab_ok from the host table builder), W % 4 == 0, 16-byte aligned tensors, 8 < C <= 160.  Everything
+ * else runs the generic kernels; results agree to fp32 rounding. */
+int sh_rmi3_fast_path(const void* logits, const void* grad, int dtype, int H, int W, int nf, int nm, int nh,
+                      int fast_tab_ok);
+
 /* Pass 1 (+ label prep, frame taps, per-(b,c) 9x9 algebra): tree BCE (rmi...py:352-470), CE (:523-526),
  * RMI lower bound (:479-517) without materialising the unfolds.  Leaves everything the backward pass and
  * sh_loss3_final need in `workspace`.
- * hier_tab (device int32): [f2m nf][f2h nf][mh_ptr nm+1][mh_idx n_mh][hsmask nm]. */
+ * hier_tab (device int32): [f2m nf][f2h nf][mh_ptr nm+1][mh_idx n_mh][hsmask nm][order C][fast_order C]
+ * (seghiero_b200/hierarchy.py::three_level_tables). */
 int sh_rmi3_forward(const void* logits, int dtype, const long long* label, int B, int H, int W, int nf, int nm, int nh,
-                    const int* hier_tab, int n_mh, float lam, float loss_weight, void* workspace, int stages,
-                    void* stream);
+                    const int* hier_tab, int n_mh, int fast_tab_ok, float lam, float loss_weight, void* workspace,
+                    int stages, void* stream);
 
 /* out[0] = loss, out[1] = ready*factor*loss_weight, out[2] = rmi term. */
 int sh_loss3_final(int B, int H, int W, int nf, int nm, int nh, void* workspace, float lam, const double* step,
@@ -94,8 +101,8 @@ int sh_loss3_final(int B, int H, int W, int nf, int nm, int nh, void* workspace,
 
 /* Pass 2: d loss / d logits written once (grad_out = device scalar handed over by autograd). */
 int sh_rmi3_backward(const void* logits, int dtype, void* grad, int B, int H, int W, int nf, int nm, int nh,
-                     const int* hier_tab, int n_mh, float loss_weight, void* workspace, const float* grad_out,
-                     int stages, void* stream);
+                     const int* hier_tab, int n_mh, int fast_tab_ok, float loss_weight, void* workspace,
+                     const float* grad_out, int stages, void* stream);
 
 /* ---- triplet: TreeTripletLoss.forward, models/loss/tree_triplet_loss.py:15-65 (mode 0) and
  *      models/loss/rmi_tree_triplet_loss.py:14-70 (mode 1) ------------------------------------- */

@@ -292,6 +292,41 @@ __device__ __forceinline__ float staged_elem<__half>(const void* slot, long idx)
   return (idx & 1) ? __high2float(h2) : __low2float(h2);
 }
 
+// named barriers (ids 1..15; id 0 is __syncthreads): producer/consumer hand-over of shared-memory buffers.
+// `n` = number of threads that take part (arrivers + waiters), a multiple of 32.
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// clamp that lets NaN through (FMNMX.NAN): NaN logits must poison the loss like they do in the reference
+__device__ __forceinline__ float clamp_nan(float v, float lo, float hi) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "f"(lo));
+  asm("min.NaN.f32 %0, %0, %1;" : "+f"(r) : "f"(hi));
+  return r;
+}
+
+// sigmoid(x) with torch's own rounding of (1 + e^-x) (the reference takes log(1 - s + eps) of that
+// quantised value) and e^x, from 3 MUFU ops.  |x| is clamped to ~80 so that sums of e^x stay finite.
+//   W = e^-x ;  s = RN(1 / (1 + W)) (rcp + one Newton step) ;  e^x = 1 / W
+__device__ __forceinline__ void sig_exp3(float x, float& s, float& ex) {
+  const float t = clamp_nan(x * (-kLog2e), -115.0f, 115.0f);
+  const float w = ex2(t);
+  const float y = 1.0f + w;
+  const float q0 = rcp(y);
+  s = fmaf(q0, fmaf(-y, q0, 1.0f), q0);
+  ex = rcp(w);
+}
+__device__ __forceinline__ float sig_only(float x) {
+  const float t = clamp_nan(x * (-kLog2e), -115.0f, 115.0f);
+  const float y = 1.0f + ex2(t);
+  const float q0 = rcp(y);
+  return fmaf(q0, fmaf(-y, q0, 1.0f), q0);
+}
+// any byte of v equal to zero?
+__device__ __forceinline__ bool has_zero_byte(unsigned int v) { return ((v - 0x01010101u) & ~v & 0x80808080u) != 0u; }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -452,8 +452,8 @@ static int run_backward3(const void* x, void* grad, int B, int H, int W, const H
 extern "C" {
 
 int sh_rmi3_backward(const void* logits, int dtype, void* grad, int B, int H, int W, int nf, int nm, int nh,
-                     const int* hier_tab, int n_mh, float loss_weight, void* workspace, const float* grad_out,
-                     int stages, void* stream) {
+                     const int* hier_tab, int n_mh, int fast_tab_ok, float loss_weight, void* workspace,
+                     const float* grad_out, int stages, void* stream) {
   if (B <= 0 || H < 8 || W < 8 || nf + nm + nh > 254) return SH_ERR_BAD_ARG;
   sh::Ws3 ws = sh::ws3_layout(workspace, B, H, W, nf, nm, nh);
   const float* bandR = (const float*)((unsigned char*)workspace + ws.bytes);

@@ -101,9 +101,17 @@ struct Ws3 {
   double* rbc;                 // [B*C]
   float* wts;                  // [B*C][64]: W1[25], W2[25], W2full at 50
   float* fwts;                 // [B*C][25 classes][50]
+  // fast path (rmi3_fast.cuh): per-(persistent CTA, channel) records, cpi CTAs per image
+  double* rec2;                // [B*cpi][C][kFastRec]: pp product taps [13], lp taps [25]
+  unsigned int* llrec;         // [B*cpi][C][16]: label-label half-plane counts [13]
+  float* bce2;                 // [B*cpi][8]
   size_t bytes;
-  int tiles_x, tiles_y, nseg;
+  int tiles_x, tiles_y, nseg, cpi;
 };
+
+constexpr int kFastRec = 40;   // doubles per (CTA, channel) record of the fast forward pass
+// persistent CTAs per image of the fast path: one CTA per SM over the whole batch
+inline int fast_ctas_per_image(int B) { int c = SH_NUM_SMS / (B > 0 ? B : 1); return c < 1 ? 1 : c; }
 
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
@@ -136,6 +144,10 @@ inline Ws3 ws3_layout(void* base, int B, int H, int W, int nf, int nm, int nh) {
   w.rbc = (double*)take((size_t)B * C * 8);
   w.wts = (float*)take((size_t)B * C * 64 * 4);
   w.fwts = (float*)take((size_t)B * C * 25 * 50 * 4);
+  w.cpi = fast_ctas_per_image(B);
+  w.rec2 = (double*)take((size_t)B * w.cpi * C * kFastRec * 8);
+  w.llrec = (unsigned int*)take((size_t)B * w.cpi * C * 16 * 4);
+  w.bce2 = (float*)take((size_t)B * w.cpi * 8 * 4);
   w.bytes = off;
   return w;
 }

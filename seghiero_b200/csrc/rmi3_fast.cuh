@@ -1,0 +1,679 @@
+// Fast path of the three-level (BCE + RMI + CE) loss: warp-specialised persistent kernels.
+//
+// Applies when the hierarchy is a tree (every mid has one high), W % 4 == 0, pointers are 16-byte
+// aligned and 8 < C <= kFastMaxC; everything else runs the generic kernels of rmi3_fwd.cu / rmi3_bwd.cu.
+// Reference arithmetic: models/loss/rmi_hiera_triplet_loss.py:323-546.
+//
+// One CTA per SM (576 threads), each walking tiles (64 x 16 pixels) of ONE image:
+//   warps 0-7   producers : thread = 4 consecutive pixels, all channels in tree order (fine children,
+//                           their mid, ..., then the high).  sigmoid / e^x from 3 MUFU ops, tree BCE +
+//                           CE sums in registers, P = s*valid + 1e-6 -> shared-memory channel plane.
+//   warps 8-9   halo      : the 2-pixel ring of every plane (sigmoid only) + the tile's label bytes.
+//   warps 10-17 consumers : warp = one channel plane of the round, thread = 4 x 8 block.  RMI moments
+//                           of the interior anchors as 13 product taps (pr_cov) + 25 label-anchored taps
+//                           (la_pr), warp-reduced and accumulated in fp64 per CTA.
+// Planes travel producer -> consumer through a ring of kNBuf round buffers (kNR planes each) guarded by
+// named barriers (bar.arrive / bar.sync); logits are prefetched 5 channels ahead with cp.async.
+#pragma once
+#include "rmi3_common.cuh"
+
+namespace sh {
+namespace fast {
+
+constexpr int TW = 64, TH = 16;
+constexpr int PW = TW + 4;           // plane pitch: cols x0-2 .. x0+65
+constexpr int PR = TH + 4;           // plane rows:  y0-2 .. y0+17
+constexpr int PLANE = PR * PW;       // 1360 floats
+constexpr int NR = 8;                // planes per round = consumer warps
+constexpr int NBUF = 3;              // round buffers
+constexpr int NPROD = 256, NHALO = 64, NCONS = 256;
+constexpr int NTHREADS = NPROD + NHALO + NCONS;   // 576
+constexpr int XD = 6;                // cp.async ring depth (channels in flight per producer thread)
+constexpr int BAR_FULL = 1, BAR_EMPTY = 1 + NBUF, BAR_PROD = 1 + 2 * NBUF;
+constexpr int kFastMaxC = 160;
+
+// order entry: kind (0 fine / 1 mid / 2 high) | class << 8 | flags << 16 | channel << 24 ; flags bit1 = flush products
+struct FastHier {
+  int nf, nm, nh;
+  const int* f2m;            // [nf]
+  const int* f2h;            // [nf]
+  const unsigned int* order; // [C] tree order of the fast path
+};
+
+struct TileCoord { int y0, x0; };
+__device__ __forceinline__ TileCoord tile_coord(int tile, int tiles_x) {
+  TileCoord t;
+  const int tyi = tile / tiles_x;
+  t.y0 = tyi * TH;
+  t.x0 = (tile - tyi * tiles_x) * TW;
+  return t;
+}
+
+// -------------------------------------------------------------------------------------------------
+// k3f_prep: labels int64 -> uint8, #valid, range check, and the label-only part of RMI:
+//   ll[c][d] = #{ interior anchors r : L(r) = c and L(r + d) = c },  d in the half plane (13 taps),
+// with L = the RMI label of the level (void pixels are class 0, rmi...py:360-370).  Persistent CTAs
+// (same tile walk as k3f_pass1), integer counts per (CTA, channel) -> ws.llrec (summed by k3f_finalize).
+// -------------------------------------------------------------------------------------------------
+constexpr int LPITCH = TW + 8;   // label tile pitch: cols x0-2 .. x0+65 (+4 pad)
+
+__global__ void __launch_bounds__(256) k3f_prep(const long long* __restrict__ label, int B, int H, int W, FastHier hg,
+                                                Ws3 ws, int cpi, int ll_only) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int C = hg.nf + hg.nm + hg.nh;
+  unsigned int* hist = reinterpret_cast<unsigned int*>(smem_raw);                       // [C][16]
+  int* s_f2m = reinterpret_cast<int*>(hist + (size_t)C * 16);
+  int* s_f2h = s_f2m + hg.nf;
+  unsigned char* rl = reinterpret_cast<unsigned char*>(s_f2h + hg.nf);                  // [3][TH+2][LPITCH]
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < C * 16; i += 256) hist[i] = 0u;
+  for (int i = tid; i < hg.nf; i += 256) { s_f2m[i] = hg.f2m[i]; s_f2h[i] = hg.f2h[i]; }
+  __syncthreads();
+  const int b = blockIdx.x / cpi, j0 = blockIdx.x - b * cpi;
+  const int tiles_x = ws.tiles_x, ntiles = ws.tiles_x * ws.tiles_y;
+  const long HW = (long)H * W;
+  const long long* lb = label + (long)b * HW;
+  unsigned char* lab8 = ws.lab8 + (long)b * HW;
+  const int ty = tid >> 4, tx = (tid & 15) << 2;
+  const int level_base[3] = {0, hg.nf, hg.nf + hg.nm};
+  long long nv = 0;
+  bool bad = false;
+#pragma unroll 1
+  for (int tile = j0; tile < ntiles; tile += cpi) {
+    const TileCoord tc = tile_coord(tile, tiles_x);
+    for (int e = tid; e < (TH + 2) * (TW + 4); e += 256) {
+      const int r = e / (TW + 4), j = e - r * (TW + 4);
+      const int y = tc.y0 + r, xx = tc.x0 - 2 + j;
+      unsigned char f = 0xff, m = 0xff, g = 0xff;
+      if (y < H && xx >= 0 && xx < W) {
+        const long long t = lb[(long)y * W + xx];
+        f = m = g = 0;
+        unsigned char l8 = SH_IGNORE;
+        if (t != SH_IGNORE) {
+          if (t >= 0 && t < hg.nf) { f = (unsigned char)t; m = (unsigned char)s_f2m[t]; g = (unsigned char)s_f2h[t]; l8 = f; }
+          else bad = !ll_only; // F.one_hot would raise in the reference
+        }
+        if (!ll_only && r < TH && j >= 2 && j < TW + 2) {
+          lab8[(long)y * W + xx] = l8;
+          nv += (t != SH_IGNORE);
+        }
+      }
+      rl[(0 * (TH + 2) + r) * LPITCH + j] = f;
+      rl[(1 * (TH + 2) + r) * LPITCH + j] = m;
+      rl[(2 * (TH + 2) + r) * LPITCH + j] = g;
+    }
+    __syncthreads();
+    const int y = tc.y0 + ty;
+    const bool row_ok = y >= 2 && y < H - 2;
+#pragma unroll 1
+    for (int l = 0; l < 3; ++l) {
+      const unsigned char* base = rl + (l * (TH + 2) + ty) * LPITCH + tx;
+      unsigned long long wn[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const unsigned int* p = reinterpret_cast<const unsigned int*>(base + q * LPITCH);
+        wn[q] = (unsigned long long)p[0] | ((unsigned long long)p[1] << 32);
+      }
+      unsigned int m13[4], cls[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int xx = tc.x0 + tx + k;
+        const unsigned int c = byte_of(wn[0], k + 2);
+        cls[k] = c;
+        unsigned int m = 0;
+        if (row_ok && xx >= 2 && xx < W - 2) {
+          m = 1u;
+          m |= (byte_of(wn[0], k + 3) == c) << 1;
+          m |= (byte_of(wn[0], k + 4) == c) << 2;
+#pragma unroll
+          for (int dx = 0; dx < 5; ++dx) {
+            m |= (byte_of(wn[1], k + dx) == c) << (3 + dx);
+            m |= (byte_of(wn[2], k + dx) == c) << (8 + dx);
+          }
+        }
+        m13[k] = m;
+      }
+      const bool uni = cls[0] == cls[1] && cls[1] == cls[2] && cls[2] == cls[3];
+      const int nround = __all_sync(0xffffffffu, uni) ? 1 : 4;
+      for (int rd = 0; rd < nround; ++rd) {
+        // packed per-tap counts of this lane (8 bits per tap, 4 taps per word)
+        unsigned int pk[4] = {0u, 0u, 0u, 0u};
+        unsigned int key;
+        if (nround == 1) {
+          key = cls[0];
+#pragma unroll
+          for (int ht = 0; ht < 13; ++ht) {
+            const unsigned int n = ((m13[0] >> ht) & 1u) + ((m13[1] >> ht) & 1u) + ((m13[2] >> ht) & 1u) + ((m13[3] >> ht) & 1u);
+            pk[ht >> 2] |= n << (8 * (ht & 3));
+          }
+        } else {
+          const unsigned int mk = rd == 0 ? m13[0] : (rd == 1 ? m13[1] : (rd == 2 ? m13[2] : m13[3]));
+          key = rd == 0 ? cls[0] : (rd == 1 ? cls[1] : (rd == 2 ? cls[2] : cls[3]));
+#pragma unroll
+          for (int ht = 0; ht < 13; ++ht) pk[ht >> 2] |= ((mk >> ht) & 1u) << (8 * (ht & 3));
+        }
+        // lanes of one class add up (hardware integer warp reduction over the peer mask)
+        const unsigned int peers = __match_any_sync(0xffffffffu, key);
+        unsigned int tot4[4][4];     // [tap word][byte] totals over the peers
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          // split the fields into two words of 16-bit lanes before the warp-wide integer reduction
+          const unsigned int lo = pk[q] & 0x00ff00ffu, hi = (pk[q] >> 8) & 0x00ff00ffu;
+          const unsigned int slo = __reduce_add_sync(peers, lo), shi = __reduce_add_sync(peers, hi);
+          tot4[q][0] = slo & 0xffffu; tot4[q][2] = slo >> 16;
+          tot4[q][1] = shi & 0xffffu; tot4[q][3] = shi >> 16;
+        }
+        if (key != 0xffu) {
+          const int rank = __popc(peers & ((1u << lane) - 1u)), gsz = __popc(peers);
+          unsigned int* hrow = hist + (size_t)(level_base[l] + key) * 16;
+          for (int ht = rank; ht < 13; ht += gsz) {
+            unsigned int v = 0;
+#pragma unroll
+            for (int q = 0; q < 13; ++q) if (q == ht) v = tot4[q >> 2][q & 3];
+            if (v) atomicAdd(hrow + ht, v);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  nv = warp_sum(nv);
+  if (lane == 0 && nv) atomicAdd(ws.counts, (unsigned long long)nv);
+  if (bad) atomicOr((unsigned int*)(ws.counts + 2), 1u);
+  __syncthreads();
+  unsigned int* out = ws.llrec + (size_t)blockIdx.x * C * 16;
+  for (int i = tid; i < C * 16; i += 256) out[i] = hist[i];
+}
+
+inline size_t prep_smem(int C, int nf) {
+  return (size_t)C * 16 * 4 + (size_t)2 * nf * 4 + (size_t)3 * (TH + 2) * LPITCH + 16;
+}
+
+inline size_t pass1_smem(int C, int nf) {
+  size_t s = (size_t)NBUF * NR * PLANE * 4;          // planes
+  s += (size_t)XD * NPROD * 16;                      // cp.async staging
+  s += (size_t)2 * 3 * TH * TW;                      // label tiles (two tile parities)
+  s += (size_t)C * kFastRec * 8;                     // fp64 totals
+  s += (size_t)(C + 2 * nf) * 4 + 64 * 4;            // tables + reduction scratch
+  return (s + 15) & ~(size_t)15;
+}
+
+// -------------------------------------------------------------------------------------------------
+// k3f_pass1
+// -------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, float eps, int cpi) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int C = hg.nf + hg.nm + hg.nh;
+  float* planes = reinterpret_cast<float*>(smem_raw);                                   // [NBUF][NR][PLANE]
+  uint4* xstage = reinterpret_cast<uint4*>(planes + NBUF * NR * PLANE);                  // [XD][NPROD]
+  unsigned char* LT = reinterpret_cast<unsigned char*>(xstage + XD * NPROD);             // [2][3][TH][TW]
+  double* tot = reinterpret_cast<double*>(LT + 2 * 3 * TH * TW);                         // [C][kFastRec]
+  unsigned int* s_order = reinterpret_cast<unsigned int*>(tot + (size_t)C * kFastRec);   // [C]
+  int* s_f2m = reinterpret_cast<int*>(s_order + C);                                      // [nf]
+  int* s_f2h = s_f2m + hg.nf;                                                            // [nf]
+  float* s_red = reinterpret_cast<float*>(s_f2h + hg.nf);                                // [64]
+
+  const int tid = threadIdx.x;
+  for (int i = tid; i < C; i += NTHREADS) s_order[i] = hg.order[i];
+  for (int i = tid; i < hg.nf; i += NTHREADS) { s_f2m[i] = hg.f2m[i]; s_f2h[i] = hg.f2h[i]; }
+  for (int i = tid; i < C * kFastRec; i += NTHREADS) tot[i] = 0.0;
+  __syncthreads();
+
+  const int b = blockIdx.x / cpi, j0 = blockIdx.x - b * cpi;
+  const int tiles_x = ws.tiles_x, ntiles = ws.tiles_x * ws.tiles_y;
+  const int nt = j0 < ntiles ? (ntiles - j0 + cpi - 1) / cpi : 0;     // tiles of this CTA: j0, j0+cpi, ...
+  const int RPT = (C + NR - 1) / NR;
+  const int total_rounds = nt * RPT;
+  const long HW = (long)H * W;
+  const unsigned char* lab8 = ws.lab8 + (long)b * HW;
+  const T* xb = x + (long)b * C * HW;
+
+  if (tid < NPROD) {
+    // ============================== producers ==============================
+    const int ty = tid >> 4, tx = (tid & 15) << 2;
+    float lacc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // [0..2] log2 units (BCE fine/mid/high), [3..5] natural (CE)
+    // prefetch stream state (runs XD-1 channels ahead, across tile boundaries)
+    int pf_it = 0, pf_ci = 0, pf_seq = 0;
+    long pf_off = 0;
+    bool pf_in = false;
+    auto pf_tile = [&]() {
+      if (pf_it < nt) {
+        const TileCoord tc = tile_coord(j0 + pf_it * cpi, tiles_x);
+        const int y = tc.y0 + ty, xg = tc.x0 + tx;
+        pf_in = y < H && xg < W;
+        pf_off = (long)y * W + xg;
+      } else {
+        pf_in = false;
+      }
+    };
+    auto pf_issue = [&]() {
+      if (pf_in) {
+        const int ch = s_order[pf_ci] >> 24;
+        cp_async_vec4<T>(xstage + (pf_seq % XD) * NPROD + tid, xb + (long)ch * HW + pf_off);
+      }
+      cp_async_commit();
+      ++pf_seq;
+      if (++pf_ci == C) { pf_ci = 0; ++pf_it; pf_tile(); }
+    };
+    pf_tile();
+#pragma unroll 1
+    for (int q = 0; q < XD - 1; ++q) pf_issue();
+
+    int seq = 0;
+#pragma unroll 1
+    for (int it = 0; it < nt; ++it) {
+      const TileCoord tc = tile_coord(j0 + it * cpi, tiles_x);
+      const int y = tc.y0 + ty, xg = tc.x0 + tx;
+      const bool inimg = y < H && xg < W;
+      const long off = (long)y * W + xg;
+      const unsigned int tf4 = inimg ? *reinterpret_cast<const unsigned int*>(lab8 + off) : 0xffffffffu;
+      unsigned int tm4 = 0xffffffffu, th4 = 0xffffffffu;
+      float vf[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const unsigned int t = (tf4 >> (8 * k)) & 0xffu;
+        vf[k] = t != SH_IGNORE ? 1.f : 0.f;
+        if (t != SH_IGNORE) {
+          tm4 = (tm4 & ~(0xffu << (8 * k))) | ((unsigned int)s_f2m[t] << (8 * k));
+          th4 = (th4 & ~(0xffu << (8 * k))) | ((unsigned int)s_f2h[t] << (8 * k));
+        }
+      }
+      float sumF[4], sumM[4], sumH[4], prodF[4], prodM[4], prodH[4], rmax[4], rmaxH[4], a_t[4], b_t[4];
+      unsigned int rhold[4], rholdH[4], hpf = 0, hpm = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        sumF[k] = sumM[k] = sumH[k] = 0.f;
+        prodF[k] = prodM[k] = prodH[k] = 1.f;
+        rmax[k] = rmaxH[k] = -1.f;
+        a_t[k] = b_t[k] = 1.f;
+        rhold[k] = rholdH[k] = 0u;
+      }
+#pragma unroll 1
+      for (int r = 0; r < RPT; ++r) {
+        const int buf = (it * RPT + r) % NBUF;
+        bar_sync(BAR_EMPTY + buf, NTHREADS);
+        const int cend = min(C, (r + 1) * NR);
+#pragma unroll 1
+        for (int ci = r * NR; ci < cend; ++ci) {
+          pf_issue();
+          cp_async_wait<XD - 1>();
+          const unsigned int oe = s_order[ci];
+          const int kind = oe & 3, cl = (oe >> 8) & 0xff, fl = (oe >> 16) & 0xff;
+          const unsigned int ch = oe >> 24;
+          float xv[4] = {0.f, 0.f, 0.f, 0.f};
+          if (inimg) staged_vec4<T>(xstage + (seq % XD) * NPROD + tid, xv);
+          ++seq;
+          float s[4], E[4], pk[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            sig_exp3(xv[k], s[k], E[k]);
+            pk[k] = fmaf(s[k], vf[k], 1e-6f);          // literally probs * valid + 1e-6 (rmi...py:487)
+          }
+          float* prow = planes + (buf * NR + (ci - r * NR)) * PLANE + (ty + 2) * PW + tx + 2;
+          *reinterpret_cast<float2*>(prow) = make_float2(pk[0], pk[1]);
+          *reinterpret_cast<float2*>(prow + 2) = make_float2(pk[2], pk[3]);
+          const unsigned int pat = (unsigned int)cl * 0x01010101u;
+          if (kind == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              sumF[k] += E[k];
+              prodF[k] *= (1.0f - s[k]) + eps;
+              if (s[k] > rmax[k]) { rmax[k] = s[k]; rhold[k] = ch; }   // lowest fine id wins ties (rmi...py:386)
+            }
+            const unsigned int z = tf4 ^ pat;
+            if (has_zero_byte(z)) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (((z >> (8 * k)) & 0xffu) == 0u) {
+                  a_t[k] = s[k];
+                  lacc[3] -= xv[k];
+                  lacc[0] -= lg2((1.0f - s[k]) + eps);     // the target's own factor does not belong to the product
+                }
+            }
+            if (fl & 2) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) { lacc[0] = fmaf(vf[k], lg2(prodF[k]), lacc[0]); prodF[k] = 1.f; }
+            }
+          } else if (kind == 1) {
+            unsigned int hd = 0;
+            float cur[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              sumM[k] += E[k];
+              cur[k] = rmax[k];
+              unsigned int hk = rhold[k];
+              if (s[k] > cur[k]) { cur[k] = s[k]; hk = ch; }                // fine max wins ties (rmi...py:386-387)
+              hd |= hk << (8 * k);
+              prodM[k] *= (1.0f - cur[k]) + eps;
+              if (cur[k] > rmaxH[k]) { rmaxH[k] = cur[k]; rholdH[k] = hk; }  // lower mid id wins ties (rmi...py:408)
+              rmax[k] = -1.f; rhold[k] = 0u;
+            }
+            if (inimg) *reinterpret_cast<unsigned int*>(ws.hold + ((size_t)cl * B + b) * HW + off) = hd;
+            const unsigned int z = tm4 ^ pat;
+            if (has_zero_byte(z)) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (((z >> (8 * k)) & 0xffu) == 0u) {
+                  b_t[k] = s[k];
+                  lacc[4] -= xv[k];
+                  lacc[1] -= lg2((1.0f - cur[k]) + eps);
+                  const bool a_holds = a_t[k] <= b_t[k];                     // fine wins ties (rmi...py:421-425)
+                  lacc[0] += lg2((a_holds ? a_t[k] : b_t[k]) + eps);
+                  hpf |= (a_holds ? ((tf4 >> (8 * k)) & 0xffu) : ch) << (8 * k);
+                }
+            }
+            if (fl & 2) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) { lacc[1] = fmaf(vf[k], lg2(prodM[k]), lacc[1]); prodM[k] = 1.f; }
+            }
+          } else {
+            unsigned int hd = 0;
+            float cur[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              sumH[k] += E[k];
+              cur[k] = rmaxH[k];
+              unsigned int hk = rholdH[k];
+              if (s[k] > cur[k]) { cur[k] = s[k]; hk = ch; }                // mid max wins ties (rmi...py:408-409)
+              hd |= hk << (8 * k);
+              prodH[k] *= (1.0f - cur[k]) + eps;
+              rmaxH[k] = -1.f; rholdH[k] = 0u;
+            }
+            if (inimg) *reinterpret_cast<unsigned int*>(ws.hold + ((size_t)(hg.nm + cl) * B + b) * HW + off) = hd;
+            const unsigned int z = th4 ^ pat;
+            if (has_zero_byte(z)) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (((z >> (8 * k)) & 0xffu) == 0u) {
+                  lacc[5] -= xv[k];
+                  lacc[2] -= lg2((1.0f - cur[k]) + eps);
+                  const bool c_holds = s[k] <= b_t[k];                       // high wins ties (rmi...py:439-440)
+                  lacc[1] += lg2((c_holds ? s[k] : b_t[k]) + eps);
+                  lacc[2] += lg2(s[k] + eps);
+                  hpm |= (c_holds ? ch : (unsigned int)hg.nf + ((tm4 >> (8 * k)) & 0xffu)) << (8 * k);
+                }
+            }
+            if (fl & 2) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) { lacc[2] = fmaf(vf[k], lg2(prodH[k]), lacc[2]); prodH[k] = 1.f; }
+            }
+          }
+        }
+        __threadfence_block();
+        bar_arrive(BAR_FULL + buf, NTHREADS);
+      }
+      // ---- per-pixel epilogue of the tile -------------------------------------------------------
+      float iv[3][4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        lacc[0] = fmaf(vf[k], lg2(prodF[k]), lacc[0]);
+        lacc[1] = fmaf(vf[k], lg2(prodM[k]), lacc[1]);
+        lacc[2] = fmaf(vf[k], lg2(prodH[k]), lacc[2]);
+        lacc[3] = fmaf(vf[k] * kLn2, lg2(sumF[k]), lacc[3]);
+        lacc[4] = fmaf(vf[k] * kLn2, lg2(sumM[k]), lacc[4]);
+        lacc[5] = fmaf(vf[k] * kLn2, lg2(sumH[k]), lacc[5]);
+        iv[0][k] = rcp(sumF[k]); iv[1][k] = rcp(sumM[k]); iv[2][k] = rcp(sumH[k]);
+      }
+      if (inimg) {
+        *reinterpret_cast<unsigned int*>(ws.hold + ((size_t)(hg.nm + hg.nh) * B + b) * HW + off) = hpf;
+        *reinterpret_cast<unsigned int*>(ws.hold + ((size_t)(hg.nm + hg.nh + 1) * B + b) * HW + off) = hpm;
+#pragma unroll
+        for (int l = 0; l < 3; ++l)
+          *reinterpret_cast<float4*>(ws.inv + ((size_t)l * B + b) * HW + off) =
+              make_float4(iv[l][0], iv[l][1], iv[l][2], iv[l][3]);
+      }
+    }
+    cp_async_wait<0>();
+    // ---- CTA totals of the six scalar sums (producer warps only) ---------------------------------
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const float v = warp_sum(lacc[k]);
+      if (lane == 0) s_red[k * 8 + warp] = v;
+    }
+    bar_sync(BAR_PROD, NPROD);
+    if (tid < 8) {
+      float r = 0.f;
+      if (tid < 6) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) r += s_red[tid * 8 + w];
+        if (tid < 3) r *= -kLn2;
+      }
+      ws.bce2[(size_t)blockIdx.x * 8 + tid] = r;
+    }
+  } else if (tid < NPROD + NHALO) {
+    // ============================== halo warps ==============================
+    const int hl = tid - NPROD;
+    // vector part: plane rows 0,1,18,19 x 16 strips ; scalar part (lanes 0..39): 20 rows x {cols 0,1 | cols 66,67}
+    const int vrow = (hl >> 4) < 2 ? (hl >> 4) : 16 + (hl >> 4), vstrip = hl & 15;
+    const bool has_s = hl < 2 * PR;
+    const int srow = has_s ? hl % PR : 0, sside = has_s ? hl / PR : 0;
+#pragma unroll 1
+    for (int it = 0; it < nt; ++it) {
+      const TileCoord tc = tile_coord(j0 + it * cpi, tiles_x);
+      const int vy = tc.y0 - 2 + vrow, vx = tc.x0 + 4 * vstrip;
+      const bool v_in = vy >= 0 && vy < H && vx < W;
+      const long v_off = (long)vy * W + vx;
+      const int sy = tc.y0 - 2 + srow, sx = sside ? tc.x0 + TW : tc.x0 - 2;
+      const bool s_in = has_s && sy >= 0 && sy < H && sx >= 0 && sx < W;
+      const long s_off = (long)sy * W + sx;
+      float vv[4] = {0.f, 0.f, 0.f, 0.f}, sv[2] = {0.f, 0.f};
+      if (v_in) {
+        const unsigned int t4 = *reinterpret_cast<const unsigned int*>(lab8 + v_off);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) vv[k] = ((t4 >> (8 * k)) & 0xffu) != SH_IGNORE ? 1.f : 0.f;
+      }
+      if (s_in) {
+        const unsigned short t2 = *reinterpret_cast<const unsigned short*>(lab8 + s_off);
+        sv[0] = (t2 & 0xffu) != SH_IGNORE ? 1.f : 0.f;
+        sv[1] = (t2 >> 8) != SH_IGNORE ? 1.f : 0.f;
+      }
+#pragma unroll 1
+      for (int r = 0; r < RPT; ++r) {
+        const int buf = (it * RPT + r) % NBUF;
+        bar_sync(BAR_EMPTY + buf, NTHREADS);
+        if (r == 0) {
+          // label bytes of the tile per level (RMI labels: void -> class 0, outside the image -> 0xff)
+          unsigned char* lt = LT + (it & 1) * 3 * TH * TW;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int wi = hl + 64 * q, row = wi >> 4, st = wi & 15;
+            const int yy = tc.y0 + row, xx = tc.x0 + 4 * st;
+            unsigned int f4 = 0xffffffffu, m4 = 0xffffffffu, g4 = 0xffffffffu;
+            if (yy < H && xx < W) {
+              const unsigned int t4 = *reinterpret_cast<const unsigned int*>(lab8 + (long)yy * W + xx);
+              f4 = m4 = g4 = 0u;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const unsigned int t = (t4 >> (8 * k)) & 0xffu;
+                if (t != SH_IGNORE) {
+                  f4 |= t << (8 * k);
+                  m4 |= (unsigned int)s_f2m[t] << (8 * k);
+                  g4 |= (unsigned int)s_f2h[t] << (8 * k);
+                }
+              }
+            }
+            *reinterpret_cast<unsigned int*>(lt + (0 * TH + row) * TW + 4 * st) = f4;
+            *reinterpret_cast<unsigned int*>(lt + (1 * TH + row) * TW + 4 * st) = m4;
+            *reinterpret_cast<unsigned int*>(lt + (2 * TH + row) * TW + 4 * st) = g4;
+          }
+        }
+        const int cend = min(C, (r + 1) * NR);
+#pragma unroll 1
+        for (int ci = r * NR; ci < cend; ++ci) {
+          const T* xc = xb + (long)(s_order[ci] >> 24) * HW;
+          float xv[4] = {0.f, 0.f, 0.f, 0.f}, xs[2] = {0.f, 0.f};
+          if (v_in) VecIO<T, 4>::load(xc + v_off, xv);
+          if (s_in) VecIO<T, 2>::load(xc + s_off, xs);
+          float* pl = planes + (buf * NR + (ci - r * NR)) * PLANE;
+          float p[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) p[k] = v_in ? fmaf(sig_only(xv[k]), vv[k], 1e-6f) : 0.f;
+          float* pr = pl + vrow * PW + 2 + 4 * vstrip;
+          *reinterpret_cast<float2*>(pr) = make_float2(p[0], p[1]);
+          *reinterpret_cast<float2*>(pr + 2) = make_float2(p[2], p[3]);
+          if (has_s) {
+            const float p0 = s_in ? fmaf(sig_only(xs[0]), sv[0], 1e-6f) : 0.f;
+            const float p1 = s_in ? fmaf(sig_only(xs[1]), sv[1], 1e-6f) : 0.f;
+            *reinterpret_cast<float2*>(pl + srow * PW + sside * (TW + 2)) = make_float2(p0, p1);
+          }
+        }
+        __threadfence_block();
+        bar_arrive(BAR_FULL + buf, NTHREADS);
+      }
+    }
+  } else {
+    // ============================== consumers ==============================
+    const int ct = tid - NPROD - NHALO, cw = ct >> 5, lane = ct & 31;
+    const int hb = lane >> 4, sb = lane & 15, i0 = hb * 8;
+    const int npre = total_rounds < NBUF ? total_rounds : NBUF;
+    for (int q = 0; q < npre; ++q) bar_arrive(BAR_EMPTY + q, NTHREADS);
+#pragma unroll 1
+    for (int it = 0; it < nt; ++it) {
+      const TileCoord tc = tile_coord(j0 + it * cpi, tiles_x);
+      const bool border = tc.y0 < 2 || tc.y0 + TH > H - 2 || tc.x0 < 2 || tc.x0 + TW > W - 2;
+      // interior masks (only used by border tiles): plane rows i0..i0+11 and window cols 0..7
+      unsigned int rowI = 0, colI = 0;
+      if (border) {
+#pragma unroll
+        for (int q = 0; q < 12; ++q) { const int yy = tc.y0 - 2 + i0 + q; if (yy >= 2 && yy < H - 2) rowI |= 1u << q; }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { const int xx = tc.x0 - 2 + 4 * sb + q; if (xx >= 2 && xx < W - 2) colI |= 1u << q; }
+      }
+      const unsigned char* lt = LT + (it & 1) * 3 * TH * TW;
+      unsigned int present[3] = {0u, 0u, 0u};
+#pragma unroll 1
+      for (int r = 0; r < RPT; ++r) {
+        const int R = it * RPT + r, buf = R % NBUF;
+        bar_sync(BAR_FULL + buf, NTHREADS);
+        if (r == 0) {
+#pragma unroll
+          for (int l = 0; l < 3; ++l) {
+            unsigned int pm = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const unsigned int wd = *reinterpret_cast<const unsigned int*>(lt + (l * TH + i0 + i) * TW + 4 * sb);
+              pm |= (1u << (wd & 31)) | (1u << ((wd >> 8) & 31)) | (1u << ((wd >> 16) & 31)) | (1u << ((wd >> 24) & 31));
+            }
+            present[l] = pm;
+          }
+        }
+        const int ci = r * NR + cw;
+        if (ci < C) {
+          const unsigned int oe = s_order[ci];
+          const int lvl = oe & 3, cl = (oe >> 8) & 0xff;
+          const unsigned int ch = oe >> 24;
+          const float* pl = planes + (buf * NR + cw) * PLANE + i0 * PW + 4 * sb;   // window row 0 = plane row i0
+          double* trow = tot + (size_t)ch * kFastRec;
+          // ---- pr_cov: 13 product taps of the interior anchors (anchor = centre row, taps forward) ----
+          {
+            float acc[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) acc[q] = 0.f;
+            float w[3][8];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const float4 a = *reinterpret_cast<const float4*>(pl + (2 + q) * PW);
+              const float4 c4 = *reinterpret_cast<const float4*>(pl + (2 + q) * PW + 4);
+              w[q][0] = a.x; w[q][1] = a.y; w[q][2] = a.z; w[q][3] = a.w;
+              w[q][4] = c4.x; w[q][5] = c4.y; w[q][6] = c4.z; w[q][7] = c4.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float(&r0)[8] = w[i % 3];
+              float(&r1)[8] = w[(i + 1) % 3];
+              float(&r2)[8] = w[(i + 2) % 3];
+              {
+                const float4 a = *reinterpret_cast<const float4*>(pl + (4 + i) * PW);
+                const float4 c4 = *reinterpret_cast<const float4*>(pl + (4 + i) * PW + 4);
+                r2[0] = a.x; r2[1] = a.y; r2[2] = a.z; r2[3] = a.w;
+                r2[4] = c4.x; r2[5] = c4.y; r2[6] = c4.z; r2[7] = c4.w;
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float p = r0[k + 2];
+                float a = p;
+                if (border) a = (((rowI >> (i + 2)) & 1u) && ((colI >> (k + 2)) & 1u)) ? p : 0.f;
+                acc[0] = fmaf(a, p, acc[0]);
+                acc[1] = fmaf(a, r0[k + 3], acc[1]);
+                acc[2] = fmaf(a, r0[k + 4], acc[2]);
+#pragma unroll
+                for (int dx = 0; dx < 5; ++dx) {
+                  acc[3 + dx] = fmaf(a, r1[k + dx], acc[3 + dx]);
+                  acc[8 + dx] = fmaf(a, r2[k + dx], acc[8 + dx]);
+                }
+              }
+            }
+            const float t = warp_reduce16(acc, lane);
+            if ((lane & 1) == 0) {
+              const int slot = reduce16_slot(lane);
+              if (slot < 13) trow[slot] += (double)t;
+            }
+          }
+          // ---- la_pr: label-anchored taps  lp[d] = sum_{q : L(q) = cl} PI(q - d),  PI = P on interior anchors, else 0 ----
+          const bool hit = (present[lvl] >> (cl & 31)) & 1u;
+          if (__any_sync(0xffffffffu, hit)) {
+            float al[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) al[q] = 0.f;
+            if (hit) {
+              const unsigned int pat = (unsigned int)cl * 0x01010101u;
+              float w[5][8];
+              auto load_row = [&](float(&dst)[8], int prow) {
+                const float4 a = *reinterpret_cast<const float4*>(pl + prow * PW);
+                const float4 c4 = *reinterpret_cast<const float4*>(pl + prow * PW + 4);
+                dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w;
+                dst[4] = c4.x; dst[5] = c4.y; dst[6] = c4.z; dst[7] = c4.w;
+                if (border) {
+                  const bool rok = (rowI >> prow) & 1u;
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) dst[q] = (rok && ((colI >> q) & 1u)) ? dst[q] : 0.f;
+                }
+              };
+#pragma unroll
+              for (int q = 0; q < 4; ++q) load_row(w[q], q);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                load_row(w[(i + 4) % 5], i + 4);
+                const unsigned int z =
+                    *reinterpret_cast<const unsigned int*>(lt + (lvl * TH + i0 + i) * TW + 4 * sb) ^ pat;
+                if (has_zero_byte(z)) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    if (((z >> (8 * k)) & 0xffu) == 0u) {
+#pragma unroll
+                      for (int a = 0; a < 5; ++a)
+#pragma unroll
+                        for (int bq = 0; bq < 5; ++bq)      // window row a <-> dy = 2 - a ; col k+bq <-> dx = 2 - bq
+                          al[24 - (a * 5 + bq)] += w[(i + a) % 5][k + bq];
+                    }
+                }
+              }
+            }
+            const float t0 = warp_reduce16(*reinterpret_cast<float(*)[16]>(al), lane);
+            const float t1 = warp_reduce16(*reinterpret_cast<float(*)[16]>(al + 16), lane);
+            if ((lane & 1) == 0) {
+              const int slot = reduce16_slot(lane);
+              trow[13 + slot] += (double)t0;
+              if (slot < 9) trow[29 + slot] += (double)t1;
+            }
+          }
+          __syncwarp();
+        }
+        if (R < total_rounds - NBUF) bar_arrive(BAR_EMPTY + buf, NTHREADS);
+      }
+    }
+    // ---- records of the channels this warp owned ------------------------------------------------
+    __syncwarp();
+    for (int ci = cw; ci < C; ci += NR) {
+      const unsigned int ch = s_order[ci] >> 24;
+      double* rec = ws.rec2 + ((size_t)blockIdx.x * C + ch) * kFastRec;
+      for (int q = lane; q < kFastRec; q += 32) rec[q] = tot[(size_t)ch * kFastRec + q];
+    }
+  }
+}
+
+}  // namespace fast
+}  // namespace sh

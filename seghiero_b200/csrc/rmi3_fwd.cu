@@ -9,6 +9,7 @@
 //   k3_loss     scalar loss assembly (device side, no host sync)
 // Reference arithmetic: models/loss/rmi_hiera_triplet_loss.py:323-546.
 #include "rmi3_common.cuh"
+#include "rmi3_fast.cuh"
 
 namespace sh {
 
@@ -677,12 +678,28 @@ __device__ void mm9(const double* X, bool xt, const double* Y, bool yt, double* 
   __syncwarp();
 }
 
+// frame records of (b, c) summed over the segments -> fr[25][kFrameRec] (doubles)
+__device__ void load_frame_records(double* fr, int bc, int B, int C, int nseg, const Ws3& ws, int tid) {
+  for (int e = tid; e < 25 * kFrameRec; e += 256) {
+    const int k = e % kFrameRec;
+    double a = 0.0;
+    if (k < 4) {
+      if ((k & 1) == 0)
+        for (int s = 0; s < nseg; ++s)
+          a += *reinterpret_cast<const double*>(ws.frameT + ((size_t)s * B * C + bc) * 25 * kFrameRec + e);
+    } else {
+      for (int s = 0; s < nseg; ++s) a += (double)ws.frameT[((size_t)s * B * C + bc) * 25 * kFrameRec + e];
+    }
+    fr[e] = a;
+  }
+}
+
+__device__ void finalize_core(const double* part, const double* fr, int bc, const Ws3& ws, double scale, int tid);
+
 __global__ void __launch_bounds__(256) k3_finalize(int B, int C, long tiles_per_img, int nseg, Ws3 ws, double scale) {
   __shared__ double part4[4][kRec];
   __shared__ double part[kRec];
   __shared__ double fr[25 * kFrameRec];
-  __shared__ double Spp[81], Slp[81], Sll[81], K[81], T1[81], M[81], Wm[81], U[81], Gpp[81], tmp[81];
-  __shared__ double piv[9], fac[9];
   const int bc = blockIdx.x, b = bc / C, c = bc % C;
   const int tid = threadIdx.x;
   {
@@ -698,21 +715,49 @@ __global__ void __launch_bounds__(256) k3_finalize(int B, int C, long tiles_per_
     }
     part4[sl][k] = a;
   }
-  for (int e = tid; e < 25 * kFrameRec; e += 256) {
-    const int k = e % kFrameRec;
-    double a = 0.0;
-    if (k < 4) {
-      if ((k & 1) == 0)
-        for (int s = 0; s < nseg; ++s)
-          a += *reinterpret_cast<const double*>(ws.frameT + ((size_t)s * B * C + bc) * 25 * kFrameRec + e);
-    } else {
-      for (int s = 0; s < nseg; ++s) a += (double)ws.frameT[((size_t)s * B * C + bc) * 25 * kFrameRec + e];
-    }
-    fr[e] = a;
-  }
+  load_frame_records(fr, bc, B, C, nseg, ws, tid);
   __syncthreads();
   if (tid < kRec) part[tid] = part4[0][tid] + part4[1][tid] + part4[2][tid] + part4[3][tid];
   __syncthreads();
+  finalize_core(part, fr, bc, ws, scale, tid);
+}
+
+// fast path: records are per (persistent CTA, channel): fp64 product taps + label-anchored lp taps
+// (ws.rec2) and integer label-label counts (ws.llrec); rewritten into the record layout of the generic path
+__global__ void __launch_bounds__(256) k3f_finalize(int B, int C, int cpi, int nseg, Ws3 ws, double scale) {
+  __shared__ double part[kRec];
+  __shared__ double fr[25 * kFrameRec];
+  __shared__ double raw[64];
+  const int bc = blockIdx.x, b = bc / C, c = bc % C;
+  const int tid = threadIdx.x;
+  if (tid < 64) {
+    double a = 0.0;
+    if (tid < 38) {
+      for (int j = 0; j < cpi; ++j) a += ws.rec2[((size_t)(b * cpi + j) * C + c) * kFastRec + tid];
+    } else if (tid < 38 + 13) {
+      unsigned long long n = 0;
+      for (int j = 0; j < cpi; ++j) n += ws.llrec[((size_t)(b * cpi + j) * C + c) * 16 + (tid - 38)];
+      a = (double)n;
+    }
+    raw[tid] = a;
+  }
+  load_frame_records(fr, bc, B, C, nseg, ws, tid);
+  __syncthreads();
+  if (tid < kRec) {
+    double v = 0.0;
+    if (tid >= kD && tid < kD + 12) v = raw[1 + (tid - kD)] - raw[0];   // difference form of the generic records
+    else if (tid == kT0) v = raw[0];
+    else if (tid >= kLPS && tid < kLPS + 25) v = raw[13 + (tid - kLPS)];
+    else if (tid >= kLLS && tid < kLLS + 13) v = raw[38 + (tid - kLLS)];
+    part[tid] = v;                                                       // kLLFull, kLPFull = 0
+  }
+  __syncthreads();
+  finalize_core(part, fr, bc, ws, scale, tid);
+}
+
+__device__ void finalize_core(const double* part, const double* fr, int bc, const Ws3& ws, double scale, int tid) {
+  __shared__ double Spp[81], Slp[81], Sll[81], K[81], T1[81], M[81], Wm[81], U[81], Gpp[81], tmp[81];
+  __shared__ double piv[9], fac[9];
   // assemble
   for (int e = tid; e < 81; e += 256) {
     const int i = e / 9, j = e % 9;
@@ -861,6 +906,57 @@ static size_t pass1_smem_bytes(int nh) {
   return (s + 15) & ~(size_t)15;
 }
 
+// Can the warp-specialised kernels of rmi3_fast.cuh run this problem?
+bool fast_path_ok(const void* x, const void* grad, int elem, int H, int W, int nf, int nm, int nh, int fast_tab_ok) {
+  const int C = nf + nm + nh;
+  if (!fast_tab_ok || C <= fast::NR || C > fast::kFastMaxC) return false;
+  if ((W & 3) != 0 || H < 8 || W < 8) return false;
+  if ((uintptr_t)x % (4 * (size_t)elem) != 0) return false;
+  if (grad != nullptr && (uintptr_t)grad % (4 * (size_t)elem) != 0) return false;
+  return true;
+}
+
+template <typename T>
+static int run_forward3_fast(const void* x, const long long* label, int B, int H, int W, const Hier3& h, const Ws3& ws,
+                             float* bandR, float* bandC, float eps, double scale, int stages, cudaStream_t st) {
+  const int C = h.nf + h.nm + h.nh;
+  fast::FastHier fh;
+  fh.nf = h.nf; fh.nm = h.nm; fh.nh = h.nh; fh.f2m = h.f2m; fh.f2h = h.f2h; fh.order = h.order + C;
+  const int cpi = ws.cpi, grid = B * cpi;
+  if (stages & 1) {
+    cudaError_t e = cudaMemsetAsync(ws.counts, 0, 4 * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return (int)e;
+    dim3 gp((W + kTW - 1) / kTW, (H + 15) / 16, B);
+    k3_prep<<<gp, 256, 0, st>>>(label, B, H, W, h, ws.lab8, ws.flags, ws.counts);
+    SH_CHECK_LAUNCH();
+    const size_t smem = fast::prep_smem(C, h.nf);
+    cudaFuncSetAttribute(fast::k3f_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    fast::k3f_prep<<<grid, 256, smem, st>>>(label, B, H, W, fh, ws, cpi, 1);
+    SH_CHECK_LAUNCH();
+  }
+  if (stages & 2) {
+    const size_t smem = fast::pass1_smem(C, h.nf);
+    if (smem > 227 * 1024) return SH_ERR_UNSUPPORTED;
+    auto kern = fast::k3f_pass1<T>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, fast::NTHREADS, smem, st>>>((const T*)x, B, H, W, fh, ws, eps, cpi);
+    SH_CHECK_LAUNCH();
+  }
+  if (stages & 4) {
+    k3_band<T><<<dim3(B * C, 4), 256, 0, st>>>((const T*)x, B, C, H, W, ws.lab8, bandR, bandC);
+    SH_CHECK_LAUNCH();
+    k3_frame1<<<dim3(B * C, ws.nseg), 256, 0, st>>>(B, H, W, h, ws, bandR, bandC);
+    SH_CHECK_LAUNCH();
+  }
+  if (stages & 8) {
+    k_reduce_partials3<<<6, 256, 0, st>>>(ws.bce2, (long)grid, 8, ws.sums);
+    SH_CHECK_LAUNCH();
+    k3f_finalize<<<B * C, 256, 0, st>>>(B, C, cpi, ws.nseg, ws, scale);
+    SH_CHECK_LAUNCH();
+  }
+  return SH_OK;
+}
+
 template <typename T>
 static int run_forward3(const void* x, const long long* label, int B, int H, int W, const Hier3& h, const Ws3& ws,
                         float* bandR, float* bandC, float eps, double scale, int stages, cudaStream_t st) {
@@ -918,11 +1014,30 @@ int sh_rmi3_workspace_offsets(int B, int H, int W, int nf, int nm, int nh, size_
 }
 
 // hier_tab (device int32): [f2m nf][f2h nf][mh_ptr nm+1][mh_idx n_mh][hsmask nm][order C]
+int sh_rmi3_fast_path(const void* logits, const void* grad, int dtype, int H, int W, int nf, int nm, int nh,
+                      int fast_tab_ok) {
+  return sh::fast_path_ok(logits, grad, dtype == SH_DT_F32 ? 4 : 2, H, W, nf, nm, nh, fast_tab_ok) ? 1 : 0;
+}
+
 int sh_rmi3_forward(const void* logits, int dtype, const long long* label, int B, int H, int W, int nf, int nm, int nh,
-                    const int* hier_tab, int n_mh, float lam, float loss_weight, void* workspace, int stages,
-                    void* stream) {
+                    const int* hier_tab, int n_mh, int fast_tab_ok, float lam, float loss_weight, void* workspace,
+                    int stages, void* stream) {
   if (B <= 0 || H < 8 || W < 8 || nf <= 0 || nm <= 0 || nh <= 0 || nf + nm + nh > 254 || nh > 32)
     return SH_ERR_BAD_ARG;
+  if (sh::fast_path_ok(logits, nullptr, dtype == SH_DT_F32 ? 4 : 2, H, W, nf, nm, nh, fast_tab_ok)) {
+    sh::Ws3 wsf = sh::ws3_layout(workspace, B, H, W, nf, nm, nh);
+    float* bR = (float*)((unsigned char*)workspace + wsf.bytes);
+    float* bC = bR + (size_t)B * (nf + nm + nh) * 8 * W;
+    sh::Hier3 hf = sh::hier3_from_tab(hier_tab, nf, nm, nh, n_mh);
+    const double sc = (double)lam * (double)loss_weight / (9.0 * B);
+    cudaStream_t s2 = (cudaStream_t)stream;
+    switch (dtype) {
+      case SH_DT_F32: return sh::run_forward3_fast<float>(logits, label, B, H, W, hf, wsf, bR, bC, 1e-6f, sc, stages, s2);
+      case SH_DT_BF16: return sh::run_forward3_fast<__nv_bfloat16>(logits, label, B, H, W, hf, wsf, bR, bC, 1e-6f, sc, stages, s2);
+      case SH_DT_F16: return sh::run_forward3_fast<__half>(logits, label, B, H, W, hf, wsf, bR, bC, 1e-6f, sc, stages, s2);
+    }
+    return SH_ERR_UNSUPPORTED;
+  }
   sh::Ws3 ws = sh::ws3_layout(workspace, B, H, W, nf, nm, nh);
   float* bandR = (float*)((unsigned char*)workspace + ws.bytes);
   float* bandC = bandR + (size_t)B * (nf + nm + nh) * 8 * W;

@@ -68,10 +68,55 @@ def three_level_tables(n_fine: int, n_mid: int, n_high: int, fine_to_mid, fine_t
         mh_ptr[m + 1] = len(mh_idx)
         for h in mh[m]:                                   # Hs(m) = {f2h[f] : f in F(m)} -- the same set
             hsmask[m] |= np.uint32(1) << np.uint32(h)
+    fast = fast_tree_order(n_fine, n_mid, n_high, f2m, f2h)
+    fast_ok = fast is not None
+    if fast is None:
+        fast = np.zeros(n_fine + n_mid + n_high, dtype=np.int32)
     blob = np.concatenate([f2m.astype(np.int32), f2h.astype(np.int32), mh_ptr,
                            np.array(mh_idx, dtype=np.int32), hsmask.view(np.int32),
-                           tree_order(n_fine, n_mid, n_high, f2m)]).astype(np.int32)
-    return blob, len(mh_idx)
+                           tree_order(n_fine, n_mid, n_high, f2m), fast]).astype(np.int32)
+    return blob, len(mh_idx), int(fast_ok)
+
+
+def fast_tree_order(n_fine: int, n_mid: int, n_high: int, f2m, f2h):
+    """Channel order of the warp-specialised kernels (csrc/rmi3_fast.cuh), or None when the maps are
+    not a tree (some mid with fine children under two different highs): per high h, per mid m under h
+    (ascending) the fine children of m (ascending) then m, then h itself; mids/highs without children
+    come in id order.  Entry = kind | class << 8 | flags << 16 | channel << 24, flags bit1 = flush the
+    level's running product of (1 - s + eps) factors (at most 5 factors of >= 1e-6 stay in fp32 range)."""
+    f2m = [int(v) for v in f2m]
+    f2h = [int(v) for v in f2h]
+    mid_high = {}
+    for f in range(n_fine):
+        if mid_high.setdefault(f2m[f], f2h[f]) != f2h[f]:
+            return None
+    entries = []
+    placed_mid = set()
+
+    def put_mid(m):
+        for f in range(n_fine):
+            if f2m[f] == m:
+                entries.append([0, f, 0, f])
+        entries.append([1, m, 0, n_fine + m])
+        placed_mid.add(m)
+
+    for h in range(n_high):
+        for m in range(n_mid):
+            if mid_high.get(m) == h:
+                put_mid(m)
+        entries.append([2, h, 0, n_fine + n_mid + h])
+    # childless mids: their max is their own sigmoid and they feed no high; order is irrelevant but
+    # they must not sit between a high's mids and the high itself
+    for m in range(n_mid):
+        if m not in placed_mid:
+            put_mid(m)
+    seen = [0, 0, 0]
+    for e in entries:
+        seen[e[0]] += 1
+        if seen[e[0]] % 5 == 0:
+            e[2] |= 2
+    assert len(entries) == n_fine + n_mid + n_high
+    return np.array([k | (c << 8) | (fl << 16) | (ch << 24) for k, c, fl, ch in entries], dtype=np.uint32).view(np.int32)
 
 
 def tree_order(n_fine: int, n_mid: int, n_high: int, f2m) -> np.ndarray:

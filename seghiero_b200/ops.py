@@ -32,6 +32,7 @@ _KERNELS = {
     ("sh_rmi3_backward", 1): 1, ("sh_rmi3_backward", 2): 1,
 }
 LAUNCHES = {"n": 0}
+FAST_PATH = {"enabled": True}   # tests flip this to cover the generic kernels on shapes the fast path would take
 STAGE_TIMER = None   # bench.py installs an object with start(name, bit) / stop(name, bit)
 
 
@@ -365,8 +366,10 @@ class RMIHieraTriplet3Fn(torch.autograd.Function):
         if hh < 8 or ww < 8:
             raise ValueError("the CUDA RMI path needs H, W >= 8 (the reference needs >= 3)")
         key = ("h3", cfg.n_fine, cfg.n_mid, cfg.n_high, cfg.fine_to_mid, cfg.fine_to_high)
-        tab, n_mh = device_table(key, lambda: H.three_level_tables(cfg.n_fine, cfg.n_mid, cfg.n_high,
-                                                                   cfg.fine_to_mid, cfg.fine_to_high), dev)
+        tab, n_mh, fast_ok = device_table(key, lambda: H.three_level_tables(cfg.n_fine, cfg.n_mid, cfg.n_high,
+                                                                            cfg.fine_to_mid, cfg.fine_to_high), dev)
+        if not FAST_PATH["enabled"]:
+            fast_ok = 0
         st = None
         if embedding is not None and cfg.use_triplet:
             tkey = ("t1", cfg.upper_ids, cfg.lower_ids)
@@ -380,14 +383,14 @@ class RMIHieraTriplet3Fn(torch.autograd.Function):
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             out = torch.empty(4, dtype=torch.float32, device=dev)
             _staged("sh_rmi3_forward", (1, 2, 4, 8), lambda st_bits: (
-                _p(x), _dtype_code(x), _p(lab), b, hh, ww, cfg.n_fine, cfg.n_mid, cfg.n_high, _p(tab), n_mh, cfg.lam,
-                cfg.loss_weight, _p(ws), st_bits, _stream()))
+                _p(x), _dtype_code(x), _p(lab), b, hh, ww, cfg.n_fine, cfg.n_mid, cfg.n_high, _p(tab), n_mh, fast_ok,
+                cfg.lam, cfg.loss_weight, _p(ws), st_bits, _stream()))
             _call("sh_loss3_final", b, hh, ww, cfg.n_fine, cfg.n_mid, cfg.n_high, _p(ws), cfg.lam, _p(step_d),
                       cfg.total_steps, _p(st.trip) if st else None, _p(st.status) if st else None, cfg.loss_weight,
                       _p(out), _stream())
         stats.update(out=out, triplet=st, workspace=ws)
         ctx.cfg = cfg
-        ctx.tab, ctx.n_mh = tab, n_mh
+        ctx.tab, ctx.n_mh, ctx.fast_ok = tab, n_mh, fast_ok
         ctx.st = st
         ctx.out = out
         ctx.ws = ws if ctx.needs_input_grad[0] else None
@@ -408,7 +411,7 @@ class RMIHieraTriplet3Fn(torch.autograd.Function):
             with torch.cuda.device(x.device):
                 _staged("sh_rmi3_backward", (1, 2), lambda st_bits: (
                     _p(x), _dtype_code(x), _p(gx), b, hh, ww, cfg.n_fine, cfg.n_mid, cfg.n_high, _p(ctx.tab), ctx.n_mh,
-                    cfg.loss_weight, _p(ctx.ws), _p(g), st_bits, _stream()))
+                    ctx.fast_ok, cfg.loss_weight, _p(ctx.ws), _p(g), st_bits, _stream()))
         gemb = None
         if ctx.st is not None and ctx.needs_input_grad[1]:
             gemb = triplet_backward(ctx.emb, ctx.st, ctx.out[1:2], g)
