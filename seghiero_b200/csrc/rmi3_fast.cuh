@@ -4,16 +4,16 @@
 // aligned and 8 < C <= kFastMaxC; everything else runs the generic kernels of rmi3_fwd.cu / rmi3_bwd.cu.
 // Reference arithmetic: models/loss/rmi_hiera_triplet_loss.py:323-546.
 //
-// One CTA per SM (576 threads), each walking tiles (64 x 16 pixels) of ONE image:
+// One CTA per SM (512 threads), each walking tiles (64 x 16 pixels) of ONE image:
 //   warps 0-7   producers : thread = 4 consecutive pixels, all channels in tree order (fine children,
 //                           their mid, ..., then the high).  sigmoid / e^x from 3 MUFU ops, tree BCE +
 //                           CE sums in registers, P = s*valid + 1e-6 -> shared-memory channel plane.
-//   warps 8-9   halo      : the 2-pixel ring of every plane (sigmoid only) + the tile's label bytes.
-//   warps 10-17 consumers : warp = one channel plane of the round, thread = 4 x 8 block.  RMI moments
+//   warp  8     halo      : the 2-pixel ring of every plane (sigmoid only) + the tile's label bytes.
+//   warps 9-15  consumers : warp = one channel plane of the round, thread = 4 x 8 block.  RMI moments
 //                           of the interior anchors as 13 product taps (pr_cov) + 25 label-anchored taps
 //                           (la_pr), warp-reduced and accumulated in fp64 per CTA.
 // Planes travel producer -> consumer through a ring of kNBuf round buffers (kNR planes each) guarded by
-// named barriers (bar.arrive / bar.sync); logits are prefetched 5 channels ahead with cp.async.
+// named barriers (bar.arrive / bar.sync); logits are prefetched 6 channels ahead with cp.async.
 #pragma once
 #include "rmi3_common.cuh"
 
@@ -24,12 +24,12 @@ constexpr int TW = 64, TH = 16;
 constexpr int PW = TW + 4;           // plane pitch: cols x0-2 .. x0+65
 constexpr int PR = TH + 4;           // plane rows:  y0-2 .. y0+17
 constexpr int PLANE = PR * PW;       // 1360 floats
-constexpr int NR = 8;                // planes per round = consumer warps
+constexpr int NR = 7;                // planes per round = consumer warps
 constexpr int NBUF = 3;              // round buffers
-constexpr int NPROD = 256, NHALO = 64, NCONS = 256;
-constexpr int NTHREADS = NPROD + NHALO + NCONS;   // 576
-constexpr int XD = 6;                // cp.async ring depth (channels in flight per producer thread)
-constexpr int BAR_FULL = 1, BAR_EMPTY = 1 + NBUF, BAR_PROD = 1 + 2 * NBUF;
+constexpr int NPROD = 256, NHALO = 32, NCONS = 32 * NR;
+constexpr int NTHREADS = NPROD + NHALO + NCONS;   // 512: 8 producer warps, 1 halo warp, 7 consumer warps (128 registers each)
+constexpr int XD = 8;                // cp.async ring depth (power of two; XD-2 channels in flight per producer thread)
+constexpr int BAR_FULL = 1, BAR_EMPTY = 1 + NBUF, BAR_PROD = 1 + 2 * NBUF, BAR_HALO = 2 + 2 * NBUF;
 constexpr int kFastMaxC = 160;
 
 // order entry: kind (0 fine / 1 mid / 2 high) | class << 8 | flags << 16 | channel << 24 ; flags bit1 = flush products
@@ -189,13 +189,137 @@ inline size_t prep_smem(int C, int nf) {
   return (size_t)C * 16 * 4 + (size_t)2 * nf * 4 + (size_t)3 * (TH + 2) * LPITCH + 16;
 }
 
+// tile walk of a persistent CTA without integer divisions: tile index advances by cpi per step
+struct TileWalk {
+  int tyi, txi, tiles_x, step_y, step_x;
+  __device__ __forceinline__ void init(int first, int cpi, int tx_count) {
+    tiles_x = tx_count;
+    tyi = first / tx_count; txi = first - tyi * tx_count;
+    step_y = cpi / tx_count; step_x = cpi - step_y * tx_count;
+  }
+  __device__ __forceinline__ void next() {
+    tyi += step_y; txi += step_x;
+    if (txi >= tiles_x) { txi -= tiles_x; ++tyi; }
+  }
+  __device__ __forceinline__ int y0() const { return tyi * TH; }
+  __device__ __forceinline__ int x0() const { return txi * TW; }
+};
+
+constexpr int PMW = 2 * 3 * 32;   // presence words per tile: [level][block] x {info, hash}
+
 inline size_t pass1_smem(int C, int nf) {
   size_t s = (size_t)NBUF * NR * PLANE * 4;          // planes
   s += (size_t)XD * NPROD * 16;                      // cp.async staging
+  s += (size_t)XD * NHALO * 48;                      // cp.async staging of the halo warp
   s += (size_t)2 * 3 * TH * TW;                      // label tiles (two tile parities)
+  s += (size_t)2 * PMW * 4;                          // presence words (two tile parities)
   s += (size_t)C * kFastRec * 8;                     // fp64 totals
+  s += (size_t)C * 8;                                // channel byte offsets
   s += (size_t)(C + 2 * nf) * 4 + 64 * 4;            // tables + reduction scratch
   return (s + 15) & ~(size_t)15;
+}
+
+// 13 product taps of one 4 x 8 block: anchors = centre rows (window rows 2..9), taps forward
+template <bool BORDER>
+__device__ __forceinline__ void pp_taps(const float* pl, unsigned int rowI, unsigned int colI, float (&acc)[16]) {
+  float w[3][8];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const float4 a = *reinterpret_cast<const float4*>(pl + (2 + q) * PW);
+    const float4 c4 = *reinterpret_cast<const float4*>(pl + (2 + q) * PW + 4);
+    w[q][0] = a.x; w[q][1] = a.y; w[q][2] = a.z; w[q][3] = a.w;
+    w[q][4] = c4.x; w[q][5] = c4.y; w[q][6] = c4.z; w[q][7] = c4.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float(&r0)[8] = w[i % 3];
+    float(&r1)[8] = w[(i + 1) % 3];
+    float(&r2)[8] = w[(i + 2) % 3];
+    {
+      const float4 a = *reinterpret_cast<const float4*>(pl + (4 + i) * PW);
+      const float4 c4 = *reinterpret_cast<const float4*>(pl + (4 + i) * PW + 4);
+      r2[0] = a.x; r2[1] = a.y; r2[2] = a.z; r2[3] = a.w;
+      r2[4] = c4.x; r2[5] = c4.y; r2[6] = c4.z; r2[7] = c4.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float p = r0[k + 2];
+      float a = p;
+      if (BORDER) a = (((rowI >> (i + 2)) & 1u) && ((colI >> (k + 2)) & 1u)) ? p : 0.f;
+      acc[0] = fmaf(a, p, acc[0]);
+      acc[1] = fmaf(a, r0[k + 3], acc[1]);
+      acc[2] = fmaf(a, r0[k + 4], acc[2]);
+#pragma unroll
+      for (int dx = 0; dx < 5; ++dx) {
+        acc[3 + dx] = fmaf(a, r1[k + dx], acc[3 + dx]);
+        acc[8 + dx] = fmaf(a, r2[k + dx], acc[8 + dx]);
+      }
+    }
+  }
+}
+
+template <bool BORDER>
+__device__ __forceinline__ void load_row8(const float* pl, int prow, unsigned int rowI, unsigned int colI, float (&dst)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(pl + prow * PW);
+  const float4 c4 = *reinterpret_cast<const float4*>(pl + prow * PW + 4);
+  dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w;
+  dst[4] = c4.x; dst[5] = c4.y; dst[6] = c4.z; dst[7] = c4.w;
+  if (BORDER) {
+    const bool rok = (rowI >> prow) & 1u;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) dst[q] = (rok && ((colI >> q) & 1u)) ? dst[q] : 0.f;
+  }
+}
+
+// la_pr taps of one 4 x 8 block, label-anchored:  lp[d] = sum_{q in block, L(q) = cl} PI(q - d).
+//   uniform block of class cl: box sums (column sums over the 8 rows, slid down 4 times, then 4-wide row sums);
+//   mixed block: per matching pixel, 25 adds from the 5-row window.
+template <bool BORDER>
+__device__ __forceinline__ void lp_taps(const float* pl, const unsigned char* ltrow, bool uniform, unsigned int pat,
+                                        unsigned int rowI, unsigned int colI, float (&al)[32]) {
+  if (uniform) {
+    float S[8], t[8];
+    load_row8<BORDER>(pl, 0, rowI, colI, S);
+#pragma unroll
+    for (int r = 1; r < 8; ++r) {
+      load_row8<BORDER>(pl, r, rowI, colI, t);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) S[q] += t[q];
+    }
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+      if (a > 0) {
+        load_row8<BORDER>(pl, a - 1, rowI, colI, t);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) S[q] -= t[q];
+        load_row8<BORDER>(pl, a + 7, rowI, colI, t);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) S[q] += t[q];
+      }
+#pragma unroll
+      for (int bq = 0; bq < 5; ++bq) al[24 - (a * 5 + bq)] += (S[bq] + S[bq + 1]) + (S[bq + 2] + S[bq + 3]);
+    }
+  } else {
+    float w[5][8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) load_row8<BORDER>(pl, q, rowI, colI, w[q]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      load_row8<BORDER>(pl, i + 4, rowI, colI, w[(i + 4) % 5]);
+      const unsigned int z = *reinterpret_cast<const unsigned int*>(ltrow + i * TW) ^ pat;
+      if (has_zero_byte(z)) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (((z >> (8 * k)) & 0xffu) == 0u) {
+#pragma unroll
+            for (int a = 0; a < 5; ++a)
+#pragma unroll
+              for (int bq = 0; bq < 5; ++bq)      // window row a <-> dy = 2 - a ; col k+bq <-> dx = 2 - bq
+                al[24 - (a * 5 + bq)] += w[(i + a) % 5][k + bq];
+          }
+      }
+    }
+  }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -208,15 +332,23 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
   const int C = hg.nf + hg.nm + hg.nh;
   float* planes = reinterpret_cast<float*>(smem_raw);                                   // [NBUF][NR][PLANE]
   uint4* xstage = reinterpret_cast<uint4*>(planes + NBUF * NR * PLANE);                  // [XD][NPROD]
-  unsigned char* LT = reinterpret_cast<unsigned char*>(xstage + XD * NPROD);             // [2][3][TH][TW]
-  double* tot = reinterpret_cast<double*>(LT + 2 * 3 * TH * TW);                         // [C][kFastRec]
-  unsigned int* s_order = reinterpret_cast<unsigned int*>(tot + (size_t)C * kFastRec);   // [C]
+  unsigned char* hstage = reinterpret_cast<unsigned char*>(xstage + XD * NPROD);         // [XD][NHALO][48]
+  unsigned char* LT = hstage + XD * NHALO * 48;                                          // [2][3][TH][TW]
+  unsigned int* PM = reinterpret_cast<unsigned int*>(LT + 2 * 3 * TH * TW);              // [2][3][32][2]
+  double* tot = reinterpret_cast<double*>(PM + 2 * PMW);                                 // [C][kFastRec]
+  long long* s_chb = reinterpret_cast<long long*>(tot + (size_t)C * kFastRec);           // [C] channel byte offsets (order index)
+  unsigned int* s_order = reinterpret_cast<unsigned int*>(s_chb + C);                    // [C]
   int* s_f2m = reinterpret_cast<int*>(s_order + C);                                      // [nf]
   int* s_f2h = s_f2m + hg.nf;                                                            // [nf]
   float* s_red = reinterpret_cast<float*>(s_f2h + hg.nf);                                // [64]
 
   const int tid = threadIdx.x;
-  for (int i = tid; i < C; i += NTHREADS) s_order[i] = hg.order[i];
+  const long HW = (long)H * W;
+  for (int i = tid; i < C; i += NTHREADS) {
+    const unsigned int oe = hg.order[i];
+    s_order[i] = oe;
+    s_chb[i] = (long long)(oe >> 24) * HW * (long long)sizeof(T);
+  }
   for (int i = tid; i < hg.nf; i += NTHREADS) { s_f2m[i] = hg.f2m[i]; s_f2h[i] = hg.f2h[i]; }
   for (int i = tid; i < C * kFastRec; i += NTHREADS) tot[i] = 0.0;
   __syncthreads();
@@ -226,49 +358,50 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
   const int nt = j0 < ntiles ? (ntiles - j0 + cpi - 1) / cpi : 0;     // tiles of this CTA: j0, j0+cpi, ...
   const int RPT = (C + NR - 1) / NR;
   const int total_rounds = nt * RPT;
-  const long HW = (long)H * W;
   const unsigned char* lab8 = ws.lab8 + (long)b * HW;
-  const T* xb = x + (long)b * C * HW;
+  const char* xbb = reinterpret_cast<const char*>(x + (long)b * C * HW);
+  const long BHW = (long)B * HW;
 
   if (tid < NPROD) {
     // ============================== producers ==============================
     const int ty = tid >> 4, tx = (tid & 15) << 2;
     float lacc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // [0..2] log2 units (BCE fine/mid/high), [3..5] natural (CE)
-    // prefetch stream state (runs XD-1 channels ahead, across tile boundaries)
-    int pf_it = 0, pf_ci = 0, pf_seq = 0;
-    long pf_off = 0;
-    bool pf_in = false;
+    // prefetch stream: runs XD-2 channels ahead of the consumer side of the ring, across tile boundaries
+    const unsigned int xs_base = (unsigned int)__cvta_generic_to_shared(xstage + tid);
+    const char* xs_gen = reinterpret_cast<const char*>(xstage + tid);
+    TileWalk pw;
+    pw.init(j0, cpi, tiles_x);
+    int pf_it = 0, pf_ci = 0;
+    unsigned int pf_seq = 0;
+    long pf_offb = 0;
     auto pf_tile = [&]() {
-      if (pf_it < nt) {
-        const TileCoord tc = tile_coord(j0 + pf_it * cpi, tiles_x);
-        const int y = tc.y0 + ty, xg = tc.x0 + tx;
-        pf_in = y < H && xg < W;
-        pf_off = (long)y * W + xg;
-      } else {
-        pf_in = false;
-      }
+      const int y = pw.y0() + ty, xg = pw.x0() + tx;
+      const bool in = pf_it < nt && y < H && xg < W;
+      pf_offb = in ? ((long)y * W + xg) * (long)sizeof(T) : 0;     // outside the image: any valid address will do
     };
     auto pf_issue = [&]() {
-      if (pf_in) {
-        const int ch = s_order[pf_ci] >> 24;
-        cp_async_vec4<T>(xstage + (pf_seq % XD) * NPROD + tid, xb + (long)ch * HW + pf_off);
-      }
+      const char* g = xbb + s_chb[pf_ci] + pf_offb;
+      const unsigned int dst = xs_base + (pf_seq & (XD - 1)) * (NPROD * 16);
+      if (sizeof(T) == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g));
+      else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(g));
       cp_async_commit();
       ++pf_seq;
-      if (++pf_ci == C) { pf_ci = 0; ++pf_it; pf_tile(); }
+      if (++pf_ci == C) { pf_ci = 0; ++pf_it; pw.next(); pf_tile(); }
     };
     pf_tile();
 #pragma unroll 1
-    for (int q = 0; q < XD - 1; ++q) pf_issue();
+    for (int q = 0; q < XD - 2; ++q) pf_issue();
 
-    int seq = 0;
+    unsigned int seq = 0;
+    TileWalk tw;
+    tw.init(j0, cpi, tiles_x);
 #pragma unroll 1
-    for (int it = 0; it < nt; ++it) {
-      const TileCoord tc = tile_coord(j0 + it * cpi, tiles_x);
-      const int y = tc.y0 + ty, xg = tc.x0 + tx;
+    for (int it = 0; it < nt; ++it, tw.next()) {
+      const int y = tw.y0() + ty, xg = tw.x0() + tx;
       const bool inimg = y < H && xg < W;
       const long off = (long)y * W + xg;
       const unsigned int tf4 = inimg ? *reinterpret_cast<const unsigned int*>(lab8 + off) : 0xffffffffu;
+      unsigned char* hold_px = ws.hold + (long)b * HW + off;     // + plane * B*HW
       unsigned int tm4 = 0xffffffffu, th4 = 0xffffffffu;
       float vf[4];
 #pragma unroll
@@ -290,115 +423,125 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
         a_t[k] = b_t[k] = 1.f;
         rhold[k] = rholdH[k] = 0u;
       }
+      // tree BCE / CE bookkeeping of one channel (s = sigmoid, E = e^x of the thread's 4 pixels)
+      auto update = [&](unsigned int oe, const float (&xv)[4], const float (&s)[4], const float (&E)[4]) {
+        const int kind = oe & 3, cl = (oe >> 8) & 0xff, fl = (oe >> 16) & 0xff;
+        const unsigned int ch = oe >> 24;
+        const unsigned int pat = (unsigned int)cl * 0x01010101u;
+        if (kind == 0) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            sumF[k] += E[k];
+            prodF[k] *= (1.0f - s[k]) + eps;
+            if (s[k] > rmax[k]) { rmax[k] = s[k]; rhold[k] = ch; }   // lowest fine id wins ties (rmi...py:386)
+          }
+          const unsigned int z = tf4 ^ pat;
+          if (has_zero_byte(z)) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (((z >> (8 * k)) & 0xffu) == 0u) {
+                a_t[k] = s[k];
+                lacc[3] -= xv[k];
+                lacc[0] -= lg2((1.0f - s[k]) + eps);     // the target's own factor does not belong to the product
+              }
+          }
+          if (fl & 2) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { lacc[0] = fmaf(vf[k], lg2(prodF[k]), lacc[0]); prodF[k] = 1.f; }
+          }
+        } else if (kind == 1) {
+          unsigned int hd = 0;
+          float cur[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            sumM[k] += E[k];
+            cur[k] = rmax[k];
+            unsigned int hk = rhold[k];
+            if (s[k] > cur[k]) { cur[k] = s[k]; hk = ch; }                // fine max wins ties (rmi...py:386-387)
+            hd |= hk << (8 * k);
+            prodM[k] *= (1.0f - cur[k]) + eps;
+            if (cur[k] > rmaxH[k]) { rmaxH[k] = cur[k]; rholdH[k] = hk; }  // lower mid id wins ties (rmi...py:408)
+            rmax[k] = -1.f; rhold[k] = 0u;
+          }
+          if (inimg) *reinterpret_cast<unsigned int*>(hold_px + (long)cl * BHW) = hd;
+          const unsigned int z = tm4 ^ pat;
+          if (has_zero_byte(z)) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (((z >> (8 * k)) & 0xffu) == 0u) {
+                b_t[k] = s[k];
+                lacc[4] -= xv[k];
+                lacc[1] -= lg2((1.0f - cur[k]) + eps);
+                const bool a_holds = a_t[k] <= b_t[k];                     // fine wins ties (rmi...py:421-425)
+                lacc[0] += lg2((a_holds ? a_t[k] : b_t[k]) + eps);
+                hpf |= (a_holds ? ((tf4 >> (8 * k)) & 0xffu) : ch) << (8 * k);
+              }
+          }
+          if (fl & 2) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { lacc[1] = fmaf(vf[k], lg2(prodM[k]), lacc[1]); prodM[k] = 1.f; }
+          }
+        } else {
+          unsigned int hd = 0;
+          float cur[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            sumH[k] += E[k];
+            cur[k] = rmaxH[k];
+            unsigned int hk = rholdH[k];
+            if (s[k] > cur[k]) { cur[k] = s[k]; hk = ch; }                // mid max wins ties (rmi...py:408-409)
+            hd |= hk << (8 * k);
+            prodH[k] *= (1.0f - cur[k]) + eps;
+            rmaxH[k] = -1.f; rholdH[k] = 0u;
+          }
+          if (inimg) *reinterpret_cast<unsigned int*>(hold_px + (long)(hg.nm + cl) * BHW) = hd;
+          const unsigned int z = th4 ^ pat;
+          if (has_zero_byte(z)) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (((z >> (8 * k)) & 0xffu) == 0u) {
+                lacc[5] -= xv[k];
+                lacc[2] -= lg2((1.0f - cur[k]) + eps);
+                const bool c_holds = s[k] <= b_t[k];                       // high wins ties (rmi...py:439-440)
+                lacc[1] += lg2((c_holds ? s[k] : b_t[k]) + eps);
+                lacc[2] += lg2(s[k] + eps);
+                hpm |= (c_holds ? ch : (unsigned int)hg.nf + ((tm4 >> (8 * k)) & 0xffu)) << (8 * k);
+              }
+          }
+          if (fl & 2) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { lacc[2] = fmaf(vf[k], lg2(prodH[k]), lacc[2]); prodH[k] = 1.f; }
+          }
+        }
+      };
 #pragma unroll 1
       for (int r = 0; r < RPT; ++r) {
         const int buf = (it * RPT + r) % NBUF;
         bar_sync(BAR_EMPTY + buf, NTHREADS);
         const int cend = min(C, (r + 1) * NR);
+        float* prow = planes + (buf * NR) * PLANE + (ty + 2) * PW + tx + 2;
 #pragma unroll 1
-        for (int ci = r * NR; ci < cend; ++ci) {
+        for (int ci = r * NR; ci < cend; ci += 2, prow += 2 * PLANE) {
+          // two channels per step: their sigmoid chains interleave (ILP 8 instead of 4)
+          const bool two = ci + 1 < cend;
           pf_issue();
-          cp_async_wait<XD - 1>();
-          const unsigned int oe = s_order[ci];
-          const int kind = oe & 3, cl = (oe >> 8) & 0xff, fl = (oe >> 16) & 0xff;
-          const unsigned int ch = oe >> 24;
-          float xv[4] = {0.f, 0.f, 0.f, 0.f};
-          if (inimg) staged_vec4<T>(xstage + (seq % XD) * NPROD + tid, xv);
-          ++seq;
-          float s[4], E[4], pk[4];
+          if (two) pf_issue();
+          if (two) cp_async_wait<XD - 2>(); else cp_async_wait<XD - 3>();
+          float xa[4], xc[4];
+          staged_vec4<T>(xs_gen + (seq & (XD - 1)) * (NPROD * 16), xa);
+          staged_vec4<T>(xs_gen + ((seq + 1) & (XD - 1)) * (NPROD * 16), xc);
+          seq += two ? 2 : 1;
+          float sa[4], Ea[4], sc[4], Ec[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            sig_exp3(xv[k], s[k], E[k]);
-            pk[k] = fmaf(s[k], vf[k], 1e-6f);          // literally probs * valid + 1e-6 (rmi...py:487)
-          }
-          float* prow = planes + (buf * NR + (ci - r * NR)) * PLANE + (ty + 2) * PW + tx + 2;
-          *reinterpret_cast<float2*>(prow) = make_float2(pk[0], pk[1]);
-          *reinterpret_cast<float2*>(prow + 2) = make_float2(pk[2], pk[3]);
-          const unsigned int pat = (unsigned int)cl * 0x01010101u;
-          if (kind == 0) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              sumF[k] += E[k];
-              prodF[k] *= (1.0f - s[k]) + eps;
-              if (s[k] > rmax[k]) { rmax[k] = s[k]; rhold[k] = ch; }   // lowest fine id wins ties (rmi...py:386)
-            }
-            const unsigned int z = tf4 ^ pat;
-            if (has_zero_byte(z)) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (((z >> (8 * k)) & 0xffu) == 0u) {
-                  a_t[k] = s[k];
-                  lacc[3] -= xv[k];
-                  lacc[0] -= lg2((1.0f - s[k]) + eps);     // the target's own factor does not belong to the product
-                }
-            }
-            if (fl & 2) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) { lacc[0] = fmaf(vf[k], lg2(prodF[k]), lacc[0]); prodF[k] = 1.f; }
-            }
-          } else if (kind == 1) {
-            unsigned int hd = 0;
-            float cur[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              sumM[k] += E[k];
-              cur[k] = rmax[k];
-              unsigned int hk = rhold[k];
-              if (s[k] > cur[k]) { cur[k] = s[k]; hk = ch; }                // fine max wins ties (rmi...py:386-387)
-              hd |= hk << (8 * k);
-              prodM[k] *= (1.0f - cur[k]) + eps;
-              if (cur[k] > rmaxH[k]) { rmaxH[k] = cur[k]; rholdH[k] = hk; }  // lower mid id wins ties (rmi...py:408)
-              rmax[k] = -1.f; rhold[k] = 0u;
-            }
-            if (inimg) *reinterpret_cast<unsigned int*>(ws.hold + ((size_t)cl * B + b) * HW + off) = hd;
-            const unsigned int z = tm4 ^ pat;
-            if (has_zero_byte(z)) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (((z >> (8 * k)) & 0xffu) == 0u) {
-                  b_t[k] = s[k];
-                  lacc[4] -= xv[k];
-                  lacc[1] -= lg2((1.0f - cur[k]) + eps);
-                  const bool a_holds = a_t[k] <= b_t[k];                     // fine wins ties (rmi...py:421-425)
-                  lacc[0] += lg2((a_holds ? a_t[k] : b_t[k]) + eps);
-                  hpf |= (a_holds ? ((tf4 >> (8 * k)) & 0xffu) : ch) << (8 * k);
-                }
-            }
-            if (fl & 2) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) { lacc[1] = fmaf(vf[k], lg2(prodM[k]), lacc[1]); prodM[k] = 1.f; }
-            }
-          } else {
-            unsigned int hd = 0;
-            float cur[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              sumH[k] += E[k];
-              cur[k] = rmaxH[k];
-              unsigned int hk = rholdH[k];
-              if (s[k] > cur[k]) { cur[k] = s[k]; hk = ch; }                // mid max wins ties (rmi...py:408-409)
-              hd |= hk << (8 * k);
-              prodH[k] *= (1.0f - cur[k]) + eps;
-              rmaxH[k] = -1.f; rholdH[k] = 0u;
-            }
-            if (inimg) *reinterpret_cast<unsigned int*>(ws.hold + ((size_t)(hg.nm + cl) * B + b) * HW + off) = hd;
-            const unsigned int z = th4 ^ pat;
-            if (has_zero_byte(z)) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (((z >> (8 * k)) & 0xffu) == 0u) {
-                  lacc[5] -= xv[k];
-                  lacc[2] -= lg2((1.0f - cur[k]) + eps);
-                  const bool c_holds = s[k] <= b_t[k];                       // high wins ties (rmi...py:439-440)
-                  lacc[1] += lg2((c_holds ? s[k] : b_t[k]) + eps);
-                  lacc[2] += lg2(s[k] + eps);
-                  hpm |= (c_holds ? ch : (unsigned int)hg.nf + ((tm4 >> (8 * k)) & 0xffu)) << (8 * k);
-                }
-            }
-            if (fl & 2) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) { lacc[2] = fmaf(vf[k], lg2(prodH[k]), lacc[2]); prodH[k] = 1.f; }
-            }
+          for (int k = 0; k < 4; ++k) { sig_exp3(xa[k], sa[k], Ea[k]); sig_exp3(xc[k], sc[k], Ec[k]); }
+          // literally probs * valid + 1e-6 (rmi...py:487)
+          *reinterpret_cast<float2*>(prow) = make_float2(fmaf(sa[0], vf[0], 1e-6f), fmaf(sa[1], vf[1], 1e-6f));
+          *reinterpret_cast<float2*>(prow + 2) = make_float2(fmaf(sa[2], vf[2], 1e-6f), fmaf(sa[3], vf[3], 1e-6f));
+          update(s_order[ci], xa, sa, Ea);
+          if (two) {
+            *reinterpret_cast<float2*>(prow + PLANE) = make_float2(fmaf(sc[0], vf[0], 1e-6f), fmaf(sc[1], vf[1], 1e-6f));
+            *reinterpret_cast<float2*>(prow + PLANE + 2) = make_float2(fmaf(sc[2], vf[2], 1e-6f), fmaf(sc[3], vf[3], 1e-6f));
+            update(s_order[ci + 1], xc, sc, Ec);
           }
         }
         __threadfence_block();
@@ -417,12 +560,12 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
         iv[0][k] = rcp(sumF[k]); iv[1][k] = rcp(sumM[k]); iv[2][k] = rcp(sumH[k]);
       }
       if (inimg) {
-        *reinterpret_cast<unsigned int*>(ws.hold + ((size_t)(hg.nm + hg.nh) * B + b) * HW + off) = hpf;
-        *reinterpret_cast<unsigned int*>(ws.hold + ((size_t)(hg.nm + hg.nh + 1) * B + b) * HW + off) = hpm;
+        *reinterpret_cast<unsigned int*>(hold_px + (long)(hg.nm + hg.nh) * BHW) = hpf;
+        *reinterpret_cast<unsigned int*>(hold_px + (long)(hg.nm + hg.nh + 1) * BHW) = hpm;
+        float* ivp = ws.inv + (long)b * HW + off;
 #pragma unroll
         for (int l = 0; l < 3; ++l)
-          *reinterpret_cast<float4*>(ws.inv + ((size_t)l * B + b) * HW + off) =
-              make_float4(iv[l][0], iv[l][1], iv[l][2], iv[l][3]);
+          *reinterpret_cast<float4*>(ivp + (long)l * BHW) = make_float4(iv[l][0], iv[l][1], iv[l][2], iv[l][3]);
       }
     }
     cp_async_wait<0>();
@@ -444,31 +587,89 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
       ws.bce2[(size_t)blockIdx.x * 8 + tid] = r;
     }
   } else if (tid < NPROD + NHALO) {
-    // ============================== halo warps ==============================
+    // ============================== halo warp ==============================
     const int hl = tid - NPROD;
-    // vector part: plane rows 0,1,18,19 x 16 strips ; scalar part (lanes 0..39): 20 rows x {cols 0,1 | cols 66,67}
-    const int vrow = (hl >> 4) < 2 ? (hl >> 4) : 16 + (hl >> 4), vstrip = hl & 15;
-    const bool has_s = hl < 2 * PR;
-    const int srow = has_s ? hl % PR : 0, sside = has_s ? hl / PR : 0;
-#pragma unroll 1
-    for (int it = 0; it < nt; ++it) {
-      const TileCoord tc = tile_coord(j0 + it * cpi, tiles_x);
-      const int vy = tc.y0 - 2 + vrow, vx = tc.x0 + 4 * vstrip;
-      const bool v_in = vy >= 0 && vy < H && vx < W;
-      const long v_off = (long)vy * W + vx;
-      const int sy = tc.y0 - 2 + srow, sx = sside ? tc.x0 + TW : tc.x0 - 2;
-      const bool s_in = has_s && sy >= 0 && sy < H && sx >= 0 && sx < W;
-      const long s_off = (long)sy * W + sx;
-      float vv[4] = {0.f, 0.f, 0.f, 0.f}, sv[2] = {0.f, 0.f};
-      if (v_in) {
-        const unsigned int t4 = *reinterpret_cast<const unsigned int*>(lab8 + v_off);
+    // per lane: 2 strips of the plane rows 0,1,18,19 (64 strips) and up to 2 of the 40 column pairs
+    // (20 rows x {cols 0,1 | cols 66,67})
+    // prefetch stream of the halo logits (cp.async ring, XD-2 channels ahead, across tile boundaries)
+    const unsigned int hs_base = (unsigned int)__cvta_generic_to_shared(hstage + hl * 48);
+    const unsigned char* hs_gen = hstage + hl * 48;
+    TileWalk pw;
+    pw.init(j0, cpi, tiles_x);
+    int pf_it = 0, pf_ci = 0;
+    unsigned int pf_seq = 0, seq = 0;
+    long pv_offb[2] = {0, 0}, ps_offb[2] = {0, 0};
+    auto halo_offsets = [&](int ty0, int tx0, int e, long& vo, long& so) {
+      const int hv = hl + 32 * e;
+      const int vrow = (hv >> 4) < 2 ? (hv >> 4) : 16 + (hv >> 4), vstrip = hv & 15;
+      const int vy = ty0 - 2 + vrow, vx = tx0 + 4 * vstrip;
+      vo = (vy >= 0 && vy < H && vx < W) ? ((long)vy * W + vx) * (long)sizeof(T) : 0;
+      const bool hs = hv < 2 * PR;
+      const int srow = hs ? hv % PR : 0, sside = hs ? hv / PR : 0;
+      const int sy = ty0 - 2 + srow, sx = sside ? tx0 + TW : tx0 - 2;
+      so = (hs && sy >= 0 && sy < H && sx >= 0 && sx < W) ? ((long)sy * W + sx) * (long)sizeof(T) : 0;
+    };
+    auto pf_tile = [&]() {
+      if (pf_it < nt) { halo_offsets(pw.y0(), pw.x0(), 0, pv_offb[0], ps_offb[0]); halo_offsets(pw.y0(), pw.x0(), 1, pv_offb[1], ps_offb[1]); }
+    };
+    auto pf_issue = [&]() {
+      const char* g = xbb + s_chb[pf_ci];
+      const unsigned int dst = hs_base + (pf_seq & (XD - 1)) * (NHALO * 48);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) vv[k] = ((t4 >> (8 * k)) & 0xffu) != SH_IGNORE ? 1.f : 0.f;
+      for (int e = 0; e < 2; ++e) {
+        if (sizeof(T) == 4) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * e), "l"(g + pv_offb[e]));
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 32 + 8 * e), "l"(g + ps_offb[e]));
+        } else {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 16 * e), "l"(g + pv_offb[e]));
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 32 + 8 * e), "l"(g + ps_offb[e]));
+        }
       }
-      if (s_in) {
-        const unsigned short t2 = *reinterpret_cast<const unsigned short*>(lab8 + s_off);
-        sv[0] = (t2 & 0xffu) != SH_IGNORE ? 1.f : 0.f;
-        sv[1] = (t2 >> 8) != SH_IGNORE ? 1.f : 0.f;
+      cp_async_commit();
+      ++pf_seq;
+      if (++pf_ci == C) { pf_ci = 0; ++pf_it; pw.next(); pf_tile(); }
+    };
+    pf_tile();
+#pragma unroll 1
+    for (int q = 0; q < XD - 2; ++q) pf_issue();
+    TileWalk tw;
+    tw.init(j0, cpi, tiles_x);
+#pragma unroll 1
+    for (int it = 0; it < nt; ++it, tw.next()) {
+      const int ty0 = tw.y0(), tx0 = tw.x0();
+      long v_offb[2], s_offb[2];
+      int v_pl[2], s_pl[2];
+      float vv[2][4], sv[2][2], vz[2], sz[2];
+      bool has_s[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int hv = hl + 32 * e;
+        const int vrow = (hv >> 4) < 2 ? (hv >> 4) : 16 + (hv >> 4), vstrip = hv & 15;
+        const int vy = ty0 - 2 + vrow, vx = tx0 + 4 * vstrip;
+        const bool v_in = vy >= 0 && vy < H && vx < W;
+        v_offb[e] = v_in ? ((long)vy * W + vx) * (long)sizeof(T) : 0;
+        v_pl[e] = vrow * PW + 2 + 4 * vstrip;
+        vz[e] = v_in ? 1e-6f : 0.f;                 // outside the image the plane holds exact zeros
+#pragma unroll
+        for (int k = 0; k < 4; ++k) vv[e][k] = 0.f;
+        if (v_in) {
+          const unsigned int t4 = *reinterpret_cast<const unsigned int*>(lab8 + (long)vy * W + vx);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) vv[e][k] = ((t4 >> (8 * k)) & 0xffu) != SH_IGNORE ? 1.f : 0.f;
+        }
+        has_s[e] = hv < 2 * PR;
+        const int srow = has_s[e] ? hv % PR : 0, sside = has_s[e] ? hv / PR : 0;
+        const int sy = ty0 - 2 + srow, sx = sside ? tx0 + TW : tx0 - 2;
+        const bool s_in = has_s[e] && sy >= 0 && sy < H && sx >= 0 && sx < W;
+        s_offb[e] = s_in ? ((long)sy * W + sx) * (long)sizeof(T) : 0;
+        s_pl[e] = srow * PW + sside * (TW + 2);
+        sz[e] = s_in ? 1e-6f : 0.f;
+        sv[e][0] = sv[e][1] = 0.f;
+        if (s_in) {
+          const unsigned short t2 = *reinterpret_cast<const unsigned short*>(lab8 + (long)sy * W + sx);
+          sv[e][0] = (t2 & 0xffu) != SH_IGNORE ? 1.f : 0.f;
+          sv[e][1] = (t2 >> 8) != SH_IGNORE ? 1.f : 0.f;
+        }
       }
 #pragma unroll 1
       for (int r = 0; r < RPT; ++r) {
@@ -477,10 +678,10 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
         if (r == 0) {
           // label bytes of the tile per level (RMI labels: void -> class 0, outside the image -> 0xff)
           unsigned char* lt = LT + (it & 1) * 3 * TH * TW;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int wi = hl + 64 * q, row = wi >> 4, st = wi & 15;
-            const int yy = tc.y0 + row, xx = tc.x0 + 4 * st;
+#pragma unroll 2
+          for (int q = 0; q < 8; ++q) {
+            const int wi = hl + 32 * q, row = wi >> 4, st = wi & 15;
+            const int yy = ty0 + row, xx = tx0 + 4 * st;
             unsigned int f4 = 0xffffffffu, m4 = 0xffffffffu, g4 = 0xffffffffu;
             if (yy < H && xx < W) {
               const unsigned int t4 = *reinterpret_cast<const unsigned int*>(lab8 + (long)yy * W + xx);
@@ -499,66 +700,90 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
             *reinterpret_cast<unsigned int*>(lt + (1 * TH + row) * TW + 4 * st) = m4;
             *reinterpret_cast<unsigned int*>(lt + (2 * TH + row) * TW + 4 * st) = g4;
           }
+          __syncwarp();
+          // per (level, 4x8 block): info = class of the first pixel | uniform << 8 ; hash = classes present (bit c & 31)
+          unsigned int* pm = PM + (it & 1) * PMW;
+#pragma unroll 1
+          for (int id = hl; id < 96; id += NHALO) {
+            const int l = id >> 5, blk = id & 31, bi0 = (blk >> 4) * 8, bsb = blk & 15;
+            const unsigned int first = *reinterpret_cast<const unsigned int*>(lt + (l * TH + bi0) * TW + 4 * bsb);
+            const unsigned int pat0 = (first & 0xffu) * 0x01010101u;
+            unsigned int diff = 0, hash = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const unsigned int wd = *reinterpret_cast<const unsigned int*>(lt + (l * TH + bi0 + i) * TW + 4 * bsb);
+              diff |= wd ^ pat0;
+              hash |= (1u << (wd & 31)) | (1u << ((wd >> 8) & 31)) | (1u << ((wd >> 16) & 31)) | (1u << ((wd >> 24) & 31));
+            }
+            pm[2 * id] = (first & 0xffu) | (diff == 0u ? 0x100u : 0u);
+            pm[2 * id + 1] = hash;
+          }
         }
         const int cend = min(C, (r + 1) * NR);
+        float* pl = planes + (buf * NR) * PLANE;
 #pragma unroll 1
-        for (int ci = r * NR; ci < cend; ++ci) {
-          const T* xc = xb + (long)(s_order[ci] >> 24) * HW;
-          float xv[4] = {0.f, 0.f, 0.f, 0.f}, xs[2] = {0.f, 0.f};
-          if (v_in) VecIO<T, 4>::load(xc + v_off, xv);
-          if (s_in) VecIO<T, 2>::load(xc + s_off, xs);
-          float* pl = planes + (buf * NR + (ci - r * NR)) * PLANE;
-          float p[4];
+        for (int ci = r * NR; ci < cend; ++ci, pl += PLANE) {
+          pf_issue();
+          cp_async_wait<XD - 2>();
+          const unsigned char* st = hs_gen + (seq & (XD - 1)) * (NHALO * 48);
+          ++seq;
+          float xv[2][4], xs[2][2];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) p[k] = v_in ? fmaf(sig_only(xv[k]), vv[k], 1e-6f) : 0.f;
-          float* pr = pl + vrow * PW + 2 + 4 * vstrip;
-          *reinterpret_cast<float2*>(pr) = make_float2(p[0], p[1]);
-          *reinterpret_cast<float2*>(pr + 2) = make_float2(p[2], p[3]);
-          if (has_s) {
-            const float p0 = s_in ? fmaf(sig_only(xs[0]), sv[0], 1e-6f) : 0.f;
-            const float p1 = s_in ? fmaf(sig_only(xs[1]), sv[1], 1e-6f) : 0.f;
-            *reinterpret_cast<float2*>(pl + srow * PW + sside * (TW + 2)) = make_float2(p0, p1);
+          for (int e = 0; e < 2; ++e) {
+            staged_vec4<T>(st + 16 * e, xv[e]);
+            if (sizeof(T) == 4) {
+              const float2 t2 = *reinterpret_cast<const float2*>(st + 32 + 8 * e);
+              xs[e][0] = t2.x; xs[e][1] = t2.y;
+            } else {
+              xs[e][0] = staged_elem<T>(st + 32 + 8 * e, 0);
+              xs[e][1] = staged_elem<T>(st + 32 + 8 * e, 1);
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            float* pr = pl + v_pl[e];
+            *reinterpret_cast<float2*>(pr) = make_float2(fmaf(sig_only(xv[e][0]), vv[e][0], vz[e]), fmaf(sig_only(xv[e][1]), vv[e][1], vz[e]));
+            *reinterpret_cast<float2*>(pr + 2) = make_float2(fmaf(sig_only(xv[e][2]), vv[e][2], vz[e]), fmaf(sig_only(xv[e][3]), vv[e][3], vz[e]));
+            if (has_s[e])
+              *reinterpret_cast<float2*>(pl + s_pl[e]) =
+                  make_float2(fmaf(sig_only(xs[e][0]), sv[e][0], sz[e]), fmaf(sig_only(xs[e][1]), sv[e][1], sz[e]));
           }
         }
         __threadfence_block();
         bar_arrive(BAR_FULL + buf, NTHREADS);
       }
     }
+    cp_async_wait<0>();
   } else {
     // ============================== consumers ==============================
     const int ct = tid - NPROD - NHALO, cw = ct >> 5, lane = ct & 31;
     const int hb = lane >> 4, sb = lane & 15, i0 = hb * 8;
     const int npre = total_rounds < NBUF ? total_rounds : NBUF;
     for (int q = 0; q < npre; ++q) bar_arrive(BAR_EMPTY + q, NTHREADS);
+    TileWalk tw;
+    tw.init(j0, cpi, tiles_x);
 #pragma unroll 1
-    for (int it = 0; it < nt; ++it) {
-      const TileCoord tc = tile_coord(j0 + it * cpi, tiles_x);
-      const bool border = tc.y0 < 2 || tc.y0 + TH > H - 2 || tc.x0 < 2 || tc.x0 + TW > W - 2;
+    for (int it = 0; it < nt; ++it, tw.next()) {
+      const int ty0 = tw.y0(), tx0 = tw.x0();
+      const bool border = ty0 < 2 || ty0 + TH > H - 2 || tx0 < 2 || tx0 + TW > W - 2;
       // interior masks (only used by border tiles): plane rows i0..i0+11 and window cols 0..7
       unsigned int rowI = 0, colI = 0;
       if (border) {
 #pragma unroll
-        for (int q = 0; q < 12; ++q) { const int yy = tc.y0 - 2 + i0 + q; if (yy >= 2 && yy < H - 2) rowI |= 1u << q; }
+        for (int q = 0; q < 12; ++q) { const int yy = ty0 - 2 + i0 + q; if (yy >= 2 && yy < H - 2) rowI |= 1u << q; }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { const int xx = tc.x0 - 2 + 4 * sb + q; if (xx >= 2 && xx < W - 2) colI |= 1u << q; }
+        for (int q = 0; q < 8; ++q) { const int xx = tx0 - 2 + 4 * sb + q; if (xx >= 2 && xx < W - 2) colI |= 1u << q; }
       }
-      const unsigned char* lt = LT + (it & 1) * 3 * TH * TW;
-      unsigned int present[3] = {0u, 0u, 0u};
+      const unsigned char* lt = LT + (it & 1) * 3 * TH * TW + i0 * TW + 4 * sb;
+      const unsigned int* pm = PM + (it & 1) * PMW + 2 * lane;
+      unsigned int pinfo[3] = {0u, 0u, 0u}, phash[3] = {0u, 0u, 0u};
 #pragma unroll 1
       for (int r = 0; r < RPT; ++r) {
         const int R = it * RPT + r, buf = R % NBUF;
         bar_sync(BAR_FULL + buf, NTHREADS);
         if (r == 0) {
 #pragma unroll
-          for (int l = 0; l < 3; ++l) {
-            unsigned int pm = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const unsigned int wd = *reinterpret_cast<const unsigned int*>(lt + (l * TH + i0 + i) * TW + 4 * sb);
-              pm |= (1u << (wd & 31)) | (1u << ((wd >> 8) & 31)) | (1u << ((wd >> 16) & 31)) | (1u << ((wd >> 24) & 31));
-            }
-            present[l] = pm;
-          }
+          for (int l = 0; l < 3; ++l) { pinfo[l] = pm[l * 64]; phash[l] = pm[l * 64 + 1]; }
         }
         const int ci = r * NR + cw;
         if (ci < C) {
@@ -567,45 +792,12 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
           const unsigned int ch = oe >> 24;
           const float* pl = planes + (buf * NR + cw) * PLANE + i0 * PW + 4 * sb;   // window row 0 = plane row i0
           double* trow = tot + (size_t)ch * kFastRec;
-          // ---- pr_cov: 13 product taps of the interior anchors (anchor = centre row, taps forward) ----
+          // ---- pr_cov: 13 product taps of the interior anchors ----
           {
             float acc[16];
 #pragma unroll
             for (int q = 0; q < 16; ++q) acc[q] = 0.f;
-            float w[3][8];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const float4 a = *reinterpret_cast<const float4*>(pl + (2 + q) * PW);
-              const float4 c4 = *reinterpret_cast<const float4*>(pl + (2 + q) * PW + 4);
-              w[q][0] = a.x; w[q][1] = a.y; w[q][2] = a.z; w[q][3] = a.w;
-              w[q][4] = c4.x; w[q][5] = c4.y; w[q][6] = c4.z; w[q][7] = c4.w;
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float(&r0)[8] = w[i % 3];
-              float(&r1)[8] = w[(i + 1) % 3];
-              float(&r2)[8] = w[(i + 2) % 3];
-              {
-                const float4 a = *reinterpret_cast<const float4*>(pl + (4 + i) * PW);
-                const float4 c4 = *reinterpret_cast<const float4*>(pl + (4 + i) * PW + 4);
-                r2[0] = a.x; r2[1] = a.y; r2[2] = a.z; r2[3] = a.w;
-                r2[4] = c4.x; r2[5] = c4.y; r2[6] = c4.z; r2[7] = c4.w;
-              }
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float p = r0[k + 2];
-                float a = p;
-                if (border) a = (((rowI >> (i + 2)) & 1u) && ((colI >> (k + 2)) & 1u)) ? p : 0.f;
-                acc[0] = fmaf(a, p, acc[0]);
-                acc[1] = fmaf(a, r0[k + 3], acc[1]);
-                acc[2] = fmaf(a, r0[k + 4], acc[2]);
-#pragma unroll
-                for (int dx = 0; dx < 5; ++dx) {
-                  acc[3 + dx] = fmaf(a, r1[k + dx], acc[3 + dx]);
-                  acc[8 + dx] = fmaf(a, r2[k + dx], acc[8 + dx]);
-                }
-              }
-            }
+            if (border) pp_taps<true>(pl, rowI, colI, acc); else pp_taps<false>(pl, rowI, colI, acc);
             const float t = warp_reduce16(acc, lane);
             if ((lane & 1) == 0) {
               const int slot = reduce16_slot(lane);
@@ -613,44 +805,19 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
             }
           }
           // ---- la_pr: label-anchored taps  lp[d] = sum_{q : L(q) = cl} PI(q - d),  PI = P on interior anchors, else 0 ----
-          const bool hit = (present[lvl] >> (cl & 31)) & 1u;
+          const unsigned int info = lvl == 0 ? pinfo[0] : (lvl == 1 ? pinfo[1] : pinfo[2]);
+          const unsigned int hash = lvl == 0 ? phash[0] : (lvl == 1 ? phash[1] : phash[2]);
+          const bool uniform = (info & 0x100u) != 0u;
+          const bool hit = uniform ? (info & 0xffu) == (unsigned int)cl : ((hash >> (cl & 31)) & 1u) != 0u;
           if (__any_sync(0xffffffffu, hit)) {
             float al[32];
 #pragma unroll
             for (int q = 0; q < 32; ++q) al[q] = 0.f;
             if (hit) {
               const unsigned int pat = (unsigned int)cl * 0x01010101u;
-              float w[5][8];
-              auto load_row = [&](float(&dst)[8], int prow) {
-                const float4 a = *reinterpret_cast<const float4*>(pl + prow * PW);
-                const float4 c4 = *reinterpret_cast<const float4*>(pl + prow * PW + 4);
-                dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w;
-                dst[4] = c4.x; dst[5] = c4.y; dst[6] = c4.z; dst[7] = c4.w;
-                if (border) {
-                  const bool rok = (rowI >> prow) & 1u;
-#pragma unroll
-                  for (int q = 0; q < 8; ++q) dst[q] = (rok && ((colI >> q) & 1u)) ? dst[q] : 0.f;
-                }
-              };
-#pragma unroll
-              for (int q = 0; q < 4; ++q) load_row(w[q], q);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                load_row(w[(i + 4) % 5], i + 4);
-                const unsigned int z =
-                    *reinterpret_cast<const unsigned int*>(lt + (lvl * TH + i0 + i) * TW + 4 * sb) ^ pat;
-                if (has_zero_byte(z)) {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    if (((z >> (8 * k)) & 0xffu) == 0u) {
-#pragma unroll
-                      for (int a = 0; a < 5; ++a)
-#pragma unroll
-                        for (int bq = 0; bq < 5; ++bq)      // window row a <-> dy = 2 - a ; col k+bq <-> dx = 2 - bq
-                          al[24 - (a * 5 + bq)] += w[(i + a) % 5][k + bq];
-                    }
-                }
-              }
+              const unsigned char* ltrow = lt + lvl * TH * TW;
+              if (border) lp_taps<true>(pl, ltrow, uniform, pat, rowI, colI, al);
+              else lp_taps<false>(pl, ltrow, uniform, pat, rowI, colI, al);
             }
             const float t0 = warp_reduce16(*reinterpret_cast<float(*)[16]>(al), lane);
             const float t1 = warp_reduce16(*reinterpret_cast<float(*)[16]>(al + 16), lane);
