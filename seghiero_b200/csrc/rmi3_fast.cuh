@@ -29,6 +29,7 @@ constexpr int NBUF = 3;              // round buffers
 constexpr int NPROD = 256, NHALO = 32, NCONS = 32 * NR;
 constexpr int NTHREADS = NPROD + NHALO + NCONS;   // 512: 8 producer warps, 1 halo warp, 7 consumer warps (128 registers each)
 constexpr int XD = 8;                // cp.async ring depth (power of two; XD-2 channels in flight per producer thread)
+constexpr int HD = 4;                // cp.async ring depth of the consumers' halo logits (planes in flight + 1)
 constexpr int BAR_FULL = 1, BAR_EMPTY = 1 + NBUF, BAR_PROD = 1 + 2 * NBUF, BAR_HALO = 2 + 2 * NBUF;
 constexpr int kFastMaxC = 160;
 
@@ -210,7 +211,7 @@ constexpr int PMW = 2 * 3 * 32;   // presence words per tile: [level][block] x {
 inline size_t pass1_smem(int C, int nf) {
   size_t s = (size_t)NBUF * NR * PLANE * 4;          // planes
   s += (size_t)XD * NPROD * 16;                      // cp.async staging
-  s += (size_t)XD * NHALO * 48;                      // cp.async staging of the halo warp
+  s += (size_t)HD * NCONS * 48;                      // cp.async staging of the consumers' plane halos
   s += (size_t)2 * 3 * TH * TW;                      // label tiles (two tile parities)
   s += (size_t)2 * PMW * 4;                          // presence words (two tile parities)
   s += (size_t)C * kFastRec * 8;                     // fp64 totals
@@ -332,8 +333,8 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
   const int C = hg.nf + hg.nm + hg.nh;
   float* planes = reinterpret_cast<float*>(smem_raw);                                   // [NBUF][NR][PLANE]
   uint4* xstage = reinterpret_cast<uint4*>(planes + NBUF * NR * PLANE);                  // [XD][NPROD]
-  unsigned char* hstage = reinterpret_cast<unsigned char*>(xstage + XD * NPROD);         // [XD][NHALO][48]
-  unsigned char* LT = hstage + XD * NHALO * 48;                                          // [2][3][TH][TW]
+  unsigned char* hstage = reinterpret_cast<unsigned char*>(xstage + XD * NPROD);         // [HD][NCONS][48]
+  unsigned char* LT = hstage + HD * NCONS * 48;                                          // [2][3][TH][TW]
   unsigned int* PM = reinterpret_cast<unsigned int*>(LT + 2 * 3 * TH * TW);              // [2][3][32][2]
   double* tot = reinterpret_cast<double*>(PM + 2 * PMW);                                 // [C][kFastRec]
   long long* s_chb = reinterpret_cast<long long*>(tot + (size_t)C * kFastRec);           // [C] channel byte offsets (order index)
@@ -588,95 +589,19 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
     }
   } else if (tid < NPROD + NHALO) {
     // ============================== halo warp ==============================
+    // tile helper: label bytes of the tile per level + per-block presence words (consumers do the plane halos)
     const int hl = tid - NPROD;
-    // per lane: 2 strips of the plane rows 0,1,18,19 (64 strips) and up to 2 of the 40 column pairs
-    // (20 rows x {cols 0,1 | cols 66,67})
-    // prefetch stream of the halo logits (cp.async ring, XD-2 channels ahead, across tile boundaries)
-    const unsigned int hs_base = (unsigned int)__cvta_generic_to_shared(hstage + hl * 48);
-    const unsigned char* hs_gen = hstage + hl * 48;
-    TileWalk pw;
-    pw.init(j0, cpi, tiles_x);
-    int pf_it = 0, pf_ci = 0;
-    unsigned int pf_seq = 0, seq = 0;
-    long pv_offb[2] = {0, 0}, ps_offb[2] = {0, 0};
-    auto halo_offsets = [&](int ty0, int tx0, int e, long& vo, long& so) {
-      const int hv = hl + 32 * e;
-      const int vrow = (hv >> 4) < 2 ? (hv >> 4) : 16 + (hv >> 4), vstrip = hv & 15;
-      const int vy = ty0 - 2 + vrow, vx = tx0 + 4 * vstrip;
-      vo = (vy >= 0 && vy < H && vx < W) ? ((long)vy * W + vx) * (long)sizeof(T) : 0;
-      const bool hs = hv < 2 * PR;
-      const int srow = hs ? hv % PR : 0, sside = hs ? hv / PR : 0;
-      const int sy = ty0 - 2 + srow, sx = sside ? tx0 + TW : tx0 - 2;
-      so = (hs && sy >= 0 && sy < H && sx >= 0 && sx < W) ? ((long)sy * W + sx) * (long)sizeof(T) : 0;
-    };
-    auto pf_tile = [&]() {
-      if (pf_it < nt) { halo_offsets(pw.y0(), pw.x0(), 0, pv_offb[0], ps_offb[0]); halo_offsets(pw.y0(), pw.x0(), 1, pv_offb[1], ps_offb[1]); }
-    };
-    auto pf_issue = [&]() {
-      const char* g = xbb + s_chb[pf_ci];
-      const unsigned int dst = hs_base + (pf_seq & (XD - 1)) * (NHALO * 48);
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        if (sizeof(T) == 4) {
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * e), "l"(g + pv_offb[e]));
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 32 + 8 * e), "l"(g + ps_offb[e]));
-        } else {
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 16 * e), "l"(g + pv_offb[e]));
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 32 + 8 * e), "l"(g + ps_offb[e]));
-        }
-      }
-      cp_async_commit();
-      ++pf_seq;
-      if (++pf_ci == C) { pf_ci = 0; ++pf_it; pw.next(); pf_tile(); }
-    };
-    pf_tile();
-#pragma unroll 1
-    for (int q = 0; q < XD - 2; ++q) pf_issue();
     TileWalk tw;
     tw.init(j0, cpi, tiles_x);
 #pragma unroll 1
     for (int it = 0; it < nt; ++it, tw.next()) {
       const int ty0 = tw.y0(), tx0 = tw.x0();
-      long v_offb[2], s_offb[2];
-      int v_pl[2], s_pl[2];
-      float vv[2][4], sv[2][2], vz[2], sz[2];
-      bool has_s[2];
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int hv = hl + 32 * e;
-        const int vrow = (hv >> 4) < 2 ? (hv >> 4) : 16 + (hv >> 4), vstrip = hv & 15;
-        const int vy = ty0 - 2 + vrow, vx = tx0 + 4 * vstrip;
-        const bool v_in = vy >= 0 && vy < H && vx < W;
-        v_offb[e] = v_in ? ((long)vy * W + vx) * (long)sizeof(T) : 0;
-        v_pl[e] = vrow * PW + 2 + 4 * vstrip;
-        vz[e] = v_in ? 1e-6f : 0.f;                 // outside the image the plane holds exact zeros
-#pragma unroll
-        for (int k = 0; k < 4; ++k) vv[e][k] = 0.f;
-        if (v_in) {
-          const unsigned int t4 = *reinterpret_cast<const unsigned int*>(lab8 + (long)vy * W + vx);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) vv[e][k] = ((t4 >> (8 * k)) & 0xffu) != SH_IGNORE ? 1.f : 0.f;
-        }
-        has_s[e] = hv < 2 * PR;
-        const int srow = has_s[e] ? hv % PR : 0, sside = has_s[e] ? hv / PR : 0;
-        const int sy = ty0 - 2 + srow, sx = sside ? tx0 + TW : tx0 - 2;
-        const bool s_in = has_s[e] && sy >= 0 && sy < H && sx >= 0 && sx < W;
-        s_offb[e] = s_in ? ((long)sy * W + sx) * (long)sizeof(T) : 0;
-        s_pl[e] = srow * PW + sside * (TW + 2);
-        sz[e] = s_in ? 1e-6f : 0.f;
-        sv[e][0] = sv[e][1] = 0.f;
-        if (s_in) {
-          const unsigned short t2 = *reinterpret_cast<const unsigned short*>(lab8 + (long)sy * W + sx);
-          sv[e][0] = (t2 & 0xffu) != SH_IGNORE ? 1.f : 0.f;
-          sv[e][1] = (t2 >> 8) != SH_IGNORE ? 1.f : 0.f;
-        }
-      }
 #pragma unroll 1
       for (int r = 0; r < RPT; ++r) {
         const int buf = (it * RPT + r) % NBUF;
         bar_sync(BAR_EMPTY + buf, NTHREADS);
         if (r == 0) {
-          // label bytes of the tile per level (RMI labels: void -> class 0, outside the image -> 0xff)
+          // RMI labels: void -> class 0, outside the image -> 0xff
           unsigned char* lt = LT + (it & 1) * 3 * TH * TW;
 #pragma unroll 2
           for (int q = 0; q < 8; ++q) {
@@ -719,47 +644,79 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
             pm[2 * id + 1] = hash;
           }
         }
-        const int cend = min(C, (r + 1) * NR);
-        float* pl = planes + (buf * NR) * PLANE;
-#pragma unroll 1
-        for (int ci = r * NR; ci < cend; ++ci, pl += PLANE) {
-          pf_issue();
-          cp_async_wait<XD - 2>();
-          const unsigned char* st = hs_gen + (seq & (XD - 1)) * (NHALO * 48);
-          ++seq;
-          float xv[2][4], xs[2][2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            staged_vec4<T>(st + 16 * e, xv[e]);
-            if (sizeof(T) == 4) {
-              const float2 t2 = *reinterpret_cast<const float2*>(st + 32 + 8 * e);
-              xs[e][0] = t2.x; xs[e][1] = t2.y;
-            } else {
-              xs[e][0] = staged_elem<T>(st + 32 + 8 * e, 0);
-              xs[e][1] = staged_elem<T>(st + 32 + 8 * e, 1);
-            }
-          }
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            float* pr = pl + v_pl[e];
-            *reinterpret_cast<float2*>(pr) = make_float2(fmaf(sig_only(xv[e][0]), vv[e][0], vz[e]), fmaf(sig_only(xv[e][1]), vv[e][1], vz[e]));
-            *reinterpret_cast<float2*>(pr + 2) = make_float2(fmaf(sig_only(xv[e][2]), vv[e][2], vz[e]), fmaf(sig_only(xv[e][3]), vv[e][3], vz[e]));
-            if (has_s[e])
-              *reinterpret_cast<float2*>(pl + s_pl[e]) =
-                  make_float2(fmaf(sig_only(xs[e][0]), sv[e][0], sz[e]), fmaf(sig_only(xs[e][1]), sv[e][1], sz[e]));
-          }
-        }
         __threadfence_block();
         bar_arrive(BAR_FULL + buf, NTHREADS);
       }
     }
-    cp_async_wait<0>();
   } else {
     // ============================== consumers ==============================
     const int ct = tid - NPROD - NHALO, cw = ct >> 5, lane = ct & 31;
     const int hb = lane >> 4, sb = lane & 15, i0 = hb * 8;
     const int npre = total_rounds < NBUF ? total_rounds : NBUF;
     for (int q = 0; q < npre; ++q) bar_arrive(BAR_EMPTY + q, NTHREADS);
+    // The 2-pixel ring of the warp's own plane (sigmoid only): per lane 2 strips of the plane rows 0,1,18,19
+    // (64 strips) and up to 2 of the 40 column pairs (20 rows x {cols 0,1 | cols 66,67}).  Their logits come
+    // through a cp.async ring that runs HD-1 of the warp's planes ahead (across tile boundaries).
+    unsigned char* hs_gen = hstage + (cw * 32 + lane) * 48;
+    const unsigned int hs_base = (unsigned int)__cvta_generic_to_shared(hs_gen);
+    auto halo_offsets = [&](int ty0, int tx0, int e, long& vo, long& so) {
+      const int hv = lane + 32 * e;
+      const int vrow = (hv >> 4) < 2 ? (hv >> 4) : 16 + (hv >> 4), vstrip = hv & 15;
+      const int vy = ty0 - 2 + vrow, vx = tx0 + 4 * vstrip;
+      vo = (vy >= 0 && vy < H && vx < W) ? ((long)vy * W + vx) * (long)sizeof(T) : -1;
+      const bool hs = hv < 2 * PR;
+      const int srow = hs ? hv % PR : 0, sside = hs ? hv / PR : 0;
+      const int sy = ty0 - 2 + srow, sx = sside ? tx0 + TW : tx0 - 2;
+      so = (hs && sy >= 0 && sy < H && sx >= 0 && sx < W) ? ((long)sy * W + sx) * (long)sizeof(T) : -1;
+    };
+    int v_pl[2], s_pl[2];
+    bool has_s[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int hv = lane + 32 * e;
+      const int vrow = (hv >> 4) < 2 ? (hv >> 4) : 16 + (hv >> 4);
+      v_pl[e] = vrow * PW + 2 + 4 * (hv & 15);
+      has_s[e] = hv < 2 * PR;
+      s_pl[e] = has_s[e] ? (hv % PR) * PW + (hv / PR) * (TW + 2) : 0;
+    }
+    TileWalk pw;
+    pw.init(j0, cpi, tiles_x);
+    int pf_it = 0, pf_r = 0;
+    unsigned int pf_seq = 0, seq = 0;
+    long pv_offb[2] = {0, 0}, ps_offb[2] = {0, 0};
+    auto pf_tile = [&]() {
+      if (pf_it < nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          halo_offsets(pw.y0(), pw.x0(), e, pv_offb[e], ps_offb[e]);
+          if (pv_offb[e] < 0) pv_offb[e] = 0;          // outside the image: any valid address will do
+          if (ps_offb[e] < 0) ps_offb[e] = 0;
+        }
+      }
+    };
+    auto pf_issue = [&]() {
+      const int pci = pf_r * NR + cw;
+      if (pf_it < nt && pci < C) {
+        const char* g = xbb + s_chb[pci];
+        const unsigned int dst = hs_base + (pf_seq & (HD - 1)) * (NCONS * 48);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          if (sizeof(T) == 4) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * e), "l"(g + pv_offb[e]));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 32 + 8 * e), "l"(g + ps_offb[e]));
+          } else {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 16 * e), "l"(g + pv_offb[e]));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 32 + 8 * e), "l"(g + ps_offb[e]));
+          }
+        }
+        ++pf_seq;
+      }
+      cp_async_commit();
+      if (++pf_r == RPT) { pf_r = 0; ++pf_it; pw.next(); pf_tile(); }
+    };
+    pf_tile();
+#pragma unroll 1
+    for (int q = 0; q < HD - 1; ++q) pf_issue();
     TileWalk tw;
     tw.init(j0, cpi, tiles_x);
 #pragma unroll 1
@@ -774,18 +731,66 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
 #pragma unroll
         for (int q = 0; q < 8; ++q) { const int xx = tx0 - 2 + 4 * sb + q; if (xx >= 2 && xx < W - 2) colI |= 1u << q; }
       }
+      // validity of this lane's halo pixels (P = s * valid + 1e-6 inside the image, exact 0 outside)
+      float vv[2][4], sv[2][2], vz[2], sz[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        long vo, so;
+        halo_offsets(ty0, tx0, e, vo, so);
+        vz[e] = vo >= 0 ? 1e-6f : 0.f;
+        sz[e] = so >= 0 ? 1e-6f : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) vv[e][k] = 0.f;
+        sv[e][0] = sv[e][1] = 0.f;
+        if (vo >= 0) {
+          const unsigned int t4 = *reinterpret_cast<const unsigned int*>(lab8 + vo / (long)sizeof(T));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) vv[e][k] = ((t4 >> (8 * k)) & 0xffu) != SH_IGNORE ? 1.f : 0.f;
+        }
+        if (so >= 0) {
+          const unsigned short t2 = *reinterpret_cast<const unsigned short*>(lab8 + so / (long)sizeof(T));
+          sv[e][0] = (t2 & 0xffu) != SH_IGNORE ? 1.f : 0.f;
+          sv[e][1] = (t2 >> 8) != SH_IGNORE ? 1.f : 0.f;
+        }
+      }
       const unsigned char* lt = LT + (it & 1) * 3 * TH * TW + i0 * TW + 4 * sb;
       const unsigned int* pm = PM + (it & 1) * PMW + 2 * lane;
       unsigned int pinfo[3] = {0u, 0u, 0u}, phash[3] = {0u, 0u, 0u};
 #pragma unroll 1
       for (int r = 0; r < RPT; ++r) {
         const int R = it * RPT + r, buf = R % NBUF;
+        const int ci = r * NR + cw;
+        pf_issue();
+        cp_async_wait<HD - 1>();
+        // halo of this warp's plane: independent of the producers, done while they finish the round
+        if (ci < C) {
+          const unsigned char* st = hs_gen + (seq & (HD - 1)) * (NCONS * 48);
+          ++seq;
+          float* plw = planes + (buf * NR + cw) * PLANE;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            float xv[4], xs[2];
+            staged_vec4<T>(st + 16 * e, xv);
+            if (sizeof(T) == 4) {
+              const float2 t2 = *reinterpret_cast<const float2*>(st + 32 + 8 * e);
+              xs[0] = t2.x; xs[1] = t2.y;
+            } else {
+              xs[0] = staged_elem<T>(st + 32 + 8 * e, 0);
+              xs[1] = staged_elem<T>(st + 32 + 8 * e, 1);
+            }
+            float* pr = plw + v_pl[e];
+            *reinterpret_cast<float2*>(pr) = make_float2(fmaf(sig_only(xv[0]), vv[e][0], vz[e]), fmaf(sig_only(xv[1]), vv[e][1], vz[e]));
+            *reinterpret_cast<float2*>(pr + 2) = make_float2(fmaf(sig_only(xv[2]), vv[e][2], vz[e]), fmaf(sig_only(xv[3]), vv[e][3], vz[e]));
+            if (has_s[e])
+              *reinterpret_cast<float2*>(plw + s_pl[e]) =
+                  make_float2(fmaf(sig_only(xs[0]), sv[e][0], sz[e]), fmaf(sig_only(xs[1]), sv[e][1], sz[e]));
+          }
+        }
         bar_sync(BAR_FULL + buf, NTHREADS);
         if (r == 0) {
 #pragma unroll
           for (int l = 0; l < 3; ++l) { pinfo[l] = pm[l * 64]; phash[l] = pm[l * 64 + 1]; }
         }
-        const int ci = r * NR + cw;
         if (ci < C) {
           const unsigned int oe = s_order[ci];
           const int lvl = oe & 3, cl = (oe >> 8) & 0xff;
@@ -832,6 +837,7 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
         if (R < total_rounds - NBUF) bar_arrive(BAR_EMPTY + buf, NTHREADS);
       }
     }
+    cp_async_wait<0>();
     // ---- records of the channels this warp owned ------------------------------------------------
     __syncwarp();
     for (int ci = cw; ci < C; ci += NR) {
