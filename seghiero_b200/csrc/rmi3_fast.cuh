@@ -4,12 +4,12 @@
 // aligned and 8 < C <= kFastMaxC; everything else runs the generic kernels of rmi3_fwd.cu / rmi3_bwd.cu.
 // Reference arithmetic: models/loss/rmi_hiera_triplet_loss.py:323-546.
 //
-// One CTA per SM (512 threads), each walking tiles (64 x 16 pixels) of ONE image:
-//   warps 0-7   producers : thread = 4 consecutive pixels, all channels in tree order (fine children,
+// One CTA per SM (512 threads), each walking tiles (64 x 24 pixels) of ONE image:
+//   warps 0-11  producers : thread = 4 consecutive pixels, all channels in tree order (fine children,
 //                           their mid, ..., then the high).  sigmoid / e^x from 3 MUFU ops, tree BCE +
 //                           CE sums in registers, P = s*valid + 1e-6 -> shared-memory channel plane.
-//   warp  8     halo      : the 2-pixel ring of every plane (sigmoid only) + the tile's label bytes.
-//   warps 9-15  consumers : warp = one channel plane of the round, thread = 4 x 8 block.  RMI moments
+//   warps 12-15 consumers : warp = two channel planes of the round, thread = 4 x 12 block.  The 2-pixel ring of
+//                           the plane (sigmoid only, own cp.async ring), the tile's label bytes, then RMI moments
 //                           of the interior anchors as 13 product taps (pr_cov) + 25 label-anchored taps
 //                           (la_pr), warp-reduced and accumulated in fp64 per CTA.
 // Planes travel producer -> consumer through a ring of kNBuf round buffers (kNR planes each) guarded by
@@ -20,18 +20,25 @@
 namespace sh {
 namespace fast {
 
-constexpr int TW = 64, TH = 16;
+constexpr int TW = 64;               // tile width (pixels)
+constexpr int PTH = 16;              // tile height of k3f_prep
+constexpr int PWARPS = 12;           // producer warps
+constexpr int CWARPS = 4;            // consumer warps
+constexpr int PPC = 2;               // planes per consumer warp and round
+constexpr int TH = 2 * PWARPS;       // tile height of the streaming kernels: one producer thread per 4-pixel strip
+constexpr int BR = TH / 2;           // rows of a consumer thread's 4-wide block
 constexpr int PW = TW + 4;           // plane pitch: cols x0-2 .. x0+65
-constexpr int PR = TH + 4;           // plane rows:  y0-2 .. y0+17
-constexpr int PLANE = PR * PW;       // 1360 floats
-constexpr int NR = 7;                // planes per round = consumer warps
-constexpr int NBUF = 3;              // round buffers
-constexpr int NPROD = 256, NHALO = 32, NCONS = 32 * NR;
-constexpr int NTHREADS = NPROD + NHALO + NCONS;   // 512: 8 producer warps, 1 halo warp, 7 consumer warps (128 registers each)
-constexpr int XD = 8;                // cp.async ring depth (power of two; XD-2 channels in flight per producer thread)
-constexpr int HD = 4;                // cp.async ring depth of the consumers' halo logits (planes in flight + 1)
-constexpr int BAR_FULL = 1, BAR_EMPTY = 1 + NBUF, BAR_PROD = 1 + 2 * NBUF, BAR_HALO = 2 + 2 * NBUF;
-constexpr int kFastMaxC = 160;
+constexpr int PR = TH + 4;           // plane rows:  y0-2 .. y0+TH+1
+constexpr int PLANE = PR * PW;
+constexpr int NR = CWARPS * PPC;     // planes per round
+constexpr int NBUF = 2;              // round buffers
+constexpr int NPROD = 32 * PWARPS, NCONS = 32 * CWARPS;
+constexpr int NTHREADS = NPROD + NCONS;   // 512 threads, 128 registers each
+constexpr int XD = 4;                // cp.async ring depth of the producers (power of two; XD-2 channels ahead)
+constexpr int HD = 4;                // cp.async ring depth of the consumers' halo logits (rounds; HD-1 ahead)
+constexpr int HSLOT = 48;            // staged halo bytes per lane and plane: 2 x 16 (strips) + 2 x 8 (column pairs)
+constexpr int BAR_FULL = 1, BAR_EMPTY = 1 + NBUF, BAR_PROD = 1 + 2 * NBUF, BAR_CONS = 2 + 2 * NBUF;
+constexpr int kFastMaxC = 64;
 
 // order entry: kind (0 fine / 1 mid / 2 high) | class << 8 | flags << 16 | channel << 24 ; flags bit1 = flush products
 struct FastHier {
@@ -42,10 +49,10 @@ struct FastHier {
 };
 
 struct TileCoord { int y0, x0; };
-__device__ __forceinline__ TileCoord tile_coord(int tile, int tiles_x) {
+__device__ __forceinline__ TileCoord tile_coord(int tile, int tiles_x, int th) {
   TileCoord t;
   const int tyi = tile / tiles_x;
-  t.y0 = tyi * TH;
+  t.y0 = tyi * th;
   t.x0 = (tile - tyi * tiles_x) * TW;
   return t;
 }
@@ -81,8 +88,8 @@ __global__ void __launch_bounds__(256) k3f_prep(const long long* __restrict__ la
   bool bad = false;
 #pragma unroll 1
   for (int tile = j0; tile < ntiles; tile += cpi) {
-    const TileCoord tc = tile_coord(tile, tiles_x);
-    for (int e = tid; e < (TH + 2) * (TW + 4); e += 256) {
+    const TileCoord tc = tile_coord(tile, tiles_x, PTH);
+    for (int e = tid; e < (PTH + 2) * (TW + 4); e += 256) {
       const int r = e / (TW + 4), j = e - r * (TW + 4);
       const int y = tc.y0 + r, xx = tc.x0 - 2 + j;
       unsigned char f = 0xff, m = 0xff, g = 0xff;
@@ -94,21 +101,21 @@ __global__ void __launch_bounds__(256) k3f_prep(const long long* __restrict__ la
           if (t >= 0 && t < hg.nf) { f = (unsigned char)t; m = (unsigned char)s_f2m[t]; g = (unsigned char)s_f2h[t]; l8 = f; }
           else bad = !ll_only; // F.one_hot would raise in the reference
         }
-        if (!ll_only && r < TH && j >= 2 && j < TW + 2) {
+        if (!ll_only && r < PTH && j >= 2 && j < TW + 2) {
           lab8[(long)y * W + xx] = l8;
           nv += (t != SH_IGNORE);
         }
       }
-      rl[(0 * (TH + 2) + r) * LPITCH + j] = f;
-      rl[(1 * (TH + 2) + r) * LPITCH + j] = m;
-      rl[(2 * (TH + 2) + r) * LPITCH + j] = g;
+      rl[(0 * (PTH + 2) + r) * LPITCH + j] = f;
+      rl[(1 * (PTH + 2) + r) * LPITCH + j] = m;
+      rl[(2 * (PTH + 2) + r) * LPITCH + j] = g;
     }
     __syncthreads();
     const int y = tc.y0 + ty;
     const bool row_ok = y >= 2 && y < H - 2;
 #pragma unroll 1
     for (int l = 0; l < 3; ++l) {
-      const unsigned char* base = rl + (l * (TH + 2) + ty) * LPITCH + tx;
+      const unsigned char* base = rl + (l * (PTH + 2) + ty) * LPITCH + tx;
       unsigned long long wn[3];
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
@@ -187,7 +194,7 @@ __global__ void __launch_bounds__(256) k3f_prep(const long long* __restrict__ la
 }
 
 inline size_t prep_smem(int C, int nf) {
-  return (size_t)C * 16 * 4 + (size_t)2 * nf * 4 + (size_t)3 * (TH + 2) * LPITCH + 16;
+  return (size_t)C * 16 * 4 + (size_t)2 * nf * 4 + (size_t)3 * (PTH + 2) * LPITCH + 16;
 }
 
 // tile walk of a persistent CTA without integer divisions: tile index advances by cpi per step
@@ -210,19 +217,22 @@ constexpr int PMW = 2 * 3 * 32;   // presence words per tile: [level][block] x {
 
 inline size_t pass1_smem(int C, int nf) {
   size_t s = (size_t)NBUF * NR * PLANE * 4;          // planes
-  s += (size_t)XD * NPROD * 16;                      // cp.async staging
-  s += (size_t)HD * NCONS * 48;                      // cp.async staging of the consumers' plane halos
-  s += (size_t)2 * 3 * TH * TW;                      // label tiles (two tile parities)
-  s += (size_t)2 * PMW * 4;                          // presence words (two tile parities)
+  s += (size_t)XD * NPROD * 16;                      // cp.async staging of the producers
+  s += (size_t)HD * NCONS * PPC * HSLOT;             // cp.async staging of the consumers' plane halos
+  s += (size_t)3 * TH * TW;                          // label tile
+  s += (size_t)PMW * 4;                              // presence words
   s += (size_t)C * kFastRec * 8;                     // fp64 totals
   s += (size_t)C * 8;                                // channel byte offsets
-  s += (size_t)(C + 2 * nf) * 4 + 64 * 4;            // tables + reduction scratch
+  s += (size_t)(C + 2 * nf) * 4 + 128 * 4;           // tables + reduction scratch
   return (s + 15) & ~(size_t)15;
 }
 
-// 13 product taps of one 4 x 8 block: anchors = centre rows (window rows 2..9), taps forward
+// 13 product taps of one 4 x BR block: anchors = centre rows (window rows 2..BR+1), taps forward.
+// The row loop stays rolled (3 rows per trip, the period of the rotating register window): fully unrolled the
+// consumer code overflows the instruction cache it shares with the producers.
 template <bool BORDER>
 __device__ __forceinline__ void pp_taps(const float* pl, unsigned int rowI, unsigned int colI, float (&acc)[16]) {
+  static_assert(BR % 3 == 0, "row loop is unrolled by the window period");
   float w[3][8];
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
@@ -231,29 +241,33 @@ __device__ __forceinline__ void pp_taps(const float* pl, unsigned int rowI, unsi
     w[q][0] = a.x; w[q][1] = a.y; w[q][2] = a.z; w[q][3] = a.w;
     w[q][4] = c4.x; w[q][5] = c4.y; w[q][6] = c4.z; w[q][7] = c4.w;
   }
+#pragma unroll 1
+  for (int ib = 0; ib < BR; ib += 3) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float(&r0)[8] = w[i % 3];
-    float(&r1)[8] = w[(i + 1) % 3];
-    float(&r2)[8] = w[(i + 2) % 3];
-    {
-      const float4 a = *reinterpret_cast<const float4*>(pl + (4 + i) * PW);
-      const float4 c4 = *reinterpret_cast<const float4*>(pl + (4 + i) * PW + 4);
-      r2[0] = a.x; r2[1] = a.y; r2[2] = a.z; r2[3] = a.w;
-      r2[4] = c4.x; r2[5] = c4.y; r2[6] = c4.z; r2[7] = c4.w;
-    }
+    for (int ii = 0; ii < 3; ++ii) {
+      const int i = ib + ii;
+      float(&r0)[8] = w[ii % 3];
+      float(&r1)[8] = w[(ii + 1) % 3];
+      float(&r2)[8] = w[(ii + 2) % 3];
+      {
+        const float4 a = *reinterpret_cast<const float4*>(pl + (4 + i) * PW);
+        const float4 c4 = *reinterpret_cast<const float4*>(pl + (4 + i) * PW + 4);
+        r2[0] = a.x; r2[1] = a.y; r2[2] = a.z; r2[3] = a.w;
+        r2[4] = c4.x; r2[5] = c4.y; r2[6] = c4.z; r2[7] = c4.w;
+      }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float p = r0[k + 2];
-      float a = p;
-      if (BORDER) a = (((rowI >> (i + 2)) & 1u) && ((colI >> (k + 2)) & 1u)) ? p : 0.f;
-      acc[0] = fmaf(a, p, acc[0]);
-      acc[1] = fmaf(a, r0[k + 3], acc[1]);
-      acc[2] = fmaf(a, r0[k + 4], acc[2]);
+      for (int k = 0; k < 4; ++k) {
+        const float p = r0[k + 2];
+        float a = p;
+        if (BORDER) a = (((rowI >> (i + 2)) & 1u) && ((colI >> (k + 2)) & 1u)) ? p : 0.f;
+        acc[0] = fmaf(a, p, acc[0]);
+        acc[1] = fmaf(a, r0[k + 3], acc[1]);
+        acc[2] = fmaf(a, r0[k + 4], acc[2]);
 #pragma unroll
-      for (int dx = 0; dx < 5; ++dx) {
-        acc[3 + dx] = fmaf(a, r1[k + dx], acc[3 + dx]);
-        acc[8 + dx] = fmaf(a, r2[k + dx], acc[8 + dx]);
+        for (int dx = 0; dx < 5; ++dx) {
+          acc[3 + dx] = fmaf(a, r1[k + dx], acc[3 + dx]);
+          acc[8 + dx] = fmaf(a, r2[k + dx], acc[8 + dx]);
+        }
       }
     }
   }
@@ -272,17 +286,17 @@ __device__ __forceinline__ void load_row8(const float* pl, int prow, unsigned in
   }
 }
 
-// la_pr taps of one 4 x 8 block, label-anchored:  lp[d] = sum_{q in block, L(q) = cl} PI(q - d).
-//   uniform block of class cl: box sums (column sums over the 8 rows, slid down 4 times, then 4-wide row sums);
-//   mixed block: per matching pixel, 25 adds from the 5-row window.
+// la_pr taps of one 4 x BR block, label-anchored:  lp[d] = sum_{q in block, L(q) = cl} PI(q - d).
+//   uniform block of class cl: box sums (column sums over the BR rows, slid down 4 times, then 4-wide row sums);
+//   mixed block: per matching pixel, 25 adds from the 5-row window (rolled loop, the window shifts through registers).
 template <bool BORDER>
 __device__ __forceinline__ void lp_taps(const float* pl, const unsigned char* ltrow, bool uniform, unsigned int pat,
                                         unsigned int rowI, unsigned int colI, float (&al)[32]) {
   if (uniform) {
     float S[8], t[8];
     load_row8<BORDER>(pl, 0, rowI, colI, S);
-#pragma unroll
-    for (int r = 1; r < 8; ++r) {
+#pragma unroll 1
+    for (int r = 1; r < BR; ++r) {
       load_row8<BORDER>(pl, r, rowI, colI, t);
 #pragma unroll
       for (int q = 0; q < 8; ++q) S[q] += t[q];
@@ -293,7 +307,7 @@ __device__ __forceinline__ void lp_taps(const float* pl, const unsigned char* lt
         load_row8<BORDER>(pl, a - 1, rowI, colI, t);
 #pragma unroll
         for (int q = 0; q < 8; ++q) S[q] -= t[q];
-        load_row8<BORDER>(pl, a + 7, rowI, colI, t);
+        load_row8<BORDER>(pl, a + BR - 1, rowI, colI, t);
 #pragma unroll
         for (int q = 0; q < 8; ++q) S[q] += t[q];
       }
@@ -303,10 +317,14 @@ __device__ __forceinline__ void lp_taps(const float* pl, const unsigned char* lt
   } else {
     float w[5][8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) load_row8<BORDER>(pl, q, rowI, colI, w[q]);
+    for (int q = 0; q < 4; ++q) load_row8<BORDER>(pl, q, rowI, colI, w[q + 1]);
+#pragma unroll 1
+    for (int i = 0; i < BR; ++i) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      load_row8<BORDER>(pl, i + 4, rowI, colI, w[(i + 4) % 5]);
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[q][j] = w[q + 1][j];
+      load_row8<BORDER>(pl, i + 4, rowI, colI, w[4]);
       const unsigned int z = *reinterpret_cast<const unsigned int*>(ltrow + i * TW) ^ pat;
       if (has_zero_byte(z)) {
 #pragma unroll
@@ -316,11 +334,25 @@ __device__ __forceinline__ void lp_taps(const float* pl, const unsigned char* lt
             for (int a = 0; a < 5; ++a)
 #pragma unroll
               for (int bq = 0; bq < 5; ++bq)      // window row a <-> dy = 2 - a ; col k+bq <-> dx = 2 - bq
-                al[24 - (a * 5 + bq)] += w[(i + a) % 5][k + bq];
+                al[24 - (a * 5 + bq)] += w[a][k + bq];
           }
       }
     }
   }
+}
+
+// Per-lane list of the 2-pixel ring of a plane: 2 strips of the plane rows 0,1,TH+2,TH+3 (64 strips) and up to 2 of
+// the 2*PR column pairs (PR rows x {cols 0,1 | cols 66,67}).  Byte offsets into a channel plane (-1 = outside the image).
+template <typename T>
+__device__ __forceinline__ void halo_offsets(int lane, int ty0, int tx0, int H, int W, int e, long& vo, long& so) {
+  const int hv = lane + 32 * e;
+  const int vrow = (hv >> 4) < 2 ? (hv >> 4) : TH + (hv >> 4), vstrip = hv & 15;
+  const int vy = ty0 - 2 + vrow, vx = tx0 + 4 * vstrip;
+  vo = (vy >= 0 && vy < H && vx < W) ? ((long)vy * W + vx) * (long)sizeof(T) : -1;
+  const bool hs = hv < 2 * PR;
+  const int srow = hs ? hv % PR : 0, sside = hs ? hv / PR : 0;
+  const int sy = ty0 - 2 + srow, sx = sside ? tx0 + TW : tx0 - 2;
+  so = (hs && sy >= 0 && sy < H && sx >= 0 && sx < W) ? ((long)sy * W + sx) * (long)sizeof(T) : -1;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -333,15 +365,15 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
   const int C = hg.nf + hg.nm + hg.nh;
   float* planes = reinterpret_cast<float*>(smem_raw);                                   // [NBUF][NR][PLANE]
   uint4* xstage = reinterpret_cast<uint4*>(planes + NBUF * NR * PLANE);                  // [XD][NPROD]
-  unsigned char* hstage = reinterpret_cast<unsigned char*>(xstage + XD * NPROD);         // [HD][NCONS][48]
-  unsigned char* LT = hstage + HD * NCONS * 48;                                          // [2][3][TH][TW]
-  unsigned int* PM = reinterpret_cast<unsigned int*>(LT + 2 * 3 * TH * TW);              // [2][3][32][2]
-  double* tot = reinterpret_cast<double*>(PM + 2 * PMW);                                 // [C][kFastRec]
+  unsigned char* hstage = reinterpret_cast<unsigned char*>(xstage + XD * NPROD);         // [HD][NCONS][PPC][HSLOT]
+  unsigned char* LT = hstage + HD * NCONS * PPC * HSLOT;                                 // [3][TH][TW]
+  unsigned int* PM = reinterpret_cast<unsigned int*>(LT + 3 * TH * TW);                  // [3][32][2]
+  double* tot = reinterpret_cast<double*>(PM + PMW);                                     // [C][kFastRec]
   long long* s_chb = reinterpret_cast<long long*>(tot + (size_t)C * kFastRec);           // [C] channel byte offsets (order index)
   unsigned int* s_order = reinterpret_cast<unsigned int*>(s_chb + C);                    // [C]
   int* s_f2m = reinterpret_cast<int*>(s_order + C);                                      // [nf]
   int* s_f2h = s_f2m + hg.nf;                                                            // [nf]
-  float* s_red = reinterpret_cast<float*>(s_f2h + hg.nf);                                // [64]
+  float* s_red = reinterpret_cast<float*>(s_f2h + hg.nf);                                // [128]
 
   const int tid = threadIdx.x;
   const long HW = (long)H * W;
@@ -355,7 +387,7 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
   __syncthreads();
 
   const int b = blockIdx.x / cpi, j0 = blockIdx.x - b * cpi;
-  const int tiles_x = ws.tiles_x, ntiles = ws.tiles_x * ws.tiles_y;
+  const int tiles_x = (W + TW - 1) / TW, ntiles = tiles_x * ((H + TH - 1) / TH);
   const int nt = j0 < ntiles ? (ntiles - j0 + cpi - 1) / cpi : 0;     // tiles of this CTA: j0, j0+cpi, ...
   const int RPT = (C + NR - 1) / NR;
   const int total_rounds = nt * RPT;
@@ -575,106 +607,34 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       const float v = warp_sum(lacc[k]);
-      if (lane == 0) s_red[k * 8 + warp] = v;
+      if (lane == 0) s_red[k * PWARPS + warp] = v;
     }
     bar_sync(BAR_PROD, NPROD);
     if (tid < 8) {
       float r = 0.f;
       if (tid < 6) {
 #pragma unroll
-        for (int w = 0; w < 8; ++w) r += s_red[tid * 8 + w];
+        for (int w = 0; w < PWARPS; ++w) r += s_red[tid * PWARPS + w];
         if (tid < 3) r *= -kLn2;
       }
       ws.bce2[(size_t)blockIdx.x * 8 + tid] = r;
     }
-  } else if (tid < NPROD + NHALO) {
-    // ============================== halo warp ==============================
-    // tile helper: label bytes of the tile per level + per-block presence words (consumers do the plane halos)
-    const int hl = tid - NPROD;
-    TileWalk tw;
-    tw.init(j0, cpi, tiles_x);
-#pragma unroll 1
-    for (int it = 0; it < nt; ++it, tw.next()) {
-      const int ty0 = tw.y0(), tx0 = tw.x0();
-#pragma unroll 1
-      for (int r = 0; r < RPT; ++r) {
-        const int buf = (it * RPT + r) % NBUF;
-        bar_sync(BAR_EMPTY + buf, NTHREADS);
-        if (r == 0) {
-          // RMI labels: void -> class 0, outside the image -> 0xff
-          unsigned char* lt = LT + (it & 1) * 3 * TH * TW;
-#pragma unroll 2
-          for (int q = 0; q < 8; ++q) {
-            const int wi = hl + 32 * q, row = wi >> 4, st = wi & 15;
-            const int yy = ty0 + row, xx = tx0 + 4 * st;
-            unsigned int f4 = 0xffffffffu, m4 = 0xffffffffu, g4 = 0xffffffffu;
-            if (yy < H && xx < W) {
-              const unsigned int t4 = *reinterpret_cast<const unsigned int*>(lab8 + (long)yy * W + xx);
-              f4 = m4 = g4 = 0u;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const unsigned int t = (t4 >> (8 * k)) & 0xffu;
-                if (t != SH_IGNORE) {
-                  f4 |= t << (8 * k);
-                  m4 |= (unsigned int)s_f2m[t] << (8 * k);
-                  g4 |= (unsigned int)s_f2h[t] << (8 * k);
-                }
-              }
-            }
-            *reinterpret_cast<unsigned int*>(lt + (0 * TH + row) * TW + 4 * st) = f4;
-            *reinterpret_cast<unsigned int*>(lt + (1 * TH + row) * TW + 4 * st) = m4;
-            *reinterpret_cast<unsigned int*>(lt + (2 * TH + row) * TW + 4 * st) = g4;
-          }
-          __syncwarp();
-          // per (level, 4x8 block): info = class of the first pixel | uniform << 8 ; hash = classes present (bit c & 31)
-          unsigned int* pm = PM + (it & 1) * PMW;
-#pragma unroll 1
-          for (int id = hl; id < 96; id += NHALO) {
-            const int l = id >> 5, blk = id & 31, bi0 = (blk >> 4) * 8, bsb = blk & 15;
-            const unsigned int first = *reinterpret_cast<const unsigned int*>(lt + (l * TH + bi0) * TW + 4 * bsb);
-            const unsigned int pat0 = (first & 0xffu) * 0x01010101u;
-            unsigned int diff = 0, hash = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const unsigned int wd = *reinterpret_cast<const unsigned int*>(lt + (l * TH + bi0 + i) * TW + 4 * bsb);
-              diff |= wd ^ pat0;
-              hash |= (1u << (wd & 31)) | (1u << ((wd >> 8) & 31)) | (1u << ((wd >> 16) & 31)) | (1u << ((wd >> 24) & 31));
-            }
-            pm[2 * id] = (first & 0xffu) | (diff == 0u ? 0x100u : 0u);
-            pm[2 * id + 1] = hash;
-          }
-        }
-        __threadfence_block();
-        bar_arrive(BAR_FULL + buf, NTHREADS);
-      }
-    }
   } else {
     // ============================== consumers ==============================
-    const int ct = tid - NPROD - NHALO, cw = ct >> 5, lane = ct & 31;
-    const int hb = lane >> 4, sb = lane & 15, i0 = hb * 8;
+    const int ct = tid - NPROD, cw = ct >> 5, lane = ct & 31;
+    const int hb = lane >> 4, sb = lane & 15, i0 = hb * BR;
     const int npre = total_rounds < NBUF ? total_rounds : NBUF;
     for (int q = 0; q < npre; ++q) bar_arrive(BAR_EMPTY + q, NTHREADS);
-    // The 2-pixel ring of the warp's own plane (sigmoid only): per lane 2 strips of the plane rows 0,1,18,19
-    // (64 strips) and up to 2 of the 40 column pairs (20 rows x {cols 0,1 | cols 66,67}).  Their logits come
-    // through a cp.async ring that runs HD-1 of the warp's planes ahead (across tile boundaries).
-    unsigned char* hs_gen = hstage + (cw * 32 + lane) * 48;
+    // The 2-pixel ring of the warp's own planes (sigmoid only); logits come through a cp.async ring that runs
+    // HD-1 rounds ahead (across tile boundaries).
+    unsigned char* hs_gen = hstage + (size_t)ct * PPC * HSLOT;
     const unsigned int hs_base = (unsigned int)__cvta_generic_to_shared(hs_gen);
-    auto halo_offsets = [&](int ty0, int tx0, int e, long& vo, long& so) {
-      const int hv = lane + 32 * e;
-      const int vrow = (hv >> 4) < 2 ? (hv >> 4) : 16 + (hv >> 4), vstrip = hv & 15;
-      const int vy = ty0 - 2 + vrow, vx = tx0 + 4 * vstrip;
-      vo = (vy >= 0 && vy < H && vx < W) ? ((long)vy * W + vx) * (long)sizeof(T) : -1;
-      const bool hs = hv < 2 * PR;
-      const int srow = hs ? hv % PR : 0, sside = hs ? hv / PR : 0;
-      const int sy = ty0 - 2 + srow, sx = sside ? tx0 + TW : tx0 - 2;
-      so = (hs && sy >= 0 && sy < H && sx >= 0 && sx < W) ? ((long)sy * W + sx) * (long)sizeof(T) : -1;
-    };
     int v_pl[2], s_pl[2];
     bool has_s[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int hv = lane + 32 * e;
-      const int vrow = (hv >> 4) < 2 ? (hv >> 4) : 16 + (hv >> 4);
+      const int vrow = (hv >> 4) < 2 ? (hv >> 4) : TH + (hv >> 4);
       v_pl[e] = vrow * PW + 2 + 4 * (hv & 15);
       has_s[e] = hv < 2 * PR;
       s_pl[e] = has_s[e] ? (hv % PR) * PW + (hv / PR) * (TW + 2) : 0;
@@ -688,30 +648,36 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
       if (pf_it < nt) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          halo_offsets(pw.y0(), pw.x0(), e, pv_offb[e], ps_offb[e]);
+          halo_offsets<T>(lane, pw.y0(), pw.x0(), H, W, e, pv_offb[e], ps_offb[e]);
           if (pv_offb[e] < 0) pv_offb[e] = 0;          // outside the image: any valid address will do
           if (ps_offb[e] < 0) ps_offb[e] = 0;
         }
       }
     };
-    auto pf_issue = [&]() {
-      const int pci = pf_r * NR + cw;
-      if (pf_it < nt && pci < C) {
-        const char* g = xbb + s_chb[pci];
-        const unsigned int dst = hs_base + (pf_seq & (HD - 1)) * (NCONS * 48);
+    auto pf_issue = [&]() {     // one commit group per round: the halo logits of the warp's PPC planes
+      if (pf_it < nt) {
+        const unsigned int dst0 = hs_base + (pf_seq & (HD - 1)) * (NCONS * PPC * HSLOT);
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          if (sizeof(T) == 4) {
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * e), "l"(g + pv_offb[e]));
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 32 + 8 * e), "l"(g + ps_offb[e]));
-          } else {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 16 * e), "l"(g + pv_offb[e]));
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 32 + 8 * e), "l"(g + ps_offb[e]));
+        for (int pp = 0; pp < PPC; ++pp) {
+          const int pci = pf_r * NR + cw * PPC + pp;
+          if (pci < C) {
+            const char* g = xbb + s_chb[pci];
+            const unsigned int dst = dst0 + pp * HSLOT;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              if (sizeof(T) == 4) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * e), "l"(g + pv_offb[e]));
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 32 + 8 * e), "l"(g + ps_offb[e]));
+              } else {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 16 * e), "l"(g + pv_offb[e]));
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 32 + 8 * e), "l"(g + ps_offb[e]));
+              }
+            }
           }
         }
-        ++pf_seq;
       }
       cp_async_commit();
+      ++pf_seq;
       if (++pf_r == RPT) { pf_r = 0; ++pf_it; pw.next(); pf_tile(); }
     };
     pf_tile();
@@ -723,11 +689,11 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
     for (int it = 0; it < nt; ++it, tw.next()) {
       const int ty0 = tw.y0(), tx0 = tw.x0();
       const bool border = ty0 < 2 || ty0 + TH > H - 2 || tx0 < 2 || tx0 + TW > W - 2;
-      // interior masks (only used by border tiles): plane rows i0..i0+11 and window cols 0..7
+      // interior masks (only used by border tiles): plane rows i0..i0+BR+3 and window cols 0..7
       unsigned int rowI = 0, colI = 0;
       if (border) {
 #pragma unroll
-        for (int q = 0; q < 12; ++q) { const int yy = ty0 - 2 + i0 + q; if (yy >= 2 && yy < H - 2) rowI |= 1u << q; }
+        for (int q = 0; q < BR + 4; ++q) { const int yy = ty0 - 2 + i0 + q; if (yy >= 2 && yy < H - 2) rowI |= 1u << q; }
 #pragma unroll
         for (int q = 0; q < 8; ++q) { const int xx = tx0 - 2 + 4 * sb + q; if (xx >= 2 && xx < W - 2) colI |= 1u << q; }
       }
@@ -736,7 +702,7 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         long vo, so;
-        halo_offsets(ty0, tx0, e, vo, so);
+        halo_offsets<T>(lane, ty0, tx0, H, W, e, vo, so);
         vz[e] = vo >= 0 ? 1e-6f : 0.f;
         sz[e] = so >= 0 ? 1e-6f : 0.f;
 #pragma unroll
@@ -753,20 +719,66 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
           sv[e][1] = (t2 >> 8) != SH_IGNORE ? 1.f : 0.f;
         }
       }
-      const unsigned char* lt = LT + (it & 1) * 3 * TH * TW + i0 * TW + 4 * sb;
-      const unsigned int* pm = PM + (it & 1) * PMW + 2 * lane;
-      unsigned int pinfo[3] = {0u, 0u, 0u}, phash[3] = {0u, 0u, 0u};
+      // ---- label bytes of the tile per level (RMI labels: void -> class 0, outside the image -> 0xff) and the
+      //      per-block presence words, built by the consumer warps together ----
+      bar_sync(BAR_CONS, NCONS);                       // every consumer is done with the previous tile's labels
+#pragma unroll 1
+      for (int wi = ct; wi < TH * 16; wi += NCONS) {
+        const int row = wi >> 4, st = wi & 15;
+        const int yy = ty0 + row, xx = tx0 + 4 * st;
+        unsigned int f4 = 0xffffffffu, m4 = 0xffffffffu, g4 = 0xffffffffu;
+        if (yy < H && xx < W) {
+          const unsigned int t4 = *reinterpret_cast<const unsigned int*>(lab8 + (long)yy * W + xx);
+          f4 = m4 = g4 = 0u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const unsigned int t = (t4 >> (8 * k)) & 0xffu;
+            if (t != SH_IGNORE) {
+              f4 |= t << (8 * k);
+              m4 |= (unsigned int)s_f2m[t] << (8 * k);
+              g4 |= (unsigned int)s_f2h[t] << (8 * k);
+            }
+          }
+        }
+        *reinterpret_cast<unsigned int*>(LT + (0 * TH + row) * TW + 4 * st) = f4;
+        *reinterpret_cast<unsigned int*>(LT + (1 * TH + row) * TW + 4 * st) = m4;
+        *reinterpret_cast<unsigned int*>(LT + (2 * TH + row) * TW + 4 * st) = g4;
+      }
+      bar_sync(BAR_CONS, NCONS);
+      // per (level, 4 x BR block): info = class of the first pixel | uniform << 8 ; hash = classes present (bit c & 31)
+      if (ct < 96) {
+        const int l = ct >> 5, blk = ct & 31, bi0 = (blk >> 4) * BR, bsb = blk & 15;
+        const unsigned int first = *reinterpret_cast<const unsigned int*>(LT + (l * TH + bi0) * TW + 4 * bsb);
+        const unsigned int pat0 = (first & 0xffu) * 0x01010101u;
+        unsigned int diff = 0, hash = 0;
+#pragma unroll
+        for (int i = 0; i < BR; ++i) {
+          const unsigned int wd = *reinterpret_cast<const unsigned int*>(LT + (l * TH + bi0 + i) * TW + 4 * bsb);
+          diff |= wd ^ pat0;
+          hash |= (1u << (wd & 31)) | (1u << ((wd >> 8) & 31)) | (1u << ((wd >> 16) & 31)) | (1u << ((wd >> 24) & 31));
+        }
+        PM[2 * ct] = (first & 0xffu) | (diff == 0u ? 0x100u : 0u);
+        PM[2 * ct + 1] = hash;
+      }
+      bar_sync(BAR_CONS, NCONS);
+      unsigned int pinfo[3], phash[3];
+#pragma unroll
+      for (int l = 0; l < 3; ++l) { pinfo[l] = PM[l * 64 + 2 * lane]; phash[l] = PM[l * 64 + 2 * lane + 1]; }
+      const unsigned char* lt = LT + i0 * TW + 4 * sb;
 #pragma unroll 1
       for (int r = 0; r < RPT; ++r) {
         const int R = it * RPT + r, buf = R % NBUF;
-        const int ci = r * NR + cw;
         pf_issue();
         cp_async_wait<HD - 1>();
-        // halo of this warp's plane: independent of the producers, done while they finish the round
-        if (ci < C) {
-          const unsigned char* st = hs_gen + (seq & (HD - 1)) * (NCONS * 48);
-          ++seq;
-          float* plw = planes + (buf * NR + cw) * PLANE;
+        // halos of this warp's planes: independent of the producers, done while they finish the round
+        const unsigned char* st0 = hs_gen + (seq & (HD - 1)) * (NCONS * PPC * HSLOT);
+        ++seq;
+#pragma unroll 1
+        for (int pp = 0; pp < PPC; ++pp) {
+          const int ci = r * NR + cw * PPC + pp;
+          if (ci >= C) break;
+          const unsigned char* st = st0 + pp * HSLOT;
+          float* plw = planes + (buf * NR + cw * PPC + pp) * PLANE;
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             float xv[4], xs[2];
@@ -787,15 +799,14 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
           }
         }
         bar_sync(BAR_FULL + buf, NTHREADS);
-        if (r == 0) {
-#pragma unroll
-          for (int l = 0; l < 3; ++l) { pinfo[l] = pm[l * 64]; phash[l] = pm[l * 64 + 1]; }
-        }
-        if (ci < C) {
+#pragma unroll 1
+        for (int pp = 0; pp < PPC; ++pp) {
+          const int ci = r * NR + cw * PPC + pp;
+          if (ci >= C) break;
           const unsigned int oe = s_order[ci];
           const int lvl = oe & 3, cl = (oe >> 8) & 0xff;
           const unsigned int ch = oe >> 24;
-          const float* pl = planes + (buf * NR + cw) * PLANE + i0 * PW + 4 * sb;   // window row 0 = plane row i0
+          const float* pl = planes + (buf * NR + cw * PPC + pp) * PLANE + i0 * PW + 4 * sb;   // window row 0 = plane row i0
           double* trow = tot + (size_t)ch * kFastRec;
           // ---- pr_cov: 13 product taps of the interior anchors ----
           {
@@ -840,7 +851,8 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
     cp_async_wait<0>();
     // ---- records of the channels this warp owned ------------------------------------------------
     __syncwarp();
-    for (int ci = cw; ci < C; ci += NR) {
+    for (int ci = 0; ci < C; ++ci) {
+      if (((ci % NR) / PPC) != cw) continue;
       const unsigned int ch = s_order[ci] >> 24;
       double* rec = ws.rec2 + ((size_t)blockIdx.x * C + ch) * kFastRec;
       for (int q = lane; q < kFastRec; q += 32) rec[q] = tot[(size_t)ch * kFastRec + q];

@@ -82,8 +82,9 @@ def fast_tree_order(n_fine: int, n_mid: int, n_high: int, f2m, f2h):
     """Channel order of the warp-specialised kernels (csrc/rmi3_fast.cuh), or None when the maps are
     not a tree (some mid with fine children under two different highs): per high h, per mid m under h
     (ascending) the fine children of m (ascending) then m, then h itself; mids/highs without children
-    come in id order.  Entry = kind | class << 8 | flags << 16 | channel << 24, flags bit1 = flush the
-    level's running product of (1 - s + eps) factors (at most 5 factors of >= 1e-6 stay in fp32 range)."""
+    come in id order.  Entry = kind | class << 8 | flags << 16 | channel << 24; flags bit0 / bit2 = first
+    entry of a mid / high group (the backward pass switches its holder bytes there), bit1 = flush the level's
+    running product of (1 - s + eps) factors (at most 5 factors of >= 1e-6 stay in fp32 range)."""
     f2m = [int(v) for v in f2m]
     f2h = [int(v) for v in f2h]
     mid_high = {}
@@ -94,22 +95,28 @@ def fast_tree_order(n_fine: int, n_mid: int, n_high: int, f2m, f2h):
     placed_mid = set()
 
     def put_mid(m):
+        first = len(entries)
         for f in range(n_fine):
             if f2m[f] == m:
                 entries.append([0, f, 0, f])
         entries.append([1, m, 0, n_fine + m])
+        entries[first][2] |= 1                            # bit0: first entry of a mid group
         placed_mid.add(m)
 
     for h in range(n_high):
+        first = len(entries)
         for m in range(n_mid):
             if mid_high.get(m) == h:
                 put_mid(m)
         entries.append([2, h, 0, n_fine + n_mid + h])
+        entries[first][2] |= 4                            # bit2: first entry of a high group
     # childless mids: their max is their own sigmoid and they feed no high; order is irrelevant but
-    # they must not sit between a high's mids and the high itself
+    # they must not sit between a high's mids and the high itself (each is a high group of its own, high = none)
     for m in range(n_mid):
         if m not in placed_mid:
+            first = len(entries)
             put_mid(m)
+            entries[first][2] |= 4
     seen = [0, 0, 0]
     for e in entries:
         seen[e[0]] += 1
