@@ -88,7 +88,7 @@ int sh_rmi3_fast_path(const void* logits, const void* grad, int dtype, int H, in
 /* Pass 1 (+ label prep, frame taps, per-(b,c) 9x9 algebra): tree BCE (rmi...py:352-470), CE (:523-526),
  * RMI lower bound (:479-517) without materialising the unfolds.  Leaves everything the backward pass and
  * sh_loss3_final need in `workspace`.
- * hier_tab (device int32): [f2m nf][f2h nf][mh_ptr nm+1][mh_idx n_mh][hsmask nm][order C][fast_order C]
+ * hier_tab (device int32): [f2m nf][f2h nf][mh_ptr nm+1][mh_idx n_mh][hsmask nm][order C][fast_order C][fast_aux C]
  * (seghiero_b200/hierarchy.py::three_level_tables). */
 int sh_rmi3_forward(const void* logits, int dtype, const long long* label, int B, int H, int W, int nf, int nm, int nh,
                     const int* hier_tab, int n_mh, int fast_tab_ok, float lam, float loss_weight, void* workspace,

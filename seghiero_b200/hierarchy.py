@@ -45,7 +45,8 @@ def two_level_tables(n_fine: int, hiera_index: Sequence[Sequence[int]]):
 
 
 def three_level_tables(n_fine: int, n_mid: int, n_high: int, fine_to_mid, fine_to_high):
-    """-> (int32 blob [f2m][f2h][mh_ptr][mh_idx][hsmask], n_mh).  Validates the maps."""
+    """-> (int32 blob [f2m][f2h][mh_ptr][mh_idx][hsmask][order C][fast order C][fast aux C], n_mh, fast_ok).
+    Validates the maps."""
     f2m = np.asarray(fine_to_mid, dtype=np.int64).reshape(-1)
     f2h = np.asarray(fine_to_high, dtype=np.int64).reshape(-1)
     if f2m.size != n_fine or f2h.size != n_fine:
@@ -71,7 +72,7 @@ def three_level_tables(n_fine: int, n_mid: int, n_high: int, fine_to_mid, fine_t
     fast = fast_tree_order(n_fine, n_mid, n_high, f2m, f2h)
     fast_ok = fast is not None
     if fast is None:
-        fast = np.zeros(n_fine + n_mid + n_high, dtype=np.int32)
+        fast = np.zeros(2 * (n_fine + n_mid + n_high), dtype=np.int32)
     blob = np.concatenate([f2m.astype(np.int32), f2h.astype(np.int32), mh_ptr,
                            np.array(mh_idx, dtype=np.int32), hsmask.view(np.int32),
                            tree_order(n_fine, n_mid, n_high, f2m), fast]).astype(np.int32)
@@ -123,7 +124,17 @@ def fast_tree_order(n_fine: int, n_mid: int, n_high: int, f2m, f2h):
         if seen[e[0]] % 5 == 0:
             e[2] |= 2
     assert len(entries) == n_fine + n_mid + n_high
-    return np.array([k | (c << 8) | (fl << 16) | (ch << 24) for k, c, fl, ch in entries], dtype=np.uint32).view(np.int32)
+    order = np.array([k | (c << 8) | (fl << 16) | (ch << 24) for k, c, fl, ch in entries], dtype=np.uint32)
+    # second table (backward pass): mid id | high id << 8 of every entry, 0xff = none
+    aux = []
+    for k, c, _, _ in entries:
+        if k == 0:
+            aux.append(f2m[c] | (f2h[c] << 8))
+        elif k == 1:
+            aux.append(c | (mid_high.get(c, 0xff) << 8))
+        else:
+            aux.append(0xff | (c << 8))
+    return np.concatenate([order, np.array(aux, dtype=np.uint32)]).view(np.int32)
 
 
 def tree_order(n_fine: int, n_mid: int, n_high: int, f2m) -> np.ndarray:
