@@ -6,6 +6,7 @@
 //              added in place
 // Analytic RMI backward: see oracle/rmi_taps.py (checked against autograd on the CPU).
 #include "rmi3_common.cuh"
+#include "rmi3_fast_bwd.cuh"
 
 namespace sh {
 
@@ -426,13 +427,27 @@ static size_t pass2_smem_bytes() {
   return (s + 15) & ~(size_t)15;
 }
 
+bool fast_path_ok(const void* x, const void* grad, int elem, int H, int W, int nf, int nm, int nh, int fast_tab_ok);
+
 template <typename T>
 static int run_backward3(const void* x, void* grad, int B, int H, int W, const Hier3& h, const Ws3& ws,
                          const float* bandR, const float* bandC, float eps, float lw, const float* gscale, int stages,
-                         cudaStream_t st) {
+                         int fast_tab_ok, cudaStream_t st) {
   const int C = h.nf + h.nm + h.nh;
   const bool vec_ok = ((W & 3) == 0) && ((uintptr_t)x % (4 * sizeof(T)) == 0) && ((uintptr_t)grad % (4 * sizeof(T)) == 0);
-  if (stages & 1) {
+  const size_t fsmem = fast2::pass2_smem(C, h.nf, h.nm, h.nh);
+  const bool fast = fast_path_ok(x, grad, (int)sizeof(T), H, W, h.nf, h.nm, h.nh, fast_tab_ok) && fsmem <= 227 * 1024;
+  if ((stages & 1) && fast) {
+    fast2::Hier2 fh;
+    fh.nf = h.nf; fh.nm = h.nm; fh.nh = h.nh; fh.f2m = h.f2m; fh.f2h = h.f2h;
+    fh.order = h.order + C; fh.aux = h.order + 2 * C;
+    auto kern = fast2::k3f_pass2<T>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+    const int tiles_x = (W + fast2::TW - 1) / fast2::TW, tiles_y = (H + fast2::TH - 1) / fast2::TH;
+    kern<<<B * tiles_x * tiles_y, fast2::NT, fsmem, st>>>((const T*)x, (T*)grad, B, H, W, fh, ws, eps, lw, gscale, tiles_x,
+                                                         tiles_x * tiles_y);
+    SH_CHECK_LAUNCH();
+  } else if (stages & 1) {
     const size_t smem = pass2_smem_bytes();
     auto kern = k3_pass2<T>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -461,9 +476,9 @@ int sh_rmi3_backward(const void* logits, int dtype, void* grad, int B, int H, in
   sh::Hier3 h = sh::hier3_from_tab(hier_tab, nf, nm, nh, n_mh);
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case SH_DT_F32: return sh::run_backward3<float>(logits, grad, B, H, W, h, ws, bandR, bandC, 1e-6f, loss_weight, grad_out, stages, st);
-    case SH_DT_BF16: return sh::run_backward3<__nv_bfloat16>(logits, grad, B, H, W, h, ws, bandR, bandC, 1e-6f, loss_weight, grad_out, stages, st);
-    case SH_DT_F16: return sh::run_backward3<__half>(logits, grad, B, H, W, h, ws, bandR, bandC, 1e-6f, loss_weight, grad_out, stages, st);
+    case SH_DT_F32: return sh::run_backward3<float>(logits, grad, B, H, W, h, ws, bandR, bandC, 1e-6f, loss_weight, grad_out, stages, fast_tab_ok, st);
+    case SH_DT_BF16: return sh::run_backward3<__nv_bfloat16>(logits, grad, B, H, W, h, ws, bandR, bandC, 1e-6f, loss_weight, grad_out, stages, fast_tab_ok, st);
+    case SH_DT_F16: return sh::run_backward3<__half>(logits, grad, B, H, W, h, ws, bandR, bandC, 1e-6f, loss_weight, grad_out, stages, fast_tab_ok, st);
   }
   return SH_ERR_UNSUPPORTED;
 }

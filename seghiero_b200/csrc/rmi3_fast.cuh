@@ -590,7 +590,8 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
         lacc[3] = fmaf(vf[k] * kLn2, lg2(sumF[k]), lacc[3]);
         lacc[4] = fmaf(vf[k] * kLn2, lg2(sumM[k]), lacc[4]);
         lacc[5] = fmaf(vf[k] * kLn2, lg2(sumH[k]), lacc[5]);
-        iv[0][k] = rcp(sumF[k]); iv[1][k] = rcp(sumM[k]); iv[2][k] = rcp(sumH[k]);
+        // 1 / sum e^x, zero on void pixels (their CE gradient is zero; the fast backward pass relies on it)
+        iv[0][k] = rcp(sumF[k]) * vf[k]; iv[1][k] = rcp(sumM[k]) * vf[k]; iv[2][k] = rcp(sumH[k]) * vf[k];
       }
       if (inimg) {
         *reinterpret_cast<unsigned int*>(hold_px + (long)(hg.nm + hg.nh) * BHW) = hpf;

@@ -1,0 +1,507 @@
+// Fast path of the three-level loss, backward side (pass 2): gradient of tree BCE + CE + RMI w.r.t. the logits.
+//
+// Same applicability as rmi3_fast.cuh (tree-shaped maps, W % 4 == 0, 16-byte aligned tensors, C <= 64).
+// Reference arithmetic: models/loss/rmi_hiera_triplet_loss.py:349-526 (autograd of it); analytic RMI backward in
+// oracle/rmi_taps.py.  The generic kernel (rmi3_bwd.cu::k3_pass2) computes the same thing for every other case.
+//
+// One CTA = one 64 x 32 tile of one image, 192 threads:
+//   threads 0..127  body : thread = 4 x 4 pixel block.  Per channel (tree order: fine children, their mid, ...,
+//                          the high):
+//                            phase A  sigmoid / e^x (3 MUFU), tree-BCE + CE gradient from the per-pixel summaries
+//                                     of pass 1 (holder bytes, 1/sum e^x) -> 16 registers; P = s*valid + 1e-6
+//                                     -> shared-memory plane
+//                            phase B  5x5 stencil over the plane (weights from k3f_finalize), + the one-hot
+//                                     stencil where the block's labels are mixed, combine, 128-bit store
+//   threads 128..191 halo: the 2-pixel ring of the plane (sigmoid only), stencil weights -> shared memory
+// Planes are double buffered; phase B of channel c and phase A of channel c+1 sit between the same pair of
+// barriers, so MUFU-heavy and FMA-heavy code overlap inside every warp.  Logits of channel c+1 travel
+// global -> shared with cp.async while phase B of channel c runs.
+#pragma once
+#include "rmi3_common.cuh"
+
+namespace sh {
+namespace fast2 {
+
+constexpr int TW = 64, TH = 32;
+constexpr int NBODY = (TH / 4) * 16;      // 128 threads, each a 4 x 4 block
+constexpr int NHALO = 64;
+constexpr int NT = NBODY + NHALO;
+constexpr int PW = TW + 4, PR = TH + 4, PLANE = PR * PW;
+constexpr int LP = TW + 8;                // label tile pitch (bytes): cols x0-2 .. x0+65 (+4 pad)
+constexpr int WS = 64;                    // floats per staged weight record: W1 at 0, W2 at 28, W2full at 56
+
+struct Hier2 {
+  int nf, nm, nh;
+  const int* f2m;             // [nf]
+  const int* f2h;             // [nf]
+  const unsigned int* order;  // [C] kind | class << 8 | flags << 16 | channel << 24 ; flags bit0/bit2 = first of a mid/high group
+  const unsigned int* aux;    // [C] mid id | high id << 8 (0xff = none)
+};
+
+inline size_t pass2_smem(int C, int nf, int nm, int nh) {
+  size_t s = (size_t)2 * PLANE * 4;                 // planes
+  s += (size_t)3 * TH * TW * 4;                     // 1 / sum e^x per level
+  s += (size_t)4 * NBODY * 16 + (size_t)NHALO * 32; // cp.async staging of the logits
+  s += (size_t)(nm + nh + 2) * TH * TW;             // holder bytes
+  s += (size_t)3 * PR * LP;                         // label tile
+  s += (size_t)2 * WS * 4;                          // stencil weights
+  s += (size_t)C * 16 + (size_t)2 * nf * 4 + 64;    // tables
+  return (s + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ bool byte_is_zero(unsigned int z, int k) { return ((z >> (8 * k)) & 0xffu) == 0u; }
+
+template <typename T>
+__global__ void __launch_bounds__(NT, 2)
+k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hier2 hg, Ws3 ws, float eps,
+          float loss_weight, const float* __restrict__ gscale_ptr, int tiles_x, int tiles_per_img) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int C = hg.nf + hg.nm + hg.nh;
+  const int NH = hg.nm + hg.nh + 2;
+  float* planes = reinterpret_cast<float*>(smem_raw);                                  // [2][PLANE]
+  float* ivt = planes + 2 * PLANE;                                                     // [3][TH][TW]
+  uint4* xst = reinterpret_cast<uint4*>(ivt + 3 * TH * TW);                            // [4][NBODY]
+  unsigned char* hst = reinterpret_cast<unsigned char*>(xst + 4 * NBODY);              // [NHALO][32]
+  unsigned char* HT = hst + NHALO * 32;                                                // [NH][TH][TW] holder bytes
+  unsigned char* LT = HT + (size_t)NH * TH * TW;                                       // [3][PR][LP]
+  float* wsm = reinterpret_cast<float*>(LT + 3 * PR * LP);                             // [2][WS]
+  long long* s_chb = reinterpret_cast<long long*>(wsm + 2 * WS);                       // [C]
+  unsigned int* s_order = reinterpret_cast<unsigned int*>(s_chb + C);                  // [C]
+  unsigned int* s_aux = s_order + C;                                                   // [C]
+  int* s_f2m = reinterpret_cast<int*>(s_aux + C);                                      // [nf]
+  int* s_f2h = s_f2m + hg.nf;                                                          // [nf]
+
+  const int tid = threadIdx.x;
+  const long HW = (long)H * W, BHW = (long)B * HW;
+  const int b = blockIdx.x / tiles_per_img, tile = blockIdx.x - b * tiles_per_img;
+  const int tyi = tile / tiles_x, ty0 = tyi * TH, tx0 = (tile - tyi * tiles_x) * TW;
+  const unsigned char* lab8 = ws.lab8 + (long)b * HW;
+  const char* xbb = reinterpret_cast<const char*>(x + (long)b * C * HW);
+  const bool border = ty0 < 2 || ty0 + TH > H - 2 || tx0 < 2 || tx0 + TW > W - 2;
+
+  for (int i = tid; i < C; i += NT) {
+    const unsigned int oe = hg.order[i];
+    s_order[i] = oe;
+    s_aux[i] = hg.aux[i];
+    s_chb[i] = (long long)(oe >> 24) * HW * (long long)sizeof(T);
+  }
+  for (int i = tid; i < hg.nf; i += NT) { s_f2m[i] = hg.f2m[i]; s_f2h[i] = hg.f2h[i]; }
+
+  // ---- per-tile summaries of pass 1: 1/sum e^x (3 levels) and the holder bytes, global -> shared ----
+  for (int e = tid; e < 3 * TH * (TW / 4); e += NT) {
+    const int l = e / (TH * (TW / 4)), rem = e - l * (TH * (TW / 4)), r = rem >> 4, s4 = (rem & 15) << 2;
+    const int y = min(ty0 + r, H - 1), xx = tx0 + s4 < W ? tx0 + s4 : 0;
+    cp_async_16(ivt + (l * TH + r) * TW + s4, ws.inv + (long)l * BHW + (long)b * HW + (long)y * W + xx);
+  }
+  for (int e = tid; e < NH * TH * (TW / 4); e += NT) {
+    const int p = e / (TH * (TW / 4)), rem = e - p * (TH * (TW / 4)), r = rem >> 4, s4 = (rem & 15) << 2;
+    const int y = min(ty0 + r, H - 1), xx = tx0 + s4 < W ? tx0 + s4 : 0;
+    cp_async_4(HT + ((size_t)p * TH + r) * TW + s4, ws.hold + (long)p * BHW + (long)b * HW + (long)y * W + xx);
+  }
+  cp_async_commit();
+  __syncthreads();                                     // tables are in place
+
+  // ---- label tile (RMI labels of the 3 levels; outside the image 0xff) ----
+  for (int e = tid; e < PR * (PW / 2); e += NT) {
+    const int r = e / (PW / 2), j = (e - r * (PW / 2)) * 2;
+    const int yy = ty0 - 2 + r, xx = tx0 - 2 + j;
+    unsigned int f2 = 0xffffu, m2 = 0xffffu, g2 = 0xffffu;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      const unsigned int t2 = *reinterpret_cast<const unsigned short*>(lab8 + (long)yy * W + xx);
+      f2 = m2 = g2 = 0u;    // void pixels are one-hot of class 0 at every level inside RMI (rmi...py:360-370)
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const unsigned int t = (t2 >> (8 * k)) & 0xffu;
+        if (t != SH_IGNORE) {
+          f2 |= t << (8 * k);
+          m2 |= (unsigned int)s_f2m[t] << (8 * k);
+          g2 |= (unsigned int)s_f2h[t] << (8 * k);
+        }
+      }
+    }
+    *reinterpret_cast<unsigned short*>(LT + (0 * PR + r) * LP + j) = (unsigned short)f2;
+    *reinterpret_cast<unsigned short*>(LT + (1 * PR + r) * LP + j) = (unsigned short)m2;
+    *reinterpret_cast<unsigned short*>(LT + (2 * PR + r) * LP + j) = (unsigned short)g2;
+  }
+
+  const float gscale = *gscale_ptr;
+  const int nchan = C;
+
+  if (tid < NBODY) {
+    // =================================== body threads ===================================
+    const int rq = tid >> 4, st = tid & 15;
+    const int xg = tx0 + 4 * st;
+    const bool colok = xg < W;
+    const float nv = fmaxf((float)ws.counts[0], 1.0f);
+    const float wF = 2.5f * loss_weight * gscale / (nv * (float)hg.nf);
+    const float wM = 2.5f * loss_weight * gscale / (nv * (float)hg.nm);
+    const float wH = 2.5f * loss_weight * gscale / (nv * (float)hg.nh);
+    const float wCE = loss_weight * gscale / ((float)B * (float)HW);
+
+    bool rowok[4];
+    long roff[4];                       // pixel offset of the strip inside one channel plane (clamped into the image)
+    unsigned int tc0[4], tc1[4], tc2[4], hmN[4], hhN[4];
+    float vf[4][4];
+    unsigned long long present = 0ull;  // channels that are the target of some pixel of the block
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int y = ty0 + 4 * rq + j;
+      rowok[j] = y < H && colok;
+      roff[j] = (long)min(y, H - 1) * W + (colok ? xg : 0);
+      const unsigned int t4 = rowok[j] ? *reinterpret_cast<const unsigned int*>(lab8 + roff[j]) : 0xffffffffu;
+      tc0[j] = t4; tc1[j] = 0xffffffffu; tc2[j] = 0xffffffffu;
+      hmN[j] = hhN[j] = 0xffffffffu;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const unsigned int t = (t4 >> (8 * k)) & 0xffu;
+        vf[j][k] = t != SH_IGNORE ? 1.f : 0.f;
+        if (t != SH_IGNORE) {
+          const unsigned int cm = (unsigned int)(hg.nf + s_f2m[t]), chh = (unsigned int)(hg.nf + hg.nm + s_f2h[t]);
+          tc1[j] = (tc1[j] & ~(0xffu << (8 * k))) | (cm << (8 * k));
+          tc2[j] = (tc2[j] & ~(0xffu << (8 * k))) | (chh << (8 * k));
+          present |= (1ull << t) | (1ull << cm) | (1ull << chh);
+        }
+      }
+    }
+    // interior masks (border tiles only): bit 4*j + k
+    unsigned int imask = 0xffffu;
+    if (border) {
+      imask = 0u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int y = ty0 + 4 * rq + j;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (y >= 2 && y < H - 2 && xg + k >= 2 && xg + k < W - 2) imask |= 1u << (4 * j + k);
+      }
+    }
+    __syncthreads();                                   // label tile is complete
+    // label structure of the block's 8 x 8 neighbourhood per level: uniform class (or 0xfe = mixed) and the classes present
+    unsigned int ublk[3], pres[3];
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+      const unsigned char* lt = LT + (l * PR + 4 * rq) * LP + 4 * st;
+      const unsigned int first = *reinterpret_cast<const unsigned int*>(lt) & 0xffu;
+      const unsigned int pat = first * 0x01010101u;
+      unsigned int diff = 0u, hash = 0u;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const unsigned int wd = *reinterpret_cast<const unsigned int*>(lt + i * LP + 4 * q);
+          diff |= wd ^ pat;
+          hash |= (1u << (wd & 31)) | (1u << ((wd >> 8) & 31)) | (1u << ((wd >> 16) & 31)) | (1u << ((wd >> 24) & 31));
+        }
+      }
+      ublk[l] = diff == 0u ? first : 0xfeu;
+      pres[l] = hash;
+    }
+
+    const unsigned int xs_base = (unsigned int)__cvta_generic_to_shared(xst + tid);
+    const char* xs_gen = reinterpret_cast<const char*>(xst + tid);
+    auto prefetch = [&](int ci) {
+      const char* g = xbb + s_chb[ci];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const char* gp = g + roff[j] * (long)sizeof(T);
+        const unsigned int dst = xs_base + j * (NBODY * 16);
+        if (sizeof(T) == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gp));
+        else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gp));
+      }
+      cp_async_commit();
+    };
+
+    float g0[4][4];
+    const unsigned char* HTt = HT + (4 * rq) * TW + 4 * st;
+    const unsigned char* hpfp = HTt + (size_t)(hg.nm + hg.nh) * TH * TW;
+    const unsigned char* hpmp = HTt + (size_t)(hg.nm + hg.nh + 1) * TH * TW;
+
+    // phase A of channel (order index) ci: plane (ci & 1), gradient of BCE + CE -> g0
+    auto phaseA = [&](int ci) {
+      const unsigned int oe = s_order[ci], ax = s_aux[ci];
+      const int kind = oe & 3;
+      const unsigned int fl = (oe >> 16) & 0xffu, ch = oe >> 24;
+      const unsigned int cc = ch * 0x01010101u;
+      if (fl & 1u) {       // first channel of a mid group: which channel holds the group's max, where that term counts
+        const unsigned int mid = ax & 0xffu;
+        const unsigned int midc = (unsigned int)(hg.nf + mid) * 0x01010101u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const unsigned int hm = *reinterpret_cast<const unsigned int*>(HTt + ((size_t)mid * TH + j) * TW);
+          hmN[j] = hm | __vcmpeq4(tc1[j], midc);       // the target's own mid has no (1 - max) term
+        }
+      }
+      if (fl & 4u) {
+        const unsigned int high = ax >> 8;
+        if (high != 0xffu) {
+          const unsigned int highc = (unsigned int)(hg.nf + hg.nm + high) * 0x01010101u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const unsigned int hh = *reinterpret_cast<const unsigned int*>(HTt + ((size_t)(hg.nm + high) * TH + j) * TW);
+            hhN[j] = hh | __vcmpeq4(tc2[j], highc);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) hhN[j] = 0xffffffffu;
+        }
+      }
+      const float wbase = kind == 0 ? wF : 0.f;
+      const bool pos = (present >> ch) & 1ull;
+      float* prow = planes + (ci & 1) * PLANE + (4 * rq + 2) * PW + 4 * st + 2;
+      const float* ivp = ivt + (kind * TH + 4 * rq) * TW + 4 * st;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float xv[4];
+        staged_vec4<T>(xs_gen + j * (NBODY * 16), xv);
+        const float4 iv4 = *reinterpret_cast<const float4*>(ivp + j * TW);
+        const float ivk[4] = {iv4.x, iv4.y, iv4.z, iv4.w};
+        const unsigned int zM = hmN[j] ^ cc, zH = hhN[j] ^ cc;
+        float s[4], E[4], t[4], A[4], oh[4], ds[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          sig_exp3(xv[k], s[k], E[k]);
+          t[k] = 1.0f - s[k];
+          A[k] = wbase;
+          oh[k] = 0.f;
+        }
+        if (pos) {
+          const unsigned int zT = (kind == 0 ? tc0[j] : (kind == 1 ? tc1[j] : tc2[j])) ^ cc;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (byte_is_zero(zT, k)) { oh[k] = 1.f; A[k] = 0.f; }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (byte_is_zero(zM, k)) A[k] += wM;
+          if (byte_is_zero(zH, k)) A[k] += wH;
+          ds[k] = A[k] * rcp(t[k] + eps);
+        }
+        if (pos) {
+          const unsigned int zPF = *reinterpret_cast<const unsigned int*>(hpfp + j * TW) ^ cc;
+          const unsigned int zPM = *reinterpret_cast<const unsigned int*>(hpmp + j * TW) ^ cc;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float Bp = byte_is_zero(zPF, k) ? wF : 0.f;
+            if (byte_is_zero(zPM, k)) Bp += wM;
+            if (kind == 2 && oh[k] != 0.f) Bp += wH;
+            ds[k] = fmaf(-Bp, rcp(s[k] + eps), ds[k]);
+          }
+        }
+        float P[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float s2 = s[k] * vf[j][k];
+          P[k] = s2 + 1e-6f;                            // = probs * valid + 1e-6 (rmi...py:487)
+          const float q = s2 * t[k];
+          const float ce = fmaf(E[k], ivk[k], -oh[k]);  // softmax - one-hot; 1/sum e^x is 0 on void pixels
+          g0[j][k] = fmaf(ds[k], q, wCE * ce);
+        }
+        *reinterpret_cast<float2*>(prow + j * PW) = make_float2(P[0], P[1]);
+        *reinterpret_cast<float2*>(prow + j * PW + 2) = make_float2(P[2], P[3]);
+      }
+    };
+
+    // phase B of channel ci: stencil over plane (ci & 1), combine with g0, store
+    auto phaseB = [&](int ci) {
+      const unsigned int oe = s_order[ci];
+      const int kind = oe & 3;
+      const unsigned int cl = (oe >> 8) & 0xffu, ch = oe >> 24;
+      const float* wp = wsm + (ci & 1) * WS;
+      const float* pl = planes + (ci & 1) * PLANE + (4 * rq) * PW + 4 * st;
+      const unsigned char* lt = LT + (kind * PR + 4 * rq) * LP + 4 * st;
+      const unsigned int ub = kind == 0 ? ublk[0] : (kind == 1 ? ublk[1] : ublk[2]);
+      const unsigned int ph = kind == 0 ? pres[0] : (kind == 1 ? pres[1] : pres[2]);
+      const float init = ub == cl ? wp[56] : 0.f;
+      const int nsweep = (ub == 0xfeu && ((ph >> (cl & 31)) & 1u)) ? 2 : 1;
+      float acc[4][4], q[4][4];
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[o][k] = init;
+#pragma unroll 1
+      for (int sw = 0; sw < nsweep; ++sw) {
+        float w[28];
+#pragma unroll
+        for (int v = 0; v < 7; ++v) {
+          const float4 t4 = *reinterpret_cast<const float4*>(wp + sw * 28 + 4 * v);
+          w[4 * v] = t4.x; w[4 * v + 1] = t4.y; w[4 * v + 2] = t4.z; w[4 * v + 3] = t4.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float win[8];
+          if (sw == 0) {
+            const float4 a = *reinterpret_cast<const float4*>(pl + i * PW);
+            const float4 c4 = *reinterpret_cast<const float4*>(pl + i * PW + 4);
+            win[0] = a.x; win[1] = a.y; win[2] = a.z; win[3] = a.w;
+            win[4] = c4.x; win[5] = c4.y; win[6] = c4.z; win[7] = c4.w;
+            if (i >= 2 && i < 6) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float s1 = win[k + 2] - 1e-6f;          // valid pixels: P = s + 1e-6 ; void: exactly 0
+                q[i - 2][k] = s1 * (1.0f - s1);
+              }
+            }
+          } else {
+            const unsigned int l0 = *reinterpret_cast<const unsigned int*>(lt + i * LP);
+            const unsigned int l1 = *reinterpret_cast<const unsigned int*>(lt + i * LP + 4);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              win[v] = ((l0 >> (8 * v)) & 0xffu) == cl ? 1.f : 0.f;
+              win[4 + v] = ((l1 >> (8 * v)) & 0xffu) == cl ? 1.f : 0.f;
+            }
+          }
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            const int dyi = i - o;
+            if (dyi < 0 || dyi > 4) continue;
+#pragma unroll
+            for (int dx = 0; dx < 5; ++dx)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) acc[o][k] = fmaf(w[dyi * 5 + dx], win[k + dx], acc[o][k]);
+          }
+        }
+      }
+      T* gp = grad + ((long)b * C + ch) * HW;
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        if (border) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {     // frame pixels: no RMI term here (k3_frame2); their stencil sums may hold garbage
+            const bool inter = (imask >> (4 * o + k)) & 1u;
+            q[o][k] = inter ? q[o][k] : 0.f;
+            acc[o][k] = inter ? acc[o][k] : 0.f;
+          }
+        }
+        float g[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) g[k] = fmaf(q[o][k], acc[o][k], g0[o][k]);
+        if (rowok[o]) VecIO<T, 4>::store(gp + roff[o], g);
+      }
+    };
+
+    prefetch(0);
+    cp_async_wait<0>();
+    __syncthreads();                                   // 1/sum e^x, holder bytes (copied by all threads) have landed
+    phaseA(0);
+    __syncthreads();
+#pragma unroll 1
+    for (int ci = 0; ci < nchan; ++ci) {
+      if (ci + 1 < nchan) prefetch(ci + 1);
+      phaseB(ci);
+      if (ci + 1 < nchan) {
+        cp_async_wait<0>();
+        phaseA(ci + 1);
+      }
+      __syncthreads();
+    }
+  } else {
+    // =================================== halo threads ===================================
+    const int hl = tid - NBODY;
+    // item 0: 4-pixel strip of plane rows 0,1,TH+2,TH+3 ; item 1: 2-pixel pair left / right of a body row ;
+    // item 2 (lanes 0..7): 2 x 2 corner pairs
+    int pidx[3];
+    long goff[3];
+    bool in[3];
+    float hv[8];
+    {
+      const int hrow = hl >> 4, pr = hrow < 2 ? hrow : TH + hrow, strip = hl & 15;
+      const int yy = ty0 - 2 + pr, xx = tx0 + 4 * strip;
+      pidx[0] = pr * PW + 2 + 4 * strip;
+      in[0] = yy >= 0 && yy < H && xx < W;
+      goff[0] = in[0] ? (long)yy * W + xx : 0;
+    }
+    {
+      const int srow = hl >> 1, side = hl & 1;
+      const int yy = ty0 + srow, xx = side ? tx0 + TW : tx0 - 2;
+      pidx[1] = (2 + srow) * PW + (side ? TW + 2 : 0);
+      in[1] = yy < H && xx >= 0 && xx < W;
+      goff[1] = in[1] ? (long)yy * W + xx : 0;
+    }
+    {
+      const int crow = (hl >> 1) & 3, pr = crow < 2 ? crow : TH + crow, side = hl & 1;
+      const int yy = ty0 - 2 + pr, xx = side ? tx0 + TW : tx0 - 2;
+      pidx[2] = pr * PW + (side ? TW + 2 : 0);
+      in[2] = hl < 8 && yy >= 0 && yy < H && xx >= 0 && xx < W;
+      goff[2] = in[2] ? (long)yy * W + xx : 0;
+    }
+    {
+      const unsigned int t4 = in[0] ? *reinterpret_cast<const unsigned int*>(lab8 + goff[0]) : 0xffffffffu;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) hv[k] = ((t4 >> (8 * k)) & 0xffu) != SH_IGNORE ? 1.f : 0.f;
+#pragma unroll
+      for (int e = 1; e < 3; ++e) {
+        const unsigned int t2 = in[e] ? *reinterpret_cast<const unsigned short*>(lab8 + goff[e]) : 0xffffu;
+        hv[2 * e + 2] = (t2 & 0xffu) != SH_IGNORE ? 1.f : 0.f;
+        hv[2 * e + 3] = (t2 >> 8) != SH_IGNORE ? 1.f : 0.f;
+      }
+    }
+    unsigned char* hs_gen = hst + hl * 32;
+    const unsigned int hs_base = (unsigned int)__cvta_generic_to_shared(hs_gen);
+    auto prefetch = [&](int ci) {
+      const char* g = xbb + s_chb[ci];
+      if (sizeof(T) == 4) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(hs_base), "l"(g + goff[0] * 4));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(hs_base + 16), "l"(g + goff[1] * 4));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(hs_base + 24), "l"(g + goff[2] * 4));
+      } else {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(hs_base), "l"(g + goff[0] * 2));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(hs_base + 16), "l"(g + goff[1] * 2));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(hs_base + 24), "l"(g + goff[2] * 2));
+      }
+      cp_async_commit();
+    };
+    auto halo = [&](int ci) {
+      float* pl = planes + (ci & 1) * PLANE;
+      float xv[4];
+      staged_vec4<T>(hs_gen, xv);
+      if (in[0]) {
+        *reinterpret_cast<float2*>(pl + pidx[0]) = make_float2(fmaf(sig_only(xv[0]), hv[0], 1e-6f), fmaf(sig_only(xv[1]), hv[1], 1e-6f));
+        *reinterpret_cast<float2*>(pl + pidx[0] + 2) = make_float2(fmaf(sig_only(xv[2]), hv[2], 1e-6f), fmaf(sig_only(xv[3]), hv[3], 1e-6f));
+      }
+#pragma unroll
+      for (int e = 1; e < 3; ++e) {
+        if (in[e]) {
+          float a0, a1;
+          if (sizeof(T) == 4) {
+            const float2 t2 = *reinterpret_cast<const float2*>(hs_gen + 8 + 8 * e);
+            a0 = t2.x; a1 = t2.y;
+          } else {
+            a0 = staged_elem<T>(hs_gen + 8 + 8 * e, 0);
+            a1 = staged_elem<T>(hs_gen + 8 + 8 * e, 1);
+          }
+          *reinterpret_cast<float2*>(pl + pidx[e]) =
+              make_float2(fmaf(sig_only(a0), hv[2 * e + 2], 1e-6f), fmaf(sig_only(a1), hv[2 * e + 3], 1e-6f));
+        }
+      }
+    };
+    // stencil weights of channel ci (k3f_finalize: W1[25], W2[25], sum W2 at 50) times the upstream gradient
+    auto weights = [&](int ci) {
+      const unsigned int ch = s_order[ci] >> 24;
+      const float* src = ws.wts + ((size_t)b * C + ch) * 64;
+      float* dst = wsm + (ci & 1) * WS;
+      if (hl < 25) { dst[hl] = src[hl] * gscale; dst[28 + hl] = src[25 + hl] * gscale; }
+      else if (hl < 28) { dst[hl] = 0.f; dst[28 + hl] = 0.f; }
+      else if (hl == 28) dst[56] = src[50] * gscale;
+    };
+    __syncthreads();                                   // label tile (all threads took part)
+    prefetch(0);
+    weights(0);
+    cp_async_wait<0>();
+    __syncthreads();
+    halo(0);
+    __syncthreads();
+#pragma unroll 1
+    for (int ci = 0; ci < nchan; ++ci) {
+      if (ci + 1 < nchan) {
+        prefetch(ci + 1);
+        weights(ci + 1);
+        cp_async_wait<0>();
+        halo(ci + 1);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace fast2
+}  // namespace sh
