@@ -66,11 +66,12 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.lines, self.proc = index, [], None
+        self.windows = []          # [t0, t1] wall-clock windows (timed regions); only samples inside them count
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -80,7 +81,10 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self, t0, t1):
+        self.windows.append((t0, t1))
 
     def __exit__(self, *exc):
         if self.proc is not None:
@@ -93,7 +97,10 @@ class ClockSampler:
 
     def summary(self):
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            # a sample describes the ~20 ms before it was printed
+            if self.windows and not any(a <= ts <= b + 0.03 for a, b in self.windows):
+                continue
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -297,6 +304,8 @@ def run_ours(args, w):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clk = ClockSampler(local)
+    clk.__enter__()                       # nvidia-smi needs ~0.1 s before its first sample: start it before the warm-up
     for _ in range(warmup):
         step()
     barrier()
@@ -306,13 +315,14 @@ def run_ours(args, w):
     ops.STAGE_TIMER = timer
     ops.LAUNCHES["n"] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        barrier()
-        e0.record()
-        for _ in range(steps):
-            out = step()
-        e1.record()
-        barrier()
+    barrier()
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(steps):
+        out = step()
+    e1.record()
+    barrier()
+    clk.mark(t_wall0, time.time())
     ops.STAGE_TIMER = None
     launches = ops.LAUNCHES["n"]
     elapsed = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -336,7 +346,11 @@ def run_ours(args, w):
                    ("sh_rmi3_backward", 1): "k3_pass2", ("sh_rmi3_backward", 2): "k3_frame2",
                    ("sh_bce2_fwdbwd", 1): "k_prep2", ("sh_bce2_fwdbwd", 2): "k_bce2_fused",
                    ("sh_bce2_fwdbwd", 4): "k_reduce_partials"}
-    stage_bytes = {"k3_pass1": ab.get("pass1"), "k3_pass2": ab.get("pass2"), "k_bce2_fused": ab.get("fused")}
+    if w["kind"] == "3level" and getattr(mod, "last_stats", {}).get("fast_path"):
+        stage_names.update({("sh_rmi3_forward", 1): "k3f_prep", ("sh_rmi3_forward", 2): "k3f_pass1",
+                            ("sh_rmi3_forward", 8): "k3f_finalize", ("sh_rmi3_backward", 1): "k3f_pass2"})
+    stage_bytes = {"k3_pass1": ab.get("pass1"), "k3_pass2": ab.get("pass2"), "k_bce2_fused": ab.get("fused"),
+                   "k3f_pass1": ab.get("pass1"), "k3f_pass2": ab.get("pass2")}
     stages = {stage_names[k]: t / n for k, (t, n) in timer.totals().items() if k in stage_names}
     roofline = None
     traffic_tab = {}
@@ -351,7 +365,8 @@ def run_ours(args, w):
         achieved = stage_bytes[top] * px / (cand[top] * 1e-3) / 1e9
         tr = traffic_tab.get(f"{args.workload}:{top}")
         roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": (tr * px if tr else None),
+                    "frac": achieved / peak, "traffic": (tr["bytes_per_px"] * px if tr else None),
+                    "traffic_source": (tr.get("source") if tr else None),
                     "algorithmic_bytes_per_launch": stage_bytes[top] * px, "ms_per_launch": cand[top],
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                     "whole_step_frac": ab["total"] * px / (ms_step * 1e-3) / 1e9 / peak}
@@ -402,11 +417,13 @@ def run_ours(args, w):
         barrier()
         k2 = max(2, min(steps, 5))
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall0 = time.time()
         a0.record()
         for _ in range(k2):
             e2e_step()
         a1.record()
         barrier()
+        clk.mark(t_wall0, time.time())
         el = torch.tensor([a0.elapsed_time(a1) / k2], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(el, op=dist.ReduceOp.MAX)
@@ -414,6 +431,7 @@ def run_ours(args, w):
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": float(el.item()),
                "steps": k2, "note": "pinned host buffers -> H2D -> fwd+bwd -> D2H of loss and gradients"}
 
+    clk.__exit__()
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu:
         res = run_cpu_oracle(w, 2, 1, args.labels)

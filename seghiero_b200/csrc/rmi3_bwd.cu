@@ -428,6 +428,7 @@ static size_t pass2_smem_bytes() {
 }
 
 bool fast_path_ok(const void* x, const void* grad, int elem, int H, int W, int nf, int nm, int nh, int fast_tab_ok);
+size_t fast_bwd_smem(int C, int nf, int nm, int nh) { return fast2::pass2_smem(C, nf, nm, nh); }
 
 template <typename T>
 static int run_backward3(const void* x, void* grad, int B, int H, int W, const Hier3& h, const Ws3& ws,
@@ -448,6 +449,9 @@ static int run_backward3(const void* x, void* grad, int B, int H, int W, const H
                                                          tiles_x * tiles_y);
     SH_CHECK_LAUNCH();
   } else if (stages & 1) {
+    // a fast forward pass skipped the per-pixel flags this kernel reads unless it knew the backward would land here
+    if (fast_path_ok(x, nullptr, (int)sizeof(T), H, W, h.nf, h.nm, h.nh, fast_tab_ok) && fsmem <= 227 * 1024)
+      return SH_ERR_UNSUPPORTED;     // only reachable with a gradient buffer that is not 16-byte aligned
     const size_t smem = pass2_smem_bytes();
     auto kern = k3_pass2<T>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

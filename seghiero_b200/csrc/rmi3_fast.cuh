@@ -21,7 +21,6 @@ namespace sh {
 namespace fast {
 
 constexpr int TW = 64;               // tile width (pixels)
-constexpr int PTH = 16;              // tile height of k3f_prep
 constexpr int PWARPS = 12;           // producer warps
 constexpr int CWARPS = 4;            // consumer warps
 constexpr int PPC = 2;               // planes per consumer warp and round
@@ -60,141 +59,157 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int tiles_x, int th) {
 // -------------------------------------------------------------------------------------------------
 // k3f_prep: labels int64 -> uint8, #valid, range check, and the label-only part of RMI:
 //   ll[c][d] = #{ interior anchors r : L(r) = c and L(r + d) = c },  d in the half plane (13 taps),
-// with L = the RMI label of the level (void pixels are class 0, rmi...py:360-370).  Persistent CTAs
-// (same tile walk as k3f_pass1), integer counts per (CTA, channel) -> ws.llrec (summed by k3f_finalize).
+// with L = the RMI label of the level (void pixels are class 0, rmi...py:360-370).  Counted as
+//   ll[c][d] = A[c] - M[c][d],   A[c] = #anchors of class c,  M[c][d] = #anchors of class c whose tap d is NOT c:
+// a strip whose 3 x 8 label window is uniform adds to A only (run-length accumulated in registers along the
+// thread's column); only strips on a label boundary look at single taps.  Persistent CTAs (cpi per image),
+// integer counts per (CTA, channel) -> ws.llrec (summed by k3f_finalize).
 // -------------------------------------------------------------------------------------------------
 constexpr int LPITCH = TW + 8;   // label tile pitch: cols x0-2 .. x0+65 (+4 pad)
+constexpr int PTH2 = 32;         // tile height of k3f_prep
+
+constexpr int PREP_MULT = 4;     // CTAs of k3f_prep per persistent-CTA record (occupancy: the kernel is load-latency bound)
 
 __global__ void __launch_bounds__(256) k3f_prep(const long long* __restrict__ label, int B, int H, int W, FastHier hg,
-                                                Ws3 ws, int cpi, int ll_only) {
+                                                Ws3 ws, int cpi, int lab_vec) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C = hg.nf + hg.nm + hg.nh;
-  unsigned int* hist = reinterpret_cast<unsigned int*>(smem_raw);                       // [C][16]
+  unsigned int* hist = reinterpret_cast<unsigned int*>(smem_raw);                       // [C][16]: A, M[1..12]
   int* s_f2m = reinterpret_cast<int*>(hist + (size_t)C * 16);
   int* s_f2h = s_f2m + hg.nf;
-  unsigned char* rl = reinterpret_cast<unsigned char*>(s_f2h + hg.nf);                  // [3][TH+2][LPITCH]
+  unsigned char* rl = reinterpret_cast<unsigned char*>(s_f2h + hg.nf);                  // [3][PTH2+2][LPITCH]
   const int tid = threadIdx.x, lane = tid & 31;
   for (int i = tid; i < C * 16; i += 256) hist[i] = 0u;
   for (int i = tid; i < hg.nf; i += 256) { s_f2m[i] = hg.f2m[i]; s_f2h[i] = hg.f2h[i]; }
   __syncthreads();
-  const int b = blockIdx.x / cpi, j0 = blockIdx.x - b * cpi;
-  const int tiles_x = ws.tiles_x, ntiles = ws.tiles_x * ws.tiles_y;
+  const int cpb = cpi * PREP_MULT;
+  const int b = blockIdx.x / cpb, j0 = blockIdx.x - b * cpb;
+  const int tiles_x = (W + TW - 1) / TW, ntiles = tiles_x * ((H + PTH2 - 1) / PTH2);
   const long HW = (long)H * W;
   const long long* lb = label + (long)b * HW;
   unsigned char* lab8 = ws.lab8 + (long)b * HW;
   const int ty = tid >> 4, tx = (tid & 15) << 2;
   const int level_base[3] = {0, hg.nf, hg.nf + hg.nm};
+  unsigned int run_c[3] = {0xffu, 0xffu, 0xffu}, run_n[3] = {0u, 0u, 0u};
   long long nv = 0;
   bool bad = false;
+  constexpr int NP = (TW + 4) / 2, NITEM = (PTH2 + 2) * NP, NIT = (NITEM + 255) / 256;   // pixel pairs of the label tile
 #pragma unroll 1
-  for (int tile = j0; tile < ntiles; tile += cpi) {
-    const TileCoord tc = tile_coord(tile, tiles_x, PTH);
-    for (int e = tid; e < (PTH + 2) * (TW + 4); e += 256) {
-      const int r = e / (TW + 4), j = e - r * (TW + 4);
+  for (int tile = j0; tile < ntiles; tile += cpb) {
+    const TileCoord tc = tile_coord(tile, tiles_x, PTH2);
+    longlong2 v[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int e = tid + 256 * it, r = e / NP, j = (e - r * NP) * 2;
       const int y = tc.y0 + r, xx = tc.x0 - 2 + j;
-      unsigned char f = 0xff, m = 0xff, g = 0xff;
+      v[it] = make_longlong2(-1, -1);                      // outside the image
+      if (e < NITEM && y < H && xx >= 0 && xx < W) {
+        const long long* p = lb + (long)y * W + xx;
+        if (lab_vec) v[it] = __ldg(reinterpret_cast<const longlong2*>(p));
+        else v[it] = make_longlong2(p[0], p[1]);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int e = tid + 256 * it, r = e / NP, j = (e - r * NP) * 2;
+      if (e >= NITEM) continue;
+      const int y = tc.y0 + r, xx = tc.x0 - 2 + j;
+      unsigned int f2 = 0xffffu, m2 = 0xffffu, g2 = 0xffffu, l2 = 0xffffu;
       if (y < H && xx >= 0 && xx < W) {
-        const long long t = lb[(long)y * W + xx];
-        f = m = g = 0;
-        unsigned char l8 = SH_IGNORE;
-        if (t != SH_IGNORE) {
-          if (t >= 0 && t < hg.nf) { f = (unsigned char)t; m = (unsigned char)s_f2m[t]; g = (unsigned char)s_f2h[t]; l8 = f; }
-          else bad = !ll_only; // F.one_hot would raise in the reference
+        f2 = m2 = g2 = 0u;
+        const long long tt[2] = {v[it].x, v[it].y};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const long long t = tt[k];
+          if (t != SH_IGNORE) {
+            if (t >= 0 && t < hg.nf) {
+              f2 |= (unsigned int)t << (8 * k);
+              m2 |= (unsigned int)s_f2m[t] << (8 * k);
+              g2 |= (unsigned int)s_f2h[t] << (8 * k);
+              l2 = (l2 & ~(0xffu << (8 * k))) | ((unsigned int)t << (8 * k));
+            } else bad = true; // F.one_hot would raise in the reference
+          }
         }
-        if (!ll_only && r < PTH && j >= 2 && j < TW + 2) {
-          lab8[(long)y * W + xx] = l8;
-          nv += (t != SH_IGNORE);
+        if (r < PTH2 && j >= 2 && j < TW + 2) {
+          *reinterpret_cast<unsigned short*>(lab8 + (long)y * W + xx) = (unsigned short)l2;
+          nv += (tt[0] != SH_IGNORE) + (tt[1] != SH_IGNORE);
         }
       }
-      rl[(0 * (PTH + 2) + r) * LPITCH + j] = f;
-      rl[(1 * (PTH + 2) + r) * LPITCH + j] = m;
-      rl[(2 * (PTH + 2) + r) * LPITCH + j] = g;
+      *reinterpret_cast<unsigned short*>(rl + (0 * (PTH2 + 2) + r) * LPITCH + j) = (unsigned short)f2;
+      *reinterpret_cast<unsigned short*>(rl + (1 * (PTH2 + 2) + r) * LPITCH + j) = (unsigned short)m2;
+      *reinterpret_cast<unsigned short*>(rl + (2 * (PTH2 + 2) + r) * LPITCH + j) = (unsigned short)g2;
     }
     __syncthreads();
-    const int y = tc.y0 + ty;
-    const bool row_ok = y >= 2 && y < H - 2;
 #pragma unroll 1
-    for (int l = 0; l < 3; ++l) {
-      const unsigned char* base = rl + (l * (PTH + 2) + ty) * LPITCH + tx;
-      unsigned long long wn[3];
+    for (int rr = 0; rr < PTH2 / 16; ++rr) {
+      const int row = ty + 16 * rr, y = tc.y0 + row;
+      if (y < 2 || y >= H - 2) continue;
+      unsigned int imask = 0u;       // interior anchors among the strip's 4 pixels
 #pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const unsigned int* p = reinterpret_cast<const unsigned int*>(base + q * LPITCH);
-        wn[q] = (unsigned long long)p[0] | ((unsigned long long)p[1] << 32);
-      }
-      unsigned int m13[4], cls[4];
+      for (int k = 0; k < 4; ++k) { const int xx = tc.x0 + tx + k; if (xx >= 2 && xx < W - 2) imask |= 1u << k; }
+      if (imask == 0u) continue;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int xx = tc.x0 + tx + k;
-        const unsigned int c = byte_of(wn[0], k + 2);
-        cls[k] = c;
-        unsigned int m = 0;
-        if (row_ok && xx >= 2 && xx < W - 2) {
-          m = 1u;
-          m |= (byte_of(wn[0], k + 3) == c) << 1;
-          m |= (byte_of(wn[0], k + 4) == c) << 2;
+      for (int l = 0; l < 3; ++l) {
+        const unsigned char* base = rl + (l * (PTH2 + 2) + row) * LPITCH + tx;
+        unsigned long long wn[3];
+        unsigned int diff = 0u;
+        const unsigned int c0 = base[2];
+        const unsigned int pat = c0 * 0x01010101u;
 #pragma unroll
-          for (int dx = 0; dx < 5; ++dx) {
-            m |= (byte_of(wn[1], k + dx) == c) << (3 + dx);
-            m |= (byte_of(wn[2], k + dx) == c) << (8 + dx);
-          }
+        for (int q = 0; q < 3; ++q) {
+          const unsigned int* p = reinterpret_cast<const unsigned int*>(base + q * LPITCH);
+          const unsigned int lo = p[0], hi = p[1];
+          wn[q] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+          diff |= (lo ^ pat) | (hi ^ pat);
         }
-        m13[k] = m;
-      }
-      const bool uni = cls[0] == cls[1] && cls[1] == cls[2] && cls[2] == cls[3];
-      const int nround = __all_sync(0xffffffffu, uni) ? 1 : 4;
-      for (int rd = 0; rd < nround; ++rd) {
-        // packed per-tap counts of this lane (8 bits per tap, 4 taps per word)
-        unsigned int pk[4] = {0u, 0u, 0u, 0u};
-        unsigned int key;
-        if (nround == 1) {
-          key = cls[0];
-#pragma unroll
-          for (int ht = 0; ht < 13; ++ht) {
-            const unsigned int n = ((m13[0] >> ht) & 1u) + ((m13[1] >> ht) & 1u) + ((m13[2] >> ht) & 1u) + ((m13[3] >> ht) & 1u);
-            pk[ht >> 2] |= n << (8 * (ht & 3));
+        if (diff == 0u) {            // uniform window (and therefore all 4 pixels interior): anchors only
+          if (c0 == run_c[l]) run_n[l] += 4u;
+          else {
+            if (run_n[l]) atomicAdd(hist + (size_t)(level_base[l] + run_c[l]) * 16, run_n[l]);
+            run_c[l] = c0; run_n[l] = 4u;
           }
         } else {
-          const unsigned int mk = rd == 0 ? m13[0] : (rd == 1 ? m13[1] : (rd == 2 ? m13[2] : m13[3]));
-          key = rd == 0 ? cls[0] : (rd == 1 ? cls[1] : (rd == 2 ? cls[2] : cls[3]));
 #pragma unroll
-          for (int ht = 0; ht < 13; ++ht) pk[ht >> 2] |= ((mk >> ht) & 1u) << (8 * (ht & 3));
-        }
-        // lanes of one class add up (hardware integer warp reduction over the peer mask)
-        const unsigned int peers = __match_any_sync(0xffffffffu, key);
-        unsigned int tot4[4][4];     // [tap word][byte] totals over the peers
+          for (int k = 0; k < 4; ++k) {
+            if (!((imask >> k) & 1u)) continue;
+            const unsigned int c = byte_of(wn[0], k + 2);
+            unsigned int mm = 1u;                                   // bit 0: the anchor itself, bit t: tap t mismatches
+            mm |= (unsigned int)(byte_of(wn[0], k + 3) != c) << 1;
+            mm |= (unsigned int)(byte_of(wn[0], k + 4) != c) << 2;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          // split the fields into two words of 16-bit lanes before the warp-wide integer reduction
-          const unsigned int lo = pk[q] & 0x00ff00ffu, hi = (pk[q] >> 8) & 0x00ff00ffu;
-          const unsigned int slo = __reduce_add_sync(peers, lo), shi = __reduce_add_sync(peers, hi);
-          tot4[q][0] = slo & 0xffffu; tot4[q][2] = slo >> 16;
-          tot4[q][1] = shi & 0xffffu; tot4[q][3] = shi >> 16;
-        }
-        if (key != 0xffu) {
-          const int rank = __popc(peers & ((1u << lane) - 1u)), gsz = __popc(peers);
-          unsigned int* hrow = hist + (size_t)(level_base[l] + key) * 16;
-          for (int ht = rank; ht < 13; ht += gsz) {
-            unsigned int v = 0;
-#pragma unroll
-            for (int q = 0; q < 13; ++q) if (q == ht) v = tot4[q >> 2][q & 3];
-            if (v) atomicAdd(hrow + ht, v);
+            for (int dx = 0; dx < 5; ++dx) {
+              mm |= (unsigned int)(byte_of(wn[1], k + dx) != c) << (3 + dx);
+              mm |= (unsigned int)(byte_of(wn[2], k + dx) != c) << (8 + dx);
+            }
+            unsigned int* hrow = hist + (size_t)(level_base[l] + c) * 16;
+            while (mm) {
+              const int t = __ffs(mm) - 1;
+              mm &= mm - 1u;
+              atomicAdd(hrow + t, 1u);
+            }
           }
         }
       }
     }
     __syncthreads();
   }
+#pragma unroll
+  for (int l = 0; l < 3; ++l)
+    if (run_n[l]) atomicAdd(hist + (size_t)(level_base[l] + run_c[l]) * 16, run_n[l]);
   nv = warp_sum(nv);
   if (lane == 0 && nv) atomicAdd(ws.counts, (unsigned long long)nv);
   if (bad) atomicOr((unsigned int*)(ws.counts + 2), 1u);
   __syncthreads();
-  unsigned int* out = ws.llrec + (size_t)blockIdx.x * C * 16;
-  for (int i = tid; i < C * 16; i += 256) out[i] = hist[i];
+  unsigned int* out = ws.llrec + (size_t)(b * cpi + j0 % cpi) * C * 16;     // zeroed by the host before the launch
+  for (int i = tid; i < C * 16; i += 256) {
+    const int t = i & 15;
+    const unsigned int val = t == 0 ? hist[i] : (t < 13 ? hist[i & ~15] - hist[i] : 0u);
+    if (val) atomicAdd(out + i, val);
+  }
 }
 
 inline size_t prep_smem(int C, int nf) {
-  return (size_t)C * 16 * 4 + (size_t)2 * nf * 4 + (size_t)3 * (PTH + 2) * LPITCH + 16;
+  return (size_t)C * 16 * 4 + (size_t)2 * nf * 4 + (size_t)3 * (PTH2 + 2) * LPITCH + 16;
 }
 
 // tile walk of a persistent CTA without integer divisions: tile index advances by cpi per step

@@ -40,7 +40,7 @@ struct Hier2 {
 
 inline size_t pass2_smem(int C, int nf, int nm, int nh) {
   size_t s = (size_t)2 * PLANE * 4;                 // planes
-  s += (size_t)3 * TH * TW * 4;                     // 1 / sum e^x per level
+  s += (size_t)4 * TH * TW * 4;                     // 1 / sum e^x per level + validity (1.0 / 0.0)
   s += (size_t)4 * NBODY * 16 + (size_t)NHALO * 32; // cp.async staging of the logits
   s += (size_t)(nm + nh + 2) * TH * TW;             // holder bytes
   s += (size_t)3 * PR * LP;                         // label tile
@@ -60,7 +60,8 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
   const int NH = hg.nm + hg.nh + 2;
   float* planes = reinterpret_cast<float*>(smem_raw);                                  // [2][PLANE]
   float* ivt = planes + 2 * PLANE;                                                     // [3][TH][TW]
-  uint4* xst = reinterpret_cast<uint4*>(ivt + 3 * TH * TW);                            // [4][NBODY]
+  float* vft = ivt + 3 * TH * TW;                                                      // [TH][TW] 1.0 = labelled pixel
+  uint4* xst = reinterpret_cast<uint4*>(vft + TH * TW);                                // [4][NBODY]
   unsigned char* hst = reinterpret_cast<unsigned char*>(xst + 4 * NBODY);              // [NHALO][32]
   unsigned char* HT = hst + NHALO * 32;                                                // [NH][TH][TW] holder bytes
   unsigned char* LT = HT + (size_t)NH * TH * TW;                                       // [3][PR][LP]
@@ -141,7 +142,6 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
     bool rowok[4];
     long roff[4];                       // pixel offset of the strip inside one channel plane (clamped into the image)
     unsigned int tc0[4], tc1[4], tc2[4], hmN[4], hhN[4];
-    float vf[4][4];
     unsigned long long present = 0ull;  // channels that are the target of some pixel of the block
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -151,10 +151,11 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
       const unsigned int t4 = rowok[j] ? *reinterpret_cast<const unsigned int*>(lab8 + roff[j]) : 0xffffffffu;
       tc0[j] = t4; tc1[j] = 0xffffffffu; tc2[j] = 0xffffffffu;
       hmN[j] = hhN[j] = 0xffffffffu;
+      float vfk[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const unsigned int t = (t4 >> (8 * k)) & 0xffu;
-        vf[j][k] = t != SH_IGNORE ? 1.f : 0.f;
+        vfk[k] = t != SH_IGNORE ? 1.f : 0.f;
         if (t != SH_IGNORE) {
           const unsigned int cm = (unsigned int)(hg.nf + s_f2m[t]), chh = (unsigned int)(hg.nf + hg.nm + s_f2h[t]);
           tc1[j] = (tc1[j] & ~(0xffu << (8 * k))) | (cm << (8 * k));
@@ -162,6 +163,7 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
           present |= (1ull << t) | (1ull << cm) | (1ull << chh);
         }
       }
+      *reinterpret_cast<float4*>(vft + (4 * rq + j) * TW + 4 * st) = make_float4(vfk[0], vfk[1], vfk[2], vfk[3]);   // own slot only
     }
     // interior masks (border tiles only): bit 4*j + k
     unsigned int imask = 0xffffu;
@@ -249,32 +251,36 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
       const bool pos = (present >> ch) & 1ull;
       float* prow = planes + (ci & 1) * PLANE + (4 * rq + 2) * PW + 4 * st + 2;
       const float* ivp = ivt + (kind * TH + 4 * rq) * TW + 4 * st;
+      const float* vfp = vft + (4 * rq) * TW + 4 * st;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float xv[4];
         staged_vec4<T>(xs_gen + j * (NBODY * 16), xv);
         const float4 iv4 = *reinterpret_cast<const float4*>(ivp + j * TW);
         const float ivk[4] = {iv4.x, iv4.y, iv4.z, iv4.w};
+        const float4 vf4 = *reinterpret_cast<const float4*>(vfp + j * TW);
+        const float vfk[4] = {vf4.x, vf4.y, vf4.z, vf4.w};
         const unsigned int zM = hmN[j] ^ cc, zH = hhN[j] ^ cc;
-        float s[4], E[4], t[4], A[4], oh[4], ds[4];
+        float s[4], E[4], t[4], oh[4], ds[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           sig_exp3(xv[k], s[k], E[k]);
           t[k] = 1.0f - s[k];
-          A[k] = wbase;
           oh[k] = 0.f;
+        }
+        // d/ds of the -log(1 - . + eps) terms this channel holds: own fine term, its mid group's max, its high group's max
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float r = rcp(t[k] + eps);
+          ds[k] = wbase * r;
+          if (byte_is_zero(zM, k)) ds[k] = fmaf(wM, r, ds[k]);
+          if (byte_is_zero(zH, k)) ds[k] = fmaf(wH, r, ds[k]);
         }
         if (pos) {
           const unsigned int zT = (kind == 0 ? tc0[j] : (kind == 1 ? tc1[j] : tc2[j])) ^ cc;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            if (byte_is_zero(zT, k)) { oh[k] = 1.f; A[k] = 0.f; }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (byte_is_zero(zM, k)) A[k] += wM;
-          if (byte_is_zero(zH, k)) A[k] += wH;
-          ds[k] = A[k] * rcp(t[k] + eps);
+            if (byte_is_zero(zT, k)) { oh[k] = 1.f; ds[k] = fmaf(-wbase, rcp(t[k] + eps), ds[k]); }   // the target has no own (1 - s) term
         }
         if (pos) {
           const unsigned int zPF = *reinterpret_cast<const unsigned int*>(hpfp + j * TW) ^ cc;
@@ -290,7 +296,7 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
         float P[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float s2 = s[k] * vf[j][k];
+          const float s2 = s[k] * vfk[k];
           P[k] = s2 + 1e-6f;                            // = probs * valid + 1e-6 (rmi...py:487)
           const float q = s2 * t[k];
           const float ce = fmaf(E[k], ivk[k], -oh[k]);  // softmax - one-hot; 1/sum e^x is 0 on void pixels

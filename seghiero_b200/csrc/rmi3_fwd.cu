@@ -906,6 +906,8 @@ static size_t pass1_smem_bytes(int nh) {
   return (s + 15) & ~(size_t)15;
 }
 
+size_t fast_bwd_smem(int C, int nf, int nm, int nh);   // rmi3_bwd.cu
+
 // Can the warp-specialised kernels of rmi3_fast.cuh run this problem?
 bool fast_path_ok(const void* x, const void* grad, int elem, int H, int W, int nf, int nm, int nh, int fast_tab_ok) {
   const int C = nf + nm + nh;
@@ -920,19 +922,27 @@ template <typename T>
 static int run_forward3_fast(const void* x, const long long* label, int B, int H, int W, const Hier3& h, const Ws3& ws,
                              float* bandR, float* bandC, float eps, double scale, int stages, cudaStream_t st) {
   const int C = h.nf + h.nm + h.nh;
+  const bool fast_bwd_ok = fast_bwd_smem(C, h.nf, h.nm, h.nh) <= 227 * 1024;
   fast::FastHier fh;
   fh.nf = h.nf; fh.nm = h.nm; fh.nh = h.nh; fh.f2m = h.f2m; fh.f2h = h.f2h; fh.order = h.order + C;
   const int cpi = ws.cpi, grid = B * cpi;
   if (stages & 1) {
     cudaError_t e = cudaMemsetAsync(ws.counts, 0, 4 * sizeof(unsigned long long), st);
     if (e != cudaSuccess) return (int)e;
-    dim3 gp((W + kTW - 1) / kTW, (H + 15) / 16, B);
-    k3_prep<<<gp, 256, 0, st>>>(label, B, H, W, h, ws.lab8, ws.flags, ws.counts);
-    SH_CHECK_LAUNCH();
+    // uint8 labels, #valid, range check and the label-label counts in one kernel; the per-pixel uniformity flags of
+    // k3_prep are only read by the generic kernels
     const size_t smem = fast::prep_smem(C, h.nf);
     cudaFuncSetAttribute(fast::k3f_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    fast::k3f_prep<<<grid, 256, smem, st>>>(label, B, H, W, fh, ws, cpi, 1);
+    e = cudaMemsetAsync(ws.llrec, 0, (size_t)grid * C * 16 * sizeof(unsigned int), st);
+    if (e != cudaSuccess) return (int)e;
+    fast::k3f_prep<<<grid * fast::PREP_MULT, 256, smem, st>>>(label, B, H, W, fh, ws, cpi,
+                                                             (uintptr_t)label % 16 == 0 ? 1 : 0);
     SH_CHECK_LAUNCH();
+    if (!fast_bwd_ok) {     // the backward pass will run the generic kernel, which wants the flags
+      dim3 gp((W + kTW - 1) / kTW, (H + 15) / 16, B);
+      k3_prep<<<gp, 256, 0, st>>>(label, B, H, W, h, ws.lab8, ws.flags, ws.counts + 3);
+      SH_CHECK_LAUNCH();
+    }
   }
   if (stages & 2) {
     const size_t smem = fast::pass1_smem(C, h.nf);

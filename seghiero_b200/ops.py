@@ -28,7 +28,7 @@ _KERNELS = {
     "sh_loss2_final": 1, "sh_loss3_final": 1, "sh_scale_inplace": 1, "sh_triplet_forward": 4,
     "sh_triplet_backward": 1,
     ("sh_bce2_fwdbwd", 1): 1, ("sh_bce2_fwdbwd", 2): 1, ("sh_bce2_fwdbwd", 4): 1,
-    ("sh_rmi3_forward", 1): 1, ("sh_rmi3_forward", 2): 1, ("sh_rmi3_forward", 4): 1, ("sh_rmi3_forward", 8): 2,
+    ("sh_rmi3_forward", 1): 1, ("sh_rmi3_forward", 2): 1, ("sh_rmi3_forward", 4): 2, ("sh_rmi3_forward", 8): 2,
     ("sh_rmi3_backward", 1): 1, ("sh_rmi3_backward", 2): 1,
 }
 LAUNCHES = {"n": 0}
@@ -388,7 +388,9 @@ class RMIHieraTriplet3Fn(torch.autograd.Function):
             _call("sh_loss3_final", b, hh, ww, cfg.n_fine, cfg.n_mid, cfg.n_high, _p(ws), cfg.lam, _p(step_d),
                       cfg.total_steps, _p(st.trip) if st else None, _p(st.status) if st else None, cfg.loss_weight,
                       _p(out), _stream())
-        stats.update(out=out, triplet=st, workspace=ws)
+        stats.update(out=out, triplet=st, workspace=ws,
+                     fast_path=bool(lib.sh_rmi3_fast_path(_p(x), None, _dtype_code(x), hh, ww, cfg.n_fine, cfg.n_mid,
+                                                          cfg.n_high, fast_ok)))
         ctx.cfg = cfg
         ctx.tab, ctx.n_mh, ctx.fast_ok = tab, n_mh, fast_ok
         ctx.st = st
