@@ -4,18 +4,17 @@
 // Reference arithmetic: models/loss/rmi_hiera_triplet_loss.py:349-526 (autograd of it); analytic RMI backward in
 // oracle/rmi_taps.py.  The generic kernel (rmi3_bwd.cu::k3_pass2) computes the same thing for every other case.
 //
-// One CTA = one 64 x 32 tile of one image, 192 threads:
-//   threads 0..127  body : thread = 4 x 4 pixel block.  Per channel (tree order: fine children, their mid, ...,
-//                          the high):
-//                            phase A  sigmoid / e^x (3 MUFU), tree-BCE + CE gradient from the per-pixel summaries
-//                                     of pass 1 (holder bytes, 1/sum e^x) -> 16 registers; P = s*valid + 1e-6
-//                                     -> shared-memory plane
-//                            phase B  5x5 stencil over the plane (weights from k3f_finalize), + the one-hot
-//                                     stencil where the block's labels are mixed, combine, 128-bit store
-//   threads 128..191 halo: the 2-pixel ring of the plane (sigmoid only), stencil weights -> shared memory
-// Planes are double buffered; phase B of channel c and phase A of channel c+1 sit between the same pair of
-// barriers, so MUFU-heavy and FMA-heavy code overlap inside every warp.  Logits of channel c+1 travel
-// global -> shared with cp.async while phase B of channel c runs.
+// One CTA = one 64 x 32 tile of one image, 128 threads, thread = 4 x 4 pixel block (+ one piece of the tile's
+// 2-pixel ring).  Per channel, in tree order (fine children, their mid, ..., the high):
+//   phase A  sigmoid / e^x (3 MUFU), tree-BCE + CE gradient from the per-pixel summaries of pass 1 (holder
+//            bytes, 1/sum e^x) -> 16 registers; P = s*valid + 1e-6 -> shared-memory plane (own block + ring piece)
+//   phase B  5x5 stencil over the plane (weights from k3f_finalize), + the one-hot stencil where the block's
+//            labels are mixed, combine, 128-bit store
+// Planes are double buffered: phase B of channel c and phase A of channel c+1 sit between the same pair of
+// barriers.  Everything a thread reads from global memory for channel c+1 (logits, 1/sum e^x of the channel's
+// level, holder bytes at group starts) travels with cp.async into the thread's own shared-memory slots while
+// phase B of channel c runs; no thread reads another thread's slots, so the only barrier is the plane hand-over.
+// Shared memory per CTA is ~57 KB and registers <= 168, so three CTAs share an SM.
 #pragma once
 #include "rmi3_common.cuh"
 
@@ -23,12 +22,11 @@ namespace sh {
 namespace fast2 {
 
 constexpr int TW = 64, TH = 32;
-constexpr int NBODY = (TH / 4) * 16;      // 128 threads, each a 4 x 4 block
-constexpr int NHALO = 64;
-constexpr int NT = NBODY + NHALO;
+constexpr int NT = (TH / 4) * 16;         // 128 threads, each a 4 x 4 block
 constexpr int PW = TW + 4, PR = TH + 4, PLANE = PR * PW;
 constexpr int LP = TW + 8;                // label tile pitch (bytes): cols x0-2 .. x0+65 (+4 pad)
 constexpr int WS = 64;                    // floats per staged weight record: W1 at 0, W2 at 28, W2full at 56
+constexpr int SLOT = NT * 16;             // bytes of one staging row (16 bytes per thread)
 
 struct Hier2 {
   int nf, nm, nh;
@@ -40,11 +38,12 @@ struct Hier2 {
 
 inline size_t pass2_smem(int C, int nf, int nm, int nh) {
   size_t s = (size_t)2 * PLANE * 4;                 // planes
-  s += (size_t)4 * TH * TW * 4;                     // 1 / sum e^x per level + validity (1.0 / 0.0)
-  s += (size_t)4 * NBODY * 16 + (size_t)NHALO * 32; // cp.async staging of the logits
-  s += (size_t)(nm + nh + 2) * TH * TW;             // holder bytes
+  s += (size_t)4 * SLOT;                            // logits of the next channel (4 rows per thread)
+  s += (size_t)4 * SLOT;                            // 1 / sum e^x of the next channel's level
+  s += (size_t)2 * SLOT;                            // ring pieces: strip / pair + corner pair
+  s += (size_t)4 * SLOT;                            // holder bytes: mid group, high group, fine target, mid target (4 rows x 4 bytes)
   s += (size_t)3 * PR * LP;                         // label tile
-  s += (size_t)2 * WS * 4;                          // stencil weights
+  s += (size_t)3 * WS * 4;                          // stencil weights (2 buffers) + their cp.async staging
   s += (size_t)C * 16 + (size_t)2 * nf * 4 + 64;    // tables
   return (s + 15) & ~(size_t)15;
 }
@@ -52,21 +51,20 @@ inline size_t pass2_smem(int C, int nf, int nm, int nh) {
 __device__ __forceinline__ bool byte_is_zero(unsigned int z, int k) { return ((z >> (8 * k)) & 0xffu) == 0u; }
 
 template <typename T>
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, 3)
 k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hier2 hg, Ws3 ws, float eps,
           float loss_weight, const float* __restrict__ gscale_ptr, int tiles_x, int tiles_per_img) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C = hg.nf + hg.nm + hg.nh;
-  const int NH = hg.nm + hg.nh + 2;
   float* planes = reinterpret_cast<float*>(smem_raw);                                  // [2][PLANE]
-  float* ivt = planes + 2 * PLANE;                                                     // [3][TH][TW]
-  float* vft = ivt + 3 * TH * TW;                                                      // [TH][TW] 1.0 = labelled pixel
-  uint4* xst = reinterpret_cast<uint4*>(vft + TH * TW);                                // [4][NBODY]
-  unsigned char* hst = reinterpret_cast<unsigned char*>(xst + 4 * NBODY);              // [NHALO][32]
-  unsigned char* HT = hst + NHALO * 32;                                                // [NH][TH][TW] holder bytes
-  unsigned char* LT = HT + (size_t)NH * TH * TW;                                       // [3][PR][LP]
+  unsigned char* xst = reinterpret_cast<unsigned char*>(planes + 2 * PLANE);           // [4][NT] x 16 B
+  unsigned char* ist = xst + 4 * SLOT;                                                 // [4][NT] x 16 B
+  unsigned char* rst = ist + 4 * SLOT;                                                 // [2][NT] x 16 B
+  unsigned char* hst = rst + 2 * SLOT;                                                 // [4 kinds][NT] x (4 rows x 4 B)
+  unsigned char* LT = hst + 4 * SLOT;                                                  // [3][PR][LP]
   float* wsm = reinterpret_cast<float*>(LT + 3 * PR * LP);                             // [2][WS]
-  long long* s_chb = reinterpret_cast<long long*>(wsm + 2 * WS);                       // [C]
+  float* wst = wsm + 2 * WS;                                                           // [WS] raw weights of the next channel
+  long long* s_chb = reinterpret_cast<long long*>(wst + WS);                           // [C]
   unsigned int* s_order = reinterpret_cast<unsigned int*>(s_chb + C);                  // [C]
   unsigned int* s_aux = s_order + C;                                                   // [C]
   int* s_f2m = reinterpret_cast<int*>(s_aux + C);                                      // [nf]
@@ -87,19 +85,6 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
     s_chb[i] = (long long)(oe >> 24) * HW * (long long)sizeof(T);
   }
   for (int i = tid; i < hg.nf; i += NT) { s_f2m[i] = hg.f2m[i]; s_f2h[i] = hg.f2h[i]; }
-
-  // ---- per-tile summaries of pass 1: 1/sum e^x (3 levels) and the holder bytes, global -> shared ----
-  for (int e = tid; e < 3 * TH * (TW / 4); e += NT) {
-    const int l = e / (TH * (TW / 4)), rem = e - l * (TH * (TW / 4)), r = rem >> 4, s4 = (rem & 15) << 2;
-    const int y = min(ty0 + r, H - 1), xx = tx0 + s4 < W ? tx0 + s4 : 0;
-    cp_async_16(ivt + (l * TH + r) * TW + s4, ws.inv + (long)l * BHW + (long)b * HW + (long)y * W + xx);
-  }
-  for (int e = tid; e < NH * TH * (TW / 4); e += NT) {
-    const int p = e / (TH * (TW / 4)), rem = e - p * (TH * (TW / 4)), r = rem >> 4, s4 = (rem & 15) << 2;
-    const int y = min(ty0 + r, H - 1), xx = tx0 + s4 < W ? tx0 + s4 : 0;
-    cp_async_4(HT + ((size_t)p * TH + r) * TW + s4, ws.hold + (long)p * BHW + (long)b * HW + (long)y * W + xx);
-  }
-  cp_async_commit();
   __syncthreads();                                     // tables are in place
 
   // ---- label tile (RMI labels of the 3 levels; outside the image 0xff) ----
@@ -126,386 +111,384 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
   }
 
   const float gscale = *gscale_ptr;
-  const int nchan = C;
+  const int rq = tid >> 4, st = tid & 15;
+  const int xg = tx0 + 4 * st;
+  const bool colok = xg < W;
+  const float nv = fmaxf((float)ws.counts[0], 1.0f);
+  const float wF = 2.5f * loss_weight * gscale / (nv * (float)hg.nf);
+  const float wM = 2.5f * loss_weight * gscale / (nv * (float)hg.nm);
+  const float wH = 2.5f * loss_weight * gscale / (nv * (float)hg.nh);
+  const float wCE = loss_weight * gscale / ((float)B * (float)HW);
 
-  if (tid < NBODY) {
-    // =================================== body threads ===================================
-    const int rq = tid >> 4, st = tid & 15;
-    const int xg = tx0 + 4 * st;
-    const bool colok = xg < W;
-    const float nv = fmaxf((float)ws.counts[0], 1.0f);
-    const float wF = 2.5f * loss_weight * gscale / (nv * (float)hg.nf);
-    const float wM = 2.5f * loss_weight * gscale / (nv * (float)hg.nm);
-    const float wH = 2.5f * loss_weight * gscale / (nv * (float)hg.nh);
-    const float wCE = loss_weight * gscale / ((float)B * (float)HW);
-
-    bool rowok[4];
-    long roff[4];                       // pixel offset of the strip inside one channel plane (clamped into the image)
-    unsigned int tc0[4], tc1[4], tc2[4], hmN[4], hhN[4];
-    unsigned long long present = 0ull;  // channels that are the target of some pixel of the block
+  bool rowok[4];
+  long roff[4];                       // pixel offset of the strip inside one channel plane (clamped into the image)
+  unsigned int tc0[4], tc1[4], tc2[4], hmN[4], hhN[4];
+  unsigned long long present = 0ull;  // channels that are the target of some pixel of the block
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int y = ty0 + 4 * rq + j;
+    rowok[j] = y < H && colok;
+    roff[j] = (long)min(y, H - 1) * W + (colok ? xg : 0);
+    const unsigned int t4 = rowok[j] ? *reinterpret_cast<const unsigned int*>(lab8 + roff[j]) : 0xffffffffu;
+    tc0[j] = t4; tc1[j] = 0xffffffffu; tc2[j] = 0xffffffffu;
+    hmN[j] = hhN[j] = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned int t = (t4 >> (8 * k)) & 0xffu;
+      if (t != SH_IGNORE) {
+        const unsigned int cm = (unsigned int)(hg.nf + s_f2m[t]), chh = (unsigned int)(hg.nf + hg.nm + s_f2h[t]);
+        tc1[j] = (tc1[j] & ~(0xffu << (8 * k))) | (cm << (8 * k));
+        tc2[j] = (tc2[j] & ~(0xffu << (8 * k))) | (chh << (8 * k));
+        present |= (1ull << t) | (1ull << cm) | (1ull << chh);
+      }
+    }
+  }
+  // interior masks (border tiles only): bit 4*j + k
+  unsigned int imask = 0xffffu;
+  if (border) {
+    imask = 0u;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int y = ty0 + 4 * rq + j;
-      rowok[j] = y < H && colok;
-      roff[j] = (long)min(y, H - 1) * W + (colok ? xg : 0);
-      const unsigned int t4 = rowok[j] ? *reinterpret_cast<const unsigned int*>(lab8 + roff[j]) : 0xffffffffu;
-      tc0[j] = t4; tc1[j] = 0xffffffffu; tc2[j] = 0xffffffffu;
-      hmN[j] = hhN[j] = 0xffffffffu;
-      float vfk[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (y >= 2 && y < H - 2 && xg + k >= 2 && xg + k < W - 2) imask |= 1u << (4 * j + k);
+    }
+  }
+  // ---- this thread's piece of the ring: tid < 64: 4-pixel strip of plane rows 0,1,TH+2,TH+3 ; tid >= 64: 2-pixel pair
+  //      left / right of a body row ; tid < 8 also a 2-pixel corner pair ----
+  int pidx0, pidx1;
+  long goff0, goff1;
+  bool in0, in1;
+  float hv[6];
+  const bool is_strip = tid < 64;
+  if (is_strip) {
+    const int hrow = tid >> 4, pr = hrow < 2 ? hrow : TH + hrow, strip = tid & 15;
+    const int yy = ty0 - 2 + pr, xx = tx0 + 4 * strip;
+    pidx0 = pr * PW + 2 + 4 * strip;
+    in0 = yy >= 0 && yy < H && xx < W;
+    goff0 = in0 ? (long)yy * W + xx : 0;
+  } else {
+    const int hl = tid - 64, srow = hl >> 1, side = hl & 1;
+    const int yy = ty0 + srow, xx = side ? tx0 + TW : tx0 - 2;
+    pidx0 = (2 + srow) * PW + (side ? TW + 2 : 0);
+    in0 = yy < H && xx >= 0 && xx < W;
+    goff0 = in0 ? (long)yy * W + xx : 0;
+  }
+  {
+    const int crow = (tid >> 1) & 3, pr = crow < 2 ? crow : TH + crow, side = tid & 1;
+    const int yy = ty0 - 2 + pr, xx = side ? tx0 + TW : tx0 - 2;
+    pidx1 = pr * PW + (side ? TW + 2 : 0);
+    in1 = tid < 8 && yy >= 0 && yy < H && xx >= 0 && xx < W;
+    goff1 = in1 ? (long)yy * W + xx : 0;
+  }
+  {
+    unsigned int t4 = 0xffffffffu;
+    if (in0) t4 = is_strip ? *reinterpret_cast<const unsigned int*>(lab8 + goff0)
+                           : (0xffff0000u | *reinterpret_cast<const unsigned short*>(lab8 + goff0));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) hv[k] = ((t4 >> (8 * k)) & 0xffu) != SH_IGNORE ? 1.f : 0.f;
+    const unsigned int t2 = in1 ? *reinterpret_cast<const unsigned short*>(lab8 + goff1) : 0xffffu;
+    hv[4] = (t2 & 0xffu) != SH_IGNORE ? 1.f : 0.f;
+    hv[5] = (t2 >> 8) != SH_IGNORE ? 1.f : 0.f;
+  }
+
+  // ---- staging slots of this thread ----
+  const unsigned int xs_base = (unsigned int)__cvta_generic_to_shared(xst + tid * 16);
+  const unsigned int is_base = (unsigned int)__cvta_generic_to_shared(ist + tid * 16);
+  const unsigned int rs_base = (unsigned int)__cvta_generic_to_shared(rst + tid * 16);
+  const unsigned int hs_base = (unsigned int)__cvta_generic_to_shared(hst + tid * 16);
+  const unsigned char* xs_gen = xst + tid * 16;
+  const unsigned char* is_gen = ist + tid * 16;
+  const unsigned char* rs_gen = rst + tid * 16;
+  const unsigned char* hs_gen = hst + tid * 16;
+  const unsigned char* holdb = ws.hold + (long)b * HW;
+  const float* invb = ws.inv + (long)b * HW;
+
+  // everything phase A of channel ci needs from global memory -> this thread's slots (one commit group)
+  auto prefetch = [&](int ci) {
+    const unsigned int oe = s_order[ci], ax = s_aux[ci];
+    const int kind = oe & 3;
+    const unsigned int fl = (oe >> 16) & 0xffu;
+    const char* g = xbb + s_chb[ci];
+    const float* ivl = invb + (long)kind * BHW;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const char* gp = g + roff[j] * (long)sizeof(T);
+      if (sizeof(T) == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(xs_base + j * SLOT), "l"(gp));
+      else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(xs_base + j * SLOT), "l"(gp));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(is_base + j * SLOT), "l"(ivl + roff[j]));
+    }
+    if (is_strip) {
+      if (sizeof(T) == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rs_base), "l"(g + goff0 * 4));
+      else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(rs_base), "l"(g + goff0 * 2));
+    } else {
+      if (sizeof(T) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(rs_base), "l"(g + goff0 * 4));
+      else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(rs_base), "l"(g + goff0 * 2));
+    }
+    if (tid < 8) {
+      if (sizeof(T) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(rs_base + SLOT), "l"(g + goff1 * 4));
+      else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(rs_base + SLOT), "l"(g + goff1 * 2));
+    }
+    if (fl & 1u) {       // first channel of a mid group: the bytes that say which channel holds the group's max
+      const unsigned char* hp = holdb + (long)(ax & 0xffu) * BHW;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(hs_base + 4 * j), "l"(hp + roff[j]));
+    }
+    if ((fl & 4u) && (ax >> 8) != 0xffu) {
+      const unsigned char* hp = holdb + (long)(hg.nm + (ax >> 8)) * BHW;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(hs_base + SLOT + 4 * j), "l"(hp + roff[j]));
+    }
+    if (tid < 25 || tid == 28) {   // stencil weights of the channel (k3f_finalize: W1[25], W2[25], sum W2 at 50)
+      const float* src = ws.wts + ((size_t)b * C + (oe >> 24)) * 64;
+      const unsigned int wb = (unsigned int)__cvta_generic_to_shared(wst);
+      if (tid < 25) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(wb + 4 * tid), "l"(src + tid));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(wb + 4 * (25 + tid)), "l"(src + 25 + tid));
+      } else {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(wb + 4 * 50), "l"(src + 50));
+      }
+    }
+    cp_async_commit();
+  };
+
+  // holders of the positive terms (fine target: min(A_t, B_m); mid target: min(C_h, B_m)) for the whole tile walk
+  {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const unsigned char* hp = holdb + (long)(hg.nm + hg.nh + q) * BHW;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(hs_base + (2 + q) * SLOT + 4 * j), "l"(hp + roff[j]));
+    }
+  }
+  prefetch(0);
+
+  __syncthreads();                                     // label tile is complete
+  // label structure of the block's 8 x 8 neighbourhood per level: uniform class (or 0xfe = mixed) and the classes present
+  unsigned int ublk[3], pres[3];
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+    const unsigned char* lt = LT + (l * PR + 4 * rq) * LP + 4 * st;
+    const unsigned int first = *reinterpret_cast<const unsigned int*>(lt) & 0xffu;
+    const unsigned int pat = first * 0x01010101u;
+    unsigned int diff = 0u, hash = 0u;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const unsigned int wd = *reinterpret_cast<const unsigned int*>(lt + i * LP + 4 * q);
+        diff |= wd ^ pat;
+        hash |= (1u << (wd & 31)) | (1u << ((wd >> 8) & 31)) | (1u << ((wd >> 16) & 31)) | (1u << ((wd >> 24) & 31));
+      }
+    }
+    ublk[l] = diff == 0u ? first : 0xfeu;
+    pres[l] = hash;
+  }
+
+  float g0[4][4];
+
+  // phase A of channel (order index) ci: plane (ci & 1), gradient of BCE + CE -> g0
+  auto phaseA = [&](int ci) {
+    const unsigned int oe = s_order[ci], ax = s_aux[ci];
+    const int kind = oe & 3;
+    const unsigned int fl = (oe >> 16) & 0xffu, ch = oe >> 24;
+    const unsigned int cc = ch * 0x01010101u;
+    float* plane = planes + (ci & 1) * PLANE;
+    if (fl & 1u) {       // where does the group's (1 - max) term count: everywhere but at pixels whose target is this mid
+      const unsigned int midc = (unsigned int)(hg.nf + (ax & 0xffu)) * 0x01010101u;
+      const uint4 hm = *reinterpret_cast<const uint4*>(hs_gen);
+      hmN[0] = hm.x | __vcmpeq4(tc1[0], midc); hmN[1] = hm.y | __vcmpeq4(tc1[1], midc);
+      hmN[2] = hm.z | __vcmpeq4(tc1[2], midc); hmN[3] = hm.w | __vcmpeq4(tc1[3], midc);
+    }
+    if (fl & 4u) {
+      const unsigned int high = ax >> 8;
+      if (high != 0xffu) {
+        const unsigned int highc = (unsigned int)(hg.nf + hg.nm + high) * 0x01010101u;
+        const uint4 hh = *reinterpret_cast<const uint4*>(hs_gen + SLOT);
+        hhN[0] = hh.x | __vcmpeq4(tc2[0], highc); hhN[1] = hh.y | __vcmpeq4(tc2[1], highc);
+        hhN[2] = hh.z | __vcmpeq4(tc2[2], highc); hhN[3] = hh.w | __vcmpeq4(tc2[3], highc);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hhN[j] = 0xffffffffu;
+      }
+    }
+    // ---- ring piece(s): sigmoid only ----
+    {
+      float xv[4];
+      if (is_strip) staged_vec4<T>(rs_gen, xv);
+      else {
+        if (sizeof(T) == 4) { const float2 t2 = *reinterpret_cast<const float2*>(rs_gen); xv[0] = t2.x; xv[1] = t2.y; }
+        else { xv[0] = staged_elem<T>(rs_gen, 0); xv[1] = staged_elem<T>(rs_gen, 1); }
+        xv[2] = xv[3] = 0.f;
+      }
+      if (in0) {
+        *reinterpret_cast<float2*>(plane + pidx0) = make_float2(fmaf(sig_only(xv[0]), hv[0], 1e-6f), fmaf(sig_only(xv[1]), hv[1], 1e-6f));
+        if (is_strip)
+          *reinterpret_cast<float2*>(plane + pidx0 + 2) = make_float2(fmaf(sig_only(xv[2]), hv[2], 1e-6f), fmaf(sig_only(xv[3]), hv[3], 1e-6f));
+      }
+      if (in1) {
+        float a0, a1;
+        if (sizeof(T) == 4) { const float2 t2 = *reinterpret_cast<const float2*>(rs_gen + SLOT); a0 = t2.x; a1 = t2.y; }
+        else { a0 = staged_elem<T>(rs_gen + SLOT, 0); a1 = staged_elem<T>(rs_gen + SLOT, 1); }
+        *reinterpret_cast<float2*>(plane + pidx1) = make_float2(fmaf(sig_only(a0), hv[4], 1e-6f), fmaf(sig_only(a1), hv[5], 1e-6f));
+      }
+    }
+    // ---- stencil weights of the channel times the upstream gradient (every thread moves the words it staged itself) ----
+    {
+      float* dst = wsm + (ci & 1) * WS;
+      if (tid < 25) { dst[tid] = wst[tid] * gscale; dst[28 + tid] = wst[25 + tid] * gscale; }
+      else if (tid < 28) { dst[tid] = 0.f; dst[28 + tid] = 0.f; }
+      else if (tid == 28) dst[56] = wst[50] * gscale;
+    }
+    const float wbase = kind == 0 ? wF : 0.f;
+    const bool pos = (present >> ch) & 1ull;
+    float* prow = plane + (4 * rq + 2) * PW + 4 * st + 2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float xv[4];
+      staged_vec4<T>(xs_gen + j * SLOT, xv);
+      const float4 iv4 = *reinterpret_cast<const float4*>(is_gen + j * SLOT);
+      const float ivk[4] = {iv4.x, iv4.y, iv4.z, iv4.w};       // 1 / sum e^x of the level; 0 on void pixels
+      const unsigned int zM = hmN[j] ^ cc, zH = hhN[j] ^ cc;
+      float s[4], E[4], t[4], oh[4], ds[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const unsigned int t = (t4 >> (8 * k)) & 0xffu;
-        vfk[k] = t != SH_IGNORE ? 1.f : 0.f;
-        if (t != SH_IGNORE) {
-          const unsigned int cm = (unsigned int)(hg.nf + s_f2m[t]), chh = (unsigned int)(hg.nf + hg.nm + s_f2h[t]);
-          tc1[j] = (tc1[j] & ~(0xffu << (8 * k))) | (cm << (8 * k));
-          tc2[j] = (tc2[j] & ~(0xffu << (8 * k))) | (chh << (8 * k));
-          present |= (1ull << t) | (1ull << cm) | (1ull << chh);
+        sig_exp3(xv[k], s[k], E[k]);
+        t[k] = 1.0f - s[k];
+        oh[k] = 0.f;
+      }
+      // d/ds of the -log(1 - . + eps) terms this channel holds: own fine term, its mid group's max, its high group's max
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float r = rcp(t[k] + eps);
+        ds[k] = wbase * r;
+        if (byte_is_zero(zM, k)) ds[k] = fmaf(wM, r, ds[k]);
+        if (byte_is_zero(zH, k)) ds[k] = fmaf(wH, r, ds[k]);
+      }
+      if (pos) {
+        const unsigned int zT = (kind == 0 ? tc0[j] : (kind == 1 ? tc1[j] : tc2[j])) ^ cc;
+        const unsigned int zPF = *reinterpret_cast<const unsigned int*>(hs_gen + 2 * SLOT + 4 * j) ^ cc;
+        const unsigned int zPM = *reinterpret_cast<const unsigned int*>(hs_gen + 3 * SLOT + 4 * j) ^ cc;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float Bp = byte_is_zero(zPF, k) ? wF : 0.f;
+          if (byte_is_zero(zPM, k)) Bp += wM;
+          if (byte_is_zero(zT, k)) {
+            oh[k] = 1.f;
+            ds[k] = fmaf(-wbase, rcp(t[k] + eps), ds[k]);      // the target has no own (1 - s) term
+            if (kind == 2) Bp += wH;
+          }
+          ds[k] = fmaf(-Bp, rcp(s[k] + eps), ds[k]);
         }
       }
-      *reinterpret_cast<float4*>(vft + (4 * rq + j) * TW + 4 * st) = make_float4(vfk[0], vfk[1], vfk[2], vfk[3]);   // own slot only
-    }
-    // interior masks (border tiles only): bit 4*j + k
-    unsigned int imask = 0xffffu;
-    if (border) {
-      imask = 0u;
+      float P[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int y = ty0 + 4 * rq + j;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (y >= 2 && y < H - 2 && xg + k >= 2 && xg + k < W - 2) imask |= 1u << (4 * j + k);
+      for (int k = 0; k < 4; ++k) {
+        const float s2 = ivk[k] != 0.f ? s[k] : 0.f;        // s * valid
+        P[k] = s2 + 1e-6f;                                    // = probs * valid + 1e-6 (rmi...py:487)
+        const float q = s2 * t[k];
+        const float ce = fmaf(E[k], ivk[k], -oh[k]);          // softmax - one-hot
+        g0[j][k] = fmaf(ds[k], q, wCE * ce);
       }
+      *reinterpret_cast<float2*>(prow + j * PW) = make_float2(P[0], P[1]);
+      *reinterpret_cast<float2*>(prow + j * PW + 2) = make_float2(P[2], P[3]);
     }
-    __syncthreads();                                   // label tile is complete
-    // label structure of the block's 8 x 8 neighbourhood per level: uniform class (or 0xfe = mixed) and the classes present
-    unsigned int ublk[3], pres[3];
+  };
+
+  // phase B of channel ci: stencil over plane (ci & 1), combine with g0, store
+  auto phaseB = [&](int ci) {
+    const unsigned int oe = s_order[ci];
+    const int kind = oe & 3;
+    const unsigned int cl = (oe >> 8) & 0xffu, ch = oe >> 24;
+    const float* wp = wsm + (ci & 1) * WS;
+    const float* pl = planes + (ci & 1) * PLANE + (4 * rq) * PW + 4 * st;
+    const unsigned char* lt = LT + (kind * PR + 4 * rq) * LP + 4 * st;
+    const unsigned int ub = kind == 0 ? ublk[0] : (kind == 1 ? ublk[1] : ublk[2]);
+    const unsigned int ph = kind == 0 ? pres[0] : (kind == 1 ? pres[1] : pres[2]);
+    const float init = ub == cl ? wp[56] : 0.f;
+    const int nsweep = (ub == 0xfeu && ((ph >> (cl & 31)) & 1u)) ? 2 : 1;
+    float acc[4][4], q[4][4];
 #pragma unroll
-    for (int l = 0; l < 3; ++l) {
-      const unsigned char* lt = LT + (l * PR + 4 * rq) * LP + 4 * st;
-      const unsigned int first = *reinterpret_cast<const unsigned int*>(lt) & 0xffu;
-      const unsigned int pat = first * 0x01010101u;
-      unsigned int diff = 0u, hash = 0u;
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[o][k] = init;
+#pragma unroll 1
+    for (int sw = 0; sw < nsweep; ++sw) {
+      float w[28];
+#pragma unroll
+      for (int v = 0; v < 7; ++v) {
+        const float4 t4 = *reinterpret_cast<const float4*>(wp + sw * 28 + 4 * v);
+        w[4 * v] = t4.x; w[4 * v + 1] = t4.y; w[4 * v + 2] = t4.z; w[4 * v + 3] = t4.w;
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
+        float win[8];
+        if (sw == 0) {
+          const float4 a = *reinterpret_cast<const float4*>(pl + i * PW);
+          const float4 c4 = *reinterpret_cast<const float4*>(pl + i * PW + 4);
+          win[0] = a.x; win[1] = a.y; win[2] = a.z; win[3] = a.w;
+          win[4] = c4.x; win[5] = c4.y; win[6] = c4.z; win[7] = c4.w;
+          if (i >= 2 && i < 6) {
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const unsigned int wd = *reinterpret_cast<const unsigned int*>(lt + i * LP + 4 * q);
-          diff |= wd ^ pat;
-          hash |= (1u << (wd & 31)) | (1u << ((wd >> 8) & 31)) | (1u << ((wd >> 16) & 31)) | (1u << ((wd >> 24) & 31));
-        }
-      }
-      ublk[l] = diff == 0u ? first : 0xfeu;
-      pres[l] = hash;
-    }
-
-    const unsigned int xs_base = (unsigned int)__cvta_generic_to_shared(xst + tid);
-    const char* xs_gen = reinterpret_cast<const char*>(xst + tid);
-    auto prefetch = [&](int ci) {
-      const char* g = xbb + s_chb[ci];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const char* gp = g + roff[j] * (long)sizeof(T);
-        const unsigned int dst = xs_base + j * (NBODY * 16);
-        if (sizeof(T) == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gp));
-        else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gp));
-      }
-      cp_async_commit();
-    };
-
-    float g0[4][4];
-    const unsigned char* HTt = HT + (4 * rq) * TW + 4 * st;
-    const unsigned char* hpfp = HTt + (size_t)(hg.nm + hg.nh) * TH * TW;
-    const unsigned char* hpmp = HTt + (size_t)(hg.nm + hg.nh + 1) * TH * TW;
-
-    // phase A of channel (order index) ci: plane (ci & 1), gradient of BCE + CE -> g0
-    auto phaseA = [&](int ci) {
-      const unsigned int oe = s_order[ci], ax = s_aux[ci];
-      const int kind = oe & 3;
-      const unsigned int fl = (oe >> 16) & 0xffu, ch = oe >> 24;
-      const unsigned int cc = ch * 0x01010101u;
-      if (fl & 1u) {       // first channel of a mid group: which channel holds the group's max, where that term counts
-        const unsigned int mid = ax & 0xffu;
-        const unsigned int midc = (unsigned int)(hg.nf + mid) * 0x01010101u;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const unsigned int hm = *reinterpret_cast<const unsigned int*>(HTt + ((size_t)mid * TH + j) * TW);
-          hmN[j] = hm | __vcmpeq4(tc1[j], midc);       // the target's own mid has no (1 - max) term
-        }
-      }
-      if (fl & 4u) {
-        const unsigned int high = ax >> 8;
-        if (high != 0xffu) {
-          const unsigned int highc = (unsigned int)(hg.nf + hg.nm + high) * 0x01010101u;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const unsigned int hh = *reinterpret_cast<const unsigned int*>(HTt + ((size_t)(hg.nm + high) * TH + j) * TW);
-            hhN[j] = hh | __vcmpeq4(tc2[j], highc);
+            for (int k = 0; k < 4; ++k) {
+              const float s1 = win[k + 2] - 1e-6f;          // valid pixels: P = s + 1e-6 ; void: exactly 0
+              q[i - 2][k] = s1 * (1.0f - s1);
+            }
           }
         } else {
+          const unsigned int l0 = *reinterpret_cast<const unsigned int*>(lt + i * LP);
+          const unsigned int l1 = *reinterpret_cast<const unsigned int*>(lt + i * LP + 4);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) hhN[j] = 0xffffffffu;
-        }
-      }
-      const float wbase = kind == 0 ? wF : 0.f;
-      const bool pos = (present >> ch) & 1ull;
-      float* prow = planes + (ci & 1) * PLANE + (4 * rq + 2) * PW + 4 * st + 2;
-      const float* ivp = ivt + (kind * TH + 4 * rq) * TW + 4 * st;
-      const float* vfp = vft + (4 * rq) * TW + 4 * st;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float xv[4];
-        staged_vec4<T>(xs_gen + j * (NBODY * 16), xv);
-        const float4 iv4 = *reinterpret_cast<const float4*>(ivp + j * TW);
-        const float ivk[4] = {iv4.x, iv4.y, iv4.z, iv4.w};
-        const float4 vf4 = *reinterpret_cast<const float4*>(vfp + j * TW);
-        const float vfk[4] = {vf4.x, vf4.y, vf4.z, vf4.w};
-        const unsigned int zM = hmN[j] ^ cc, zH = hhN[j] ^ cc;
-        float s[4], E[4], t[4], oh[4], ds[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          sig_exp3(xv[k], s[k], E[k]);
-          t[k] = 1.0f - s[k];
-          oh[k] = 0.f;
-        }
-        // d/ds of the -log(1 - . + eps) terms this channel holds: own fine term, its mid group's max, its high group's max
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float r = rcp(t[k] + eps);
-          ds[k] = wbase * r;
-          if (byte_is_zero(zM, k)) ds[k] = fmaf(wM, r, ds[k]);
-          if (byte_is_zero(zH, k)) ds[k] = fmaf(wH, r, ds[k]);
-        }
-        if (pos) {
-          const unsigned int zT = (kind == 0 ? tc0[j] : (kind == 1 ? tc1[j] : tc2[j])) ^ cc;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (byte_is_zero(zT, k)) { oh[k] = 1.f; ds[k] = fmaf(-wbase, rcp(t[k] + eps), ds[k]); }   // the target has no own (1 - s) term
-        }
-        if (pos) {
-          const unsigned int zPF = *reinterpret_cast<const unsigned int*>(hpfp + j * TW) ^ cc;
-          const unsigned int zPM = *reinterpret_cast<const unsigned int*>(hpmp + j * TW) ^ cc;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float Bp = byte_is_zero(zPF, k) ? wF : 0.f;
-            if (byte_is_zero(zPM, k)) Bp += wM;
-            if (kind == 2 && oh[k] != 0.f) Bp += wH;
-            ds[k] = fmaf(-Bp, rcp(s[k] + eps), ds[k]);
+          for (int v = 0; v < 4; ++v) {
+            win[v] = ((l0 >> (8 * v)) & 0xffu) == cl ? 1.f : 0.f;
+            win[4 + v] = ((l1 >> (8 * v)) & 0xffu) == cl ? 1.f : 0.f;
           }
         }
-        float P[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float s2 = s[k] * vfk[k];
-          P[k] = s2 + 1e-6f;                            // = probs * valid + 1e-6 (rmi...py:487)
-          const float q = s2 * t[k];
-          const float ce = fmaf(E[k], ivk[k], -oh[k]);  // softmax - one-hot; 1/sum e^x is 0 on void pixels
-          g0[j][k] = fmaf(ds[k], q, wCE * ce);
+        for (int o = 0; o < 4; ++o) {
+          const int dyi = i - o;
+          if (dyi < 0 || dyi > 4) continue;
+#pragma unroll
+          for (int dx = 0; dx < 5; ++dx)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[o][k] = fmaf(w[dyi * 5 + dx], win[k + dx], acc[o][k]);
         }
-        *reinterpret_cast<float2*>(prow + j * PW) = make_float2(P[0], P[1]);
-        *reinterpret_cast<float2*>(prow + j * PW + 2) = make_float2(P[2], P[3]);
       }
-    };
+    }
+    T* gp = grad + ((long)b * C + ch) * HW;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      if (border) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {     // frame pixels: no RMI term here (k3_frame2); their stencil sums may hold garbage
+          const bool inter = (imask >> (4 * o + k)) & 1u;
+          q[o][k] = inter ? q[o][k] : 0.f;
+          acc[o][k] = inter ? acc[o][k] : 0.f;
+        }
+      }
+      float g[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) g[k] = fmaf(q[o][k], acc[o][k], g0[o][k]);
+      if (rowok[o]) VecIO<T, 4>::store(gp + roff[o], g);
+    }
+  };
 
-    // phase B of channel ci: stencil over plane (ci & 1), combine with g0, store
-    auto phaseB = [&](int ci) {
-      const unsigned int oe = s_order[ci];
-      const int kind = oe & 3;
-      const unsigned int cl = (oe >> 8) & 0xffu, ch = oe >> 24;
-      const float* wp = wsm + (ci & 1) * WS;
-      const float* pl = planes + (ci & 1) * PLANE + (4 * rq) * PW + 4 * st;
-      const unsigned char* lt = LT + (kind * PR + 4 * rq) * LP + 4 * st;
-      const unsigned int ub = kind == 0 ? ublk[0] : (kind == 1 ? ublk[1] : ublk[2]);
-      const unsigned int ph = kind == 0 ? pres[0] : (kind == 1 ? pres[1] : pres[2]);
-      const float init = ub == cl ? wp[56] : 0.f;
-      const int nsweep = (ub == 0xfeu && ((ph >> (cl & 31)) & 1u)) ? 2 : 1;
-      float acc[4][4], q[4][4];
-#pragma unroll
-      for (int o = 0; o < 4; ++o)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) acc[o][k] = init;
+  cp_async_wait<0>();
+  phaseA(0);
+  __syncthreads();
 #pragma unroll 1
-      for (int sw = 0; sw < nsweep; ++sw) {
-        float w[28];
-#pragma unroll
-        for (int v = 0; v < 7; ++v) {
-          const float4 t4 = *reinterpret_cast<const float4*>(wp + sw * 28 + 4 * v);
-          w[4 * v] = t4.x; w[4 * v + 1] = t4.y; w[4 * v + 2] = t4.z; w[4 * v + 3] = t4.w;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float win[8];
-          if (sw == 0) {
-            const float4 a = *reinterpret_cast<const float4*>(pl + i * PW);
-            const float4 c4 = *reinterpret_cast<const float4*>(pl + i * PW + 4);
-            win[0] = a.x; win[1] = a.y; win[2] = a.z; win[3] = a.w;
-            win[4] = c4.x; win[5] = c4.y; win[6] = c4.z; win[7] = c4.w;
-            if (i >= 2 && i < 6) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float s1 = win[k + 2] - 1e-6f;          // valid pixels: P = s + 1e-6 ; void: exactly 0
-                q[i - 2][k] = s1 * (1.0f - s1);
-              }
-            }
-          } else {
-            const unsigned int l0 = *reinterpret_cast<const unsigned int*>(lt + i * LP);
-            const unsigned int l1 = *reinterpret_cast<const unsigned int*>(lt + i * LP + 4);
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              win[v] = ((l0 >> (8 * v)) & 0xffu) == cl ? 1.f : 0.f;
-              win[4 + v] = ((l1 >> (8 * v)) & 0xffu) == cl ? 1.f : 0.f;
-            }
-          }
-#pragma unroll
-          for (int o = 0; o < 4; ++o) {
-            const int dyi = i - o;
-            if (dyi < 0 || dyi > 4) continue;
-#pragma unroll
-            for (int dx = 0; dx < 5; ++dx)
-#pragma unroll
-              for (int k = 0; k < 4; ++k) acc[o][k] = fmaf(w[dyi * 5 + dx], win[k + dx], acc[o][k]);
-          }
-        }
-      }
-      T* gp = grad + ((long)b * C + ch) * HW;
-#pragma unroll
-      for (int o = 0; o < 4; ++o) {
-        if (border) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {     // frame pixels: no RMI term here (k3_frame2); their stencil sums may hold garbage
-            const bool inter = (imask >> (4 * o + k)) & 1u;
-            q[o][k] = inter ? q[o][k] : 0.f;
-            acc[o][k] = inter ? acc[o][k] : 0.f;
-          }
-        }
-        float g[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) g[k] = fmaf(q[o][k], acc[o][k], g0[o][k]);
-        if (rowok[o]) VecIO<T, 4>::store(gp + roff[o], g);
-      }
-    };
-
-    prefetch(0);
-    cp_async_wait<0>();
-    __syncthreads();                                   // 1/sum e^x, holder bytes (copied by all threads) have landed
-    phaseA(0);
+  for (int ci = 0; ci < C; ++ci) {
+    if (ci + 1 < C) prefetch(ci + 1);
+    phaseB(ci);
+    if (ci + 1 < C) {
+      cp_async_wait<0>();
+      phaseA(ci + 1);
+    }
     __syncthreads();
-#pragma unroll 1
-    for (int ci = 0; ci < nchan; ++ci) {
-      if (ci + 1 < nchan) prefetch(ci + 1);
-      phaseB(ci);
-      if (ci + 1 < nchan) {
-        cp_async_wait<0>();
-        phaseA(ci + 1);
-      }
-      __syncthreads();
-    }
-  } else {
-    // =================================== halo threads ===================================
-    const int hl = tid - NBODY;
-    // item 0: 4-pixel strip of plane rows 0,1,TH+2,TH+3 ; item 1: 2-pixel pair left / right of a body row ;
-    // item 2 (lanes 0..7): 2 x 2 corner pairs
-    int pidx[3];
-    long goff[3];
-    bool in[3];
-    float hv[8];
-    {
-      const int hrow = hl >> 4, pr = hrow < 2 ? hrow : TH + hrow, strip = hl & 15;
-      const int yy = ty0 - 2 + pr, xx = tx0 + 4 * strip;
-      pidx[0] = pr * PW + 2 + 4 * strip;
-      in[0] = yy >= 0 && yy < H && xx < W;
-      goff[0] = in[0] ? (long)yy * W + xx : 0;
-    }
-    {
-      const int srow = hl >> 1, side = hl & 1;
-      const int yy = ty0 + srow, xx = side ? tx0 + TW : tx0 - 2;
-      pidx[1] = (2 + srow) * PW + (side ? TW + 2 : 0);
-      in[1] = yy < H && xx >= 0 && xx < W;
-      goff[1] = in[1] ? (long)yy * W + xx : 0;
-    }
-    {
-      const int crow = (hl >> 1) & 3, pr = crow < 2 ? crow : TH + crow, side = hl & 1;
-      const int yy = ty0 - 2 + pr, xx = side ? tx0 + TW : tx0 - 2;
-      pidx[2] = pr * PW + (side ? TW + 2 : 0);
-      in[2] = hl < 8 && yy >= 0 && yy < H && xx >= 0 && xx < W;
-      goff[2] = in[2] ? (long)yy * W + xx : 0;
-    }
-    {
-      const unsigned int t4 = in[0] ? *reinterpret_cast<const unsigned int*>(lab8 + goff[0]) : 0xffffffffu;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) hv[k] = ((t4 >> (8 * k)) & 0xffu) != SH_IGNORE ? 1.f : 0.f;
-#pragma unroll
-      for (int e = 1; e < 3; ++e) {
-        const unsigned int t2 = in[e] ? *reinterpret_cast<const unsigned short*>(lab8 + goff[e]) : 0xffffu;
-        hv[2 * e + 2] = (t2 & 0xffu) != SH_IGNORE ? 1.f : 0.f;
-        hv[2 * e + 3] = (t2 >> 8) != SH_IGNORE ? 1.f : 0.f;
-      }
-    }
-    unsigned char* hs_gen = hst + hl * 32;
-    const unsigned int hs_base = (unsigned int)__cvta_generic_to_shared(hs_gen);
-    auto prefetch = [&](int ci) {
-      const char* g = xbb + s_chb[ci];
-      if (sizeof(T) == 4) {
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(hs_base), "l"(g + goff[0] * 4));
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(hs_base + 16), "l"(g + goff[1] * 4));
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(hs_base + 24), "l"(g + goff[2] * 4));
-      } else {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(hs_base), "l"(g + goff[0] * 2));
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(hs_base + 16), "l"(g + goff[1] * 2));
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(hs_base + 24), "l"(g + goff[2] * 2));
-      }
-      cp_async_commit();
-    };
-    auto halo = [&](int ci) {
-      float* pl = planes + (ci & 1) * PLANE;
-      float xv[4];
-      staged_vec4<T>(hs_gen, xv);
-      if (in[0]) {
-        *reinterpret_cast<float2*>(pl + pidx[0]) = make_float2(fmaf(sig_only(xv[0]), hv[0], 1e-6f), fmaf(sig_only(xv[1]), hv[1], 1e-6f));
-        *reinterpret_cast<float2*>(pl + pidx[0] + 2) = make_float2(fmaf(sig_only(xv[2]), hv[2], 1e-6f), fmaf(sig_only(xv[3]), hv[3], 1e-6f));
-      }
-#pragma unroll
-      for (int e = 1; e < 3; ++e) {
-        if (in[e]) {
-          float a0, a1;
-          if (sizeof(T) == 4) {
-            const float2 t2 = *reinterpret_cast<const float2*>(hs_gen + 8 + 8 * e);
-            a0 = t2.x; a1 = t2.y;
-          } else {
-            a0 = staged_elem<T>(hs_gen + 8 + 8 * e, 0);
-            a1 = staged_elem<T>(hs_gen + 8 + 8 * e, 1);
-          }
-          *reinterpret_cast<float2*>(pl + pidx[e]) =
-              make_float2(fmaf(sig_only(a0), hv[2 * e + 2], 1e-6f), fmaf(sig_only(a1), hv[2 * e + 3], 1e-6f));
-        }
-      }
-    };
-    // stencil weights of channel ci (k3f_finalize: W1[25], W2[25], sum W2 at 50) times the upstream gradient
-    auto weights = [&](int ci) {
-      const unsigned int ch = s_order[ci] >> 24;
-      const float* src = ws.wts + ((size_t)b * C + ch) * 64;
-      float* dst = wsm + (ci & 1) * WS;
-      if (hl < 25) { dst[hl] = src[hl] * gscale; dst[28 + hl] = src[25 + hl] * gscale; }
-      else if (hl < 28) { dst[hl] = 0.f; dst[28 + hl] = 0.f; }
-      else if (hl == 28) dst[56] = src[50] * gscale;
-    };
-    __syncthreads();                                   // label tile (all threads took part)
-    prefetch(0);
-    weights(0);
-    cp_async_wait<0>();
-    __syncthreads();
-    halo(0);
-    __syncthreads();
-#pragma unroll 1
-    for (int ci = 0; ci < nchan; ++ci) {
-      if (ci + 1 < nchan) {
-        prefetch(ci + 1);
-        weights(ci + 1);
-        cp_async_wait<0>();
-        halo(ci + 1);
-      }
-      __syncthreads();
-    }
   }
 }
 
