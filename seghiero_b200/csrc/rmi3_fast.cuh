@@ -21,16 +21,16 @@ namespace sh {
 namespace fast {
 
 constexpr int TW = 64;               // tile width (pixels)
-constexpr int PWARPS = 12;           // producer warps
-constexpr int CWARPS = 4;            // consumer warps
-constexpr int PPC = 2;               // planes per consumer warp and round
+constexpr int PWARPS = 9;            // producer warps
+constexpr int CWARPS = 7;            // consumer warps
+constexpr int PPC = 1;               // planes per consumer warp and round
 constexpr int TH = 2 * PWARPS;       // tile height of the streaming kernels: one producer thread per 4-pixel strip
 constexpr int BR = TH / 2;           // rows of a consumer thread's 4-wide block
 constexpr int PW = TW + 4;           // plane pitch: cols x0-2 .. x0+65
 constexpr int PR = TH + 4;           // plane rows:  y0-2 .. y0+TH+1
 constexpr int PLANE = PR * PW;
 constexpr int NR = CWARPS * PPC;     // planes per round
-constexpr int NBUF = 2;              // round buffers
+constexpr int NBUF = 3;              // round buffers
 constexpr int NPROD = 32 * PWARPS, NCONS = 32 * CWARPS;
 constexpr int NTHREADS = NPROD + NCONS;   // 512 threads, 128 registers each
 constexpr int XD = 4;                // cp.async ring depth of the producers (power of two; XD-2 channels ahead)

@@ -448,15 +448,16 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
             win[4 + v] = ((l1 >> (8 * v)) & 0xffu) == cl ? 1.f : 0.f;
           }
         }
+        // up to 16 independent accumulators between two updates of the same one
 #pragma unroll
-        for (int o = 0; o < 4; ++o) {
-          const int dyi = i - o;
-          if (dyi < 0 || dyi > 4) continue;
+        for (int dx = 0; dx < 5; ++dx)
 #pragma unroll
-          for (int dx = 0; dx < 5; ++dx)
+          for (int o = 0; o < 4; ++o) {
+            const int dyi = i - o;
+            if (dyi < 0 || dyi > 4) continue;
 #pragma unroll
             for (int k = 0; k < 4; ++k) acc[o][k] = fmaf(w[dyi * 5 + dx], win[k + dx], acc[o][k]);
-        }
+          }
       }
     }
     T* gp = grad + ((long)b * C + ch) * HW;

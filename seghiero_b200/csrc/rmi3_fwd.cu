@@ -807,38 +807,46 @@ __device__ void finalize_core(const double* part, const double* fr, int bc, cons
     }
     mm9(Wm, false, T1, false, U, lane);            // U = W Slp K ;  G_lp = -U
     mm9(T1, true, U, false, Gpp, lane);            // 2 * G_pp = T1^T U
-    float* wout = ws.wts + (size_t)bc * 64;
-    float* fout = ws.fwts + (size_t)bc * 25 * 50;
-    if (lane < 25) {
+  }
+  __shared__ unsigned char s_tap[81], s_jy[81], s_jx[81];
+  if (tid >= 32 && tid < 32 + 81) {
+    const int e = tid - 32, i = e / 9, j = e % 9;
+    s_tap[e] = (unsigned char)tap_index(i / 3 - j / 3, i % 3 - j % 3);
+    s_jy[e] = (unsigned char)(j / 3);
+    s_jx[e] = (unsigned char)(j % 3);
+  }
+  __syncthreads();
+  // adjoints -> stencil weights, spread over the whole CTA
+  float* wout = ws.wts + (size_t)bc * 64;
+  float* fout = ws.fwts + (size_t)bc * 25 * 50;
+  if (tid < 25) {
+    double w1 = 0.0, w2 = 0.0;
+    for (int e = 0; e < 81; ++e)
+      if (s_tap[e] == tid) { w1 += Gpp[e]; w2 -= U[e]; }
+    wout[tid] = (float)(scale * w1);
+    wout[25 + tid] = (float)(scale * w2);
+  } else if (tid == 32) {
+    // sums over the 25 taps in tap order (same association as adding the per-tap values)
+    double s2 = 0.0, s1 = 0.0;
+    for (int t = 0; t < 25; ++t) {
       double w1 = 0.0, w2 = 0.0;
-      for (int e = 0; e < 81; ++e) {
-        const int i = e / 9, j = e % 9;
-        if (tap_index(i / 3 - j / 3, i % 3 - j % 3) == lane) { w1 += Gpp[e]; w2 -= U[e]; }
-      }
-      wout[lane] = (float)(scale * w1);
-      wout[25 + lane] = (float)(scale * w2);
-      tmp[lane] = scale * w2;
-      tmp[32 + lane] = scale * w1;
+      for (int e = 0; e < 81; ++e)
+        if (s_tap[e] == t) { w1 += Gpp[e]; w2 -= U[e]; }
+      s2 += scale * w2; s1 += scale * w1;
     }
-    __syncwarp();
-    if (lane == 0) {
-      double s2 = 0.0, s1 = 0.0;
-      for (int t = 0; t < 25; ++t) { s2 += tmp[t]; s1 += tmp[32 + t]; }
-      wout[50] = (float)s2;      // sum of the lp weights: label-uniform pixels
-      wout[51] = (float)s1;      // sum of the pp weights: difference form of the stencil
+    wout[50] = (float)s2;      // sum of the lp weights: label-uniform pixels
+    wout[51] = (float)s1;      // sum of the pp weights: difference form of the stencil
+  }
+  for (int q = tid; q < 25 * 25; q += 256) {
+    const int cls = q / 25, t = q % 25, ky = cls / 5, kx = cls % 5;
+    double w1 = 0.0, w2 = 0.0;
+    for (int e = 0; e < 81; ++e) {
+      if (s_tap[e] != t) continue;
+      if (!offset_valid(ky, s_jy[e]) || !offset_valid(kx, s_jx[e])) continue;
+      w1 += Gpp[e]; w2 -= U[e];
     }
-    for (int q = lane; q < 25 * 25; q += 32) {
-      const int cls = q / 25, t = q % 25, ky = cls / 5, kx = cls % 5;
-      double w1 = 0.0, w2 = 0.0;
-      for (int e = 0; e < 81; ++e) {
-        const int i = e / 9, j = e % 9;
-        if (tap_index(i / 3 - j / 3, i % 3 - j % 3) != t) continue;
-        if (!offset_valid(ky, j / 3) || !offset_valid(kx, j % 3)) continue;
-        w1 += Gpp[e]; w2 -= U[e];
-      }
-      fout[cls * 50 + t] = (float)(scale * w1);
-      fout[cls * 50 + 25 + t] = (float)(scale * w2);
-    }
+    fout[cls * 50 + t] = (float)(scale * w1);
+    fout[cls * 50 + 25 + t] = (float)(scale * w2);
   }
 }
 
