@@ -373,49 +373,65 @@ k3_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hie
   }
 }
 
-// grid (B*C, nseg), block 256: threads stride over the frame pixels of one (b, c) plane
+// grid (B*C, nseg), block 256: the frame pixels of one (b, c) plane, side by side; the 4-pixel band segments the
+// stencil touches are staged in shared memory
 template <typename T>
 __global__ void __launch_bounds__(256) k3_frame2(T* __restrict__ grad, int B, int H, int W, Hier3 h, Ws3 ws,
                                                  const float* __restrict__ bandR, const float* __restrict__ bandC,
                                                  const float* __restrict__ gscale_ptr) {
   __shared__ float fw[25 * 50];
+  __shared__ BandSeg bs;
   const int C = h.nf + h.nm + h.nh;
   const int bc = blockIdx.x, b = bc / C, c = bc % C;
+  const int seg = blockIdx.y, nseg = gridDim.y;
   const int lvl = c < h.nf ? 0 : (c < h.nf + h.nm ? 1 : 2);
   const int cl = lvl == 0 ? c : (lvl == 1 ? c - h.nf : c - h.nf - h.nm);
   const long HW = (long)H * W;
-  BandView bv;
-  bv.bandR = bandR + (size_t)bc * 8 * W; bv.bandC = bandC + (size_t)bc * 8 * H;
-  bv.lab8 = ws.lab8 + (long)b * HW; bv.lmap = lvl == 0 ? nullptr : (lvl == 1 ? h.f2m : h.f2h);
-  bv.H = H; bv.W = W;
+  const float* bR = bandR + (size_t)bc * 8 * W;
+  const float* bC = bandC + (size_t)bc * 8 * H;
+  const unsigned char* lab8 = ws.lab8 + (long)b * HW;
+  const int* lmap = lvl == 0 ? nullptr : (lvl == 1 ? h.f2m : h.f2h);
   T* gc = grad + ((long)b * C + c) * HW;
   const float gscale = *gscale_ptr;
-  for (int i = threadIdx.x; i < 25 * 50; i += 256) fw[i] = ws.fwts[(size_t)bc * 25 * 50 + i];
-  __syncthreads();
-  const int nframe = 4 * W + 4 * (H - 4);
-  const int per = (nframe + gridDim.y - 1) / gridDim.y;
-  const int lo = blockIdx.y * per, hi = min(nframe, lo + per);
-  for (int idx = lo + threadIdx.x; idx < hi; idx += 256) {
-    int yy, xx;
-    if (idx < 4 * W) { const int r = idx / W; yy = r < 2 ? r : H - 4 + r; xx = idx - r * W; }
-    else { const int i2 = idx - 4 * W; const int q = i2 / (H - 4); xx = q < 2 ? q : W - 4 + q; yy = 2 + (i2 - q * (H - 4)); }
-    if (bv.lab8[(long)yy * W + xx] == SH_IGNORE) continue;   // dP/ds = valid
-    const float* w = fw + (axis_class(yy, H) * 5 + axis_class(xx, W)) * 50;
-    float dP = 0.f;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 25 * 50; i += 256) fw[i] = ws.fwts[(size_t)bc * 25 * 50 + i];
+#pragma unroll 1
+  for (int side = 0; side < 4; ++side) {
+    const bool is_row = side < 2;
+    // rows 0,1,H-2,H-1 over all columns; columns 0,1,W-2,W-1 over the rows in between
+    const int N = is_row ? W : H, first = is_row ? 0 : 2, len = is_row ? W : H - 4;
+    const int per = (len + nseg - 1) / nseg, lo = first + seg * per, hi = min(first + len, lo + per);
+    for (int u0 = lo; u0 < hi; u0 += kSegMax) {
+      const int n = min(kSegMax, hi - u0);
+      __syncthreads();
+      stage_band(bs, side, u0, n, bR, bC, lab8, lmap, cl, H, W, tid, 256);
+      __syncthreads();
+      for (int idx = tid; idx < 2 * n; idx += 256) {
+        const int line = idx / n, i = idx - line * n, u = u0 + i;
+        const int va = line + 2 * (side & 1);
+        const float s = bs.P[va][i + 2] - 1e-6f;              // void pixels: P = 1e-6, no gradient
+        if (s == 0.f) continue;
+        const int vg = (side & 1) ? (is_row ? H : W) - 4 + va : va;
+        const int yy = is_row ? vg : u, xx = is_row ? u : vg;
+        const float* w = fw + (axis_class(yy, H) * 5 + axis_class(xx, W)) * 50;
+        float dP = 0.f;
 #pragma unroll
-    for (int dy = -2; dy <= 2; ++dy) {
+        for (int dv = -2; dv <= 2; ++dv) {
+          const int vv = va + dv;
+          if (vv < 0 || vv > 3) continue;
 #pragma unroll
-      for (int dx = -2; dx <= 2; ++dx) {
-        const int y2 = yy + dy, x2 = xx + dx;
-        if (y2 < 0 || y2 >= H || x2 < 0 || x2 >= W) continue;
-        const int t = (dy + 2) * 5 + dx + 2;
-        dP = fmaf(w[t], bv.P(y2, x2), dP);
-        if (bv.L(y2, x2) == cl) dP += w[25 + t];
+          for (int du = -2; du <= 2; ++du) {
+            if (u + du < 0 || u + du >= N) continue;
+            const int t = is_row ? (dv + 2) * 5 + du + 2 : (du + 2) * 5 + dv + 2;
+            dP = fmaf(w[t], bs.P[vv][i + 2 + du], dP);
+            dP = fmaf(w[25 + t], bs.L[vv][i + 2 + du], dP);
+          }
+        }
+        const float add = dP * gscale * s * (1.0f - s);
+        const long off = (long)yy * W + xx;
+        gc[off] = from_f32<T>(to_f32<T>(gc[off]) + add);
       }
     }
-    const float s = bv.P(yy, xx) - 1e-6f;
-    const float add = dP * gscale * s * (1.0f - s);
-    gc[(long)yy * W + xx] = from_f32<T>(to_f32<T>(gc[(long)yy * W + xx]) + add);
   }
 }
 

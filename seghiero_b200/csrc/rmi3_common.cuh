@@ -116,9 +116,38 @@ inline int fast_ctas_per_image(int B) { int c = SH_NUM_SMS / (B > 0 ? B : 1); re
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 // frame runs are split into segments so that long image edges spread over more CTAs
+constexpr int kSegMax = 256;        // pixels of a band segment staged in shared memory at a time
 inline int frame_segments(int H, int W) {
-  int n = ((H > W ? H : W) + 255) / 256;
-  return n < 1 ? 1 : (n > 8 ? 8 : n);
+  int n = ((H > W ? H : W) + kSegMax - 1) / kSegMax;
+  return n < 1 ? 1 : (n > 32 ? 32 : n);
+}
+
+// A segment of one of the four 4-pixel border bands, staged in shared memory: P and the indicator of the
+// channel's class (1.0 where the RMI label equals cl).  Band coordinates: u along the image edge, v = 0..3 across
+// it; side 0 = rows 0..3, 1 = rows H-4..H-1, 2 = cols 0..3, 3 = cols W-4..W-1.
+struct BandSeg {
+  float P[4][kSegMax + 4];
+  float L[4][kSegMax + 4];
+};
+__device__ __forceinline__ void stage_band(BandSeg& s, int side, int u0, int n, const float* bandR, const float* bandC,
+                                           const unsigned char* lab8, const int* lmap, int cl, int H, int W, int tid,
+                                           int nthreads) {
+  const int N = side < 2 ? W : H;
+  for (int e = tid; e < 4 * (n + 4); e += nthreads) {
+    const int v = e / (n + 4), i = e - v * (n + 4), u = u0 - 2 + i;
+    float p = 0.f, l = 0.f;
+    if (u >= 0 && u < N) {
+      const int q = (side & 1) ? 4 + v : v;
+      int yy, xx;
+      if (side < 2) { p = bandR[(size_t)q * W + u]; yy = (side & 1) ? H - 4 + v : v; xx = u; }
+      else { p = bandC[(size_t)q * H + u]; xx = (side & 1) ? W - 4 + v : v; yy = u; }
+      const int t = lab8[(long)yy * W + xx];
+      const int lab = t == SH_IGNORE ? 0 : (lmap ? lmap[t] : t);
+      l = lab == cl ? 1.f : 0.f;
+    }
+    s.P[v][i] = p;
+    s.L[v][i] = l;
+  }
 }
 
 inline Ws3 ws3_layout(void* base, int B, int H, int W, int nf, int nm, int nh) {

@@ -587,6 +587,7 @@ __device__ __forceinline__ void frame_pixel_taps(const BandView& bv, int cl, int
 
 __global__ void __launch_bounds__(256) k3_frame1(int B, int H, int W, Hier3 h, Ws3 ws, const float* __restrict__ bandR,
                                                  const float* __restrict__ bandC) {
+  __shared__ BandSeg bs[4];
   const int C = h.nf + h.nm + h.nh;
   const int bc = blockIdx.x, b = bc / C, c = bc % C;
   const int seg = blockIdx.y, nseg = gridDim.y;
@@ -596,27 +597,62 @@ __global__ void __launch_bounds__(256) k3_frame1(int B, int H, int W, Hier3 h, W
   bv.bandR = bandR + (size_t)bc * 8 * W; bv.bandC = bandC + (size_t)bc * 8 * H;
   bv.lab8 = ws.lab8 + (long)b * H * W; bv.lmap = lvl == 0 ? nullptr : (lvl == 1 ? h.f2m : h.f2h);
   bv.H = H; bv.W = W;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float* out = ws.frameT + ((size_t)seg * B * C + bc) * 25 * kFrameRec;
 
-  float acc[75];
+  // warp -> line: warps 0,1 rows 0,1 ; 2,3 rows H-2,H-1 ; 4,5 cols 0,1 ; 6,7 cols W-2,W-1
+  const int side = warp >> 1, va = (warp & 1) + 2 * (side & 1);
+  const bool is_row = side < 2;
+  float acc[75];     // canonical order: index (dv + 2) * 5 + (du + 2), dv across the band, du along it
 #pragma unroll
   for (int i = 0; i < 75; ++i) acc[i] = 0.f;
   double t0 = 0.0, lp0 = 0.0;
-  const bool is_row = warp < 4;
-  const int line = (warp & 3) < 2 ? (warp & 3) : (is_row ? H : W) - 4 + (warp & 3);  // 0,1,n-2,n-1
-  const int len = (is_row ? W : H) - 4;
-  const int per = (len + nseg - 1) / nseg;
-  const int lo = 2 + seg * per, hi = min(2 + len, lo + per);
-  for (int i = lo + lane; i < hi; i += 32)
-    frame_pixel_taps(bv, cl, is_row ? line : i, is_row ? i : line, t0, lp0, acc);
+  int lo[2], hi[2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {      // anchors are the middle pixels of the line: 2 .. N-3
+    const int len = (a == 0 ? W : H) - 4, per = (len + nseg - 1) / nseg;
+    lo[a] = 2 + seg * per;
+    hi[a] = min(2 + len, lo[a] + per);
+  }
+  const int span = max(hi[0] - lo[0], hi[1] - lo[1]);
+  for (int c0 = 0; c0 < span; c0 += kSegMax) {
+    __syncthreads();
+#pragma unroll 1
+    for (int sd = 0; sd < 4; ++sd) {
+      const int a = sd >> 1, u0 = lo[a] + c0, n = min(kSegMax, hi[a] - u0);
+      if (n > 0) stage_band(bs[sd], sd, u0, n, bv.bandR, bv.bandC, bv.lab8, bv.lmap, cl, H, W, tid, 256);
+    }
+    __syncthreads();
+    const int a = side >> 1, u0 = lo[a] + c0, n = min(kSegMax, hi[a] - u0);
+    const BandSeg& s = bs[side];
+    for (int i = lane; i < n; i += 32) {
+      const float pr = s.P[va][i + 2], lr = s.L[va][i + 2];
+      t0 += (double)pr * (double)pr;
+      lp0 += (double)(pr * lr);
+#pragma unroll
+      for (int dv = -2; dv <= 2; ++dv) {
+        const int vv = va + dv;
+        if (vv < 0 || vv > 3) continue;                      // such taps have no valid window
+#pragma unroll
+        for (int du = -2; du <= 2; ++du) {
+          const float pn = s.P[vv][i + 2 + du], ln = s.L[vv][i + 2 + du];
+          const int t = (dv + 2) * 5 + du + 2;
+          acc[t] = fmaf(pr, pn - pr, acc[t]);
+          acc[25 + t] = fmaf(pr, ln - lr, acc[25 + t]);
+          acc[50 + t] = fmaf(lr, ln, acc[50 + t]);
+        }
+      }
+    }
+  }
   const int kline = (warp & 3) < 2 ? (warp & 3) : 1 + (warp & 3);  // class 0,1,3,4
   const int cls = is_row ? kline * 5 + 2 : 2 * 5 + kline;
   float* oc = out + cls * kFrameRec;
 #pragma unroll
   for (int i = 0; i < 75; ++i) {
     const float r = warp_sum(acc[i]);
-    if (lane == 0) oc[kFD + i] = r;
+    // canonical (dv, du) -> tap (dy, dx): rows: dy = dv, dx = du ; columns: dy = du, dx = dv
+    const int grp = i / 25, t = i % 25, tt = is_row ? t : (t % 5) * 5 + t / 5;
+    if (lane == 0) oc[kFD + grp * 25 + tt] = r;
   }
   t0 = warp_sum(t0); lp0 = warp_sum(lp0);
   if (lane == 0) { reinterpret_cast<double*>(oc)[0] = t0; reinterpret_cast<double*>(oc)[1] = lp0; }
