@@ -44,6 +44,16 @@ def two_level_tables(n_fine: int, hiera_index: Sequence[Sequence[int]]):
     return blob, len(fb_idx), lut_size
 
 
+def two_level_is_tree(n_fine: int, hiera_index: Sequence[Sequence[int]]) -> bool:
+    """True when no fine class sits in two buckets (disjoint ranges): the fast 2-level kernel applies."""
+    seen = np.zeros(n_fine, dtype=np.int32)
+    for s, e in hiera_index:
+        lo, hi = max(0, min(int(s), n_fine)), max(0, min(int(e), n_fine))
+        if hi > lo:
+            seen[lo:hi] += 1
+    return bool((seen <= 1).all())
+
+
 def three_level_tables(n_fine: int, n_mid: int, n_high: int, fine_to_mid, fine_to_high):
     """-> (int32 blob [f2m][f2h][mh_ptr][mh_idx][hsmask][order C][fast order C][fast aux C], n_mh, fast_ok).
     Validates the maps."""

@@ -300,9 +300,10 @@ class HieraTriplet2Fn(torch.autograd.Function):
             partials = torch.empty(grid * 4, dtype=torch.float32, device=dev)
             sums = torch.empty(4, dtype=torch.float64, device=dev)
             out = torch.empty(4, dtype=torch.float32, device=dev)
+            tree = 256 if (FAST_PATH["enabled"] and H.two_level_is_tree(cfg.n_fine, cfg.hiera_index)) else 0
             _staged("sh_bce2_fwdbwd", (1, 2, 4), lambda st_bits: (
                 _p(x), _dtype_code(x), _p(lab), _p(grad), b, hw, cfg.n_fine, cfg.n_coarse, _p(tab), n_fb, lut_size,
-                cfg.eps, cfg.loss_weight, _p(lab8), _p(counts), _p(partials), _p(sums), st_bits, _stream()))
+                cfg.eps, cfg.loss_weight, _p(lab8), _p(counts), _p(partials), _p(sums), st_bits | tree, _stream()))
             _call("sh_loss2_final", _p(sums), _p(counts), cfg.n_fine, cfg.n_coarse, float(b * hw), _p(step_d),
                       cfg.total_steps, _p(st.trip) if st else None, _p(st.status) if st else None, cfg.loss_weight,
                       _p(out), _stream())

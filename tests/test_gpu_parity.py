@@ -165,8 +165,21 @@ def test_two_level_golden(sb, golden, name):
     dict(b=2, h=32, w=32, hi=[[0, 4], [2, 6], [6, 7]], hm=[0, 0, 1, 1, 1, 1, 2, 0, 0], step=80000,
          dtype=torch.float32, labels="iid"),                                                  # overlapping buckets + orphans
     dict(b=2, h=24, w=40, hi=HI, hm=HM, step=80000, dtype=torch.float16, labels="blob"),
+    dict(b=2, h=32, w=34, hi=[[0, 4], [5, 7], [7, 7]], hm=[0, 0, 0, 0, 0, 1, 1, 1, 1], step=80000,
+         dtype=torch.float32, labels="iid"),                                                  # disjoint buckets, orphans, empty bucket
+    dict(b=2, h=40, w=64, hi=HI, hm=HM, step=80000, dtype=torch.bfloat16, labels="blob"),
+    dict(b=1, h=64, w=96, hi=HI, hm=HM, step=40000, dtype=torch.float32, labels="blob", generic=True),
 ])
 def test_two_level_vs_oracle(sb, case):
+    from seghiero_b200 import ops
+    ops.FAST_PATH["enabled"] = not case.get("generic", False)   # generic=True: the any-bucket kernel on a tree-shaped case
+    try:
+        _two_level_vs_oracle(sb, case)
+    finally:
+        ops.FAST_PATH["enabled"] = True
+
+
+def _two_level_vs_oracle(sb, case):
     g = torch.Generator().manual_seed(case["h"] * 7 + case["w"])
     nf = len(case["hm"])
     nc = len(case["hi"])
