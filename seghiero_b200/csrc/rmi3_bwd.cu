@@ -5,7 +5,6 @@
 //   k3_frame2  RMI gradient of the 2-pixel image frame (class-dependent stencil weights),
 //              added in place
 // Analytic RMI backward: see oracle/rmi_taps.py (checked against autograd on the CPU).
-#include <stdlib.h>
 #include "rmi3_common.cuh"
 #include "rmi3_fast_bwd.cuh"
 
@@ -460,8 +459,7 @@ static int run_backward3(const void* x, void* grad, int B, int H, int W, const H
     fh.nf = h.nf; fh.nm = h.nm; fh.nh = h.nh; fh.f2m = h.f2m; fh.f2h = h.f2h;
     fh.order = h.order + C; fh.aux = h.order + 2 * C;
     auto kern = fast2::k3f_pass2<T>;
-    size_t fsm = fsmem;
-    if (const char* pad = getenv("SH_P2_PAD")) fsm += (size_t)atoi(pad) * 1024;   // occupancy experiments
+    const size_t fsm = fsmem;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
     const int tiles_x = (W + fast2::TW - 1) / fast2::TW, tiles_y = (H + fast2::TH - 1) / fast2::TH;
     kern<<<B * tiles_x * tiles_y, fast2::NT, fsm, st>>>((const T*)x, (T*)grad, B, H, W, fh, ws, eps, lw, gscale, tiles_x,

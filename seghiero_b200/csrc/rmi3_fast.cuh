@@ -75,12 +75,18 @@ __global__ void __launch_bounds__(256) k3f_prep(const long long* __restrict__ la
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C = hg.nf + hg.nm + hg.nh;
   unsigned int* hist = reinterpret_cast<unsigned int*>(smem_raw);                       // [C][16]: A, M[1..12]
-  int* s_f2m = reinterpret_cast<int*>(hist + (size_t)C * 16);
-  int* s_f2h = s_f2m + hg.nf;
-  unsigned char* rl = reinterpret_cast<unsigned char*>(s_f2h + hg.nf);                  // [3][PTH2+2][LPITCH]
+  unsigned int* lut = hist + (size_t)C * 16;                                            // [256] fine | mid << 8 | high << 16 | lab8 << 24
+  unsigned char* rl = reinterpret_cast<unsigned char*>(lut + 256);                      // [3][PTH2+2][LPITCH]
   const int tid = threadIdx.x, lane = tid & 31;
   for (int i = tid; i < C * 16; i += 256) hist[i] = 0u;
-  for (int i = tid; i < hg.nf; i += 256) { s_f2m[i] = hg.f2m[i]; s_f2h[i] = hg.f2h[i]; }
+  {
+    // label byte -> RMI labels of the 3 levels (void = class 0 at every level) and the uint8 label; bit 31..24 = 0xfe marks
+    // a value F.one_hot would reject
+    unsigned int e = 0xfe000000u;
+    if (tid == SH_IGNORE) e = 0xff000000u;
+    else if (tid < hg.nf) e = (unsigned)tid | ((unsigned)hg.f2m[tid] << 8) | ((unsigned)hg.f2h[tid] << 16) | ((unsigned)tid << 24);
+    lut[tid] = e;
+  }
   __syncthreads();
   const int cpb = cpi * PREP_MULT;
   const int b = blockIdx.x / cpb, j0 = blockIdx.x - b * cpb;
@@ -91,7 +97,7 @@ __global__ void __launch_bounds__(256) k3f_prep(const long long* __restrict__ la
   const int ty = tid >> 4, tx = (tid & 15) << 2;
   const int level_base[3] = {0, hg.nf, hg.nf + hg.nm};
   unsigned int run_c[3] = {0xffu, 0xffu, 0xffu}, run_n[3] = {0u, 0u, 0u};
-  long long nv = 0;
+  unsigned int nv = 0;
   bool bad = false;
   constexpr int NP = (TW + 4) / 2, NITEM = (PTH2 + 2) * NP, NIT = (NITEM + 255) / 256;   // pixel pairs of the label tile
 #pragma unroll 1
@@ -114,25 +120,20 @@ __global__ void __launch_bounds__(256) k3f_prep(const long long* __restrict__ la
       const int e = tid + 256 * it, r = e / NP, j = (e - r * NP) * 2;
       if (e >= NITEM) continue;
       const int y = tc.y0 + r, xx = tc.x0 - 2 + j;
-      unsigned int f2 = 0xffffu, m2 = 0xffffu, g2 = 0xffffu, l2 = 0xffffu;
+      unsigned int f2 = 0xffffu, m2 = 0xffffu, g2 = 0xffffu;
       if (y < H && xx >= 0 && xx < W) {
-        f2 = m2 = g2 = 0u;
-        const long long tt[2] = {v[it].x, v[it].y};
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const long long t = tt[k];
-          if (t != SH_IGNORE) {
-            if (t >= 0 && t < hg.nf) {
-              f2 |= (unsigned int)t << (8 * k);
-              m2 |= (unsigned int)s_f2m[t] << (8 * k);
-              g2 |= (unsigned int)s_f2h[t] << (8 * k);
-              l2 = (l2 & ~(0xffu << (8 * k))) | ((unsigned int)t << (8 * k));
-            } else bad = true; // F.one_hot would raise in the reference
-          }
-        }
+        const unsigned long long t0 = (unsigned long long)v[it].x, t1 = (unsigned long long)v[it].y;
+        const unsigned int e0 = t0 < 256ull ? lut[(unsigned int)t0] : 0xfe000000u;
+        const unsigned int e1 = t1 < 256ull ? lut[(unsigned int)t1] : 0xfe000000u;
+        bad |= (e0 >> 24) == 0xfeu || (e1 >> 24) == 0xfeu;       // F.one_hot would raise in the reference
+        f2 = (e0 & 0xffu) | ((e1 & 0xffu) << 8);
+        m2 = ((e0 >> 8) & 0xffu) | (e1 & 0xff00u);
+        g2 = ((e0 >> 16) & 0xffu) | ((e1 >> 8) & 0xff00u);
         if (r < PTH2 && j >= 2 && j < TW + 2) {
-          *reinterpret_cast<unsigned short*>(lab8 + (long)y * W + xx) = (unsigned short)l2;
-          nv += (tt[0] != SH_IGNORE) + (tt[1] != SH_IGNORE);
+          // out-of-range labels are stored as void (the loss is poisoned through the error flag)
+          const unsigned int l0 = (e0 >> 24) == 0xfeu ? 0xffu : e0 >> 24, l1 = (e1 >> 24) == 0xfeu ? 0xffu : e1 >> 24;
+          *reinterpret_cast<unsigned short*>(lab8 + (long)y * W + xx) = (unsigned short)(l0 | (l1 << 8));
+          nv += (t0 != SH_IGNORE) + (t1 != SH_IGNORE);
         }
       }
       *reinterpret_cast<unsigned short*>(rl + (0 * (PTH2 + 2) + r) * LPITCH + j) = (unsigned short)f2;
@@ -144,23 +145,22 @@ __global__ void __launch_bounds__(256) k3f_prep(const long long* __restrict__ la
     for (int rr = 0; rr < PTH2 / 16; ++rr) {
       const int row = ty + 16 * rr, y = tc.y0 + row;
       if (y < 2 || y >= H - 2) continue;
-      unsigned int imask = 0u;       // interior anchors among the strip's 4 pixels
+      unsigned int imask = 0u;       // interior anchors among the strip's 4 pixels: byte mask
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { const int xx = tc.x0 + tx + k; if (xx >= 2 && xx < W - 2) imask |= 1u << k; }
+      for (int k = 0; k < 4; ++k) { const int xx = tc.x0 + tx + k; if (xx >= 2 && xx < W - 2) imask |= 0xffu << (8 * k); }
       if (imask == 0u) continue;
 #pragma unroll
       for (int l = 0; l < 3; ++l) {
         const unsigned char* base = rl + (l * (PTH2 + 2) + row) * LPITCH + tx;
-        unsigned long long wn[3];
+        unsigned int lo[3], hi[3];
         unsigned int diff = 0u;
         const unsigned int c0 = base[2];
         const unsigned int pat = c0 * 0x01010101u;
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
           const unsigned int* p = reinterpret_cast<const unsigned int*>(base + q * LPITCH);
-          const unsigned int lo = p[0], hi = p[1];
-          wn[q] = (unsigned long long)lo | ((unsigned long long)hi << 32);
-          diff |= (lo ^ pat) | (hi ^ pat);
+          lo[q] = p[0]; hi[q] = p[1];
+          diff |= (lo[q] ^ pat) | (hi[q] ^ pat);
         }
         if (diff == 0u) {            // uniform window (and therefore all 4 pixels interior): anchors only
           if (c0 == run_c[l]) run_n[l] += 4u;
@@ -169,23 +169,24 @@ __global__ void __launch_bounds__(256) k3f_prep(const long long* __restrict__ la
             run_c[l] = c0; run_n[l] = 4u;
           }
         } else {
+          // the 4 anchors' classes as one word; tap (q, dx): neighbours = window bytes dx .. dx+3 of row q.
+          // A nonzero byte of (anchors ^ neighbours) is a mismatch of that pixel and tap.
+          const unsigned int cw = __funnelshift_r(lo[0], hi[0], 16);
+          unsigned int hrow[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (!((imask >> k) & 1u)) continue;
-            const unsigned int c = byte_of(wn[0], k + 2);
-            unsigned int mm = 1u;                                   // bit 0: the anchor itself, bit t: tap t mismatches
-            mm |= (unsigned int)(byte_of(wn[0], k + 3) != c) << 1;
-            mm |= (unsigned int)(byte_of(wn[0], k + 4) != c) << 2;
+          for (int k = 0; k < 4; ++k) hrow[k] = (unsigned int)(level_base[l] + ((cw >> (8 * k)) & 0xffu)) * 16u;
 #pragma unroll
-            for (int dx = 0; dx < 5; ++dx) {
-              mm |= (unsigned int)(byte_of(wn[1], k + dx) != c) << (3 + dx);
-              mm |= (unsigned int)(byte_of(wn[2], k + dx) != c) << (8 + dx);
-            }
-            unsigned int* hrow = hist + (size_t)(level_base[l] + c) * 16;
-            while (mm) {
-              const int t = __ffs(mm) - 1;
-              mm &= mm - 1u;
-              atomicAdd(hrow + t, 1u);
+          for (int k = 0; k < 4; ++k)
+            if ((imask >> (8 * k)) & 1u) atomicAdd(hist + hrow[k], 1u);
+#pragma unroll
+          for (int t = 1; t < 13; ++t) {
+            const int q = t < 3 ? 0 : (t < 8 ? 1 : 2), sh = t < 3 ? t + 2 : (t < 8 ? t - 3 : t - 8);
+            const unsigned int nw = sh == 0 ? lo[q] : (sh == 4 ? hi[q] : __funnelshift_r(lo[q], hi[q], 8 * sh));
+            const unsigned int mm = (cw ^ nw) & imask;
+            if (mm) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if ((mm >> (8 * k)) & 0xffu) atomicAdd(hist + hrow[k] + t, 1u);
             }
           }
         }
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(256) k3f_prep(const long long* __restrict__ la
 #pragma unroll
   for (int l = 0; l < 3; ++l)
     if (run_n[l]) atomicAdd(hist + (size_t)(level_base[l] + run_c[l]) * 16, run_n[l]);
-  nv = warp_sum(nv);
+  nv = __reduce_add_sync(0xffffffffu, nv);
   if (lane == 0 && nv) atomicAdd(ws.counts, (unsigned long long)nv);
   if (bad) atomicOr((unsigned int*)(ws.counts + 2), 1u);
   __syncthreads();
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(256) k3f_prep(const long long* __restrict__ la
 }
 
 inline size_t prep_smem(int C, int nf) {
-  return (size_t)C * 16 * 4 + (size_t)2 * nf * 4 + (size_t)3 * (PTH2 + 2) * LPITCH + 16;
+  return (size_t)C * 16 * 4 + (size_t)256 * 4 + (size_t)3 * (PTH2 + 2) * LPITCH + 16;
 }
 
 // tile walk of a persistent CTA without integer divisions: tile index advances by cpi per step
