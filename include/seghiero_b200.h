@@ -56,7 +56,10 @@ int sh_bce2_grid(int B, long HW, int C, int n_coarse);
  * it is the gradient for grad_output == 1, already scaled by loss_weight.
  * hier_tab (device int32): [bucket_start nc][bucket_end nc][owner nf][fb_ptr nf+1][fb_idx n_fb][lut lut_size].
  * Outputs: sums[0..3] = un-normalised BCE fine, BCE coarse, CE fine, CE coarse; counts[0..2] = #valid fine,
- * #valid coarse, label-range error flag. */
+ * #valid coarse, label-range error flag.
+ * stages: bit 0 = label prep, bit 1 = fused loss kernel, bit 2 = reduction of the per-CTA partials; bit 8 (256)
+ * is a hint from the host table builder that the buckets are disjoint ranges (no fine class in two buckets,
+ * hierarchy.py::two_level_is_tree): the tree-order kernel k_bce2_fast runs then, else the any-bucket kernel. */
 int sh_bce2_fwdbwd(const void* logits, int dtype, const long long* label, void* grad, int B, long HW, int n_fine,
                    int n_coarse, const int* hier_tab, int n_fb, int lut_size, float eps, float loss_weight,
                    unsigned char* lab8, unsigned long long* counts, float* partials, double* sums, int stages,
@@ -80,7 +83,7 @@ size_t sh_rmi3_workspace_bytes(int B, int H, int W, int nf, int nm, int nh);
 int sh_rmi3_workspace_offsets(int B, int H, int W, int nf, int nm, int nh, size_t* out);
 
 /* 1 when the warp-specialised kernels (csrc/rmi3_fast.cuh) will run this problem: tree-shaped maps
- * (fast_tab_ok from the host table builder), W % 4 == 0, 16-byte aligned tensors, 8 < C <= 160.  Everything
+ * (fast_tab_ok from the host table builder), W % 4 == 0, 16-byte aligned tensors, 7 < C <= 64.  Everything
  * else runs the generic kernels; results agree to fp32 rounding. */
 int sh_rmi3_fast_path(const void* logits, const void* grad, int dtype, int H, int W, int nf, int nm, int nh,
                       int fast_tab_ok);

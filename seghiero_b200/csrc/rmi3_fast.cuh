@@ -1,19 +1,20 @@
-// Fast path of the three-level (BCE + RMI + CE) loss: warp-specialised persistent kernels.
+// Fast path of the three-level (BCE + RMI + CE) loss, forward side: warp-specialised persistent kernel + label prep.
 //
 // Applies when the hierarchy is a tree (every mid has one high), W % 4 == 0, pointers are 16-byte
-// aligned and 8 < C <= kFastMaxC; everything else runs the generic kernels of rmi3_fwd.cu / rmi3_bwd.cu.
+// aligned and NR < C <= kFastMaxC; everything else runs the generic kernels of rmi3_fwd.cu / rmi3_bwd.cu.
 // Reference arithmetic: models/loss/rmi_hiera_triplet_loss.py:323-546.
+// The backward side of the fast path is rmi3_fast_bwd.cuh.
 //
-// One CTA per SM (512 threads), each walking tiles (64 x 24 pixels) of ONE image:
-//   warps 0-11  producers : thread = 4 consecutive pixels, all channels in tree order (fine children,
+// k3f_pass1: one CTA per SM (512 threads), each walking tiles (64 x 18 pixels) of ONE image:
+//   warps 0-8   producers : thread = 4 consecutive pixels, all channels in tree order (fine children,
 //                           their mid, ..., then the high).  sigmoid / e^x from 3 MUFU ops, tree BCE +
 //                           CE sums in registers, P = s*valid + 1e-6 -> shared-memory channel plane.
-//   warps 12-15 consumers : warp = two channel planes of the round, thread = 4 x 12 block.  The 2-pixel ring of
+//   warps 9-15  consumers : warp = one channel plane of the round, thread = 4 x 9 block.  The 2-pixel ring of
 //                           the plane (sigmoid only, own cp.async ring), the tile's label bytes, then RMI moments
 //                           of the interior anchors as 13 product taps (pr_cov) + 25 label-anchored taps
 //                           (la_pr), warp-reduced and accumulated in fp64 per CTA.
-// Planes travel producer -> consumer through a ring of kNBuf round buffers (kNR planes each) guarded by
-// named barriers (bar.arrive / bar.sync); logits are prefetched 6 channels ahead with cp.async.
+// Planes travel producer -> consumer through a ring of NBUF round buffers (NR = 7 planes each, 28 channels =
+// 4 rounds) guarded by named barriers (bar.arrive / bar.sync); logits are prefetched with cp.async.
 #pragma once
 #include "rmi3_common.cuh"
 
