@@ -39,6 +39,12 @@ WORKLOADS = {
                  desc="config 2: HieraTripletLoss 19/7, 512x1024, batch 16, bf16 logits"),
     "cfg4": dict(kind="3level", nf=150, nm=30, nh=6, B=32, H=512, W=512, dtype="fp32", triplet=False,
                  desc="config 4: 150/30/6 classes, 512x512, batch 32/GPU (triplet undefined in the reference, off)"),
+    "train-cfg3": dict(kind="train", levels=3, nf=19, nm=7, nh=2, B=8, H=1024, W=2048, dtype="fp32", depth=101,
+                       desc="config 3 end to end: ResNet-101 + SepASPP head (context, stock cuDNN) + RMIHieraTripletLoss, "
+                            "1024x2048, batch 8/GPU, bf16 autocast network, fp32 full-resolution logits"),
+    "train-cfg2": dict(kind="train", levels=2, nf=19, nc=7, B=16, H=512, W=1024, dtype="bf16", depth=50,
+                       desc="config 2 end to end: ResNet-50 + SepASPP head (context) + HieraTripletLoss, 512x1024, "
+                            "batch 16, bf16 network and logits"),
     "cfg5": dict(kind="decode", nf=19, nm=7, nh=2, B=64, H=2048, W=2048, dtype="bf16",
                  desc="config 5: hierarchical argmax decode, 2048x2048, batch 64, bf16 logits"),
 }
@@ -493,6 +499,101 @@ def run_ours(args, w):
         dist.destroy_process_group()
 
 
+
+# ------------------------------------------------------------------------------------------------
+# end-to-end train throughput (the loss inside a segmentation training step; network = context)
+# ------------------------------------------------------------------------------------------------
+def run_train(args, w):
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    import seghiero_b200 as sb
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from train_context import ContextSegNet
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.benchmark = True
+    b, h, wd = args.batch or w["B"], w["H"], w["W"]
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    if w["levels"] == 3:
+        c = w["nf"] + w["nm"] + w["nh"]
+        f2m, f2h = hierarchy_maps(w)
+        crit = sb.RMIHieraTripletLoss(w["nf"], w["nm"], w["nh"], torch.tensor(f2m), torch.tensor(f2h))
+    else:
+        c = w["nf"] + w["nc"]
+        crit = sb.HieraTripletLoss(w["nf"], HM_19_7, HI_19_7)
+    net = ContextSegNet(w["depth"], c).to(dev).to(memory_format=torch.channels_last)
+    model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local]) if world > 1 else net
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
+    img = torch.randn(b, 3, h, wd, generator=g, device=dev).contiguous(memory_format=torch.channels_last)
+    lab = make_labels(torch, g, b, h, wd, w["nf"], args.labels, dev)
+    step_t = torch.tensor([100000], device=dev)
+    logit_dt = torch.float32 if w["dtype"] == "fp32" else torch.bfloat16
+
+    def step(with_loss=True):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits, emb = model(img)
+        full = F.interpolate(logits.to(logit_dt), size=(h, wd), mode="bilinear", align_corners=False)
+        if with_loss:
+            loss = crit(step_t, emb.float(), None, full, lab)
+        else:   # same graph without the hierarchical loss: what the rest of the step costs
+            loss = full.float().mean() + emb.float().mean()
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(k, with_loss):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            step(with_loss)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / k], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    warmup, steps = max(args.warmup, 3), max(1, min(args.steps, 10))
+    clk = ClockSampler(local)
+    clk.__enter__()
+    for _ in range(warmup):
+        step(True)
+    t0 = time.time()
+    ms = timed(steps, True)
+    clk.mark(t0, time.time())
+    for _ in range(2):
+        step(False)
+    ms_noloss = timed(steps, False)
+    clk.__exit__()
+    if rank == 0:
+        print(json.dumps({
+            "metric": "train_throughput", "value": world * b / (ms * 1e-3), "unit": "img/s", "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 network / %s logits" % w["dtype"], "data": "synthetic",
+            "config": {"workload": args.workload, "description": w["desc"], "labels": args.labels, "batch_per_gpu": b,
+                       "network": "torchvision ResNet-%d (stride 32) + DeepLabV3+-style SepASPP head, random init, "
+                                  "context only (stock cuDNN/ATen)" % w["depth"],
+                       "optimizer": "SGD momentum 0.9", "parallelism": f"DDP x{world}" if world > 1 else "single GPU"},
+            "ms_per_step_without_hier_loss": ms_noloss, "hier_loss_share": max(0.0, 1.0 - ms_noloss / ms),
+            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9, "clocks": clk.summary()}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -508,6 +609,8 @@ def main():
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference_arm(args, w)
+    elif w["kind"] == "train":
+        run_train(args, w)
     else:
         run_ours(args, w)
 
