@@ -8,6 +8,26 @@ from .. import ops
 from .tree_triplet_loss import TreeTripletLoss
 
 
+class FusedCrossEntropy(nn.Module):
+    """Stands where the reference keeps `self.ce = CrossEntropyLoss()` (hiera_triplet_loss.py:141): same attribute
+    names, no parameters.  The per-level softmax CE itself (cross_entropy_loss.py:7-30, mean over ALL pixels) is
+    computed inside the fused loss kernel from the same read of the logits, so this module is never called by
+    the parent; calling it directly is refused rather than answered by an eager fallback."""
+
+    def __init__(self, ignore_index: int = 255):
+        super().__init__()
+        self.use_sigmoid = False
+        self.use_mask = False
+        self.reduction = "mean"
+        self.loss_weight = 1.0
+        self.class_weight = None
+        self.ignore_index = ignore_index
+
+    def forward(self, *args, **kwargs):
+        raise RuntimeError("the per-level cross entropy is fused into the hierarchical loss kernel; "
+                           "call the parent loss module (seghiero_b200 has no eager fallback)")
+
+
 class HieraTripletLoss(nn.Module):
     """2-level (fine -> coarse) hierarchical BCE + softmax CE + scheduled triplet loss.
 
@@ -30,6 +50,7 @@ class HieraTripletLoss(nn.Module):
         self.hiera_map = hiera_map
         self.hiera_index = hiera_index
         self.ignore_index = ignore_index
+        self.ce = FusedCrossEntropy(ignore_index)
         self.triplet_loss_fn = TreeTripletLoss(num_classes=len(hiera_map), hiera_map=hiera_map,
                                                hiera_index=hiera_index, ignore_index=ignore_index)
         self.loss_weight = loss_weight

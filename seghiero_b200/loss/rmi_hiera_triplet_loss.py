@@ -6,6 +6,7 @@ import torch.nn as nn
 
 from .. import hierarchy as H
 from .. import ops
+from .hiera_triplet_loss import FusedCrossEntropy
 from .rmi_tree_triplet_loss import TreeTripletLoss
 
 
@@ -53,6 +54,7 @@ class RMIHieraTripletLoss(nn.Module):
         self.kernel_padding = self.rmi_pool_size // 2
         self.triplet_loss = TreeTripletLoss(num_classes=self.n_fine, upper_ids=self.upper_ids,
                                             lower_ids=self.lower_ids, ignore_index=self.ignore_index)
+        self.ce = FusedCrossEntropy(ignore_index)
         self.strict = strict
         self.last_stats: dict = {}
         # validate once on the host (raises ValueError on out-of-range map entries)
