@@ -208,13 +208,28 @@ __global__ void __launch_bounds__(128) k_bce2_fused(const T* __restrict__ x, con
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fast path: buckets are disjoint ranges (every fine class sits in at most one bucket).  Channels are walked in
-// tree order (a bucket's fine children, then its coarse channel; orphan fines last), so the bucket max and its
-// holder live in registers; logits arrive through a thread-private cp.async ring that runs XD-2 channels ahead
-// (also across work items); sigmoid / e^x are parked as float2 in shared memory for the gradient sweep.
+// Fast path: buckets are disjoint ranges (every fine class sits in at most one bucket), HW % 4 == 0, C <= 64.
+// Thread = 4 consecutive pixels.  Channels are walked in tree order (a bucket's fine children, then its coarse
+// channel; orphan fines last) in BOTH sweeps, so the bucket max / its holder live in registers in sweep A and the
+// holder bytes are decoded once per bucket in sweep B.  Logits arrive through a thread-private cp.async ring that
+// runs XD-2 channels ahead (also across work items).  Only w = e^-x is parked in shared memory (16 bytes per
+// thread and channel); sweep B rebuilds sigmoid and e^x from it with the same instructions, i.e. the same bits.
+// Label logic is SIMD over the 4 label bytes; the terms of a pixel's own target classes take a separate path
+// that only runs for channels that are a target somewhere in the strip.
 // Same arithmetic as k_bce2_fused (hiera_triplet_loss.py:41-107, cross_entropy_loss.py:7-30).
 // ---------------------------------------------------------------------------------------------
-constexpr int F2_NT = 128, F2_VEC = 2, F2_PX = F2_NT * F2_VEC, F2_XD = 8;
+constexpr int F2_NT = 128, F2_VEC = 4, F2_PX = F2_NT * F2_VEC, F2_XD = 8;
+
+__device__ __forceinline__ bool b0(unsigned int z, int k) { return ((z >> (8 * k)) & 0xffu) == 0u; }
+
+// w = e^-x (|x| clamped), s = sigmoid with torch's rounding of 1 + w, E = e^x
+__device__ __forceinline__ float exp_neg(float x) { return ex2(clamp_nan(x * (-kLog2e), -115.0f, 115.0f)); }
+__device__ __forceinline__ void sig_from_w(float w, float& s, float& E) {
+  const float y = 1.0f + w;
+  const float q0 = rcp(y);
+  s = fmaf(q0, fmaf(-y, q0, 1.0f), q0);
+  E = rcp(w);
+}
 
 template <typename T, bool GRAD>
 __global__ void __launch_bounds__(F2_NT, 3) k_bce2_fast(const T* __restrict__ x, const unsigned char* __restrict__ lab8,
@@ -223,17 +238,13 @@ __global__ void __launch_bounds__(F2_NT, 3) k_bce2_fast(const T* __restrict__ x,
                                                         float* __restrict__ partials) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C = h.nf + h.nc;
-  float2* S = reinterpret_cast<float2*>(smem_raw);                                     // [C][NT] sigmoid of the 2 pixels
-  float2* V = S + (size_t)C * F2_NT;                                                   // [C][NT] e^x
-  unsigned long long* xst = reinterpret_cast<unsigned long long*>(V + (size_t)C * F2_NT);   // [XD][NT] 8-byte slots
-  unsigned int* s_order = reinterpret_cast<unsigned int*>(xst + F2_XD * F2_NT);        // [C] channel | kind << 8 | first << 10 | bucket << 16
-  int* s_owner = reinterpret_cast<int*>(s_order + C);                                  // [nf]
-  int* s_lut = s_owner + h.nf;                                                         // [lut_size]
-  unsigned short* HOLD = reinterpret_cast<unsigned short*>(s_lut + h.lut_size);        // [nc][NT] holder channel of the 2 pixels
-  __shared__ int s_n;
+  float4* Wp = reinterpret_cast<float4*>(smem_raw);                                    // [C][NT] e^-x of the 4 pixels
+  uint4* xst = reinterpret_cast<uint4*>(Wp + (size_t)C * F2_NT);                       // [XD][NT] 16-byte slots
+  unsigned int* HOLD = reinterpret_cast<unsigned int*>(xst + F2_XD * F2_NT);           // [nc][NT] holder channel of the 4 pixels
+  unsigned int* s_order = HOLD + (size_t)h.nc * F2_NT;                                 // [C] channel | kind << 8 | first << 10 | bucket << 16
+  int* s_lut = reinterpret_cast<int*>(s_order + C);                                    // [lut_size]
 
   const int tid = threadIdx.x;
-  for (int i = tid; i < h.nf; i += F2_NT) s_owner[i] = h.owner[i];
   for (int i = tid; i < h.lut_size; i += F2_NT) s_lut[i] = h.lut[i];
   if (tid == 0) {
     int n = 0;
@@ -243,8 +254,7 @@ __global__ void __launch_bounds__(F2_NT, 3) k_bce2_fast(const T* __restrict__ x,
       s_order[n++] = (unsigned)(h.nf + i) | (1u << 8) | (first ? 1u << 10 : 0u) | ((unsigned)i << 16);
     }
     for (int f = 0; f < h.nf; ++f)
-      if (h.owner[f] < 0) s_order[n++] = (unsigned)f | (3u << 8);
-    s_n = n;
+      if (h.owner[f] < 0) s_order[n++] = (unsigned)f | (3u << 8) | (0xffu << 16);
   }
   __syncthreads();
 
@@ -262,7 +272,7 @@ __global__ void __launch_bounds__(F2_NT, 3) k_bce2_fast(const T* __restrict__ x,
   long pf_item = blockIdx.x;
   int pf_ci = 0;
   unsigned int pf_seq = 0;
-  const char* pf_ptr = nullptr;
+  const char* pf_ptr = reinterpret_cast<const char*>(x);
   auto pf_setup = [&]() {
     if (pf_item < items) {
       const int b = (int)(pf_item / chunks);
@@ -274,9 +284,9 @@ __global__ void __launch_bounds__(F2_NT, 3) k_bce2_fast(const T* __restrict__ x,
   auto pf_issue = [&]() {
     if (pf_item < items) {
       const char* g = pf_ptr + (long)(s_order[pf_ci] & 0xffu) * HW * (long)sizeof(T);
-      const unsigned int dst = xs_base + (pf_seq & (F2_XD - 1)) * (F2_NT * 8);
-      if (sizeof(T) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(g));
-      else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(g));
+      const unsigned int dst = xs_base + (pf_seq & (F2_XD - 1)) * (F2_NT * 16);
+      if (sizeof(T) == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g));
+      else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(g));
     }
     cp_async_commit();
     ++pf_seq;
@@ -292,21 +302,34 @@ __global__ void __launch_bounds__(F2_NT, 3) k_bce2_fast(const T* __restrict__ x,
     const int b = (int)(item / chunks);
     const long p0 = (item - (long)b * chunks) * F2_PX + tid * F2_VEC;
     const bool inb = p0 < HW;
-    int tf[2], tc[2];
-    {
-      const unsigned int t2 = inb ? *reinterpret_cast<const unsigned short*>(lab8 + (long)b * HW + p0) : 0xffffu;
+    // ---- labels of the strip: fine target channel bytes, coarse target channel bytes (0xff = none) ----
+    const unsigned int tf4 = inb ? *reinterpret_cast<const unsigned int*>(lab8 + (long)b * HW + p0) : 0xffffffffu;
+    unsigned int tb4 = 0xffffffffu;       // coarse target bucket per pixel
+    unsigned int tc4 = 0xffffffffu;       // coarse target channel per pixel
+    unsigned long long present = 0ull;    // channels that are a target of some pixel of the strip
+    float vf[4];
 #pragma unroll
-      for (int v = 0; v < 2; ++v) {
-        const int t = (t2 >> (8 * v)) & 0xff;
-        tf[v] = t;
-        tc[v] = (t != SH_IGNORE && t < h.lut_size) ? s_lut[t] : SH_IGNORE;
+    for (int k = 0; k < 4; ++k) {
+      const unsigned int t = (tf4 >> (8 * k)) & 0xffu;
+      vf[k] = t != SH_IGNORE ? 1.f : 0.f;
+      if (t != SH_IGNORE) {
+        present |= 1ull << t;
+        const unsigned int i = t < (unsigned)h.lut_size ? (unsigned)s_lut[t] : 0xffu;
+        if (i != 0xffu) {
+          tb4 = (tb4 & ~(0xffu << (8 * k))) | (i << (8 * k));
+          tc4 = (tc4 & ~(0xffu << (8 * k))) | (((unsigned)h.nf + i) << (8 * k));
+          present |= 1ull << (h.nf + i);
+        }
       }
     }
-    float sumF[2] = {0.f, 0.f}, sumC[2] = {0.f, 0.f}, prodF[2] = {1.f, 1.f}, prodC[2] = {1.f, 1.f};
-    float lf[2] = {0.f, 0.f}, lc[2] = {0.f, 0.f}, rmax[2] = {-1.f, -1.f}, a_t[2] = {1.f, 1.f}, b_t[2] = {1.f, 1.f};
-    float xt_f[2] = {0.f, 0.f}, xt_c[2] = {0.f, 0.f};
-    unsigned int rhold[2] = {0u, 0u};
-    bool hold_pos_a[2] = {true, true};
+    float sumF[4], sumC[4], prodF[4], prodC[4], Lf[4], Lc[4], rmax[4], a_t[4], b_t[4], xt_f[4], xt_c[4];
+    unsigned int rhold[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      sumF[k] = sumC[k] = 0.f; prodF[k] = prodC[k] = 1.f; Lf[k] = Lc[k] = 0.f;
+      rmax[k] = -1.f; a_t[k] = b_t[k] = 1.f; xt_f[k] = xt_c[k] = 0.f; rhold[k] = 0u;
+    }
+    unsigned int hpa4 = 0xffffffffu;      // byte k = 0xff: the fine channel holds min(A_t, B_c(t)) (fine wins ties, :91-92)
     int nF = 0, nC = 0;
 
     // ---- sweep A: the only HBM read of the logits -------------------------------------------
@@ -314,112 +337,129 @@ __global__ void __launch_bounds__(F2_NT, 3) k_bce2_fast(const T* __restrict__ x,
     for (int ci = 0; ci < C; ++ci) {
       pf_issue();
       cp_async_wait<F2_XD - 2>();
-      float xv[2];
-      {
-        const unsigned char* slot = xs_gen + (seq & (F2_XD - 1)) * (F2_NT * 8);
-        ++seq;
-        if (sizeof(T) == 4) { const float2 t2 = *reinterpret_cast<const float2*>(slot); xv[0] = t2.x; xv[1] = t2.y; }
-        else { xv[0] = staged_elem<T>(slot, 0); xv[1] = staged_elem<T>(slot, 1); }
-      }
+      float xv[4];
+      staged_vec4<T>(xs_gen + (seq & (F2_XD - 1)) * (F2_NT * 16), xv);
+      ++seq;
       const unsigned int oe = s_order[ci];
-      const int ch = oe & 0xff, kind = (oe >> 8) & 3, bucket = oe >> 16;
-      float s[2], E[2];
+      const unsigned int ch = oe & 0xffu, kind = (oe >> 8) & 3u, bucket = oe >> 16;
+      const unsigned int cc = ch * 0x01010101u;
+      float w[4], s[4], E[4];
 #pragma unroll
-      for (int v = 0; v < 2; ++v) sig_exp3(xv[v], s[v], E[v]);
-      S[(size_t)ch * F2_NT + tid] = make_float2(s[0], s[1]);
-      V[(size_t)ch * F2_NT + tid] = make_float2(E[0], E[1]);
-      if (kind != 1) {
+      for (int k = 0; k < 4; ++k) { w[k] = exp_neg(xv[k]); sig_from_w(w[k], s[k], E[k]); }
+      Wp[(size_t)ch * F2_NT + tid] = make_float4(w[0], w[1], w[2], w[3]);
+      if (kind != 1u) {
 #pragma unroll
-        for (int v = 0; v < 2; ++v) {
-          sumF[v] += E[v];
-          if (ch != tf[v]) prodF[v] *= (1.0f - s[v]) + eps;   // literal fp32 order of the reference
-          else { a_t[v] = s[v]; xt_f[v] = xv[v]; }
-          if (kind == 0) {
-            if (oe & (1u << 10)) { rmax[v] = -1.f; rhold[v] = 0u; }
-            if (s[v] > rmax[v]) { rmax[v] = s[v]; rhold[v] = (unsigned)ch; }     // lowest fine id wins ties (:84-85)
+        for (int k = 0; k < 4; ++k) {
+          sumF[k] += E[k];
+          prodF[k] *= (1.0f - s[k]) + eps;                    // literal fp32 order of the reference
+          if (kind == 0u) {
+            if (oe & (1u << 10)) { rmax[k] = -1.f; rhold[k] = 0u; }
+            if (s[k] > rmax[k]) { rmax[k] = s[k]; rhold[k] = ch; }               // lowest fine id wins ties (:84-85)
           }
+        }
+        if ((present >> ch) & 1ull) {
+          const unsigned int z = tf4 ^ cc;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (b0(z, k)) { a_t[k] = s[k]; xt_f[k] = xv[k]; Lf[k] -= lg2((1.0f - s[k]) + eps); }   // the target's own factor is not in the product
         }
         if (((++nF) & 3) == 0) {   // one log per <= 4 factors: each factor >= eps = 1e-8
 #pragma unroll
-          for (int v = 0; v < 2; ++v) { lf[v] -= fast_log(prodF[v]); prodF[v] = 1.f; }
+          for (int k = 0; k < 4; ++k) { Lf[k] += lg2(prodF[k]); prodF[k] = 1.f; }
         }
       } else {
         unsigned int hd = 0;
+        float best[4];
 #pragma unroll
-        for (int v = 0; v < 2; ++v) {
-          sumC[v] += E[v];
-          float best = (oe & (1u << 10)) ? -1.f : rmax[v];
-          unsigned int hold = (oe & (1u << 10)) ? 0u : rhold[v];
-          if (s[v] > best) { best = s[v]; hold = (unsigned)ch; }                 // the coarse logit comes last in the cat
-          hd |= hold << (8 * v);
-          if (bucket != tc[v]) prodC[v] *= (1.0f - best) + eps;
-          else {
-            b_t[v] = s[v]; xt_c[v] = xv[v];
-            if (tf[v] != SH_IGNORE && !(a_t[v] <= s[v])) hold_pos_a[v] = false;  // fine wins ties (:91-92)
-          }
+        for (int k = 0; k < 4; ++k) {
+          sumC[k] += E[k];
+          best[k] = (oe & (1u << 10)) ? -1.f : rmax[k];
+          unsigned int hold = (oe & (1u << 10)) ? 0u : rhold[k];
+          if (s[k] > best[k]) { best[k] = s[k]; hold = ch; }                     // the coarse logit comes last in the cat
+          hd |= hold << (8 * k);
+          prodC[k] *= (1.0f - best[k]) + eps;
         }
-        HOLD[(size_t)bucket * F2_NT + tid] = (unsigned short)hd;
+        HOLD[(size_t)bucket * F2_NT + tid] = hd;
+        if ((present >> ch) & 1ull) {
+          const unsigned int z = tb4 ^ (bucket * 0x01010101u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (b0(z, k)) {
+              b_t[k] = s[k]; xt_c[k] = xv[k];
+              Lc[k] -= lg2((1.0f - best[k]) + eps);
+              if (!(a_t[k] <= s[k])) hpa4 &= ~(0xffu << (8 * k));
+            }
+        }
         if (((++nC) & 3) == 0) {
 #pragma unroll
-          for (int v = 0; v < 2; ++v) { lc[v] -= fast_log(prodC[v]); prodC[v] = 1.f; }
+          for (int k = 0; k < 4; ++k) { Lc[k] += lg2(prodC[k]); prodC[k] = 1.f; }
         }
       }
     }
-    float inv_f[2], inv_c[2];
+    float inv_f[4], inv_c[4];
+    unsigned int fpos4 = 0xffffffffu;     // channel that holds the fine target's positive term, per pixel
 #pragma unroll
-    for (int v = 0; v < 2; ++v) {
-      lf[v] -= fast_log(prodF[v]);
-      lc[v] -= fast_log(prodC[v]);
-      const bool vf = tf[v] != SH_IGNORE, vc = tc[v] != SH_IGNORE;
-      if (vf) {
-        const float m = (vc && !hold_pos_a[v]) ? b_t[v] : a_t[v];
-        acc[0] += lf[v] - fast_log(m + eps);
-        acc[2] += fast_log(sumF[v]) - xt_f[v];
+    for (int k = 0; k < 4; ++k) {
+      const unsigned int t = (tf4 >> (8 * k)) & 0xffu, i = (tb4 >> (8 * k)) & 0xffu;
+      const bool vfk = t != SH_IGNORE, vck = i != 0xffu;
+      const bool fine_holds = !vck || ((hpa4 >> (8 * k)) & 1u);
+      if (vfk) {
+        const float m = fine_holds ? a_t[k] : b_t[k];
+        acc[0] += -kLn2 * (Lf[k] + lg2(prodF[k])) - fast_log(m + eps);
+        acc[2] += fast_log(sumF[k]) - xt_f[k];
+        fpos4 = (fpos4 & ~(0xffu << (8 * k))) | ((fine_holds ? t : (unsigned)h.nf + i) << (8 * k));
       }
-      if (vc) {
-        acc[1] += lc[v] - fast_log(b_t[v] + eps);
-        acc[3] += fast_log(sumC[v]) - xt_c[v];
+      if (vck) {
+        acc[1] += -kLn2 * (Lc[k] + lg2(prodC[k])) - fast_log(b_t[k] + eps);
+        acc[3] += fast_log(sumC[k]) - xt_c[k];
       }
-      inv_f[v] = rcp(sumF[v]);
-      inv_c[v] = rcp(sumC[v]);
+      inv_f[k] = vfk ? rcp(sumF[k]) : 0.f;      // zero on pixels the level ignores: their CE gradient vanishes
+      inv_c[k] = vck ? rcp(sumC[k]) : 0.f;
     }
 
     // ---- sweep B: gradient, written once ------------------------------------------------------
     if (GRAD) {
       T* gb = grad + (long)b * C * HW + p0;
-#pragma unroll 2
-      for (int c = 0; c < C; ++c) {
-        const float2 s2 = S[(size_t)c * F2_NT + tid], e2 = V[(size_t)c * F2_NT + tid];
-        const float s[2] = {s2.x, s2.y}, ev[2] = {e2.x, e2.y};
-        const bool fine = c < h.nf;
-        const int i = fine ? s_owner[c] : c - h.nf;
-        const unsigned int hd = i >= 0 ? (unsigned int)HOLD[(size_t)i * F2_NT + tid] : 0xffffu;
-        float g[2];
+      const unsigned int novc = __vcmpeq4(tb4, 0xffffffffu);
+      unsigned int hdN = 0xffffffffu;
+#pragma unroll 1
+      for (int ci = 0; ci < C; ++ci) {
+        const unsigned int oe = s_order[ci];
+        const unsigned int ch = oe & 0xffu, kind = (oe >> 8) & 3u, bucket = oe >> 16;
+        const unsigned int cc = ch * 0x01010101u;
+        if (oe & (1u << 10))          // bucket start: who holds the bucket max, where that term counts (not at the bucket's own targets)
+          hdN = HOLD[(size_t)bucket * F2_NT + tid] | __vcmpeq4(tb4, bucket * 0x01010101u) | novc;
+        if (kind == 3u) hdN = 0xffffffffu;
+        const float4 w4 = Wp[(size_t)ch * F2_NT + tid];
+        const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+        const float wbase = kind == 1u ? 0.f : wF;
+        const float* invp = kind == 1u ? inv_c : inv_f;
+        const unsigned int zH = hdN ^ cc;
+        const bool pos = (present >> ch) & 1ull;
+        const unsigned int zT = (kind == 1u ? tc4 : tf4) ^ cc, zP = fpos4 ^ cc;
+        float g[4];
 #pragma unroll
-        for (int v = 0; v < 2; ++v) {
-          const bool vf = tf[v] != SH_IGNORE, vc = tc[v] != SH_IGNORE;
-          const float q = 1.0f - s[v];
-          const float rneg = rcp(q + eps);
-          const bool holds = ((hd >> (8 * v)) & 0xffu) == (unsigned)c;
-          float ds = 0.f, ce = 0.f;
-          if (fine) {
-            const bool isT = c == tf[v];
-            if (vf && !isT) ds = wF * rneg;
-            if (vc && i >= 0 && i != tc[v] && holds) ds = fmaf(wC, rneg, ds);
-            if (vf && isT && !(vc && !hold_pos_a[v])) ds -= wF * rcp(s[v] + eps);
-            if (vf) ce = wCE * (ev[v] * inv_f[v] - (isT ? 1.f : 0.f));
-          } else {
-            const bool isT = i == tc[v];
-            if (vc) {
-              if (isT) ds = -wC * rcp(s[v] + eps);
-              else if (holds) ds = wC * rneg;
-              ce = wCE * (ev[v] * inv_c[v] - (isT ? 1.f : 0.f));
+        for (int k = 0; k < 4; ++k) {
+          float s, E;
+          sig_from_w(w[k], s, E);
+          const float t = 1.0f - s;
+          const float r = rcp(t + eps);
+          float ds = wbase * r;
+          if (b0(zH, k)) ds = fmaf(wC, r, ds);
+          float oh = 0.f;
+          if (pos) {
+            float Bp = b0(zP, k) ? wF : 0.f;
+            if (b0(zT, k)) {
+              oh = 1.f;
+              ds = fmaf(-wbase, r, ds);                        // the target has no own (1 - s) term
+              if (kind == 1u) Bp += wC;
             }
-            if (vf && vc && isT && !hold_pos_a[v]) ds -= wF * rcp(s[v] + eps);
+            ds = fmaf(-Bp, rcp(s + eps), ds);
           }
-          g[v] = fmaf(ds, q * s[v], ce);
+          const float qv = s * t * vf[k];
+          g[k] = fmaf(ds, qv, wCE * fmaf(E, invp[k], -oh));
         }
-        if (inb) VecIO<T, 2>::store(gb + (long)c * HW, g);
+        if (inb) VecIO<T, 4>::store(gb + (long)ch * HW, g);
       }
     }
   }
@@ -432,8 +472,8 @@ __global__ void __launch_bounds__(F2_NT, 3) k_bce2_fast(const T* __restrict__ x,
 
 static size_t bce2_fast_smem(int nf, int nc, int lut_size) {
   const int C = nf + nc;
-  size_t s = (size_t)C * F2_NT * 8 * 2 + (size_t)nc * F2_NT * 2 + 16;
-  s += (size_t)F2_XD * F2_NT * 8 + (size_t)C * 4 + (size_t)nf * 4 + (size_t)lut_size * 4 + 32;
+  size_t s = (size_t)C * F2_NT * 16 + (size_t)F2_XD * F2_NT * 16 + (size_t)nc * F2_NT * 4;
+  s += (size_t)C * 4 + (size_t)lut_size * 4 + 32;
   return (s + 15) & ~(size_t)15;
 }
 
@@ -495,8 +535,8 @@ template <typename T>
 static int launch_bce2(const void* x, const unsigned char* lab8, void* grad, int B, long HW, const Hier2& h, float eps,
                        float lw, const unsigned long long* counts, float* partials, int grid, bool tree, cudaStream_t st) {
   const size_t fsm = bce2_fast_smem(h.nf, h.nc, h.lut_size);
-  if (tree && HW % 2 == 0 && (uintptr_t)x % (2 * sizeof(T)) == 0 && (uintptr_t)grad % (2 * sizeof(T)) == 0 &&
-      fsm <= 113 * 1024) {
+  if (tree && HW % 4 == 0 && h.nf + h.nc <= 64 && (uintptr_t)x % (4 * sizeof(T)) == 0 &&
+      (uintptr_t)grad % (4 * sizeof(T)) == 0 && fsm <= 113 * 1024) {
     if (grad) {
       auto kern = k_bce2_fast<T, true>;
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
@@ -538,7 +578,7 @@ int sh_bce2_grid(int B, long HW, int C, int n_coarse) {
   const int PX = 256;
   long items = ((HW + PX - 1) / PX) * (long)B;
   // shared memory of the larger of the two kernels (the fast one adds its cp.async ring and tables)
-  size_t smem = (size_t)C * PX * 8 + (size_t)n_coarse * PX + (size_t)sh::F2_XD * sh::F2_NT * 8 + 2048;
+  size_t smem = (size_t)C * PX * 8 + (size_t)n_coarse * PX + (size_t)sh::F2_XD * sh::F2_NT * 16 + 2048;
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 16) per_sm = 16;
