@@ -12,12 +12,14 @@ out = subprocess.run(["ncu", "-i", rep, "--csv", "--page", "source", "--print-so
 ops = collections.Counter()
 rows = []
 active = False
+seen = False
 hdr = None
 for r in csv.reader(io.StringIO(out)):
     if not r:
         continue
     if r[0] == "Kernel Name":
-        active = kern in r[1]
+        active = kern in r[1] and not seen      # the report lists every kernel twice: keep the first listing
+        seen = seen or active
         continue
     if r[0] == "Address":
         hdr = r
