@@ -267,11 +267,27 @@ def test_three_level_flat_predictions(sb, golden):
     dict(b=2, h=21, w=64, labels="blob", step=200000, lam=0.25, dtype=torch.float32),
     dict(b=1, h=8, w=9, labels="iid", step=0, lam=0.5, dtype=torch.float32),                 # minimum size of the CUDA path
     dict(b=1, h=40, w=72, labels="blob", step=100000, lam=0.5, dtype=torch.float16),
+    dict(b=2, h=70, w=136, labels="iid", step=100000, lam=0.5, dtype=torch.float32),         # fast path, every block mixed
+    dict(b=1, h=64, w=128, labels="blob", step=100000, lam=0.5, dtype=torch.bfloat16),       # whole tiles, bf16
+    dict(b=1, h=33, w=68, labels="blob", step=0, lam=1.0, dtype=torch.float32, void_rows=True),
+    dict(b=1, h=48, w=132, labels="blob", step=100000, lam=1.0, dtype=torch.float32, generic=True),
 ])
 def test_three_level_vs_oracle(sb, case):
+    from seghiero_b200 import ops
+    ops.FAST_PATH["enabled"] = not case.get("generic", False)   # generic=True: the any-hierarchy kernels on a fast-path shape
+    try:
+        _three_level_vs_oracle(sb, case)
+    finally:
+        ops.FAST_PATH["enabled"] = True
+
+
+def _three_level_vs_oracle(sb, case):
     g = torch.Generator().manual_seed(case["h"] * 11 + case["w"])
     b, h, w = case["b"], case["h"], case["w"]
     lab = (iid_labels(g, b, h, w, 19, 0.15) if case["labels"] == "iid" else blob_labels(g, b, h, w, 19, 7, 0.1))
+    if case.get("void_rows"):
+        lab[:, :3, :] = 255          # void band on the image frame and a void block in the interior
+        lab[:, 10:20, 30:50] = 255
     x = (torch.randn(b, 28, h, w, generator=g) * 2).to(case["dtype"])
     eh, ew = max(h // 8, 1), max(w // 8, 1)
     emb = F.normalize(torch.randn(b, 12, eh, ew, generator=g), dim=1)
