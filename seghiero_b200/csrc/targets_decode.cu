@@ -117,6 +117,124 @@ __global__ void __launch_bounds__(256) k_decode(const T* __restrict__ x, int B, 
   }
 }
 
+// Vector path (HW % VEC == 0, 16-byte aligned logits): the channels are walked in batches of DEPTH raw 128-bit loads
+// that are all in flight before the first compare (the kernel is bound by load latency, not by arithmetic), level
+// boundaries are handled inside the walk, int64 results leave as 16-byte stores.
+template <typename T, int VEC>
+__device__ __forceinline__ void raw_to_f32(const uint4& r, float (&o)[VEC]);
+template <>
+__device__ __forceinline__ void raw_to_f32<float, 4>(const uint4& r, float (&o)[4]) {
+  o[0] = __uint_as_float(r.x); o[1] = __uint_as_float(r.y); o[2] = __uint_as_float(r.z); o[3] = __uint_as_float(r.w);
+}
+template <>
+__device__ __forceinline__ void raw_to_f32<__nv_bfloat16, 8>(const uint4& r, float (&o)[8]) {
+  const unsigned int w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { o[2 * k] = __uint_as_float(w[k] << 16); o[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u); }
+}
+template <>
+__device__ __forceinline__ void raw_to_f32<__half, 8>(const uint4& r, float (&o)[8]) {
+  const unsigned int w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+    o[2 * k] = f.x; o[2 * k + 1] = f.y;
+  }
+}
+
+template <int VEC, typename OutT>
+__device__ __forceinline__ void store_args(OutT* dst, const int (&arg)[VEC]);
+template <>
+__device__ __forceinline__ void store_args<4, long long>(long long* dst, const int (&arg)[4]) {
+  __stcs(reinterpret_cast<longlong2*>(dst), make_longlong2(arg[0], arg[1]));
+  __stcs(reinterpret_cast<longlong2*>(dst) + 1, make_longlong2(arg[2], arg[3]));
+}
+template <>
+__device__ __forceinline__ void store_args<8, long long>(long long* dst, const int (&arg)[8]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) __stcs(reinterpret_cast<longlong2*>(dst) + q, make_longlong2(arg[2 * q], arg[2 * q + 1]));
+}
+template <>
+__device__ __forceinline__ void store_args<4, unsigned char>(unsigned char* dst, const int (&arg)[4]) {
+  *reinterpret_cast<unsigned int*>(dst) = (unsigned)arg[0] | ((unsigned)arg[1] << 8) | ((unsigned)arg[2] << 16) | ((unsigned)arg[3] << 24);
+}
+template <>
+__device__ __forceinline__ void store_args<8, unsigned char>(unsigned char* dst, const int (&arg)[8]) {
+  uint2 v;
+  v.x = (unsigned)arg[0] | ((unsigned)arg[1] << 8) | ((unsigned)arg[2] << 16) | ((unsigned)arg[3] << 24);
+  v.y = (unsigned)arg[4] | ((unsigned)arg[5] << 8) | ((unsigned)arg[6] << 16) | ((unsigned)arg[7] << 24);
+  *reinterpret_cast<uint2*>(dst) = v;
+}
+
+template <typename T, int VEC, typename OutT>
+__global__ void __launch_bounds__(256, 3) k_decode_vec(const T* __restrict__ x, int B, int C, long HW, int n0, int n1, int n2,
+                                                    OutT* __restrict__ o0, OutT* __restrict__ o1, OutT* __restrict__ o2,
+                                                    const long long* __restrict__ label,
+                                                    unsigned long long* __restrict__ counts) {
+  constexpr int DEPTH = 8;
+  const long groups_per_img = HW / VEC;
+  const long total = groups_per_img * B;
+  const int e0 = n0, e1 = n0 + max(n1, 0), e2 = e1 + max(n2, 0);     // level ends in channel units
+  long long correct = 0, valid = 0;
+  for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+    const int b = (int)(g / groups_per_img);
+    const long p = (g - (long)b * groups_per_img) * VEC;
+    const char* base = reinterpret_cast<const char*>(x + (long)b * C * HW + p);
+    const long cstride = HW * (long)sizeof(T);
+    float best[VEC];
+    int arg[VEC];
+    int lvl = 0, cbeg = 0;
+#pragma unroll 1
+    for (int cb = 0; cb < e2; cb += DEPTH) {
+      uint4 raw[DEPTH];
+#pragma unroll
+      for (int j = 0; j < DEPTH; ++j)
+        if (cb + j < e2) raw[j] = __ldcs(reinterpret_cast<const uint4*>(base + (long)(cb + j) * cstride));
+#pragma unroll
+      for (int j = 0; j < DEPTH; ++j) {
+        const int c = cb + j;
+        if (c >= e2) break;
+        float val[VEC];
+        raw_to_f32<T, VEC>(raw[j], val);
+        if (c == cbeg) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) { best[v] = val[v]; arg[v] = 0; }
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            // strictly greater, or first NaN (torch.argmax treats NaN as the maximum)
+            const bool take = (val[v] > best[v]) || (val[v] != val[v] && best[v] == best[v]);
+            if (take) { best[v] = val[v]; arg[v] = c - cbeg; }
+          }
+        }
+        const int lend = lvl == 0 ? e0 : (lvl == 1 ? e1 : e2);
+        if (c + 1 == lend) {            // last channel of the level: results out, next level starts
+          OutT* out = lvl == 0 ? o0 : (lvl == 1 ? o1 : o2);
+          if (out != nullptr) store_args<VEC, OutT>(out + (long)b * HW + p, arg);
+          if (lvl == 0 && label != nullptr) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+              const long long t = label[(long)b * HW + p + v];
+              if (t != SH_IGNORE) { valid++; correct += (t == arg[v]); }
+            }
+          }
+          cbeg = lend;
+          ++lvl;
+          while (lvl < 3 && (lvl == 1 ? e1 : e2) == cbeg) ++lvl;     // empty levels
+        }
+      }
+    }
+  }
+  if (label != nullptr && counts != nullptr) {
+    correct = warp_sum(correct);
+    valid = warp_sum(valid);
+    if ((threadIdx.x & 31) == 0 && valid) {
+      atomicAdd(counts, (unsigned long long)correct);
+      atomicAdd(counts + 1, (unsigned long long)valid);
+    }
+  }
+}
+
 template <typename T, typename OutT>
 static int launch_decode(const void* x, int B, int C, long HW, int n0, int n1, int n2, void* o0, void* o1, void* o2,
                          const long long* label, unsigned long long* counts, cudaStream_t st) {
@@ -126,6 +244,13 @@ static int launch_decode(const void* x, int B, int C, long HW, int n0, int n1, i
   long blocks = (groups + 255) / 256;
   if (blocks > SH_NUM_SMS * 16L) blocks = SH_NUM_SMS * 16L;
   if (blocks < 1) blocks = 1;
+  const bool out_al = ((uintptr_t)o0 | (uintptr_t)o1 | (uintptr_t)o2) % 16 == 0;
+  if (vec_ok && out_al && n0 > 0) {
+    k_decode_vec<T, VEC, OutT><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, B, C, HW, n0, n1, n2, (OutT*)o0, (OutT*)o1,
+                                                                  (OutT*)o2, label, counts);
+    SH_CHECK_LAUNCH();
+    return SH_OK;
+  }
   k_decode<T, VEC, OutT><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, B, C, HW, n0, n1, n2, (OutT*)o0, (OutT*)o1,
                                                             (OutT*)o2, label, counts, vec_ok ? 1 : 0);
   SH_CHECK_LAUNCH();
