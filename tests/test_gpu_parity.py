@@ -332,6 +332,34 @@ def test_three_level_large_hierarchy(sb):
     assert rel(to_np(xc.grad), to_np(xr.grad)) <= FP32_TOL
 
 
+@pytest.mark.parametrize("maps", [
+    # non-contiguous fine -> mid map, a mid with a single child, uneven highs
+    dict(nf=12, nm=5, nh=3, f2m=[0, 3, 0, 1, 1, 4, 2, 2, 2, 3, 4, 0], m2h=[0, 0, 1, 2, 1]),
+    # a childless mid (id 2) and a childless high (id 1): they take no part in any tree term but their logits do in CE
+    dict(nf=9, nm=4, nh=3, f2m=[0, 0, 1, 1, 1, 3, 3, 3, 3], m2h=[0, 0, 1, 2]),
+    # not a tree (mid 1 has children under two highs): generic kernels, general set semantics
+    dict(nf=10, nm=4, nh=2, f2m=[0, 0, 1, 1, 1, 2, 2, 3, 3, 3], f2h=[0, 0, 0, 1, 0, 1, 1, 1, 1, 1]),
+])
+def test_three_level_other_hierarchies(sb, maps):
+    """Hierarchies other than the Cityscapes 19/7/2 maps (triplet off: the reference's id lists do not cover them)."""
+    g = torch.Generator().manual_seed(maps["nf"])
+    nf, nm, nh, f2m = maps["nf"], maps["nm"], maps["nh"], maps["f2m"]
+    f2h = maps.get("f2h") or [maps["m2h"][m] for m in f2m]
+    lab = blob_labels(g, 2, 40, 68, nf, 5, 0.1)
+    x = torch.randn(2, nf + nm + nh, 40, 68, generator=g) * 2
+    xr = x.clone().requires_grad_(True)
+    ref, parts = O.rmi_hiera_triplet_loss(0, None, xr, lab, nf, nm, nh, f2m, f2h, with_triplet=False)
+    ref.backward()
+    mod = sb.RMIHieraTripletLoss(nf, nm, nh, torch.tensor(f2m), torch.tensor(f2h))
+    mod.triplet_loss = None
+    xc = x.cuda().requires_grad_(True)
+    loss = mod(torch.tensor([0]), None, None, xc, lab.cuda())
+    loss.backward()
+    assert mod.last_stats["fast_path"] == ("m2h" in maps)
+    assert abs(float(loss) - float(ref)) <= FP32_TOL * abs(float(ref)), (float(loss), float(ref), parts)
+    assert rel(to_np(xc.grad), to_np(xr.grad)) <= FP32_TOL
+
+
 # ------------------------------------------------------------------------------------------------
 # full-size, size-independent properties (BASELINE configs 2, 3, 5)
 # ------------------------------------------------------------------------------------------------
