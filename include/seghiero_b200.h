@@ -83,7 +83,7 @@ size_t sh_rmi3_workspace_bytes(int B, int H, int W, int nf, int nm, int nh);
 int sh_rmi3_workspace_offsets(int B, int H, int W, int nf, int nm, int nh, size_t* out);
 
 /* 1 when the warp-specialised kernels (csrc/rmi3_fast.cuh) will run this problem: tree-shaped maps
- * (fast_tab_ok from the host table builder), W % 4 == 0, 16-byte aligned tensors, 7 < C <= 64.  Everything
+ * (fast_tab_ok from the host table builder), W % 4 == 0, 16-byte aligned tensors, 7 < C <= 254.  Everything
  * else runs the generic kernels; results agree to fp32 rounding. */
 int sh_rmi3_fast_path(const void* logits, const void* grad, int dtype, int H, int W, int nf, int nm, int nh,
                       int fast_tab_ok);

@@ -453,7 +453,9 @@ static int run_backward3(const void* x, void* grad, int B, int H, int W, const H
   const int C = h.nf + h.nm + h.nh;
   const bool vec_ok = ((W & 3) == 0) && ((uintptr_t)x % (4 * sizeof(T)) == 0) && ((uintptr_t)grad % (4 * sizeof(T)) == 0);
   const size_t fsmem = fast2::pass2_smem(C, h.nf, h.nm, h.nh);
-  const bool fast = fast_path_ok(x, grad, (int)sizeof(T), H, W, h.nf, h.nm, h.nh, fast_tab_ok) && fsmem <= 227 * 1024;
+  // the tiled backward kernel takes any tree-shaped hierarchy up to 254 channels, whichever pass 1 ran
+  const bool fast = fast_tab_ok && (W & 3) == 0 && C <= 254 && (uintptr_t)x % (4 * sizeof(T)) == 0 &&
+                    (uintptr_t)grad % (4 * sizeof(T)) == 0 && fsmem <= 227 * 1024;
   if ((stages & 1) && fast) {
     fast2::Hier2 fh;
     fh.nf = h.nf; fh.nm = h.nm; fh.nh = h.nh; fh.f2m = h.f2m; fh.f2h = h.f2h;

@@ -31,14 +31,14 @@ constexpr int PW = TW + 4;           // plane pitch: cols x0-2 .. x0+65
 constexpr int PR = TH + 4;           // plane rows:  y0-2 .. y0+TH+1
 constexpr int PLANE = PR * PW;
 constexpr int NR = CWARPS * PPC;     // planes per round
-constexpr int NBUF = 3;              // round buffers
+constexpr int NBUF = 3;              // round buffers (2 when the per-channel fp64 totals of a large hierarchy need the room)
 constexpr int NPROD = 32 * PWARPS, NCONS = 32 * CWARPS;
 constexpr int NTHREADS = NPROD + NCONS;   // 512 threads, 128 registers each
 constexpr int XD = 4;                // cp.async ring depth of the producers (power of two; XD-2 channels ahead)
 constexpr int HD = 4;                // cp.async ring depth of the consumers' halo logits (rounds; HD-1 ahead)
 constexpr int HSLOT = 48;            // staged halo bytes per lane and plane: 2 x 16 (strips) + 2 x 8 (column pairs)
 constexpr int BAR_FULL = 1, BAR_EMPTY = 1 + NBUF, BAR_PROD = 1 + 2 * NBUF, BAR_CONS = 2 + 2 * NBUF;
-constexpr int kFastMaxC = 64;
+constexpr int kFastMaxC = 254;
 
 // order entry: kind (0 fine / 1 mid / 2 high) | class << 8 | flags << 16 | channel << 24 ; flags bit1 = flush products
 struct FastHier {
@@ -232,8 +232,8 @@ struct TileWalk {
 
 constexpr int PMW = 2 * 3 * 32;   // presence words per tile: [level][block] x {info, hash}
 
-inline size_t pass1_smem(int C, int nf) {
-  size_t s = (size_t)NBUF * NR * PLANE * 4;          // planes
+inline size_t pass1_smem(int C, int nf, int nbuf) {
+  size_t s = (size_t)nbuf * NR * PLANE * 4;          // planes
   s += (size_t)XD * NPROD * 16;                      // cp.async staging of the producers
   s += (size_t)HD * NCONS * PPC * HSLOT;             // cp.async staging of the consumers' plane halos
   s += (size_t)3 * TH * TW;                          // label tile
@@ -377,11 +377,11 @@ __device__ __forceinline__ void halo_offsets(int lane, int ty0, int tx0, int H, 
 // -------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(NTHREADS, 1)
-k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, float eps, int cpi) {
+k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, float eps, int cpi, int nbuf) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C = hg.nf + hg.nm + hg.nh;
   float* planes = reinterpret_cast<float*>(smem_raw);                                   // [NBUF][NR][PLANE]
-  uint4* xstage = reinterpret_cast<uint4*>(planes + NBUF * NR * PLANE);                  // [XD][NPROD]
+  uint4* xstage = reinterpret_cast<uint4*>(planes + nbuf * NR * PLANE);                  // [XD][NPROD]
   unsigned char* hstage = reinterpret_cast<unsigned char*>(xstage + XD * NPROD);         // [HD][NCONS][PPC][HSLOT]
   unsigned char* LT = hstage + HD * NCONS * PPC * HSLOT;                                 // [3][TH][TW]
   unsigned int* PM = reinterpret_cast<unsigned int*>(LT + 3 * TH * TW);                  // [3][32][2]
@@ -566,7 +566,7 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
       };
 #pragma unroll 1
       for (int r = 0; r < RPT; ++r) {
-        const int buf = (it * RPT + r) % NBUF;
+        const int buf = (it * RPT + r) % nbuf;
         bar_sync(BAR_EMPTY + buf, NTHREADS);
         const int cend = min(C, (r + 1) * NR);
         float* prow = planes + (buf * NR) * PLANE + (ty + 2) * PW + tx + 2;
@@ -641,7 +641,7 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
     // ============================== consumers ==============================
     const int ct = tid - NPROD, cw = ct >> 5, lane = ct & 31;
     const int hb = lane >> 4, sb = lane & 15, i0 = hb * BR;
-    const int npre = total_rounds < NBUF ? total_rounds : NBUF;
+    const int npre = total_rounds < nbuf ? total_rounds : nbuf;
     for (int q = 0; q < npre; ++q) bar_arrive(BAR_EMPTY + q, NTHREADS);
     // The 2-pixel ring of the warp's own planes (sigmoid only); logits come through a cp.async ring that runs
     // HD-1 rounds ahead (across tile boundaries).
@@ -785,7 +785,7 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
       const unsigned char* lt = LT + i0 * TW + 4 * sb;
 #pragma unroll 1
       for (int r = 0; r < RPT; ++r) {
-        const int R = it * RPT + r, buf = R % NBUF;
+        const int R = it * RPT + r, buf = R % nbuf;
         pf_issue();
         cp_async_wait<HD - 1>();
         // halos of this warp's planes: independent of the producers, done while they finish the round
@@ -863,7 +863,7 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
           }
           __syncwarp();
         }
-        if (R < total_rounds - NBUF) bar_arrive(BAR_EMPTY + buf, NTHREADS);
+        if (R < total_rounds - nbuf) bar_arrive(BAR_EMPTY + buf, NTHREADS);
       }
     }
     cp_async_wait<0>();

@@ -1,6 +1,7 @@
 // Fast path of the three-level loss, backward side (pass 2): gradient of tree BCE + CE + RMI w.r.t. the logits.
 //
-// Same applicability as rmi3_fast.cuh (tree-shaped maps, W % 4 == 0, 16-byte aligned tensors, C <= 64).
+// Applies to tree-shaped maps, W % 4 == 0, 16-byte aligned tensors, C <= 254 (the forward side may be either the
+// fast or the generic pass 1: both leave the same summaries).
 // Reference arithmetic: models/loss/rmi_hiera_triplet_loss.py:349-526 (autograd of it); analytic RMI backward in
 // oracle/rmi_taps.py.  The generic kernel (rmi3_bwd.cu::k3_pass2) computes the same thing for every other case.
 //
@@ -123,7 +124,9 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
   bool rowok[4];
   long roff[4];                       // pixel offset of the strip inside one channel plane (clamped into the image)
   unsigned int tc0[4], tc1[4], tc2[4], hmN[4], hhN[4];
-  unsigned long long present = 0ull;  // channels that are the target of some pixel of the block
+  // classes (mod 64, per level) that are the target of some pixel of the block: a set bit sends the channel through
+  // the positive-term path; a collision only costs that detour
+  unsigned long long presF = 0ull, presM = 0ull, presH = 0ull;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int y = ty0 + 4 * rq + j;
@@ -139,7 +142,9 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
         const unsigned int cm = (unsigned int)(hg.nf + s_f2m[t]), chh = (unsigned int)(hg.nf + hg.nm + s_f2h[t]);
         tc1[j] = (tc1[j] & ~(0xffu << (8 * k))) | (cm << (8 * k));
         tc2[j] = (tc2[j] & ~(0xffu << (8 * k))) | (chh << (8 * k));
-        present |= (1ull << t) | (1ull << cm) | (1ull << chh);
+        presF |= 1ull << (t & 63u);
+        presM |= 1ull << (s_f2m[t] & 63);
+        presH |= 1ull << (s_f2h[t] & 63);
       }
     }
   }
@@ -345,7 +350,8 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
       else if (tid == 28) dst[56] = wst[50] * gscale;
     }
     const float wbase = kind == 0 ? wF : 0.f;
-    const bool pos = (present >> ch) & 1ull;
+    const unsigned int clA = (oe >> 8) & 0xffu;
+    const bool pos = ((kind == 0 ? presF : (kind == 1 ? presM : presH)) >> (clA & 63u)) & 1ull;
     float* prow = plane + (4 * rq + 2) * PW + 4 * st + 2;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

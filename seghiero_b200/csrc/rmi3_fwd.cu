@@ -500,7 +500,9 @@ k3_pass1(const T* __restrict__ x, int B, int H, int W, Hier3 hg, Ws3 ws, float e
     float iv[3][4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      iv[0][k] = rcp(sumvF[k]); iv[1][k] = rcp(sumvM[k]); iv[2][k] = rcp(sumvH[k]);
+      // 1 / sum e^x, zero on void pixels (their CE gradient is zero; the fast backward pass relies on it)
+      const float vk = tf[k] != SH_IGNORE ? 1.f : 0.f;
+      iv[0][k] = rcp(sumvF[k]) * vk; iv[1][k] = rcp(sumvM[k]) * vk; iv[2][k] = rcp(sumvH[k]) * vk;
       if (tf[k] != SH_IGNORE) {
         const bool a_holds = a_t[k] <= b_t[k];                 // fine wins ties (rmi...py:421-425)
         const float mcla = a_holds ? a_t[k] : b_t[k];
@@ -956,6 +958,7 @@ size_t fast_bwd_smem(int C, int nf, int nm, int nh);   // rmi3_bwd.cu
 bool fast_path_ok(const void* x, const void* grad, int elem, int H, int W, int nf, int nm, int nh, int fast_tab_ok) {
   const int C = nf + nm + nh;
   if (!fast_tab_ok || C <= fast::NR || C > fast::kFastMaxC) return false;
+  if (fast::pass1_smem(C, nf, 2) > 227 * 1024) return false;
   if ((W & 3) != 0 || H < 8 || W < 8) return false;
   if ((uintptr_t)x % (4 * (size_t)elem) != 0) return false;
   if (grad != nullptr && (uintptr_t)grad % (4 * (size_t)elem) != 0) return false;
@@ -989,11 +992,12 @@ static int run_forward3_fast(const void* x, const long long* label, int B, int H
     }
   }
   if (stages & 2) {
-    const size_t smem = fast::pass1_smem(C, h.nf);
+    const int nbuf = fast::pass1_smem(C, h.nf, fast::NBUF) <= 227 * 1024 ? fast::NBUF : 2;
+    const size_t smem = fast::pass1_smem(C, h.nf, nbuf);
     if (smem > 227 * 1024) return SH_ERR_UNSUPPORTED;
     auto kern = fast::k3f_pass1<T>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, fast::NTHREADS, smem, st>>>((const T*)x, B, H, W, fh, ws, eps, cpi);
+    kern<<<grid, fast::NTHREADS, smem, st>>>((const T*)x, B, H, W, fh, ws, eps, cpi, nbuf);
     SH_CHECK_LAUNCH();
   }
   if (stages & 4) {
