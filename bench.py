@@ -355,8 +355,10 @@ def run_ours(args, w):
     if w["kind"] == "3level" and getattr(mod, "last_stats", {}).get("fast_path"):
         stage_names.update({("sh_rmi3_forward", 1): "k3f_prep", ("sh_rmi3_forward", 2): "k3f_pass1",
                             ("sh_rmi3_forward", 8): "k3f_finalize", ("sh_rmi3_backward", 1): "k3f_pass2"})
+    if w["kind"] == "2level" and mod.last_stats.get("fast_path"):
+        stage_names[("sh_bce2_fwdbwd", 2)] = "k_bce2_fast"
     stage_bytes = {"k3_pass1": ab.get("pass1"), "k3_pass2": ab.get("pass2"), "k_bce2_fused": ab.get("fused"),
-                   "k3f_pass1": ab.get("pass1"), "k3f_pass2": ab.get("pass2")}
+                   "k_bce2_fast": ab.get("fused"), "k3f_pass1": ab.get("pass1"), "k3f_pass2": ab.get("pass2")}
     stages = {stage_names[k]: t / n for k, (t, n) in timer.totals().items() if k in stage_names}
     roofline = None
     traffic_tab = {}
@@ -378,8 +380,11 @@ def run_ours(args, w):
                     "whole_step_frac": ab["total"] * px / (ms_step * 1e-3) / 1e9 / peak}
     elif w["kind"] == "decode":
         achieved = ab["total"] * px / (ms_step * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_decode", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": ab["total"] * px,
+        tr = traffic_tab.get(f"{args.workload}:k_decode")
+        roofline = {"bound": "hbm", "kernel": "k_decode_vec", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": (tr["bytes_per_px"] * px if tr else None),
+                    "traffic_source": (tr.get("source") if tr else None),
+                    "algorithmic_bytes_per_launch": ab["total"] * px,
                     "ms_per_launch": ms_step,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"}
 

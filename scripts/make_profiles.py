@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 STAGE = {"k3f_pass1": "k3f_pass1", "k3f_pass2": "k3f_pass2", "k3_pass1": "k3_pass1", "k3_pass2": "k3_pass2",
-         "k_bce2_fast": "k_bce2_fused", "k_bce2_fused": "k_bce2_fused", "k_decode": "k_decode", "k3f_prep": "k3f_prep"}
+         "k_bce2_fast": "k_bce2_fast", "k_bce2_fused": "k_bce2_fused", "k_decode_vec": "k_decode", "k_decode": "k_decode", "k3f_prep": "k3f_prep"}
 
 
 def raw(rep):

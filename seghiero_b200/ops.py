@@ -307,7 +307,8 @@ class HieraTriplet2Fn(torch.autograd.Function):
             _call("sh_loss2_final", _p(sums), _p(counts), cfg.n_fine, cfg.n_coarse, float(b * hw), _p(step_d),
                       cfg.total_steps, _p(st.trip) if st else None, _p(st.status) if st else None, cfg.loss_weight,
                       _p(out), _stream())
-        stats.update(sums=sums, counts=counts, out=out, triplet=st)
+        stats.update(sums=sums, counts=counts, out=out, triplet=st,
+                     fast_path=bool(tree) and hw % 4 == 0 and c <= 64 and x.data_ptr() % 16 == 0)
         ctx.grad = grad
         ctx.st = st
         ctx.out = out
