@@ -45,11 +45,14 @@ __device__ __forceinline__ void classify(int lab, int c, int mode, int lo, int h
   }
 }
 
-// one CTA per class: ordered compaction of the first `maxT` anchors / positives / negatives
+// one CTA per class: ordered compaction of the first `maxT` anchors / positives / negatives.
+// Rows are scanned 4 x 256 at a time (sub-step q holds rows r0 + 256 q + tid, so raster order is q-major, then
+// warp, then lane): one round of barriers per 1024 rows.
 __global__ void __launch_bounds__(256) k_trip_select(const int* __restrict__ lab_ds, long R, int mode,
                                                      const int* __restrict__ tab, int ncls, int maxT,
                                                      int* __restrict__ sel, int* __restrict__ kcount) {
-  __shared__ int wtot[3][8];
+  constexpr int SUB = 4;
+  __shared__ int wtot[3][SUB * 8];
   __shared__ int base[3];
   const int c = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -62,30 +65,45 @@ __global__ void __launch_bounds__(256) k_trip_select(const int* __restrict__ lab
   if (threadIdx.x < 3) base[threadIdx.x] = 0;
   __syncthreads();
   int* out = sel + (size_t)c * 3 * maxT;
-  for (long r0 = 0; r0 < R; r0 += 256) {
-    const long r = r0 + threadIdx.x;
-    bool f[3] = {false, false, false};
-    if (r < R) classify(lab_ds[r], c, mode, lo, hi, grp_c, tab, f[0], f[1], f[2]);
-    int pre[3];
+  for (long r0 = 0; r0 < R; r0 += SUB * 256) {
+    bool f[SUB][3];
+    int pre[SUB][3];
 #pragma unroll
-    for (int s = 0; s < 3; ++s) {
-      const unsigned int bal = __ballot_sync(0xffffffffu, f[s]);
-      pre[s] = __popc(bal & ((1u << lane) - 1u));
-      if (lane == 0) wtot[s][warp] = __popc(bal);
+    for (int q = 0; q < SUB; ++q) {
+      const long r = r0 + q * 256 + threadIdx.x;
+      f[q][0] = f[q][1] = f[q][2] = false;
+      if (r < R) classify(lab_ds[r], c, mode, lo, hi, grp_c, tab, f[q][0], f[q][1], f[q][2]);
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const unsigned int bal = __ballot_sync(0xffffffffu, f[q][s]);
+        pre[q][s] = __popc(bal & ((1u << lane) - 1u));
+        if (lane == 0) wtot[s][q * 8 + warp] = __popc(bal);
+      }
     }
     __syncthreads();
-    int b3[3];
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
       int off = base[s];
-      for (int q = 0; q < warp; ++q) off += wtot[s][q];
-      b3[s] = off;
-      if (f[s] && off + pre[s] < maxT) out[s * maxT + off + pre[s]] = (int)r;
+      int before[SUB];                    // rows of this list that precede (sub-step q, this warp)
+#pragma unroll
+      for (int q = 0; q < SUB; ++q) {
+        before[q] = off;
+        for (int w2 = 0; w2 < 8; ++w2) {
+          const int n = wtot[s][q * 8 + w2];
+          if (w2 < warp) before[q] += n;
+          off += n;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < SUB; ++q) {
+        const int pos = before[q] + pre[q][s];
+        if (f[q][s] && pos < maxT) out[s * maxT + pos] = (int)(r0 + q * 256 + threadIdx.x);
+      }
     }
     __syncthreads();
     if (threadIdx.x < 3) {
       int tot = 0;
-      for (int q = 0; q < 8; ++q) tot += wtot[threadIdx.x][q];
+      for (int q = 0; q < SUB * 8; ++q) tot += wtot[threadIdx.x][q];
       base[threadIdx.x] += tot;
     }
     __syncthreads();
