@@ -460,12 +460,17 @@ static int run_backward3(const void* x, void* grad, int B, int H, int W, const H
     fast2::Hier2 fh;
     fh.nf = h.nf; fh.nm = h.nm; fh.nh = h.nh; fh.f2m = h.f2m; fh.f2h = h.f2h;
     fh.order = h.order + C; fh.aux = h.order + 2 * C;
-    auto kern = fast2::k3f_pass2<T>;
-    const size_t fsm = fsmem;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
     const int tiles_x = (W + fast2::TW - 1) / fast2::TW, tiles_y = (H + fast2::TH - 1) / fast2::TH;
-    kern<<<B * tiles_x * tiles_y, fast2::NT, fsm, st>>>((const T*)x, (T*)grad, B, H, W, fh, ws, eps, lw, gscale, tiles_x,
-                                                         tiles_x * tiles_y);
+    auto kern0 = fast2::k3f_pass2<T, false>;
+    auto kern1 = fast2::k3f_pass2<T, true>;
+    cudaFuncSetAttribute(kern0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+    cudaFuncSetAttribute(kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+    // every image is served by exactly one of the two (label-noise statistics of k3f_prep, read on the device)
+    kern0<<<B * tiles_x * tiles_y, fast2::NT, fsmem, st>>>((const T*)x, (T*)grad, B, H, W, fh, ws, eps, lw, gscale, tiles_x,
+                                                          tiles_x * tiles_y);
+    SH_CHECK_LAUNCH();
+    kern1<<<B * tiles_x * tiles_y, fast2::NT, fsmem, st>>>((const T*)x, (T*)grad, B, H, W, fh, ws, eps, lw, gscale, tiles_x,
+                                                          tiles_x * tiles_y);
     SH_CHECK_LAUNCH();
   } else if (stages & 1) {
     // a fast forward pass skipped the per-pixel flags this kernel reads unless it knew the backward would land here

@@ -105,6 +105,7 @@ struct Ws3 {
   double* rec2;                // [B*cpi][C][kFastRec]: pp product taps [13], lp taps [25]
   unsigned int* llrec;         // [B*cpi][C][16]: label-label half-plane counts [13]
   float* bce2;                 // [B*cpi][8]
+  unsigned int* strips;        // [B][2]: label strips with a mixed 3x8 window (fine level), all strips (k3f_prep)
   size_t bytes;
   int tiles_x, tiles_y, nseg, cpi;
 };
@@ -177,6 +178,7 @@ inline Ws3 ws3_layout(void* base, int B, int H, int W, int nf, int nm, int nh) {
   w.rec2 = (double*)take((size_t)B * w.cpi * C * kFastRec * 8);
   w.llrec = (unsigned int*)take((size_t)B * w.cpi * C * 16 * 4);
   w.bce2 = (float*)take((size_t)B * w.cpi * 8 * 4);
+  w.strips = (unsigned int*)take((size_t)B * 2 * 4);
   w.bytes = off;
   return w;
 }

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) k3f_prep(const long long* __restrict__ la
   const int ty = tid >> 4, tx = (tid & 15) << 2;
   const int level_base[3] = {0, hg.nf, hg.nf + hg.nm};
   unsigned int run_c[3] = {0xffu, 0xffu, 0xffu}, run_n[3] = {0u, 0u, 0u};
-  unsigned int nv = 0;
+  unsigned int nv = 0, n_strip = 0, n_mixed = 0;
   bool bad = false;
   constexpr int NP = (TW + 4) / 2, NITEM = (PTH2 + 2) * NP, NIT = (NITEM + 255) / 256;   // pixel pairs of the label tile
 #pragma unroll 1
@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(256) k3f_prep(const long long* __restrict__ la
           lo[q] = p[0]; hi[q] = p[1];
           diff |= (lo[q] ^ pat) | (hi[q] ^ pat);
         }
+        if (l == 0) { ++n_strip; n_mixed += diff != 0u; }
         if (diff == 0u) {            // uniform window (and therefore all 4 pixels interior): anchors only
           if (c0 == run_c[l]) run_n[l] += 4u;
           else {
@@ -200,6 +201,9 @@ __global__ void __launch_bounds__(256) k3f_prep(const long long* __restrict__ la
     if (run_n[l]) atomicAdd(hist + (size_t)(level_base[l] + run_c[l]) * 16, run_n[l]);
   nv = __reduce_add_sync(0xffffffffu, nv);
   if (lane == 0 && nv) atomicAdd(ws.counts, (unsigned long long)nv);
+  n_strip = __reduce_add_sync(0xffffffffu, n_strip);
+  n_mixed = __reduce_add_sync(0xffffffffu, n_mixed);
+  if (lane == 0 && n_strip) { atomicAdd(ws.strips + 2 * b, n_mixed); atomicAdd(ws.strips + 2 * b + 1, n_strip); }
   if (bad) atomicOr((unsigned int*)(ws.counts + 2), 1u);
   __syncthreads();
   unsigned int* out = ws.llrec + (size_t)(b * cpi + j0 % cpi) * C * 16;     // zeroed by the host before the launch

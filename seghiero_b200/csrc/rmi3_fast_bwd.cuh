@@ -17,6 +17,7 @@
 // phase B of channel c runs; no thread reads another thread's slots, so the only barrier is the plane hand-over.
 // Shared memory per CTA is ~57 KB and registers <= 168, so three CTAs share an SM.
 #pragma once
+#include <type_traits>
 #include "rmi3_common.cuh"
 
 namespace sh {
@@ -46,12 +47,13 @@ inline size_t pass2_smem(int C, int nf, int nm, int nh) {
   s += (size_t)3 * PR * LP;                         // label tile
   s += (size_t)3 * WS * 4;                          // stencil weights (2 buffers) + their cp.async staging
   s += (size_t)C * 16 + (size_t)2 * nf * 4 + 64;    // tables
+  s += (size_t)256 * 2 + 16;                        // deferred one-hot stencils: work list + counter
   return (s + 15) & ~(size_t)15;
 }
 
 __device__ __forceinline__ bool byte_is_zero(unsigned int z, int k) { return ((z >> (8 * k)) & 0xffu) == 0u; }
 
-template <typename T>
+template <typename T, bool INLINE_OH>
 __global__ void __launch_bounds__(NT, 3)
 k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hier2 hg, Ws3 ws, float eps,
           float loss_weight, const float* __restrict__ gscale_ptr, int tiles_x, int tiles_per_img) {
@@ -70,8 +72,19 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
   unsigned int* s_aux = s_order + C;                                                   // [C]
   int* s_f2m = reinterpret_cast<int*>(s_aux + C);                                      // [nf]
   int* s_f2h = s_f2m + hg.nf;                                                          // [nf]
+  int* s_nwork = s_f2h + hg.nf;                                                        // [4] (one used)
+  unsigned short* s_work = reinterpret_cast<unsigned short*>(s_nwork + 4);             // [256] block | order index << 7
 
   const int tid = threadIdx.x;
+  {
+    // Two instantiations are launched back to back; each image is served by one of them.  Images whose labels are
+    // noisy (most 3x8 strips see more than one class, counted by k3f_prep) do their one-hot stencils inline, the
+    // others defer them to a work list (see phase B).  Without statistics (generic pass 1) everything defers.
+    const int bb = blockIdx.x / tiles_per_img;
+    const bool noisy = 2u * ws.strips[2 * bb] > ws.strips[2 * bb + 1];
+    if (noisy != INLINE_OH) return;
+  }
+  if (tid == 0) s_nwork[0] = 0;
   const long HW = (long)H * W, BHW = (long)B * HW;
   const int b = blockIdx.x / tiles_per_img, tile = blockIdx.x - b * tiles_per_img;
   const int tyi = tile / tiles_x, ty0 = tyi * TH, tx0 = (tile - tyi * tiles_x) * TW;
@@ -412,11 +425,16 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
     const unsigned int cl = (oe >> 8) & 0xffu, ch = oe >> 24;
     const float* wp = wsm + (ci & 1) * WS;
     const float* pl = planes + (ci & 1) * PLANE + (4 * rq) * PW + 4 * st;
-    const unsigned char* lt = LT + (kind * PR + 4 * rq) * LP + 4 * st;
     const unsigned int ub = kind == 0 ? ublk[0] : (kind == 1 ? ublk[1] : ublk[2]);
     const unsigned int ph = kind == 0 ? pres[0] : (kind == 1 ? pres[1] : pres[2]);
     const float init = ub == cl ? wp[56] : 0.f;
-    const int nsweep = (ub == 0xfeu && ((ph >> (cl & 31)) & 1u)) ? 2 : 1;
+    // mixed labels around the block and this class among them: the block needs the one-hot stencil too.  In images
+    // where few strips are mixed it is deferred to a work list that the whole CTA drains 128 blocks at a time (inline
+    // it would idle the other lanes of the warp); in noisy images (INLINE_OH) a second sweep right here is cheaper.
+    const bool mixed_hit = ub == 0xfeu && ((ph >> (cl & 31)) & 1u);
+    if (!INLINE_OH && mixed_hit) s_work[atomicAdd(s_nwork, 1)] = (unsigned short)(tid | (ci << 7));
+    const int nsweep = (INLINE_OH && mixed_hit) ? 2 : 1;
+    const unsigned char* lt = LT + (kind * PR + 4 * rq) * LP + 4 * st;
     float acc[4][4], q[4][4];
 #pragma unroll
     for (int o = 0; o < 4; ++o)
@@ -484,6 +502,86 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
     }
   };
 
+  // One deferred one-hot stencil: block `blk` (thread id of its owner), order index wci.  Adds
+  //   gscale * valid * s(1-s) * sum_d W2[d] [L(r+d) == cl]   to the gradient the owner has already stored.
+  auto onehot_item = [&](unsigned int item) {
+    const int blk = item & 127, wci = item >> 7;
+    const int brq = blk >> 4, bst = blk & 15;
+    const unsigned int oe = s_order[wci];
+    const int kind = oe & 3;
+    const unsigned int cl = (oe >> 8) & 0xffu, ch = oe >> 24;
+    const int bx = tx0 + 4 * bst;
+    if (bx >= W) return;
+    const float* wsrc = ws.wts + ((size_t)b * C + ch) * 64 + 25;
+    float w[25];
+#pragma unroll
+    for (int v = 0; v < 25; ++v) w[v] = __ldg(wsrc + v);
+    float acc[4][4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[o][k] = 0.f;
+    const unsigned char* lt = LT + (kind * PR + 4 * brq) * LP + 4 * bst;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const unsigned int l0 = *reinterpret_cast<const unsigned int*>(lt + i * LP);
+      const unsigned int l1 = *reinterpret_cast<const unsigned int*>(lt + i * LP + 4);
+      float win[8];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        win[v] = ((l0 >> (8 * v)) & 0xffu) == cl ? 1.f : 0.f;
+        win[4 + v] = ((l1 >> (8 * v)) & 0xffu) == cl ? 1.f : 0.f;
+      }
+#pragma unroll
+      for (int dx = 0; dx < 5; ++dx)
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const int dyi = i - o;
+          if (dyi < 0 || dyi > 4) continue;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[o][k] = fmaf(w[dyi * 5 + dx], win[k + dx], acc[o][k]);
+        }
+    }
+    const T* xc = x + ((long)b * C + ch) * HW;
+    T* gc = grad + ((long)b * C + ch) * HW;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const int y = ty0 + 4 * brq + o;
+      if (y >= H) break;
+      const long off = (long)y * W + bx;
+      const unsigned int t4 = *reinterpret_cast<const unsigned int*>(lab8 + off);
+      float xv[4], g[4];
+      VecIO<T, 4>::load(xc + off, xv);
+      {   // the gradient was written earlier in this kernel: coherent load, not the read-only path
+        uint4 raw;
+        if (sizeof(T) == 4) raw = __ldcg(reinterpret_cast<const uint4*>(gc + off));
+        else { const uint2 r2 = __ldcg(reinterpret_cast<const uint2*>(gc + off)); raw = make_uint4(r2.x, r2.y, 0u, 0u); }
+        staged_vec4<T>(&raw, g);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool inter = !border || (y >= 2 && y < H - 2 && bx + k >= 2 && bx + k < W - 2);
+        const bool valid = ((t4 >> (8 * k)) & 0xffu) != SH_IGNORE;
+        const float sg = sig_only(xv[k]);
+        const float qk = (valid && inter) ? sg * (1.0f - sg) * gscale : 0.f;
+        g[k] = fmaf(qk, acc[o][k], g[k]);
+      }
+      VecIO<T, 4>::store(gc + off, g);
+    }
+  };
+  // drain 128 items (all threads busy) whenever that many are queued; `flush` takes whatever is left
+  auto drain = [&](bool flush) {
+    const int n = s_nwork[0];
+    if (n < NT && !(flush && n > 0)) return;
+    const int take = n < NT ? n : NT;
+    unsigned int item = 0xffffffffu;
+    if (tid < take) item = s_work[n - take + tid];
+    __syncthreads();                                   // everyone has its item: the counter may move
+    if (tid == 0) s_nwork[0] = n - take;
+    if (item != 0xffffffffu) onehot_item(item);
+    __syncthreads();                                   // counter visible before the next pushes
+  };
+
   cp_async_wait<0>();
   phaseA(0);
   __syncthreads();
@@ -495,8 +593,10 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
       cp_async_wait<0>();
       phaseA(ci + 1);
     }
-    __syncthreads();
+    __syncthreads();                                   // planes handed over; gradient stores of phase B visible to the CTA
+    if (!INLINE_OH) drain(false);
   }
+  if (!INLINE_OH) drain(true);
 }
 
 }  // namespace fast2

@@ -982,6 +982,8 @@ static int run_forward3_fast(const void* x, const long long* label, int B, int H
     cudaFuncSetAttribute(fast::k3f_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     e = cudaMemsetAsync(ws.llrec, 0, (size_t)grid * C * 16 * sizeof(unsigned int), st);
     if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(ws.strips, 0, (size_t)B * 2 * sizeof(unsigned int), st);
+    if (e != cudaSuccess) return (int)e;
     fast::k3f_prep<<<grid * fast::PREP_MULT, 256, smem, st>>>(label, B, H, W, fh, ws, cpi,
                                                              (uintptr_t)label % 16 == 0 ? 1 : 0);
     SH_CHECK_LAUNCH();
@@ -1021,6 +1023,8 @@ static int run_forward3(const void* x, const long long* label, int B, int H, int
   const int C = h.nf + h.nm + h.nh;
   if (stages & 1) {
     cudaError_t e = cudaMemsetAsync(ws.counts, 0, 4 * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(ws.strips, 0, (size_t)B * 2 * sizeof(unsigned int), st);
     if (e != cudaSuccess) return (int)e;
     dim3 gp((W + kTW - 1) / kTW, (H + 15) / 16, B);
     k3_prep<<<gp, 256, 0, st>>>(label, B, H, W, h, ws.lab8, ws.flags, ws.counts);

@@ -29,7 +29,7 @@ _KERNELS = {
     "sh_triplet_backward": 1,
     ("sh_bce2_fwdbwd", 1): 1, ("sh_bce2_fwdbwd", 2): 1, ("sh_bce2_fwdbwd", 4): 1,
     ("sh_rmi3_forward", 1): 1, ("sh_rmi3_forward", 2): 1, ("sh_rmi3_forward", 4): 2, ("sh_rmi3_forward", 8): 2,
-    ("sh_rmi3_backward", 1): 1, ("sh_rmi3_backward", 2): 1,
+    ("sh_rmi3_backward", 1): 2, ("sh_rmi3_backward", 2): 1,
 }
 LAUNCHES = {"n": 0}
 FAST_PATH = {"enabled": True}   # tests flip this to cover the generic kernels on shapes the fast path would take
