@@ -513,9 +513,29 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
     const int bx = tx0 + 4 * bst;
     if (bx >= W) return;
     const float* wsrc = ws.wts + ((size_t)b * C + ch) * 64 + 25;
+    const T* xc = x + ((long)b * C + ch) * HW;
+    T* gc = grad + ((long)b * C + ch) * HW;
+    // everything from global memory first: the latency hides behind the stencil sweep
     float w[25];
 #pragma unroll
     for (int v = 0; v < 25; ++v) w[v] = __ldg(wsrc + v);
+    uint4 xraw[4], graw[4];
+    unsigned int t4[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const int y = min(ty0 + 4 * brq + o, H - 1);
+      const long off = (long)y * W + bx;
+      t4[o] = *reinterpret_cast<const unsigned int*>(lab8 + off);
+      if (sizeof(T) == 4) {
+        xraw[o] = __ldg(reinterpret_cast<const uint4*>(xc + off));
+        graw[o] = __ldcg(reinterpret_cast<const uint4*>(gc + off));     // written earlier in this kernel: coherent load
+      } else {
+        const uint2 xr = __ldg(reinterpret_cast<const uint2*>(xc + off));
+        const uint2 gr = __ldcg(reinterpret_cast<const uint2*>(gc + off));
+        xraw[o] = make_uint4(xr.x, xr.y, 0u, 0u);
+        graw[o] = make_uint4(gr.x, gr.y, 0u, 0u);
+      }
+    }
     float acc[4][4];
 #pragma unroll
     for (int o = 0; o < 4; ++o)
@@ -542,26 +562,18 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
           for (int k = 0; k < 4; ++k) acc[o][k] = fmaf(w[dyi * 5 + dx], win[k + dx], acc[o][k]);
         }
     }
-    const T* xc = x + ((long)b * C + ch) * HW;
-    T* gc = grad + ((long)b * C + ch) * HW;
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
       const int y = ty0 + 4 * brq + o;
       if (y >= H) break;
       const long off = (long)y * W + bx;
-      const unsigned int t4 = *reinterpret_cast<const unsigned int*>(lab8 + off);
       float xv[4], g[4];
-      VecIO<T, 4>::load(xc + off, xv);
-      {   // the gradient was written earlier in this kernel: coherent load, not the read-only path
-        uint4 raw;
-        if (sizeof(T) == 4) raw = __ldcg(reinterpret_cast<const uint4*>(gc + off));
-        else { const uint2 r2 = __ldcg(reinterpret_cast<const uint2*>(gc + off)); raw = make_uint4(r2.x, r2.y, 0u, 0u); }
-        staged_vec4<T>(&raw, g);
-      }
+      staged_vec4<T>(&xraw[o], xv);
+      staged_vec4<T>(&graw[o], g);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const bool inter = !border || (y >= 2 && y < H - 2 && bx + k >= 2 && bx + k < W - 2);
-        const bool valid = ((t4 >> (8 * k)) & 0xffu) != SH_IGNORE;
+        const bool valid = ((t4[o] >> (8 * k)) & 0xffu) != SH_IGNORE;
         const float sg = sig_only(xv[k]);
         const float qk = (valid && inter) ? sg * (1.0f - sg) * gscale : 0.f;
         g[k] = fmaf(qk, acc[o][k], g[k]);
