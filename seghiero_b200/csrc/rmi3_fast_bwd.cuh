@@ -581,17 +581,20 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
       VecIO<T, 4>::store(gc + off, g);
     }
   };
-  // drain 128 items (all threads busy) whenever that many are queued; `flush` takes whatever is left
+  // drain 128 items (all threads busy) whenever that many are queued; `flush` takes whatever is left as well
   auto drain = [&](bool flush) {
-    const int n = s_nwork[0];
-    if (n < NT && !(flush && n > 0)) return;
-    const int take = n < NT ? n : NT;
-    unsigned int item = 0xffffffffu;
-    if (tid < take) item = s_work[n - take + tid];
-    __syncthreads();                                   // everyone has its item: the counter may move
-    if (tid == 0) s_nwork[0] = n - take;
-    if (item != 0xffffffffu) onehot_item(item);
-    __syncthreads();                                   // counter visible before the next pushes
+#pragma unroll 1
+    for (;;) {
+      const int n = s_nwork[0];
+      if (n < NT && !(flush && n > 0)) break;
+      const int take = n < NT ? n : NT;
+      unsigned int item = 0xffffffffu;
+      if (tid < take) item = s_work[n - take + tid];
+      __syncthreads();                                 // everyone has its item: the counter may move
+      if (tid == 0) s_nwork[0] = n - take;
+      if (item != 0xffffffffu) onehot_item(item);
+      __syncthreads();                                 // counter visible before the next pushes / the next look
+    }
   };
 
   cp_async_wait<0>();
@@ -606,9 +609,8 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
       phaseA(ci + 1);
     }
     __syncthreads();                                   // planes handed over; gradient stores of phase B visible to the CTA
-    if (!INLINE_OH) drain(false);
+    if (!INLINE_OH) drain(ci + 1 == C);
   }
-  if (!INLINE_OH) drain(true);
 }
 
 }  // namespace fast2
