@@ -271,6 +271,7 @@ def test_three_level_flat_predictions(sb, golden):
     dict(b=1, h=64, w=128, labels="blob", step=100000, lam=0.5, dtype=torch.bfloat16),       # whole tiles, bf16
     dict(b=1, h=33, w=68, labels="blob", step=0, lam=1.0, dtype=torch.float32, void_rows=True),
     dict(b=1, h=48, w=132, labels="blob", step=100000, lam=1.0, dtype=torch.float32, generic=True),
+    dict(b=2, h=66, w=132, labels="blob", step=100000, lam=0.5, dtype=torch.float32, noisy_second=True),
 ])
 def test_three_level_vs_oracle(sb, case):
     from seghiero_b200 import ops
@@ -285,6 +286,8 @@ def _three_level_vs_oracle(sb, case):
     g = torch.Generator().manual_seed(case["h"] * 11 + case["w"])
     b, h, w = case["b"], case["h"], case["w"]
     lab = (iid_labels(g, b, h, w, 19, 0.15) if case["labels"] == "iid" else blob_labels(g, b, h, w, 19, 7, 0.1))
+    if case.get("noisy_second"):     # image 0 keeps its blobs, image 1 gets per-pixel labels: both backward instantiations run
+        lab[1] = iid_labels(g, 1, h, w, 19, 0.15)[0]
     if case.get("void_rows"):
         lab[:, :3, :] = 255          # void band on the image frame and a void block in the interior
         lab[:, 10:20, 30:50] = 255
