@@ -309,15 +309,35 @@ __device__ __forceinline__ void load_row8(const float* pl, int prow, unsigned in
 
 // la_pr taps of one 4 x BR block, label-anchored:  lp[d] = sum_{q in block, L(q) = cl} PI(q - d).
 //   uniform block of class cl: box sums (column sums over the BR rows, slid down 4 times, then 4-wide row sums);
-//   mixed block: per matching pixel, 25 adds from the 5-row window (rolled loop, the window shifts through registers).
+//   a run of whole rows of class cl inside a mixed block: the same box sums over that run;
+//   anything else: per matching pixel, 25 adds from the 5-row window (rolled loop, the window shifts through registers).
 template <bool BORDER>
 __device__ __forceinline__ void lp_taps(const float* pl, const unsigned char* ltrow, bool uniform, unsigned int pat,
                                         unsigned int rowI, unsigned int colI, float (&al)[32]) {
-  if (uniform) {
+  // rows of the block that are entirely of this class; a single run of such rows (and no partly matching row) is a
+  // uniform sub-block and takes the box sums -- the usual case on a label boundary that crosses the block horizontally
+  int r0 = 0, r1 = BR;
+  bool box = uniform;
+  if (!uniform) {
+    unsigned int full = 0u, part = 0u;
+#pragma unroll
+    for (int i = 0; i < BR; ++i) {
+      const unsigned int z = *reinterpret_cast<const unsigned int*>(ltrow + i * TW) ^ pat;
+      full |= (z == 0u ? 1u : 0u) << i;
+      part |= ((z != 0u && has_zero_byte(z)) ? 1u : 0u) << i;
+    }
+    if (part == 0u) {
+      if (full == 0u) return;                       // the class is not in the block (hash collision)
+      r0 = __ffs(full) - 1;
+      r1 = 32 - __clz(full);
+      box = __popc(full) == r1 - r0;
+    }
+  }
+  if (box) {
     float S[8], t[8];
-    load_row8<BORDER>(pl, 0, rowI, colI, S);
+    load_row8<BORDER>(pl, r0, rowI, colI, S);
 #pragma unroll 1
-    for (int r = 1; r < BR; ++r) {
+    for (int r = r0 + 1; r < r1; ++r) {
       load_row8<BORDER>(pl, r, rowI, colI, t);
 #pragma unroll
       for (int q = 0; q < 8; ++q) S[q] += t[q];
@@ -325,10 +345,10 @@ __device__ __forceinline__ void lp_taps(const float* pl, const unsigned char* lt
 #pragma unroll
     for (int a = 0; a < 5; ++a) {
       if (a > 0) {
-        load_row8<BORDER>(pl, a - 1, rowI, colI, t);
+        load_row8<BORDER>(pl, a - 1 + r0, rowI, colI, t);
 #pragma unroll
         for (int q = 0; q < 8; ++q) S[q] -= t[q];
-        load_row8<BORDER>(pl, a + BR - 1, rowI, colI, t);
+        load_row8<BORDER>(pl, a + r1 - 1, rowI, colI, t);
 #pragma unroll
         for (int q = 0; q < 8; ++q) S[q] += t[q];
       }
