@@ -857,21 +857,20 @@ __device__ void finalize_core(const double* part, const double* fr, int bc, cons
   // adjoints -> stencil weights, spread over the whole CTA
   float* wout = ws.wts + (size_t)bc * 64;
   float* fout = ws.fwts + (size_t)bc * 25 * 50;
+  __shared__ double s_w[50];
   if (tid < 25) {
     double w1 = 0.0, w2 = 0.0;
     for (int e = 0; e < 81; ++e)
       if (s_tap[e] == tid) { w1 += Gpp[e]; w2 -= U[e]; }
     wout[tid] = (float)(scale * w1);
     wout[25 + tid] = (float)(scale * w2);
-  } else if (tid == 32) {
-    // sums over the 25 taps in tap order (same association as adding the per-tap values)
+    s_w[tid] = scale * w1;
+    s_w[25 + tid] = scale * w2;
+  }
+  __syncthreads();
+  if (tid == 32) {
     double s2 = 0.0, s1 = 0.0;
-    for (int t = 0; t < 25; ++t) {
-      double w1 = 0.0, w2 = 0.0;
-      for (int e = 0; e < 81; ++e)
-        if (s_tap[e] == t) { w1 += Gpp[e]; w2 -= U[e]; }
-      s2 += scale * w2; s1 += scale * w1;
-    }
+    for (int t = 0; t < 25; ++t) { s1 += s_w[t]; s2 += s_w[25 + t]; }
     wout[50] = (float)s2;      // sum of the lp weights: label-uniform pixels
     wout[51] = (float)s1;      // sum of the pp weights: difference form of the stencil
   }
