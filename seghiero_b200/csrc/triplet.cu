@@ -46,13 +46,14 @@ __device__ __forceinline__ void classify(int lab, int c, int mode, int lo, int h
 }
 
 // one CTA per class: ordered compaction of the first `maxT` anchors / positives / negatives.
-// Rows are scanned 4 x 256 at a time (sub-step q holds rows r0 + 256 q + tid, so raster order is q-major, then
-// warp, then lane): one round of barriers per 1024 rows.
+// Rows are scanned 8192 at a time: warp w owns rows [r0 + 1024 w, r0 + 1024 (w + 1)) in raster order (32 steps of 32
+// consecutive rows), counts its three lists with ballots, the eight warp totals are prefix-summed once, and a second
+// walk over the same (cached) labels writes the row indices: two barriers per 8192 rows.
 __global__ void __launch_bounds__(256) k_trip_select(const int* __restrict__ lab_ds, long R, int mode,
                                                      const int* __restrict__ tab, int ncls, int maxT,
                                                      int* __restrict__ sel, int* __restrict__ kcount) {
-  constexpr int SUB = 4;
-  __shared__ int wtot[3][SUB * 8];
+  constexpr int STEPS = 32, WROWS = 32 * STEPS, CHUNK = 8 * WROWS;
+  __shared__ int wtot[3][8];
   __shared__ int base[3];
   const int c = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -65,47 +66,48 @@ __global__ void __launch_bounds__(256) k_trip_select(const int* __restrict__ lab
   if (threadIdx.x < 3) base[threadIdx.x] = 0;
   __syncthreads();
   int* out = sel + (size_t)c * 3 * maxT;
-  for (long r0 = 0; r0 < R; r0 += SUB * 256) {
-    bool f[SUB][3];
-    int pre[SUB][3];
+  const unsigned int lt_mask = (1u << lane) - 1u;
+  for (long r0 = 0; r0 < R; r0 += CHUNK) {
+    const long wbase = r0 + (long)warp * WROWS;
+    int cnt[3] = {0, 0, 0};
+    for (int t = 0; t < STEPS; ++t) {
+      const long r = wbase + t * 32 + lane;
+      bool f[3] = {false, false, false};
+      if (r < R) classify(lab_ds[r], c, mode, lo, hi, grp_c, tab, f[0], f[1], f[2]);
 #pragma unroll
-    for (int q = 0; q < SUB; ++q) {
-      const long r = r0 + q * 256 + threadIdx.x;
-      f[q][0] = f[q][1] = f[q][2] = false;
-      if (r < R) classify(lab_ds[r], c, mode, lo, hi, grp_c, tab, f[q][0], f[q][1], f[q][2]);
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const unsigned int bal = __ballot_sync(0xffffffffu, f[q][s]);
-        pre[q][s] = __popc(bal & ((1u << lane) - 1u));
-        if (lane == 0) wtot[s][q * 8 + warp] = __popc(bal);
-      }
+      for (int s = 0; s < 3; ++s) cnt[s] += __popc(__ballot_sync(0xffffffffu, f[s]));
     }
+    if (lane < 3) wtot[lane][warp] = lane == 0 ? cnt[0] : (lane == 1 ? cnt[1] : cnt[2]);
     __syncthreads();
+    int off[3], tot[3];
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
-      int off = base[s];
-      int before[SUB];                    // rows of this list that precede (sub-step q, this warp)
+      off[s] = base[s];
+      tot[s] = 0;
 #pragma unroll
-      for (int q = 0; q < SUB; ++q) {
-        before[q] = off;
-        for (int w2 = 0; w2 < 8; ++w2) {
-          const int n = wtot[s][q * 8 + w2];
-          if (w2 < warp) before[q] += n;
-          off += n;
-        }
+      for (int w2 = 0; w2 < 8; ++w2) {
+        const int n = wtot[s][w2];
+        if (w2 < warp) off[s] += n;
+        tot[s] += n;
       }
+    }
+    // second walk: positions (only while the list still has room)
+    if (off[0] < maxT || off[1] < maxT || off[2] < maxT) {
+      for (int t = 0; t < STEPS; ++t) {
+        const long r = wbase + t * 32 + lane;
+        bool f[3] = {false, false, false};
+        if (r < R) classify(lab_ds[r], c, mode, lo, hi, grp_c, tab, f[0], f[1], f[2]);
 #pragma unroll
-      for (int q = 0; q < SUB; ++q) {
-        const int pos = before[q] + pre[q][s];
-        if (f[q][s] && pos < maxT) out[s * maxT + pos] = (int)(r0 + q * 256 + threadIdx.x);
+        for (int s = 0; s < 3; ++s) {
+          const unsigned int bal = __ballot_sync(0xffffffffu, f[s]);
+          const int pos = off[s] + __popc(bal & lt_mask);
+          if (f[s] && pos < maxT) out[s * maxT + pos] = (int)r;
+          off[s] += __popc(bal);
+        }
       }
     }
     __syncthreads();
-    if (threadIdx.x < 3) {
-      int tot = 0;
-      for (int q = 0; q < SUB * 8; ++q) tot += wtot[threadIdx.x][q];
-      base[threadIdx.x] += tot;
-    }
+    if (threadIdx.x < 3) base[threadIdx.x] += threadIdx.x == 0 ? tot[0] : (threadIdx.x == 1 ? tot[1] : tot[2]);
     __syncthreads();
     if (base[0] >= maxT && base[1] >= maxT && base[2] >= maxT) break;
   }
