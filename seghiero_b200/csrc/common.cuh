@@ -45,27 +45,18 @@ __device__ __forceinline__ float rcp(float x) {
 // natural log through the MUFU lg2 (abs error ~1e-7 for arguments in [1e-8, 2])
 __device__ __forceinline__ float fast_log(float x) { return lg2(x) * kLn2; }
 
-// e^x and sigmoid(x) from one ex2 and two rcp.  The sigmoid follows torch's own formula
-// 1/(1+e^-x) INCLUDING its fp32 rounding of (1 + e^-x): the reference takes log(1 - s + eps) of that
-// quantised value, so large positive logits must saturate exactly the way torch does.
-//   w = e^-|x| ;  x >= 0: s = 1/(1+w) (refined to a correctly rounded reciprocal), e^x = 1/w
-//                 x <  0: s = w/(1+w),                                               e^x = w
-// |x| is clamped to 80 so that sums of e^x over a level's channels stay finite.
+// e^x and sigmoid(x) from three MUFU ops (see sig_exp3 below, which every kernel uses through this wrapper or
+// directly): the sigmoid follows torch's own formula 1/(1+e^-x) INCLUDING its fp32 rounding of (1 + e^-x) -- the
+// reference takes log(1 - s + eps) of that quantised value and breaks ties between equal sigmoids by index, so all
+// kernels must round the same way.
 struct SigExp {
   float v;  // e^x
   float s;  // sigmoid(x)
 };
+__device__ __forceinline__ void sig_exp3(float x, float& s, float& ex);
 __device__ __forceinline__ SigExp sig_exp(float x) {
-  const float ax = fminf(fabsf(x), 80.0f);
-  const float w = ex2(-ax * kLog2e);
-  const float y = 1.0f + w;
-  const float q0 = rcp(y);
-  const float q = fmaf(q0, fmaf(-y, q0, 1.0f), q0);   // one Newton step: IEEE-quality 1/y
-  const bool pos = x >= 0.0f;
   SigExp r;
-  r.s = pos ? q : w * q;
-  r.v = pos ? rcp(w) : w;
-  if (x != x) { r.s = x; r.v = x; }
+  sig_exp3(x, r.s, r.v);
   return r;
 }
 
