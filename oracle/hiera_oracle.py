@@ -109,8 +109,10 @@ def build_fine_to_level_map(map_cfg, n_fine: int) -> np.ndarray:
 # --------------------------------------------------------------------------- #
 # helpers
 # --------------------------------------------------------------------------- #
-def _as_long(t):
-    return t if isinstance(t, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(t)).long()
+def _as_long(t, device=None):
+    """index tensor on the device of the logits it will index (the restatement runs on CPU or, for full-size checks, CUDA)"""
+    t = t if isinstance(t, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(t)).long()
+    return t if device is None else t.to(device)
 
 
 def _dsum(t: torch.Tensor) -> torch.Tensor:
@@ -147,7 +149,7 @@ def _bce_level(pos_plane, neg_planes, target0, valid, eps):
 # --------------------------------------------------------------------------- #
 def tree_bce_two_level(x, tf, tc, n_fine, hiera_index, eps=1e-8):
     """models/loss/hiera_triplet_loss.py:41-107 -> 5*(L_fine+L_coarse)."""
-    tf, tc = _as_long(tf), _as_long(tc)
+    tf, tc = _as_long(tf, x.device), _as_long(tc, x.device)
     n_coarse = len(hiera_index)
     s = torch.sigmoid(x.float())
     A = [s[:, f] for f in range(n_fine)]
@@ -191,7 +193,7 @@ def tree_sets(fine_to_mid, fine_to_high, n_mid, n_high):
 def tree_bce_three_level(x, tf, tm, th, fine_to_mid, fine_to_high, n_fine, n_mid, n_high,
                          eps=1e-6, ignore_index=IGNORE):
     """models/loss/rmi_hiera_triplet_loss.py:352-470 -> 5*(L_f+L_m+L_h)."""
-    tf, tm, th = _as_long(tf), _as_long(tm), _as_long(th)
+    tf, tm, th = _as_long(tf, x.device), _as_long(tm, x.device), _as_long(th, x.device)
     Fm, Ms, Hs = tree_sets(fine_to_mid, fine_to_high, n_mid, n_high)
     f2m = [int(v) for v in np.asarray(fine_to_mid)]
     s = torch.sigmoid(x.float())
@@ -217,7 +219,7 @@ def tree_bce_three_level(x, tf, tm, th, fine_to_mid, fine_to_high, n_fine, n_mid
 # --------------------------------------------------------------------------- #
 def ce_level(x_level, target, ignore_index=IGNORE):
     """models/loss/cross_entropy_loss.py:7-30 + utils.py:45-47."""
-    target = _as_long(target)
+    target = _as_long(target, x_level.device)
     v = target != ignore_index
     t0 = torch.where(v, target, torch.zeros_like(target))
     xl = x_level.float()
@@ -238,7 +240,7 @@ def rmi_windows(z: torch.Tensor) -> torch.Tensor:
 def rmi_onehot_and_probs(x, tf, tm, th, n_fine, n_mid, n_high, ignore_index=IGNORE, clip=1e-6):
     """rmi_hiera_triplet_loss.py:355-370, 479-487: void pixels are one-hot of
     class 0 at every level (not masked); P = sigmoid*valid + 1e-6 (fp32)."""
-    tf, tm, th = _as_long(tf), _as_long(tm), _as_long(th)
+    tf, tm, th = _as_long(tf, x.device), _as_long(tm, x.device), _as_long(th, x.device)
     s = torch.sigmoid(x.float())
     hot, val = [], []
     for tgt, k in ((tf, n_fine), (tm, n_mid), (th, n_high)):
@@ -251,7 +253,7 @@ def rmi_onehot_and_probs(x, tf, tm, th, n_fine, n_mid, n_high, ignore_index=IGNO
 
 def rmi_from_moments(s_ll, s_pp, s_lp, alpha=1e-3):
     """rmi_hiera_triplet_loss.py:505-517 on float64 [B,C,9,9] moments -> scalar."""
-    eye = torch.eye(9, dtype=torch.float64)
+    eye = torch.eye(9, dtype=torch.float64, device=s_pp.device)
     k_inv = torch.linalg.inv(s_pp + alpha * eye)
     m = s_ll - s_lp @ k_inv @ s_lp.transpose(-1, -2) + alpha * eye
     chol = torch.linalg.cholesky(m)
@@ -296,9 +298,9 @@ def _triplet_from_sets(rows, sets, max_triplet):
         k = min(len(a), len(p), len(n), max_triplet)
         if k == 0:
             continue
-        fa = rows[torch.from_numpy(a[:k])]
-        fp = rows[torch.from_numpy(p[:k])]
-        fn = rows[torch.from_numpy(n[:k])]
+        fa = rows[torch.from_numpy(a[:k]).to(rows.device)]
+        fp = rows[torch.from_numpy(p[:k]).to(rows.device)]
+        fn = rows[torch.from_numpy(n[:k]).to(rows.device)]
         d_pos = 1 - (fa * fp).sum(1)
         d_neg = 1 - (fa * fn).sum(1)
         total = total + F.relu(d_pos - d_neg + 0.6).mean()
