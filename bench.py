@@ -481,6 +481,38 @@ def run_ours(args, w):
                                     "the loop incl. the final drain"}
 
     clk.__exit__()
+    x_gb = x.numel() * x.element_size() / 1e9
+    # optional context: the oracle's torch restatement run as eager ATen ON THE GPU (what a user of the reference gets
+    # on this box); one sample per step because the fp64 RMI unfolds need ~21 GB per 1024x2048 image
+    eager = None
+    if args.eager_gpu and rank == 0 and w["kind"] in ("3level", "2level"):
+        from oracle import hiera_oracle as O
+        x_gb = x.numel() * x.element_size() / 1e9
+        del x
+        torch.cuda.empty_cache()
+        eb = 1 if w["kind"] == "3level" else b
+        xe = (torch.randn(eb, c, h, wd, generator=g, device=dev) * 2).to(dt).requires_grad_(True)
+        le, ee = lab[:eb].contiguous(), emb[:eb].detach().clone().requires_grad_(True)
+
+        def eager_step():
+            xe.grad = None
+            ee.grad = None
+            if w["kind"] == "3level":
+                l_, _ = O.rmi_hiera_triplet_loss(100000, ee if use_emb is not None else None, xe, le, w["nf"], w["nm"],
+                                                 w["nh"], f2m, f2h, with_triplet=w.get("triplet", True))
+            else:
+                l_, _ = O.hiera_triplet_loss(100000, ee, xe, le, w["nf"], HM_19_7, HI_19_7)
+            l_.backward()
+        eager_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            eager_step()
+        torch.cuda.synchronize()
+        dt_s = (time.perf_counter() - t0) / 3
+        eager = {"value": eb * h * wd / dt_s / 1e9, "unit": "Gpix/s", "ms_per_step": dt_s * 1e3, "batch": eb,
+                 "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
+                 "what": "oracle restatement of the reference loss as eager ATen on this GPU (fwd+bwd, wall clock)"}
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu:
         res = run_cpu_oracle(w, 2, 1, args.labels)
@@ -494,11 +526,13 @@ def run_ours(args, w):
             "data": "synthetic",
             "config": {"workload": args.workload, "description": w["desc"], "labels": args.labels,
                        "batch_per_gpu": b, "pixels_per_step_per_gpu": px,
-                       "l2": "inputs larger than L2 (logits %.2f GB per GPU)" % (x.numel() * x.element_size() / 1e9),
+                       "l2": "inputs larger than L2 (logits %.2f GB per GPU)" % x_gb,
                        "parallelism": f"dp{world} by sample, no data-path collective"},
             "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": launches,
             "clocks": clk.summary(), "kernel_ms": stages,
         }
+        if eager is not None:
+            line["eager_gpu_baseline"] = eager
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -610,6 +644,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--eager-gpu", action="store_true", help="also time the oracle restatement as eager ATen on the GPU")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
