@@ -478,3 +478,26 @@ def test_full_size_against_oracle_on_cuda(sb):
             _assert_grad_close_up_to_tie_flips(xc.grad, xr.grad, tol)
         else:
             assert float((xc.grad.float() - xr.grad.float()).norm() / xr.grad.float().norm()) <= tol
+
+
+def test_config4_image_against_oracle_on_cuda(sb):
+    """150 / 30 / 6 classes at the ADE20K image size (config 4): the fast kernels with two round buffers and 27
+    rounds per tile, against the oracle restatement on CUDA tensors (triplet off: undefined in the reference there)."""
+    dev = "cuda"
+    nf, nm, nh = 150, 30, 6
+    f2m = [f // 5 for f in range(nf)]
+    f2h = [f // 25 for f in range(nf)]
+    g = torch.Generator().manual_seed(150)
+    lab = blob_labels(g, 2, 512, 512, nf, 32, 0.1).to(dev)
+    x = (torch.randn(2, nf + nm + nh, 512, 512, generator=g) * 2).to(dev)
+    xr = x.clone().requires_grad_(True)
+    ref, _ = O.rmi_hiera_triplet_loss(0, None, xr, lab, nf, nm, nh, f2m, f2h, with_triplet=False)
+    ref.backward()
+    mod = sb.RMIHieraTripletLoss(nf, nm, nh, torch.tensor(f2m), torch.tensor(f2h))
+    mod.triplet_loss = None
+    xc = x.clone().requires_grad_(True)
+    loss = mod(torch.tensor([0], device=dev), None, None, xc, lab)
+    loss.backward()
+    assert mod.last_stats["fast_path"]
+    assert abs(float(loss.detach()) - float(ref.detach())) <= FP32_TOL * abs(float(ref.detach()))
+    _assert_grad_close_up_to_tie_flips(xc.grad, xr.grad, FP32_TOL)
