@@ -356,28 +356,23 @@ __device__ __forceinline__ void lp_taps(const float* pl, const unsigned char* lt
       for (int bq = 0; bq < 5; ++bq) al[24 - (a * 5 + bq)] += (S[bq] + S[bq + 1]) + (S[bq + 2] + S[bq + 3]);
     }
   } else {
-    float w[5][8];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) load_row8<BORDER>(pl, q, rowI, colI, w[q + 1]);
+    // scattered pixels of the class (noisy labels): the 5-row window of a block row is fetched only when that row has one
 #pragma unroll 1
     for (int i = 0; i < BR; ++i) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) w[q][j] = w[q + 1][j];
-      load_row8<BORDER>(pl, i + 4, rowI, colI, w[4]);
       const unsigned int z = *reinterpret_cast<const unsigned int*>(ltrow + i * TW) ^ pat;
-      if (has_zero_byte(z)) {
+      if (!has_zero_byte(z)) continue;
+      float w[5][8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (((z >> (8 * k)) & 0xffu) == 0u) {
+      for (int a = 0; a < 5; ++a) load_row8<BORDER>(pl, i + a, rowI, colI, w[a]);
 #pragma unroll
-            for (int a = 0; a < 5; ++a)
+      for (int k = 0; k < 4; ++k)
+        if (((z >> (8 * k)) & 0xffu) == 0u) {
 #pragma unroll
-              for (int bq = 0; bq < 5; ++bq)      // window row a <-> dy = 2 - a ; col k+bq <-> dx = 2 - bq
-                al[24 - (a * 5 + bq)] += w[a][k + bq];
-          }
-      }
+          for (int a = 0; a < 5; ++a)
+#pragma unroll
+            for (int bq = 0; bq < 5; ++bq)      // window row a <-> dy = 2 - a ; col k+bq <-> dx = 2 - bq
+              al[24 - (a * 5 + bq)] += w[a][k + bq];
+        }
     }
   }
 }
