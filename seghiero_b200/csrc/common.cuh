@@ -287,6 +287,21 @@ __device__ __forceinline__ float staged_elem<__half>(const void* slot, long idx)
 // `n` = number of threads that take part (arrivers + waiters), a multiple of 32.
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+// shared-memory mbarriers: data hand-over between warps without making the waiters rendezvous with each other
+// (a named barrier synchronises everyone who takes part; here only the dependency is waited for).
+__device__ __forceinline__ void mbar_init(unsigned int addr, int count) {
+  asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned int addr) {      // release: the thread's earlier stores are visible to waiters
+  asm volatile("mbarrier.arrive.shared.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned int addr, unsigned int parity) {   // acquire
+  unsigned int ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  } while (!ok);
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 

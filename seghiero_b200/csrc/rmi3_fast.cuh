@@ -245,6 +245,7 @@ inline size_t pass1_smem(int C, int nf, int nbuf) {
   s += (size_t)C * kFastRec * 8;                     // fp64 totals
   s += (size_t)C * 8;                                // channel byte offsets
   s += (size_t)(C + 2 * nf) * 4 + 128 * 4;           // tables + reduction scratch
+  s += 8 * 8 + 16;                                   // mbarriers (full / empty per round buffer)
   return (s + 15) & ~(size_t)15;
 }
 
@@ -410,6 +411,10 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
   int* s_f2m = reinterpret_cast<int*>(s_order + C);                                      // [nf]
   int* s_f2h = s_f2m + hg.nf;                                                            // [nf]
   float* s_red = reinterpret_cast<float*>(s_f2h + hg.nf);                                // [128]
+  unsigned long long* s_mbar = reinterpret_cast<unsigned long long*>(
+      (reinterpret_cast<uintptr_t>(s_red + 128) + 7) & ~(uintptr_t)7);                  // [4] full, [4] empty
+  const unsigned int mb_full = (unsigned int)__cvta_generic_to_shared(s_mbar);
+  const unsigned int mb_empty = mb_full + 4 * 8;
 
   const int tid = threadIdx.x;
   const long HW = (long)H * W;
@@ -420,6 +425,9 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
   }
   for (int i = tid; i < hg.nf; i += NTHREADS) { s_f2m[i] = hg.f2m[i]; s_f2h[i] = hg.f2h[i]; }
   for (int i = tid; i < C * kFastRec; i += NTHREADS) tot[i] = 0.0;
+  if (tid == 0) {
+    for (int q = 0; q < nbuf; ++q) { mbar_init(mb_full + 8 * q, NPROD); mbar_init(mb_empty + 8 * q, NCONS); }
+  }
   __syncthreads();
 
   const int b = blockIdx.x / cpi, j0 = blockIdx.x - b * cpi;
@@ -585,8 +593,8 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
       };
 #pragma unroll 1
       for (int r = 0; r < RPT; ++r) {
-        const int buf = (it * RPT + r) % nbuf;
-        bar_sync(BAR_EMPTY + buf, NTHREADS);
+        const int R = it * RPT + r, use = R / nbuf, buf = R - use * nbuf;
+        if (use > 0) mbar_wait(mb_empty + 8 * buf, (use - 1) & 1);     // the consumers are done with the buffer's previous round
         const int cend = min(C, (r + 1) * NR);
         float* prow = planes + (buf * NR) * PLANE + (ty + 2) * PW + tx + 2;
 #pragma unroll 1
@@ -613,8 +621,7 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
             update(s_order[ci + 1], xc, sc, Ec);
           }
         }
-        __threadfence_block();
-        bar_arrive(BAR_FULL + buf, NTHREADS);
+        mbar_arrive(mb_full + 8 * buf);
       }
       // ---- per-pixel epilogue of the tile -------------------------------------------------------
       float iv[3][4];
@@ -660,8 +667,6 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
     // ============================== consumers ==============================
     const int ct = tid - NPROD, cw = ct >> 5, lane = ct & 31;
     const int hb = lane >> 4, sb = lane & 15, i0 = hb * BR;
-    const int npre = total_rounds < nbuf ? total_rounds : nbuf;
-    for (int q = 0; q < npre; ++q) bar_arrive(BAR_EMPTY + q, NTHREADS);
     // The 2-pixel ring of the warp's own planes (sigmoid only); logits come through a cp.async ring that runs
     // HD-1 rounds ahead (across tile boundaries).
     unsigned char* hs_gen = hstage + (size_t)ct * PPC * HSLOT;
@@ -804,7 +809,7 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
       const unsigned char* lt = LT + i0 * TW + 4 * sb;
 #pragma unroll 1
       for (int r = 0; r < RPT; ++r) {
-        const int R = it * RPT + r, buf = R % nbuf;
+        const int R = it * RPT + r, use = R / nbuf, buf = R - use * nbuf;
         pf_issue();
         cp_async_wait<HD - 1>();
         // halos of this warp's planes: independent of the producers, done while they finish the round
@@ -835,7 +840,7 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
                   make_float2(fmaf(sig_only(xs[0]), sv[e][0], sz[e]), fmaf(sig_only(xs[1]), sv[e][1], sz[e]));
           }
         }
-        bar_sync(BAR_FULL + buf, NTHREADS);
+        mbar_wait(mb_full + 8 * buf, use & 1);                         // the producers have filled this round's planes
 #pragma unroll 1
         for (int pp = 0; pp < PPC; ++pp) {
           const int ci = r * NR + cw * PPC + pp;
@@ -882,7 +887,7 @@ k3f_pass1(const T* __restrict__ x, int B, int H, int W, FastHier hg, Ws3 ws, flo
           }
           __syncwarp();
         }
-        if (R < total_rounds - nbuf) bar_arrive(BAR_EMPTY + buf, NTHREADS);
+        mbar_arrive(mb_empty + 8 * buf);
       }
     }
     cp_async_wait<0>();
