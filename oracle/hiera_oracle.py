@@ -3,9 +3,12 @@
 This module is a from-scratch CPU restatement (numpy for the integer work,
 torch-CPU autograd for the floating-point terms) of the arithmetic performed by
 the reference's `models/loss` modules.  It is the *checker* for the CUDA path:
-only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline /
-`--impl reference` legs may import it.  Nothing under `seghiero_b200/` imports
-it, and the product path raises if its CUDA library is missing.
+only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s baseline legs
+(cpu_baseline, `--impl reference`, and the optional `--eager-gpu` context line
+that times this same restatement as eager ATen on the GPU) may import it.
+Nothing under `seghiero_b200/` imports it, and the product path raises if its
+CUDA library is missing.  The functions are device-agnostic torch code, so the
+full-size parity tests can evaluate them on CUDA tensors.
 
 Parity pinning: the reference ships no tests or golden vectors,
 so this oracle is pinned against outputs of the reference modules themselves,
