@@ -597,19 +597,18 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
     }
   };
 
-  cp_async_wait<0>();
-  phaseA(0);
-  __syncthreads();
+  // one copy of each phase in the instruction stream: iteration -1 only runs phase A of channel 0 (its logits were
+  // requested above, before the label scan)
 #pragma unroll 1
-  for (int ci = 0; ci < C; ++ci) {
-    if (ci + 1 < C) prefetch(ci + 1);
-    phaseB(ci);
+  for (int ci = -1; ci < C; ++ci) {
+    if (ci >= 0 && ci + 1 < C) prefetch(ci + 1);
+    if (ci >= 0) phaseB(ci);
     if (ci + 1 < C) {
       cp_async_wait<0>();
       phaseA(ci + 1);
     }
     __syncthreads();                                   // planes handed over; gradient stores of phase B visible to the CTA
-    if (!INLINE_OH) drain(ci + 1 == C);
+    if (!INLINE_OH && ci >= 0) drain(ci + 1 == C);
   }
 }
 
