@@ -549,14 +549,16 @@ __global__ void __launch_bounds__(256) k3_band(const T* __restrict__ x, int B, i
   const T* xc = x + (long)bc * HW;
   const unsigned char* lab8 = lab8_all + (long)b * HW;
   const int n = 8 * W + 8 * H;
+#pragma unroll 4
   for (int i = blockIdx.y * 256 + threadIdx.x; i < n; i += gridDim.y * 256) {
     int yy, xx;
     float* dst;
     if (i < 8 * W) { const int q = i / W; xx = i - q * W; yy = q < 4 ? q : H - 8 + q; dst = bandR + ((size_t)bc * 8 + q) * W + xx; }
     else { const int i2 = i - 8 * W; const int q = i2 / H; yy = i2 - q * H; xx = q < 4 ? q : W - 8 + q; dst = bandC + ((size_t)bc * 8 + q) * H + yy; }
     const long off = (long)yy * W + xx;
+    const float xv = to_f32<T>(xc[off]);          // both loads issue together (the kernel is load-latency bound)
     const bool valid = lab8[off] != SH_IGNORE;
-    *dst = (valid ? sig_exp(to_f32<T>(xc[off])).s : 0.f) + 1e-6f;
+    *dst = (valid ? sig_exp(xv).s : 0.f) + 1e-6f;
   }
 }
 
@@ -846,22 +848,22 @@ __device__ void finalize_core(const double* part, const double* fr, int bc, cons
     mm9(Wm, false, T1, false, U, lane);            // U = W Slp K ;  G_lp = -U
     mm9(T1, true, U, false, Gpp, lane);            // 2 * G_pp = T1^T U
   }
-  __shared__ unsigned char s_tap[81], s_jy[81], s_jx[81];
-  if (tid >= 32 && tid < 32 + 81) {
-    const int e = tid - 32, i = e / 9, j = e % 9;
-    s_tap[e] = (unsigned char)tap_index(i / 3 - j / 3, i % 3 - j % 3);
-    s_jy[e] = (unsigned char)(j / 3);
-    s_jx[e] = (unsigned char)(j % 3);
-  }
   __syncthreads();
-  // adjoints -> stencil weights, spread over the whole CTA
+  // adjoints -> stencil weights, spread over the whole CTA.  Tap t = (dy, dx) collects the matrix entries
+  // e = (i, j) with window offsets i = j + (dy, dx): at most 9, walked in ascending e.
   float* wout = ws.wts + (size_t)bc * 64;
   float* fout = ws.fwts + (size_t)bc * 25 * 50;
   __shared__ double s_w[50];
   if (tid < 25) {
     double w1 = 0.0, w2 = 0.0;
-    for (int e = 0; e < 81; ++e)
-      if (s_tap[e] == tid) { w1 += Gpp[e]; w2 -= U[e]; }
+    const int dy = tid / 5 - 2, dx = tid % 5 - 2;
+    for (int yj = 0; yj < 3; ++yj)
+      for (int xj = 0; xj < 3; ++xj) {
+        const int yi = yj + dy, xi = xj + dx;
+        if (yi < 0 || yi > 2 || xi < 0 || xi > 2) continue;
+        const int e = (yi * 3 + xi) * 9 + yj * 3 + xj;
+        w1 += Gpp[e]; w2 -= U[e];
+      }
     wout[tid] = (float)(scale * w1);
     wout[25 + tid] = (float)(scale * w2);
     s_w[tid] = scale * w1;
@@ -877,10 +879,16 @@ __device__ void finalize_core(const double* part, const double* fr, int bc, cons
   for (int q = tid; q < 25 * 25; q += 256) {
     const int cls = q / 25, t = q % 25, ky = cls / 5, kx = cls % 5;
     double w1 = 0.0, w2 = 0.0;
-    for (int e = 0; e < 81; ++e) {
-      if (s_tap[e] != t) continue;
-      if (!offset_valid(ky, s_jy[e]) || !offset_valid(kx, s_jx[e])) continue;
-      w1 += Gpp[e]; w2 -= U[e];
+    const int dy = t / 5 - 2, dx = t % 5 - 2;
+    for (int yj = 0; yj < 3; ++yj) {
+      const int yi = yj + dy;
+      if (yi < 0 || yi > 2 || !offset_valid(ky, yj)) continue;
+      for (int xj = 0; xj < 3; ++xj) {
+        const int xi = xj + dx;
+        if (xi < 0 || xi > 2 || !offset_valid(kx, xj)) continue;
+        const int e = (yi * 3 + xi) * 9 + yj * 3 + xj;
+        w1 += Gpp[e]; w2 -= U[e];
+      }
     }
     fout[cls * 50 + t] = (float)(scale * w1);
     fout[cls * 50 + 25 + t] = (float)(scale * w2);
