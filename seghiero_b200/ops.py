@@ -7,6 +7,7 @@ inside forward/backward (no .item(), no .tolist()): `step`, the `ready` gate and
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 from dataclasses import dataclass
 from typing import Optional, Sequence
@@ -108,6 +109,35 @@ def _world_ready(status: torch.Tensor) -> None:
         dist.all_reduce(status[:1], op=dist.ReduceOp.MIN)
 
 
+class _Fork:
+    """Fork / join of a per-device side stream: the triplet kernels are small and latency bound, so they run next to
+    the streaming loss kernels instead of in front of them.  Tensors are allocated on the caller's stream before the
+    fork and the caller's stream waits for the side stream (`join`) before anything reads the results, so the caching
+    allocator never hands a block to work that is not ordered after its last use."""
+    _streams = {}
+
+    def __init__(self, dev: torch.device):
+        self.cur = torch.cuda.current_stream(dev)
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        side = _Fork._streams.get(idx)
+        if side is None:
+            side = _Fork._streams[idx] = torch.cuda.Stream(device=dev)
+        self.side = side
+        self._ctx = None
+
+    def __enter__(self):
+        self.side.wait_stream(self.cur)
+        self._ctx = torch.cuda.stream(self.side)
+        self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        return self._ctx.__exit__(*exc)
+
+    def join(self):
+        self.cur.wait_stream(self.side)
+
+
 # ----------------------------------------------------------------------------------------------
 # targets / decode
 # ----------------------------------------------------------------------------------------------
@@ -204,7 +234,7 @@ class TripletState:
 
 
 def triplet_forward(feats: torch.Tensor, label: torch.Tensor, mode: int, tab: torch.Tensor, ncls: int,
-                    max_triplet: int = 200) -> TripletState:
+                    max_triplet: int = 200, fork: Optional[_Fork] = None) -> TripletState:
     _need_cuda(feats, label)
     b, d, h, w = feats.shape
     hh, ww = label.shape[-2:]
@@ -216,19 +246,24 @@ def triplet_forward(feats: torch.Tensor, label: torch.Tensor, mode: int, tab: to
     tl = torch.empty(ncls * max_triplet, dtype=torch.float32, device=dev)
     trip = torch.empty(2, dtype=torch.float32, device=dev)
     status = torch.empty(2, dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), (fork if fork is not None else contextlib.nullcontext()):
         _call("sh_triplet_forward", _p(feats), _dtype_code(feats), _p(label), b, d, h, w, hh, ww, mode, _p(tab),
                   ncls, max_triplet, _p(lab_ds), _p(sel), _p(kcount), _p(tl), _p(trip), _p(status), _stream())
     return TripletState(mode, ncls, max_triplet, (b, d, h, w), sel, kcount, tl, trip, status, lab_ds)
 
 
 def triplet_backward(feats: torch.Tensor, st: TripletState, tscale: torch.Tensor,
-                     gscale: Optional[torch.Tensor]) -> torch.Tensor:
+                     gscale: Optional[torch.Tensor], fork: Optional[_Fork] = None) -> torch.Tensor:
+    """fp32 gradient of the embedding; with a fork the caller joins and then converts (`_grad_as`)."""
     b, d, h, w = st.dims
     gfeat = torch.empty((b, d, h, w), dtype=torch.float32, device=feats.device)
-    with torch.cuda.device(feats.device):
+    with torch.cuda.device(feats.device), (fork if fork is not None else contextlib.nullcontext()):
         _call("sh_triplet_backward", _p(feats), _dtype_code(feats), b, d, h, w, st.ncls, st.max_triplet,
                   _p(st.sel), _p(st.kcount), _p(st.tl), _p(st.trip), _p(tscale), _p(gscale), _p(gfeat), _stream())
+    return gfeat if fork is not None else _grad_as(gfeat, feats)
+
+
+def _grad_as(gfeat: torch.Tensor, feats: torch.Tensor) -> torch.Tensor:
     return gfeat if feats.dtype == torch.float32 else gfeat.to(feats.dtype)
 
 
@@ -288,8 +323,8 @@ class HieraTriplet2Fn(torch.autograd.Function):
             tkey = ("t0", tuple(int(v) for v in cfg.hiera_map), key[2])
             ttab, ncls = device_table(tkey, lambda: H.triplet_tables_hierarchy(cfg.hiera_map, cfg.hiera_index), dev)
             emb = embedding.contiguous()
-            st = triplet_forward(emb, lab, 0, ttab, ncls)
-            _world_ready(st.status)
+            fork = _Fork(dev)
+            st = triplet_forward(emb, lab, 0, ttab, ncls, fork=fork)
 
         want_grad = ctx.needs_input_grad[0]
         grad = torch.empty_like(x) if want_grad else None
@@ -304,6 +339,9 @@ class HieraTriplet2Fn(torch.autograd.Function):
             _staged("sh_bce2_fwdbwd", (1, 2, 4), lambda st_bits: (
                 _p(x), _dtype_code(x), _p(lab), _p(grad), b, hw, cfg.n_fine, cfg.n_coarse, _p(tab), n_fb, lut_size,
                 cfg.eps, cfg.loss_weight, _p(lab8), _p(counts), _p(partials), _p(sums), st_bits | tree, _stream()))
+            if st is not None:
+                fork.join()
+                _world_ready(st.status)
             _call("sh_loss2_final", _p(sums), _p(counts), cfg.n_fine, cfg.n_coarse, float(b * hw), _p(step_d),
                       cfg.total_steps, _p(st.trip) if st else None, _p(st.status) if st else None, cfg.loss_weight,
                       _p(out), _stream())
@@ -320,6 +358,10 @@ class HieraTriplet2Fn(torch.autograd.Function):
     def backward(ctx, gout):
         g = gout.detach().to(torch.float32).reshape(1).contiguous()
         gx = None
+        gemb = fork = None
+        if ctx.st is not None and ctx.needs_input_grad[1]:
+            fork = _Fork(ctx.emb.device)
+            gemb = triplet_backward(ctx.emb, ctx.st, ctx.out[1:2], g, fork=fork)
         if ctx.needs_input_grad[0]:
             gx = ctx.grad
             if gx is None:
@@ -327,9 +369,9 @@ class HieraTriplet2Fn(torch.autograd.Function):
             ctx.grad = None
             with torch.cuda.device(gx.device):
                 _call("sh_scale_inplace", _p(gx), _dtype_code(gx), gx.numel(), _p(g), _stream())
-        gemb = None
-        if ctx.st is not None and ctx.needs_input_grad[1]:
-            gemb = triplet_backward(ctx.emb, ctx.st, ctx.out[1:2], g)
+        if fork is not None:
+            fork.join()
+            gemb = _grad_as(gemb, ctx.emb)
         return gx, gemb, None, None, None, None
 
 
@@ -377,8 +419,8 @@ class RMIHieraTriplet3Fn(torch.autograd.Function):
             tkey = ("t1", cfg.upper_ids, cfg.lower_ids)
             ttab, ncls = device_table(tkey, lambda: H.triplet_tables_id_lists(cfg.upper_ids, cfg.lower_ids), dev)
             emb = embedding.contiguous()
-            st = triplet_forward(emb, lab, 1, ttab, ncls)
-            _world_ready(st.status)
+            fork = _Fork(dev)
+            st = triplet_forward(emb, lab, 1, ttab, ncls, fork=fork)
         with torch.cuda.device(dev):
             lib = _lib.load()
             nbytes = lib.sh_rmi3_workspace_bytes(b, hh, ww, cfg.n_fine, cfg.n_mid, cfg.n_high)
@@ -387,6 +429,9 @@ class RMIHieraTriplet3Fn(torch.autograd.Function):
             _staged("sh_rmi3_forward", (1, 2, 4, 8), lambda st_bits: (
                 _p(x), _dtype_code(x), _p(lab), b, hh, ww, cfg.n_fine, cfg.n_mid, cfg.n_high, _p(tab), n_mh, fast_ok,
                 cfg.lam, cfg.loss_weight, _p(ws), st_bits, _stream()))
+            if st is not None:
+                fork.join()
+                _world_ready(st.status)
             _call("sh_loss3_final", b, hh, ww, cfg.n_fine, cfg.n_mid, cfg.n_high, _p(ws), cfg.lam, _p(step_d),
                       cfg.total_steps, _p(st.trip) if st else None, _p(st.status) if st else None, cfg.loss_weight,
                       _p(out), _stream())
@@ -408,6 +453,10 @@ class RMIHieraTriplet3Fn(torch.autograd.Function):
         g = gout.detach().to(torch.float32).reshape(1).contiguous()
         cfg = ctx.cfg
         gx = None
+        gemb = fork = None
+        if ctx.st is not None and ctx.needs_input_grad[1]:
+            fork = _Fork(ctx.emb.device)
+            gemb = triplet_backward(ctx.emb, ctx.st, ctx.out[1:2], g, fork=fork)
         if ctx.needs_input_grad[0]:
             x = ctx.x
             b, c, hh, ww = x.shape
@@ -416,7 +465,7 @@ class RMIHieraTriplet3Fn(torch.autograd.Function):
                 _staged("sh_rmi3_backward", (1, 2), lambda st_bits: (
                     _p(x), _dtype_code(x), _p(gx), b, hh, ww, cfg.n_fine, cfg.n_mid, cfg.n_high, _p(ctx.tab), ctx.n_mh,
                     ctx.fast_ok, cfg.loss_weight, _p(ctx.ws), _p(g), st_bits, _stream()))
-        gemb = None
-        if ctx.st is not None and ctx.needs_input_grad[1]:
-            gemb = triplet_backward(ctx.emb, ctx.st, ctx.out[1:2], g)
+        if fork is not None:
+            fork.join()
+            gemb = _grad_as(gemb, ctx.emb)
         return gx, gemb, None, None, None, None
