@@ -501,3 +501,51 @@ def test_config4_image_against_oracle_on_cuda(sb):
     assert mod.last_stats["fast_path"]
     assert abs(float(loss.detach()) - float(ref.detach())) <= FP32_TOL * abs(float(ref.detach()))
     _assert_grad_close_up_to_tie_flips(xc.grad, xr.grad, FP32_TOL)
+
+
+@pytest.mark.gpu
+def test_streams_and_graph_capture(sb):
+    """The triplet kernels fork to a side stream and join again (ops._Fork): on the default stream, on a user stream
+    and replayed from a CUDA graph the loss and the logit gradient must be bit-identical; the embedding gradient is a
+    float atomicAdd scatter (order not fixed), so it is compared to 1e-6."""
+    g = torch.Generator().manual_seed(77)
+    b, h, w = 2, 64, 96
+    lab = blob_labels(g, b, h, w, 19, 8, 0.1).cuda()
+    x0 = (torch.randn(b, 28, h, w, generator=g) * 2).cuda()
+    e0 = F.normalize(torch.randn(b, 16, h // 8, w // 8, generator=g), dim=1).cuda()
+    step = torch.tensor([170000]).cuda()
+    mod = sb.RMIHieraTripletLoss(19, 7, 2, torch.tensor(F2M), torch.tensor(F2H))
+
+    def run(x, e):
+        loss = mod(step, e, None, x, lab)
+        gx, ge = torch.autograd.grad(loss, (x, e))
+        return loss.detach(), gx, ge
+
+    x, e = x0.clone().requires_grad_(True), e0.clone().requires_grad_(True)
+    ref = [t.clone() for t in run(x, e)]
+    assert float(ref[2].abs().max()) > 0          # the triplet term is live in this case
+    torch.cuda.synchronize()
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        got = run(x, e)
+    side.synchronize()
+    _same(got, ref)
+
+    graph = torch.cuda.CUDAGraph()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        run(x, e)                                  # warm-up on the capture stream (tables, side stream, allocator)
+    side.synchronize()
+    with torch.cuda.graph(graph):
+        cap = run(x, e)
+    for _ in range(2):
+        graph.replay()
+    torch.cuda.synchronize()
+    _same(cap, ref)
+
+
+def _same(got, ref):
+    assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])
+    assert rel(to_np(got[2]), to_np(ref[2])) <= 1e-6
