@@ -372,6 +372,25 @@ k3_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hie
   }
 }
 
+// stencil of one frame pixel over the staged band segment; WITH_L = false when the segment holds no pixel of the class
+template <bool WITH_L>
+__device__ __forceinline__ float frame2_stencil(const BandSeg& bs, const float* w, int va, int i, int u, int N, bool is_row) {
+  float dP = 0.f;
+#pragma unroll
+  for (int dv = -2; dv <= 2; ++dv) {
+    const int vv = va + dv;
+    if (vv < 0 || vv > 3) continue;
+#pragma unroll
+    for (int du = -2; du <= 2; ++du) {
+      if (u + du < 0 || u + du >= N) continue;
+      const int t = is_row ? (dv + 2) * 5 + du + 2 : (du + 2) * 5 + dv + 2;
+      dP = fmaf(w[t], bs.P[vv][i + 2 + du], dP);
+      if (WITH_L) dP = fmaf(w[25 + t], bs.L[vv][i + 2 + du], dP);
+    }
+  }
+  return dP;
+}
+
 // grid (B*C, nseg), block 256: the frame pixels of one (b, c) plane, side by side; the 4-pixel band segments the
 // stencil touches are staged in shared memory
 template <typename T>
@@ -388,8 +407,7 @@ __global__ void __launch_bounds__(256) k3_frame2(T* __restrict__ grad, int B, in
   const long HW = (long)H * W;
   const float* bR = bandR + (size_t)bc * 8 * W;
   const float* bC = bandC + (size_t)bc * 8 * H;
-  const unsigned char* lab8 = ws.lab8 + (long)b * HW;
-  const int* lmap = lvl == 0 ? nullptr : (lvl == 1 ? h.f2m : h.f2h);
+  const unsigned char* lb = ws.labB + ((size_t)b * 3 + lvl) * 8 * ((size_t)W + H);
   T* gc = grad + ((long)b * C + c) * HW;
   const float gscale = *gscale_ptr;
   const int tid = threadIdx.x;
@@ -403,8 +421,8 @@ __global__ void __launch_bounds__(256) k3_frame2(T* __restrict__ grad, int B, in
     for (int u0 = lo; u0 < hi; u0 += kSegMax) {
       const int n = min(kSegMax, hi - u0);
       __syncthreads();
-      stage_band(bs, side, u0, n, bR, bC, lab8, lmap, cl, H, W, tid, 256);
-      __syncthreads();
+      const bool saw = stage_band(bs, side, u0, n, bR, bC, lb, cl, H, W, tid, 256);
+      const bool any = __syncthreads_or(saw) != 0;       // a pixel of this class in the segment? (else L == 0)
       for (int idx = tid; idx < 2 * n; idx += 256) {
         const int line = idx / n, i = idx - line * n, u = u0 + i;
         const int va = line + 2 * (side & 1);
@@ -413,19 +431,8 @@ __global__ void __launch_bounds__(256) k3_frame2(T* __restrict__ grad, int B, in
         const int vg = (side & 1) ? (is_row ? H : W) - 4 + va : va;
         const int yy = is_row ? vg : u, xx = is_row ? u : vg;
         const float* w = fw + (axis_class(yy, H) * 5 + axis_class(xx, W)) * 50;
-        float dP = 0.f;
-#pragma unroll
-        for (int dv = -2; dv <= 2; ++dv) {
-          const int vv = va + dv;
-          if (vv < 0 || vv > 3) continue;
-#pragma unroll
-          for (int du = -2; du <= 2; ++du) {
-            if (u + du < 0 || u + du >= N) continue;
-            const int t = is_row ? (dv + 2) * 5 + du + 2 : (du + 2) * 5 + dv + 2;
-            dP = fmaf(w[t], bs.P[vv][i + 2 + du], dP);
-            dP = fmaf(w[25 + t], bs.L[vv][i + 2 + du], dP);
-          }
-        }
+        const float dP = any ? frame2_stencil<true>(bs, w, va, i, u, N, is_row)
+                             : frame2_stencil<false>(bs, w, va, i, u, N, is_row);
         const float add = dP * gscale * s * (1.0f - s);
         const long off = (long)yy * W + xx;
         gc[off] = from_f32<T>(to_f32<T>(gc[off]) + add);

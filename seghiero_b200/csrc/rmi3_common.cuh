@@ -106,6 +106,8 @@ struct Ws3 {
   unsigned int* llrec;         // [B*cpi][C][16]: label-label half-plane counts [13]
   float* bce2;                 // [B*cpi][8]
   unsigned int* strips;        // [B][2]: label strips with a mixed 3x8 window (fine level), all strips (k3f_prep)
+  unsigned char* labB;         // [B][3 levels][8 W + 8 H]: RMI labels (void = 0) of the 4-pixel border bands, laid out
+                               // like bandR / bandC (k3_band writes them, the frame kernels stage them)
   size_t bytes;
   int tiles_x, tiles_y, nseg, cpi;
 };
@@ -130,25 +132,29 @@ struct BandSeg {
   float P[4][kSegMax + 4];
   float L[4][kSegMax + 4];
 };
-__device__ __forceinline__ void stage_band(BandSeg& s, int side, int u0, int n, const float* bandR, const float* bandC,
-                                           const unsigned char* lab8, const int* lmap, int cl, int H, int W, int tid,
-                                           int nthreads) {
+// Returns whether this thread staged a pixel of class cl (callers skip the label taps of segments without one).
+// `lb` = the (image, level) block of Ws3::labB.
+__device__ __forceinline__ bool stage_band(BandSeg& s, int side, int u0, int n, const float* bandR, const float* bandC,
+                                           const unsigned char* lb, int cl, int H, int W, int tid, int nthreads) {
   const int N = side < 2 ? W : H;
+  const float* pb = side < 2 ? bandR : bandC;
+  const unsigned char* lbb = side < 2 ? lb : lb + 8 * W;
+  bool saw = false;
+#pragma unroll 4
   for (int e = tid; e < 4 * (n + 4); e += nthreads) {
     const int v = e / (n + 4), i = e - v * (n + 4), u = u0 - 2 + i;
     float p = 0.f, l = 0.f;
     if (u >= 0 && u < N) {
-      const int q = (side & 1) ? 4 + v : v;
-      int yy, xx;
-      if (side < 2) { p = bandR[(size_t)q * W + u]; yy = (side & 1) ? H - 4 + v : v; xx = u; }
-      else { p = bandC[(size_t)q * H + u]; xx = (side & 1) ? W - 4 + v : v; yy = u; }
-      const int t = lab8[(long)yy * W + xx];
-      const int lab = t == SH_IGNORE ? 0 : (lmap ? lmap[t] : t);
-      l = lab == cl ? 1.f : 0.f;
+      const size_t at = (size_t)((side & 1) ? 4 + v : v) * N + u;
+      p = pb[at];
+      const bool is = lbb[at] == cl;
+      l = is ? 1.f : 0.f;
+      saw |= is;
     }
     s.P[v][i] = p;
     s.L[v][i] = l;
   }
+  return saw;
 }
 
 inline Ws3 ws3_layout(void* base, int B, int H, int W, int nf, int nm, int nh) {
@@ -179,6 +185,7 @@ inline Ws3 ws3_layout(void* base, int B, int H, int W, int nf, int nm, int nh) {
   w.llrec = (unsigned int*)take((size_t)B * w.cpi * C * 16 * 4);
   w.bce2 = (float*)take((size_t)B * w.cpi * 8 * 4);
   w.strips = (unsigned int*)take((size_t)B * 2 * 4);
+  w.labB = (unsigned char*)take((size_t)B * 3 * 8 * ((size_t)W + H));
   w.bytes = off;
   return w;
 }

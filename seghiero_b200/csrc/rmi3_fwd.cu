@@ -543,8 +543,12 @@ k3_pass1(const T* __restrict__ x, int B, int H, int W, Hier3 hg, Ws3 ws, float e
 template <typename T>
 __global__ void __launch_bounds__(256) k3_band(const T* __restrict__ x, int B, int C, int H, int W,
                                                const unsigned char* __restrict__ lab8_all, float* __restrict__ bandR,
-                                               float* __restrict__ bandC) {
-  const int bc = blockIdx.x, b = bc / C;
+                                               float* __restrict__ bandC, Hier3 h, unsigned char* __restrict__ labB) {
+  const int bc = blockIdx.x, b = bc / C, c = bc - b * C;
+  // the first channel of each level also writes the level's RMI labels of the bands (Ws3::labB)
+  const int lvl = c == 0 ? 0 : (c == h.nf ? 1 : (c == h.nf + h.nm ? 2 : -1));
+  const int* lmap = lvl == 1 ? h.f2m : h.f2h;
+  unsigned char* lbo = labB + ((size_t)b * 3 + (lvl < 0 ? 0 : lvl)) * 8 * ((size_t)W + H);
   const long HW = (long)H * W;
   const T* xc = x + (long)bc * HW;
   const unsigned char* lab8 = lab8_all + (long)b * HW;
@@ -557,8 +561,10 @@ __global__ void __launch_bounds__(256) k3_band(const T* __restrict__ x, int B, i
     else { const int i2 = i - 8 * W; const int q = i2 / H; yy = i2 - q * H; xx = q < 4 ? q : W - 8 + q; dst = bandC + ((size_t)bc * 8 + q) * H + yy; }
     const long off = (long)yy * W + xx;
     const float xv = to_f32<T>(xc[off]);          // both loads issue together (the kernel is load-latency bound)
-    const bool valid = lab8[off] != SH_IGNORE;
+    const int t = lab8[off];
+    const bool valid = t != SH_IGNORE;
     *dst = (valid ? sig_exp(xv).s : 0.f) + 1e-6f;
+    if (lvl >= 0) lbo[i] = (unsigned char)(valid ? (lvl == 0 ? t : lmap[t]) : 0);
   }
 }
 
@@ -601,6 +607,7 @@ __global__ void __launch_bounds__(256) k3_frame1(int B, int H, int W, Hier3 h, W
   bv.bandR = bandR + (size_t)bc * 8 * W; bv.bandC = bandC + (size_t)bc * 8 * H;
   bv.lab8 = ws.lab8 + (long)b * H * W; bv.lmap = lvl == 0 ? nullptr : (lvl == 1 ? h.f2m : h.f2h);
   bv.H = H; bv.W = W;
+  const unsigned char* lb = ws.labB + ((size_t)b * 3 + lvl) * 8 * ((size_t)W + H);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float* out = ws.frameT + ((size_t)seg * B * C + bc) * 25 * kFrameRec;
 
@@ -624,7 +631,7 @@ __global__ void __launch_bounds__(256) k3_frame1(int B, int H, int W, Hier3 h, W
 #pragma unroll 1
     for (int sd = 0; sd < 4; ++sd) {
       const int a = sd >> 1, u0 = lo[a] + c0, n = min(kSegMax, hi[a] - u0);
-      if (n > 0) stage_band(bs[sd], sd, u0, n, bv.bandR, bv.bandC, bv.lab8, bv.lmap, cl, H, W, tid, 256);
+      if (n > 0) stage_band(bs[sd], sd, u0, n, bv.bandR, bv.bandC, lb, cl, H, W, tid, 256);
     }
     __syncthreads();
     const int a = side >> 1, u0 = lo[a] + c0, n = min(kSegMax, hi[a] - u0);
@@ -1010,7 +1017,7 @@ static int run_forward3_fast(const void* x, const long long* label, int B, int H
     SH_CHECK_LAUNCH();
   }
   if (stages & 4) {
-    k3_band<T><<<dim3(B * C, 4), 256, 0, st>>>((const T*)x, B, C, H, W, ws.lab8, bandR, bandC);
+    k3_band<T><<<dim3(B * C, 4), 256, 0, st>>>((const T*)x, B, C, H, W, ws.lab8, bandR, bandC, h, ws.labB);
     SH_CHECK_LAUNCH();
     k3_frame1<<<dim3(B * C, ws.nseg), 256, 0, st>>>(B, H, W, h, ws, bandR, bandC);
     SH_CHECK_LAUNCH();
@@ -1048,7 +1055,7 @@ static int run_forward3(const void* x, const long long* label, int B, int H, int
     SH_CHECK_LAUNCH();
   }
   if (stages & 4) {
-    k3_band<T><<<dim3(B * C, 4), 256, 0, st>>>((const T*)x, B, C, H, W, ws.lab8, bandR, bandC);
+    k3_band<T><<<dim3(B * C, 4), 256, 0, st>>>((const T*)x, B, C, H, W, ws.lab8, bandR, bandC, h, ws.labB);
     SH_CHECK_LAUNCH();
     k3_frame1<<<dim3(B * C, ws.nseg), 256, 0, st>>>(B, H, W, h, ws, bandR, bandC);
     SH_CHECK_LAUNCH();
