@@ -234,7 +234,7 @@ class TripletState:
 
 
 def triplet_forward(feats: torch.Tensor, label: torch.Tensor, mode: int, tab: torch.Tensor, ncls: int,
-                    max_triplet: int = 200, fork: Optional[_Fork] = None) -> TripletState:
+                    max_triplet: int = 200, fork: Optional[_Fork] = None, world_ready: bool = False) -> TripletState:
     _need_cuda(feats, label)
     b, d, h, w = feats.shape
     hh, ww = label.shape[-2:]
@@ -249,6 +249,8 @@ def triplet_forward(feats: torch.Tensor, label: torch.Tensor, mode: int, tab: to
     with torch.cuda.device(dev), (fork if fork is not None else contextlib.nullcontext()):
         _call("sh_triplet_forward", _p(feats), _dtype_code(feats), _p(label), b, d, h, w, hh, ww, mode, _p(tab),
                   ncls, max_triplet, _p(lab_ds), _p(sel), _p(kcount), _p(tl), _p(trip), _p(status), _stream())
+        if world_ready:
+            _world_ready(status)      # on the side stream too: the all-reduce overlaps the loss kernels
     return TripletState(mode, ncls, max_triplet, (b, d, h, w), sel, kcount, tl, trip, status, lab_ds)
 
 
@@ -324,7 +326,7 @@ class HieraTriplet2Fn(torch.autograd.Function):
             ttab, ncls = device_table(tkey, lambda: H.triplet_tables_hierarchy(cfg.hiera_map, cfg.hiera_index), dev)
             emb = embedding.contiguous()
             fork = _Fork(dev)
-            st = triplet_forward(emb, lab, 0, ttab, ncls, fork=fork)
+            st = triplet_forward(emb, lab, 0, ttab, ncls, fork=fork, world_ready=True)
 
         want_grad = ctx.needs_input_grad[0]
         grad = torch.empty_like(x) if want_grad else None
@@ -341,7 +343,6 @@ class HieraTriplet2Fn(torch.autograd.Function):
                 cfg.eps, cfg.loss_weight, _p(lab8), _p(counts), _p(partials), _p(sums), st_bits | tree, _stream()))
             if st is not None:
                 fork.join()
-                _world_ready(st.status)
             _call("sh_loss2_final", _p(sums), _p(counts), cfg.n_fine, cfg.n_coarse, float(b * hw), _p(step_d),
                       cfg.total_steps, _p(st.trip) if st else None, _p(st.status) if st else None, cfg.loss_weight,
                       _p(out), _stream())
@@ -420,7 +421,7 @@ class RMIHieraTriplet3Fn(torch.autograd.Function):
             ttab, ncls = device_table(tkey, lambda: H.triplet_tables_id_lists(cfg.upper_ids, cfg.lower_ids), dev)
             emb = embedding.contiguous()
             fork = _Fork(dev)
-            st = triplet_forward(emb, lab, 1, ttab, ncls, fork=fork)
+            st = triplet_forward(emb, lab, 1, ttab, ncls, fork=fork, world_ready=True)
         with torch.cuda.device(dev):
             lib = _lib.load()
             nbytes = lib.sh_rmi3_workspace_bytes(b, hh, ww, cfg.n_fine, cfg.n_mid, cfg.n_high)
@@ -431,7 +432,6 @@ class RMIHieraTriplet3Fn(torch.autograd.Function):
                 cfg.lam, cfg.loss_weight, _p(ws), st_bits, _stream()))
             if st is not None:
                 fork.join()
-                _world_ready(st.status)
             _call("sh_loss3_final", b, hh, ww, cfg.n_fine, cfg.n_mid, cfg.n_high, _p(ws), cfg.lam, _p(step_d),
                       cfg.total_steps, _p(st.trip) if st else None, _p(st.status) if st else None, cfg.loss_weight,
                       _p(out), _stream())
