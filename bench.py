@@ -3,7 +3,9 @@
 fraction of the HBM roofline).
 
     python bench.py --gpus N --steps K --warmup W            # our CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # reference CPU arm (oracle port, rank 0 only)
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU arm (the reference's own modules when
+                                                             # /root/reference or baseline/_ref exists, else the oracle
+                                                             # port; rank 0 only)
 
 A "step" is one forward+backward of the loss module over one synthetic batch (per rank; weak scaling).
 Default workload = BASELINE config 3 (the configuration the target is quoted on):
@@ -180,10 +182,19 @@ def cpu_sample_shape(w):
     return (1, 512, 1024) if w["nf"] <= 32 else (1, 256, 256)
 
 
+def _reference_root():
+    """Where the UNMODIFIED reference can be imported from on this box (None on the GPU box: it does not travel)."""
+    for cand in (os.environ.get("SEGHIERO_REFERENCE"), "/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "models", "loss", "rmi_hiera_triplet_loss.py")):
+            return cand
+    return None
+
+
 def run_cpu_oracle(w, steps, warmup, label_kind):
+    """CPU arm on a bounded crop of the workload: the reference's own loss modules (kind "reference", CPU tensors,
+    `.cuda()` shim for its hard-coded device moves) when the reference can be imported here, else the oracle port."""
     import torch
     import torch.nn.functional as F
-    from oracle import hiera_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     b, h, wd = cpu_sample_shape(w)
@@ -191,6 +202,19 @@ def run_cpu_oracle(w, steps, warmup, label_kind):
     lab = make_labels(torch, g, b, h, wd, w["nf"], label_kind, "cpu")
     dt = torch.float32 if w["dtype"] == "fp32" else torch.bfloat16
     f2m, f2h = hierarchy_maps(w)
+    ref_root = _reference_root() if w["kind"] in ("2level", "3level") else None
+    kind = "port"
+    if ref_root is not None:
+        try:
+            sys.dont_write_bytecode = True
+            sys.path.insert(0, ref_root)
+            torch.Tensor.cuda = lambda self, *a, **k: self      # the reference hard-codes .cuda() in its triplet losses
+            from models.loss.hiera_triplet_loss import HieraTripletLoss as RefH2
+            from models.loss.rmi_hiera_triplet_loss import RMIHieraTripletLoss as RefH3
+            kind = "reference"
+        except Exception:                                        # noqa: BLE001 -- any import problem: fall back to the port
+            kind = "port"
+    from oracle import hiera_oracle as O
     if w["kind"] == "decode":
         x = torch.randn(b, w["nf"] + w["nm"] + w["nh"], h, wd, generator=g).to(dt)
 
@@ -199,22 +223,34 @@ def run_cpu_oracle(w, steps, warmup, label_kind):
     elif w["kind"] == "2level":
         x = (torch.randn(b, w["nf"] + w["nc"], h, wd, generator=g) * 2).to(dt).requires_grad_(True)
         emb = F.normalize(torch.randn(b, 256, h // 32, wd // 32, generator=g), dim=1).requires_grad_(True)
+        ref_mod = RefH2(w["nf"], HM_19_7, HI_19_7) if kind == "reference" else None
 
         def step():
             x.grad = None
             emb.grad = None
-            loss, _ = O.hiera_triplet_loss(100000, emb, x, lab, w["nf"], HM_19_7, HI_19_7)
+            if ref_mod is not None:
+                loss = ref_mod(torch.tensor([100000]), emb, None, x, lab)
+            else:
+                loss, _ = O.hiera_triplet_loss(100000, emb, x, lab, w["nf"], HM_19_7, HI_19_7)
             loss.backward()
     else:
         x = (torch.randn(b, w["nf"] + w["nm"] + w["nh"], h, wd, generator=g) * 2).to(dt).requires_grad_(True)
         emb = F.normalize(torch.randn(b, 256, h // 32, wd // 32, generator=g), dim=1).requires_grad_(True)
         trip = w.get("triplet", True)
+        ref_mod = None
+        if kind == "reference" and trip:       # config 4's labels are outside the reference's id lists: port
+            ref_mod = RefH3(w["nf"], w["nm"], w["nh"], torch.tensor(f2m), torch.tensor(f2h))
+        elif kind == "reference":
+            kind = "port"
 
         def step():
             x.grad = None
             emb.grad = None
-            loss, _ = O.rmi_hiera_triplet_loss(100000, emb, x, lab, w["nf"], w["nm"], w["nh"], f2m, f2h,
-                                               with_triplet=trip)
+            if ref_mod is not None:
+                loss = ref_mod(torch.tensor([100000]), emb, None, x, lab)
+            else:
+                loss, _ = O.rmi_hiera_triplet_loss(100000, emb, x, lab, w["nf"], w["nm"], w["nh"], f2m, f2h,
+                                                   with_triplet=trip)
             loss.backward()
     for _ in range(warmup):
         step()
@@ -223,9 +259,20 @@ def run_cpu_oracle(w, steps, warmup, label_kind):
         step()
     dt_s = (time.perf_counter() - t0) / max(steps, 1)
     px = b * h * wd
-    return dict(value=px / dt_s / 1e9, unit="Gpix/s", cores=cores, kind="port",
-                sample=f"oracle port (torch-CPU restatement of the reference loss), {b}x{h}x{wd} crop of the "
-                       f"workload, fwd+bwd, {steps} steps, all {cores} host threads", ms_per_step=dt_s * 1e3)
+    what = ("the reference's own loss module (CPU tensors, .cuda() shim)" if kind == "reference"
+            else "oracle port (torch-CPU restatement of the reference loss)")
+    return dict(value=px / dt_s / 1e9, unit="Gpix/s", cores=cores, kind=kind,
+                sample=f"{what}, {b}x{h}x{wd} crop of the workload, fwd+bwd, {steps} steps, all {cores} host threads",
+                ms_per_step=dt_s * 1e3)
+
+
+def bench_config(args, w, b, px, world, x_gb=None):
+    cfg = {"workload": args.workload, "description": w["desc"], "labels": args.labels,
+           "batch_per_gpu": b, "pixels_per_step_per_gpu": px,
+           "parallelism": f"dp{world} by sample, no data-path collective"}
+    if x_gb is not None:
+        cfg["l2"] = "inputs larger than L2 (logits %.2f GB per GPU)" % x_gb
+    return cfg
 
 
 def run_reference_arm(args, w):
@@ -234,11 +281,16 @@ def run_reference_arm(args, w):
         return
     steps = max(1, min(args.steps, 5))
     res = run_cpu_oracle(w, steps, 1, args.labels)
+    b = args.batch or w["B"]
+    e = 4 if w["dtype"] == "fp32" else 2
+    c = w["nf"] + (w["nc"] if w["kind"] == "2level" else w["nm"] + w["nh"])
     line = {
         "impl": "reference", "metric": "hier_loss_fwd_bwd_throughput", "value": res["value"], "unit": "Gpix/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": res["ms_per_step"],
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "description": w["desc"], "labels": args.labels},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if w["dtype"] == "fp32" else "bf16 in / f32 accumulate", "data": "synthetic",
+        "config": bench_config(args, w, b, b * w["H"] * w["W"], max(args.gpus, 1),
+                               b * c * w["H"] * w["W"] * e / 1e9),
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": "Gpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -249,6 +301,66 @@ def run_reference_arm(args, w):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+STAGE_NAMES = {("sh_rmi3_forward", 1): "k3_prep", ("sh_rmi3_forward", 2): "k3_pass1",
+               ("sh_rmi3_forward", 4): "k3_frame1", ("sh_rmi3_forward", 8): "k3_finalize",
+               ("sh_rmi3_backward", 1): "k3_pass2", ("sh_rmi3_backward", 2): "k3_frame2",
+               ("sh_bce2_fwdbwd", 1): "k_prep2", ("sh_bce2_fwdbwd", 2): "k_bce2_fused",
+               ("sh_bce2_fwdbwd", 4): "k_reduce_partials", ("sh_upsample_bilinear", 0): "k_upsample",
+               ("sh_upsample_bilinear_adjoint", 0): "k_upsample_adjoint", ("sh_aux_ce_fwdbwd", 0): "k_aux_ce"}
+FAST_NAMES = {("sh_rmi3_forward", 1): "k3f_prep", ("sh_rmi3_forward", 2): "k3f_pass1",
+              ("sh_rmi3_forward", 8): "k3f_finalize", ("sh_rmi3_backward", 1): "k3f_pass2",
+              ("sh_bce2_fwdbwd", 2): "k_bce2_fast"}
+
+
+def _dist_env():
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    return rank, world, local, dev
+
+
+def _peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh).get("hbm_gbs", 6650.0)), "MEASURED_PEAKS.json hbm_gbs (measured)"
+    except (OSError, ValueError):
+        return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+
+
+def _timed_steps(torch, dist, world, dev, step, steps, timer=None):
+    """K device-timed steps between barriers; returns (ms per step as the max over ranks, wall window, last output)."""
+    from seghiero_b200 import ops
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    ctx = ops.stage_timing(timer) if timer is not None else None
+    if ctx is not None:
+        ctx.__enter__()
+    e0.record()
+    for _ in range(steps):
+        out = step()
+    e1.record()
+    if ctx is not None:
+        ctx.__exit__(None, None, None)
+    barrier()
+    t1 = time.time()
+    el = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    return float(el.item()), (t0, t1), out
+
+
 def run_ours(args, w):
     import torch
     import torch.distributed as dist
@@ -256,13 +368,7 @@ def run_ours(args, w):
     import seghiero_b200 as sb
     from seghiero_b200 import ops
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    rank, world, local, dev = _dist_env()
     warmup = max(args.warmup, 3)
     steps = max(args.steps, 1)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -272,7 +378,7 @@ def run_ours(args, w):
     f2m, f2h = hierarchy_maps(w)
     lab = make_labels(torch, g, b, h, wd, w["nf"], args.labels, dev)
     step_t = torch.tensor([100000], device=dev)
-    grads_out = []
+    mod = None
 
     if w["kind"] == "decode":
         c = w["nf"] + w["nm"] + w["nh"]
@@ -282,7 +388,6 @@ def run_ours(args, w):
         def step():
             preds, counts = sb.hierarchical_argmax(x, [w["nf"], w["nm"], w["nh"]], lab)
             return counts
-        host_in = [x]
     else:
         if w["kind"] == "2level":
             c = w["nf"] + w["nc"]
@@ -295,71 +400,44 @@ def run_ours(args, w):
         x = (torch.randn(b, c, h, wd, generator=g, device=dev) * 2).to(dt).requires_grad_(True)
         emb = F.normalize(torch.randn(b, 256, h // 32, wd // 32, generator=g, device=dev), dim=1).requires_grad_(True)
         use_emb = emb if (w["kind"] == "2level" or w.get("triplet", True)) else None
+        cur = {"lab": lab}
 
         def step():
             x.grad = None
             emb.grad = None
-            loss = mod(step_t, use_emb, None, x, lab)
+            loss = mod(step_t, use_emb, None, x, cur["lab"])
             loss.backward()
             if world > 1:   # scalar loss sum across ranks (the path's only data collective besides `ready`)
                 dist.all_reduce(loss.detach(), op=dist.ReduceOp.SUM)
             return loss
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     clk = ClockSampler(local)
     clk.__enter__()                       # nvidia-smi needs ~0.1 s before its first sample: start it before the warm-up
     for _ in range(warmup):
         step()
-    barrier()
 
     # ---- timed region: K steps, device-timed, stage events on --------------------------------------
     timer = StageTimer()
-    ops.STAGE_TIMER = timer
     ops.LAUNCHES["n"] = 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_wall0 = time.time()
-    e0.record()
-    for _ in range(steps):
-        out = step()
-    e1.record()
-    barrier()
-    clk.mark(t_wall0, time.time())
-    ops.STAGE_TIMER = None
+    ms_step, win, _ = _timed_steps(torch, dist, world, dev, step, steps, timer)
+    clk.mark(*win)
     launches = ops.LAUNCHES["n"]
-    elapsed = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
-    ms_total = float(elapsed.item())
-    ms_step = ms_total / steps
     value = world * px / (ms_step * 1e-3) / 1e9
 
     # ---- roofline of the dominant kernel (from the stage events of the same timed region) ------------
     ab = algorithmic_bytes_per_px(w)
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-            peaks = json.load(fh)
-    except OSError:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    stage_names = {("sh_rmi3_forward", 1): "k3_prep", ("sh_rmi3_forward", 2): "k3_pass1",
-                   ("sh_rmi3_forward", 4): "k3_frame1", ("sh_rmi3_forward", 8): "k3_finalize",
-                   ("sh_rmi3_backward", 1): "k3_pass2", ("sh_rmi3_backward", 2): "k3_frame2",
-                   ("sh_bce2_fwdbwd", 1): "k_prep2", ("sh_bce2_fwdbwd", 2): "k_bce2_fused",
-                   ("sh_bce2_fwdbwd", 4): "k_reduce_partials"}
-    if w["kind"] == "3level" and getattr(mod, "last_stats", {}).get("fast_path"):
-        stage_names.update({("sh_rmi3_forward", 1): "k3f_prep", ("sh_rmi3_forward", 2): "k3f_pass1",
-                            ("sh_rmi3_forward", 8): "k3f_finalize", ("sh_rmi3_backward", 1): "k3f_pass2"})
-    if w["kind"] == "2level" and mod.last_stats.get("fast_path"):
-        stage_names[("sh_bce2_fwdbwd", 2)] = "k_bce2_fast"
+    peak, peak_src = _peak()
+    names = dict(STAGE_NAMES)
+    fast3 = w["kind"] == "3level" and mod.uses_fast_path(x, lab)
+    fast2 = w["kind"] == "2level"
+    if fast3 or fast2:
+        names.update(FAST_NAMES)
     stage_bytes = {"k3_pass1": ab.get("pass1"), "k3_pass2": ab.get("pass2"), "k_bce2_fused": ab.get("fused"),
                    "k_bce2_fast": ab.get("fused"), "k3f_pass1": ab.get("pass1"), "k3f_pass2": ab.get("pass2")}
-    stages = {stage_names[k]: t / n for k, (t, n) in timer.totals().items() if k in stage_names}
+
+    def stage_ms(tm):
+        return {names[k]: t / n for k, (t, n) in tm.totals().items() if k in names}
+    stages = stage_ms(timer)
     roofline = None
     traffic_tab = {}
     try:
@@ -376,8 +454,9 @@ def run_ours(args, w):
                     "frac": achieved / peak, "traffic": (tr["bytes_per_px"] * px if tr else None),
                     "traffic_source": (tr.get("source") if tr else None),
                     "algorithmic_bytes_per_launch": stage_bytes[top] * px, "ms_per_launch": cand[top],
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                    "whole_step_frac": ab["total"] * px / (ms_step * 1e-3) / 1e9 / peak}
+                    "peak_source": peak_src,
+                    "whole_step_frac": ab["total"] * px / (ms_step * 1e-3) / 1e9 / peak,
+                    "per_kernel_frac": {k: stage_bytes[k] * px / (v * 1e-3) / 1e9 / peak for k, v in cand.items()}}
     elif w["kind"] == "decode":
         achieved = ab["total"] * px / (ms_step * 1e-3) / 1e9
         tr = traffic_tab.get(f"{args.workload}:k_decode")
@@ -385,109 +464,62 @@ def run_ours(args, w):
                     "frac": achieved / peak, "traffic": (tr["bytes_per_px"] * px if tr else None),
                     "traffic_source": (tr.get("source") if tr else None),
                     "algorithmic_bytes_per_launch": ab["total"] * px,
-                    "ms_per_launch": ms_step,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"}
+                    "ms_per_launch": ms_step, "peak_source": peak_src}
+
+    # ---- worst-case label distribution (per-pixel labels), same shapes, same timed-region rules ---------------
+    iid = None
+    if mod is not None and args.labels == "blob" and not args.no_iid:
+        cur["lab"] = make_labels(torch, g, b, h, wd, w["nf"], "iid", dev)
+        for _ in range(3):
+            step()
+        t2 = StageTimer()
+        ms_iid, win, _ = _timed_steps(torch, dist, world, dev, step, steps, t2)
+        clk.mark(*win)
+        iid = {"labels": "iid", "ms_per_step": ms_iid, "value": world * px / (ms_iid * 1e-3) / 1e9, "unit": "Gpix/s",
+               "whole_step_frac": ab["total"] * px / (ms_iid * 1e-3) / 1e9 / peak, "ratio_to_blob": ms_iid / ms_step,
+               "kernel_ms": stage_ms(t2)}
+        cur["lab"] = lab
+
+    # ---- decode from the head's H/4 logits (N3), same number of output pixels ---------------------------------
+    decode_up = None
+    if w["kind"] == "decode" and h % 4 == 0 and wd % 4 == 0:
+        xl = torch.randn(b, c, h // 4, wd // 4, generator=g, device=dev, dtype=torch.float32).to(dt)
+        lab8 = lab.to(torch.uint8)
+
+        def step_up():
+            preds, counts = sb.hierarchical_argmax(xl, [w["nf"], w["nm"], w["nh"]], lab8, out_dtype=torch.uint8)
+            return counts
+        for _ in range(3):
+            step_up()
+        ms_up, win, _ = _timed_steps(torch, dist, world, dev, step_up, steps)
+        clk.mark(*win)
+        alg = (c * (2 if dt != torch.float32 else 4) / 16 + 3 + 1) * px
+        decode_up = {"what": "argmax of F.interpolate(H/4 logits) + accuracy counts, fused (no full-resolution logits), "
+                             "uint8 labels and predictions", "ms_per_step": ms_up,
+                     "value": world * px / (ms_up * 1e-3) / 1e9, "unit": "Gpix/s",
+                     "algorithmic_bytes": alg, "hbm_frac": alg / (ms_up * 1e-3) / 1e9 / peak,
+                     "bound": "issue (interpolation arithmetic), not HBM"}
+        del xl, lab8
 
     # ---- end-to-end through the public API with HOST buffers -----------------------------------------
     e2e = None
+    e2e_full = None
     if not args.no_e2e:
         if w["kind"] == "decode":
-            hx = torch.empty(x.shape, dtype=x.dtype, pin_memory=True).copy_(x)
-            hlab = torch.empty(lab.shape, dtype=lab.dtype, pin_memory=True).copy_(lab)
-            hout = [torch.empty((b, h, wd), dtype=torch.int64, pin_memory=True) for _ in range(3)]
-
-            def e2e_step():
-                xd = hx.to(dev, non_blocking=True)
-                ld = hlab.to(dev, non_blocking=True)
-                preds, counts = sb.hierarchical_argmax(xd, [w["nf"], w["nm"], w["nh"]], ld)
-                for o, p in zip(hout, preds):
-                    o.copy_(p, non_blocking=True)
-                return counts.cpu()
-            h2d = hx.numel() * hx.element_size() + hlab.numel() * 8
-            d2h = 3 * b * h * wd * 8 + 16
+            e2e = _e2e_decode(torch, dist, sb, w, world, dev, x, lab, clk, steps)
         else:
-            hx = torch.empty(x.shape, dtype=x.dtype, pin_memory=True).copy_(x.detach())
-            hlab = torch.empty(lab.shape, dtype=lab.dtype, pin_memory=True).copy_(lab)
-            hemb = torch.empty(emb.shape, dtype=emb.dtype, pin_memory=True).copy_(emb.detach())
-            hgx = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
-            hge = torch.empty(emb.shape, dtype=emb.dtype, pin_memory=True)
-            hloss = torch.empty(1, dtype=torch.float32, pin_memory=True)
-            # three streams: the H2D copy of step i+1 and the D2H copy of step i-1 overlap the kernels of step i
-            # (every step still moves all of its inputs and results; device input buffers are double buffered)
-            s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-            s_cmp = torch.cuda.current_stream(dev)
-            dbuf = [(torch.empty_like(x.detach()), torch.empty_like(lab), torch.empty_like(emb.detach())) for _ in range(2)]
-            free_ev = [None, None]
-            state = {"i": 0, "last": None}
+            # the reference-facing call a training loop makes with the head's output: logits at H/4 (upsampled inside
+            # the op, train.py:282-284), uint8 labels; gradients come back at H/4
+            e2e = _e2e_loss(torch, dist, mod, w, world, dev, x, lab, emb, use_emb, step_t, clk, steps, low_res=True)
+            e2e_full = _e2e_loss(torch, dist, mod, w, world, dev, x, lab, emb, use_emb, step_t, clk, min(steps, 3),
+                                 low_res=False)
 
-            def e2e_step():
-                i = state["i"]
-                state["i"] += 1
-                xb, lb, eb = dbuf[i % 2]
-                with torch.cuda.stream(s_in):
-                    if free_ev[i % 2] is not None:
-                        s_in.wait_event(free_ev[i % 2])      # the step that last used this buffer set has finished
-                    xb.copy_(hx, non_blocking=True)
-                    lb.copy_(hlab, non_blocking=True)
-                    eb.copy_(hemb, non_blocking=True)
-                    ev_in = torch.cuda.Event()
-                    ev_in.record(s_in)
-                s_cmp.wait_event(ev_in)
-                xd = xb.detach().requires_grad_(True)
-                ed = eb.detach().requires_grad_(True)
-                loss = mod(step_t, ed if use_emb is not None else None, None, xd, lb)
-                loss.backward()
-                ev_cmp = torch.cuda.Event()
-                ev_cmp.record(s_cmp)
-                free_ev[i % 2] = ev_cmp
-                with torch.cuda.stream(s_out):
-                    s_out.wait_event(ev_cmp)
-                    xd.grad.record_stream(s_out)
-                    hgx.copy_(xd.grad, non_blocking=True)
-                    if ed.grad is not None:
-                        ed.grad.record_stream(s_out)
-                        hge.copy_(ed.grad, non_blocking=True)
-                    loss.record_stream(s_out)
-                    hloss.copy_(loss.detach().reshape(1), non_blocking=True)   # device->host read of the step's result
-                state["last"] = s_out
-                return loss
-
-            def e2e_drain():
-                s_out.synchronize()
-                return float(hloss[0])
-            h2d = hx.numel() * hx.element_size() + hlab.numel() * 8 + hemb.numel() * hemb.element_size()
-            d2h = hgx.numel() * hgx.element_size() + hge.numel() * hge.element_size() + 4
-        e2e_step()
-        if w["kind"] != "decode":
-            e2e_drain()
-        barrier()
-        k2 = max(2, min(steps, 10))
-        t_wall0 = time.time()
-        for _ in range(k2):
-            e2e_step()
-        if w["kind"] != "decode":
-            e2e_drain()                   # the last step's results are on the host
-        barrier()
-        t_wall1 = time.time()
-        clk.mark(t_wall0, t_wall1)
-        # host-side clock: the region spans three streams and ends when the last D2H copy has landed
-        el = torch.tensor([(t_wall1 - t_wall0) * 1e3 / k2], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(el, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * px / (float(el.item()) * 1e-3) / 1e9, "unit": "Gpix/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": float(el.item()),
-               "steps": k2, "note": "pinned host buffers -> H2D -> fwd+bwd -> D2H of loss and gradients, every step; "
-                                    "copies of neighbouring steps overlap the kernels (3 streams); wall clock around "
-                                    "the loop incl. the final drain"}
-
-    clk.__exit__()
     x_gb = x.numel() * x.element_size() / 1e9
-    # optional context: the oracle's torch restatement run as eager ATen ON THE GPU (what a user of the reference gets
-    # on this box); one sample per step because the fp64 RMI unfolds need ~21 GB per 1024x2048 image
+    # ---- context: the oracle's torch restatement run as eager ATen ON THIS GPU (what a user of the reference gets on
+    #      this box; one sample per step because the fp64 RMI unfolds need ~21 GB per 1024x2048 image) -------------
     eager = None
-    if args.eager_gpu and rank == 0 and w["kind"] in ("3level", "2level"):
+    if not args.no_eager and rank == 0 and world == 1 and w["kind"] in ("3level", "2level"):
         from oracle import hiera_oracle as O
-        x_gb = x.numel() * x.element_size() / 1e9
         del x
         torch.cuda.empty_cache()
         eb = 1 if w["kind"] == "3level" else b
@@ -503,16 +535,34 @@ def run_ours(args, w):
             else:
                 l_, _ = O.hiera_triplet_loss(100000, ee, xe, le, w["nf"], HM_19_7, HI_19_7)
             l_.backward()
-        eager_step()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(3):
+        try:
             eager_step()
-        torch.cuda.synchronize()
-        dt_s = (time.perf_counter() - t0) / 3
-        eager = {"value": eb * h * wd / dt_s / 1e9, "unit": "Gpix/s", "ms_per_step": dt_s * 1e3, "batch": eb,
-                 "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
-                 "what": "oracle restatement of the reference loss as eager ATen on this GPU (fwd+bwd, wall clock)"}
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                eager_step()
+            torch.cuda.synchronize()
+            dt_s = (time.perf_counter() - t0) / 3
+            eager = {"value": eb * h * wd / dt_s / 1e9, "unit": "Gpix/s", "ms_per_step": dt_s * 1e3, "batch": eb,
+                     "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
+                     "what": "oracle restatement of the reference loss as eager ATen on this GPU (fwd+bwd, wall clock)"}
+        except torch.cuda.OutOfMemoryError:
+            eager = {"unavailable": "out of memory"}
+        del xe, le, ee
+        torch.cuda.empty_cache()
+    clk.__exit__()
+    clocks = clk.summary()
+
+    # ---- the loss inside a training step (north-star metric, second half): few steps, every N --------------------
+    train = None
+    if not args.no_train and args.workload in ("cfg3", "cfg2"):
+        try:
+            del x
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        train = train_record(args, WORKLOADS["train-" + args.workload], min(steps, 6), brief=True)
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu:
         res = run_cpu_oracle(w, 2, 1, args.labels)
@@ -523,40 +573,199 @@ def run_ours(args, w):
             "metric": "hier_loss_fwd_bwd_throughput", "value": value, "unit": "Gpix/s", "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if w["dtype"] == "fp32" else "bf16 in / f32 accumulate",
-            "data": "synthetic",
-            "config": {"workload": args.workload, "description": w["desc"], "labels": args.labels,
-                       "batch_per_gpu": b, "pixels_per_step_per_gpu": px,
-                       "l2": "inputs larger than L2 (logits %.2f GB per GPU)" % x_gb,
-                       "parallelism": f"dp{world} by sample, no data-path collective"},
+            "data": "synthetic", "config": bench_config(args, w, b, px, world, x_gb),
             "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clk.summary(), "kernel_ms": stages,
+            "clocks": clocks, "kernel_ms": stages,
         }
+        if e2e_full is not None:
+            line["e2e_full_resolution_inputs"] = e2e_full
+        if iid is not None:
+            line["labels_iid"] = iid
+        if decode_up is not None:
+            line["decode_from_h4_logits"] = decode_up
         if eager is not None:
             line["eager_gpu_baseline"] = eager
+        if train is not None:
+            line["train"] = train
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+def _e2e_decode(torch, dist, sb, w, world, dev, x, lab, clk, steps):
+    b, h, wd = lab.shape
+    px = b * h * wd
+    hx = torch.empty(x.shape, dtype=x.dtype, pin_memory=True).copy_(x)
+    hlab = torch.empty(lab.shape, dtype=torch.uint8, pin_memory=True).copy_(lab.to(torch.uint8))
+    hout = [torch.empty((b, h, wd), dtype=torch.uint8, pin_memory=True) for _ in range(3)]
+
+    def e2e_step():
+        xd = hx.to(dev, non_blocking=True)
+        ld = hlab.to(dev, non_blocking=True)
+        preds, counts = sb.hierarchical_argmax(xd, [w["nf"], w["nm"], w["nh"]], ld, out_dtype=torch.uint8)
+        for o, p in zip(hout, preds):
+            o.copy_(p, non_blocking=True)
+        return counts.cpu()
+    e2e_step()
+    torch.cuda.synchronize()
+    k2 = max(2, min(steps, 10))
+    if world > 1:
+        dist.barrier()
+    t0 = time.time()
+    for _ in range(k2):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t1 = time.time()
+    clk.mark(t0, t1)
+    el = torch.tensor([(t1 - t0) * 1e3 / k2], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    return {"value": world * px / (float(el.item()) * 1e-3) / 1e9, "unit": "Gpix/s",
+            "h2d_bytes_per_step": int(hx.numel() * hx.element_size() + hlab.numel()),
+            "d2h_bytes_per_step": int(3 * px + 16), "ms_per_step": float(el.item()), "steps": k2,
+            "note": "pinned host logits + uint8 labels -> H2D -> decode -> D2H of uint8 predictions and counts, every step"}
+
+
+def _e2e_loss(torch, dist, mod, w, world, dev, x, lab, emb, use_emb, step_t, clk, steps, low_res):
+    """Same metric through the module call with HOST buffers; every step copies its inputs host->device from pinned
+    memory and its results (loss, logit gradient, embedding gradient) device->host.  Three streams so that the copies
+    of neighbouring steps overlap the kernels; device input buffers are double buffered.
+    low_res=True: what a training loop hands over -- the head's logits at H/4 and uint8 labels (rows N1 + N4)."""
+    b, c, h, wd = x.shape
+    px = b * h * wd
+    if low_res:
+        xin = torch.nn.functional.avg_pool2d(x.detach().float(), 4).to(x.dtype)     # any H/4 tensor of the right statistics
+        labin = lab.to(torch.uint8)
+    else:
+        xin, labin = x.detach(), lab
+    hx = torch.empty(xin.shape, dtype=xin.dtype, pin_memory=True).copy_(xin)
+    hlab = torch.empty(labin.shape, dtype=labin.dtype, pin_memory=True).copy_(labin)
+    hemb = torch.empty(emb.shape, dtype=emb.dtype, pin_memory=True).copy_(emb.detach())
+    hgx = torch.empty(xin.shape, dtype=xin.dtype, pin_memory=True)
+    hge = torch.empty(emb.shape, dtype=emb.dtype, pin_memory=True)
+    hloss = torch.empty(1, dtype=torch.float32, pin_memory=True)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    s_cmp = torch.cuda.current_stream(dev)
+    dbuf = [(torch.empty_like(xin), torch.empty_like(labin), torch.empty_like(emb.detach())) for _ in range(2)]
+    del xin, labin
+    free_ev = [None, None]
+    state = {"i": 0}
+
+    def e2e_step():
+        i = state["i"]
+        state["i"] += 1
+        xb, lb, eb = dbuf[i % 2]
+        with torch.cuda.stream(s_in):
+            if free_ev[i % 2] is not None:
+                s_in.wait_event(free_ev[i % 2])      # the step that last used this buffer set has finished
+            xb.copy_(hx, non_blocking=True)
+            lb.copy_(hlab, non_blocking=True)
+            eb.copy_(hemb, non_blocking=True)
+            ev_in = torch.cuda.Event()
+            ev_in.record(s_in)
+        s_cmp.wait_event(ev_in)
+        xd = xb.detach().requires_grad_(True)
+        ed = eb.detach().requires_grad_(True)
+        loss = mod(step_t, ed if use_emb is not None else None, None, xd, lb)
+        loss.backward()
+        ev_cmp = torch.cuda.Event()
+        ev_cmp.record(s_cmp)
+        free_ev[i % 2] = ev_cmp
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_cmp)
+            xd.grad.record_stream(s_out)
+            hgx.copy_(xd.grad, non_blocking=True)
+            if ed.grad is not None:
+                ed.grad.record_stream(s_out)
+                hge.copy_(ed.grad, non_blocking=True)
+            loss.record_stream(s_out)
+            hloss.copy_(loss.detach().reshape(1), non_blocking=True)   # device->host read of the step's result
+        return loss
+
+    def drain():
+        s_out.synchronize()
+        return float(hloss[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    e2e_step()
+    drain()
+    barrier()
+    k2 = max(2, min(steps, 10))
+    t0 = time.time()
+    for _ in range(k2):
+        e2e_step()
+    drain()                   # the last step's results are on the host
+    barrier()
+    t1 = time.time()
+    clk.mark(t0, t1)
+    # host-side clock: the region spans three streams and ends when the last D2H copy has landed
+    el = torch.tensor([(t1 - t0) * 1e3 / k2], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    h2d = hx.numel() * hx.element_size() + hlab.numel() * hlab.element_size() + hemb.numel() * hemb.element_size()
+    d2h = hgx.numel() * hgx.element_size() + hge.numel() * hge.element_size() + 4
+    what = ("logits at the head's resolution [B,C,H/4,W/4] (upsampled inside the op as train.py:282-284 does outside) "
+            "and uint8 labels; gradients return at H/4" if low_res else
+            "full-resolution logits and int64 labels (the reference's own tensors)")
+    return {"value": world * px / (float(el.item()) * 1e-3) / 1e9, "unit": "Gpix/s",
+            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": float(el.item()),
+            "steps": k2, "inputs": what,
+            "note": "pinned host buffers -> H2D -> fwd+bwd -> D2H of loss and gradients, every step; copies of "
+                    "neighbouring steps overlap the kernels (3 streams); wall clock around the loop incl. the final drain"}
+
 
 # ------------------------------------------------------------------------------------------------
 # end-to-end train throughput (the loss inside a segmentation training step; network = context)
 # ------------------------------------------------------------------------------------------------
-def run_train(args, w):
+def _context_net(depth, c, dev):
+    """The network around the loss.  The reference's own ResNetBackbone + DepthwiseSeparableASPPContrastHead when the
+    reference can be imported on this box, else the equivalent context net of scripts/train_context.py."""
+    import torch
+    root = _reference_root()
+    if root is not None:
+        try:
+            sys.dont_write_bytecode = True
+            sys.path.insert(0, root)
+            from models.backbone.resnet import ResNetBackbone
+            from models.head.sep_aspp_contrast_head import DepthwiseSeparableASPPContrastHead
+
+            class RefNet(torch.nn.Module):
+                def __init__(self):
+                    super().__init__()
+                    self.backbone = ResNetBackbone(depth=depth, pretrained=False)
+                    self.head = DepthwiseSeparableASPPContrastHead(          # arguments of train.py:157-167
+                        in_channels=2048, c1_in_channels=256, c1_channels=48, aspp_channels=512,
+                        dilations=(1, 12, 24, 36), num_classes=c, proj_dim=256, proj_type="convmlp")
+
+                def forward(self, img):
+                    feats = self.backbone(img)
+                    logits, emb = self.head(list(feats))
+                    return logits, emb, feats[2]
+            net = RefNet().to(dev)
+            return net, "reference ResNetBackbone-%d + DepthwiseSeparableASPPContrastHead (imported unmodified)" % depth
+        except Exception:                    # noqa: BLE001
+            pass
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from train_context import ContextSegNet
+    return (ContextSegNet(depth, c).to(dev),
+            "context net: torchvision ResNet-%d (stride 32) + DeepLabV3+-style SepASPP head with projection branch "
+            "(scripts/train_context.py; the reference does not travel to this box)" % depth)
+
+
+def train_record(args, w, steps, brief=False):
+    """Whole training step of the config (network fwd/bwd on stock cuDNN, our loss fed with the head's H/4 logits and
+    uint8 labels, aux-head CE of train.py:309-313 through the fused kernel, SGD), DDP when world > 1."""
     import torch
     import torch.distributed as dist
     import torch.nn.functional as F
     import seghiero_b200 as sb
-    sys.path.insert(0, os.path.join(ROOT, "scripts"))
-    from train_context import ContextSegNet
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    rank, world, local, dev = _dist_env()
     torch.backends.cudnn.benchmark = True
     b, h, wd = args.batch or w["B"], w["H"], w["W"]
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -567,68 +776,79 @@ def run_train(args, w):
     else:
         c = w["nf"] + w["nc"]
         crit = sb.HieraTripletLoss(w["nf"], HM_19_7, HI_19_7)
-    net = ContextSegNet(w["depth"], c).to(dev).to(memory_format=torch.channels_last)
-    model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local]) if world > 1 else net
-    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
+    net, net_desc = _context_net(w["depth"], c, dev)
+    c3_ch = 1024 if w["depth"] >= 50 else 256
+
+    class TrainNet(torch.nn.Module):
+        """network + aux head (1x1 conv + BN + ReLU on c3, train.py:169-173) behind one forward, so that DDP sees one module"""
+
+        def __init__(self):
+            super().__init__()
+            self.net = net
+            self.aux = torch.nn.Sequential(torch.nn.Conv2d(c3_ch, w["nf"], 1, bias=False), torch.nn.BatchNorm2d(w["nf"]),
+                                           torch.nn.ReLU(inplace=True))
+
+        def forward(self, img_):
+            logits_, emb_, c3 = self.net(img_)
+            return logits_, emb_, self.aux(c3)
+    full = TrainNet().to(dev).to(memory_format=torch.channels_last)
+    model = torch.nn.parallel.DistributedDataParallel(full, device_ids=[local]) if world > 1 else full
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)      # train.py:239-246
     img = torch.randn(b, 3, h, wd, generator=g, device=dev).contiguous(memory_format=torch.channels_last)
-    lab = make_labels(torch, g, b, h, wd, w["nf"], args.labels, dev)
+    lab = make_labels(torch, g, b, h, wd, w["nf"], args.labels, dev).to(torch.uint8)
     step_t = torch.tensor([100000], device=dev)
     logit_dt = torch.float32 if w["dtype"] == "fp32" else torch.bfloat16
 
     def step(with_loss=True):
         opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            logits, emb = model(img)
-        full = F.interpolate(logits.to(logit_dt), size=(h, wd), mode="bilinear", align_corners=False)
+            logits, emb, aux_logits = model(img)
         if with_loss:
-            loss = crit(step_t, emb.float(), None, full, lab)
-        else:   # same graph without the hierarchical loss: what the rest of the step costs
-            loss = full.float().mean() + emb.float().mean()
+            # the head's logits go in as they are: the x4 upsample of train.py:282-284 happens inside the op, and the
+            # aux-head CE of train.py:309-313 reads the H/16 aux logits directly
+            loss = crit(step_t, emb.float(), None, logits.to(logit_dt), lab)
+            loss = loss + 0.4 * sb.aux_cross_entropy(aux_logits.float(), lab)
+        else:   # same graph without the two losses: what the rest of the step costs
+            loss = logits.float().mean() + emb.float().mean() + aux_logits.float().mean()
         loss.backward()
         opt.step()
         return loss
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(k, with_loss):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(k):
-            step(with_loss)
-        e1.record()
-        barrier()
-        t = torch.tensor([e0.elapsed_time(e1) / k], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    warmup, steps = max(args.warmup, 3), max(1, min(args.steps, 10))
+    warmup = 3
     clk = ClockSampler(local)
     clk.__enter__()
     for _ in range(warmup):
         step(True)
-    t0 = time.time()
-    ms = timed(steps, True)
-    clk.mark(t0, time.time())
+    ms, win, _ = _timed_steps(torch, dist, world, dev, lambda: step(True), steps)
+    clk.mark(*win)
     for _ in range(2):
         step(False)
-    ms_noloss = timed(steps, False)
+    ms_noloss, _, _ = _timed_steps(torch, dist, world, dev, lambda: step(False), max(2, steps // 2))
     clk.__exit__()
+    rec = {"metric": "train_throughput", "value": world * b / (ms * 1e-3), "unit": "img/s", "n_gpus": world,
+           "steps": steps, "warmup": warmup, "ms_per_step": ms, "batch_per_gpu": b,
+           "ms_per_step_without_hier_loss": ms_noloss, "hier_loss_share": max(0.0, 1.0 - ms_noloss / ms),
+           "network": net_desc + ", random init, bf16 autocast, stock cuDNN/ATen (context, not product)",
+           "loss_inputs": "head logits at H/4 (%s) + uint8 labels -> seghiero_b200 (upsample inside the op); aux-head CE "
+                          "from the H/16 aux logits through sh_aux_ce_fwdbwd" % w["dtype"],
+           "optimizer": "SGD momentum 0.9", "parallelism": f"DDP x{world}" if world > 1 else "single GPU",
+           "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
+    if not brief:
+        rec.update({"higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                    "dtype": "bf16 network / %s logits" % w["dtype"], "data": "synthetic",
+                    "config": {"workload": args.workload, "description": w["desc"], "labels": args.labels},
+                    "clocks": clk.summary()})
+    del model, full, opt, img
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_train(args, w):
+    import torch.distributed as dist
+    rank, world, _, _ = _dist_env()
+    rec = train_record(args, w, max(1, min(args.steps, 10)))
     if rank == 0:
-        print(json.dumps({
-            "metric": "train_throughput", "value": world * b / (ms * 1e-3), "unit": "img/s", "n_gpus": world,
-            "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16 network / %s logits" % w["dtype"], "data": "synthetic",
-            "config": {"workload": args.workload, "description": w["desc"], "labels": args.labels, "batch_per_gpu": b,
-                       "network": "torchvision ResNet-%d (stride 32) + DeepLabV3+-style SepASPP head, random init, "
-                                  "context only (stock cuDNN/ATen)" % w["depth"],
-                       "optimizer": "SGD momentum 0.9", "parallelism": f"DDP x{world}" if world > 1 else "single GPU"},
-            "ms_per_step_without_hier_loss": ms_noloss, "hier_loss_share": max(0.0, 1.0 - ms_noloss / ms),
-            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9, "clocks": clk.summary()}))
+        print(json.dumps(rec))
     if world > 1:
         dist.destroy_process_group()
 
@@ -644,8 +864,13 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--eager-gpu", action="store_true", help="also time the oracle restatement as eager ATen on the GPU")
+    ap.add_argument("--no-iid", action="store_true", help="skip the per-pixel-label sub-record")
+    ap.add_argument("--no-train", action="store_true", help="skip the train img/s sub-record")
+    ap.add_argument("--no-eager", action="store_true", help="skip the eager-ATen-on-this-GPU baseline")
+    ap.add_argument("--kernels-only", action="store_true", help="= --no-e2e --no-cpu --no-iid --no-train --no-eager")
     args = ap.parse_args()
+    if args.kernels_only:
+        args.no_e2e = args.no_cpu = args.no_iid = args.no_train = args.no_eager = True
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference_arm(args, w)

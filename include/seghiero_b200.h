@@ -10,7 +10,8 @@
  * a negative SH_ERR_* code for bad arguments, or a positive cudaError_t from the launch.
  *
  * dtype codes: 0 = float32, 1 = bfloat16, 2 = float16 (logits / embeddings / gradients).
- * Labels are int64 as in the reference; 255 is the ignore label.
+ * label_dtype codes: 0 = int64 (what the reference passes), 1 = int32, 2 = uint8 (1 byte per pixel instead of 8 from
+ * the dataloader to the loss: SURVEY section 8f row N4); 255 is the ignore label in every type.
  * Paths below are relative to the reference root.
  */
 #ifndef SEGHIERO_B200_H
@@ -23,19 +24,26 @@ extern "C" {
 /* ---- target builders (bit-exact integer gathers) ------------------------------------------- */
 
 /* Replaces _prepare_targets_two_level, models/loss/hiera_triplet_loss.py:11-38.
- * lut[t] = last bucket [start,end) containing t, else 255; labels outside [0,lut_size) -> 255. */
-int sh_targets_two_level(const long long* label, long long* coarse, long n, const int* lut, int lut_size,
+ * lut[t] = last bucket [start,end) containing t, else 255; labels outside [0,lut_size) -> 255.
+ * Outputs of the three builders have the element type of the input labels. */
+int sh_targets_two_level(const void* label, int label_dtype, void* coarse, long n, const int* lut, int lut_size,
                          void* stream);
 
 /* Replaces _prepare_targets_three_level, models/loss/rmi_hiera_triplet_loss.py:21-63.
  * mid = f2m[t], high = f2h[t] where t != 255 (negative t wraps like torch indexing); out-of-range
  * labels set *err_flag (the reference raises IndexError). */
-int sh_targets_three_level(const long long* label, long long* mid, long long* high, long n, const long long* f2m,
+int sh_targets_three_level(const void* label, int label_dtype, void* mid, void* high, long n, const long long* f2m,
                            const long long* f2h, int n_fine, int* err_flag, void* stream);
 
 /* Replaces the dataloader gather `map[fine_mask]`, dataset/dataloader.py:166-177 (no ignore handling). */
-int sh_targets_gather(const long long* label, long long* out, long n, const long long* map, int map_size,
+int sh_targets_gather(const void* label, int label_dtype, void* out, long n, const long long* map, int map_size,
                       int* err_flag, void* stream);
+
+/* Replaces mask_to_color_image, infer.py:117-131 (a per-pixel interpreted loop there): class-id mask [n] ->
+ * RGB bytes [n][3].  palette = n_colors x 3 bytes; negative ids are black; ids >= n_colors (IndexError in the
+ * reference) set *err_flag. */
+int sh_colorize(const void* mask, int label_dtype, long n, const unsigned char* palette, int n_colors,
+                unsigned char* rgb, int* err_flag, void* stream);
 
 /* ---- decode --------------------------------------------------------------------------------- */
 
@@ -44,7 +52,7 @@ int sh_targets_gather(const long long* label, long long* out, long n, const long
  * [n0+n1,n0+n1+n2) (n1/n2 may be 0).  Outputs int64 (or uint8 when out_is_u8) [B,HW]; first max
  * wins, NaN counts as max.  If label != NULL, counts[0] += #correct fine, counts[1] += #valid. */
 int sh_decode(const void* logits, int dtype, int B, int C, long HW, int n0, int n1, int n2, void* out0, void* out1,
-              void* out2, int out_is_u8, const long long* label, unsigned long long* counts, void* stream);
+              void* out2, int out_is_u8, const void* label, int label_dtype, unsigned long long* counts, void* stream);
 
 /* ---- two-level loss: HieraTripletLoss.forward, models/loss/hiera_triplet_loss.py:152-211 ---- */
 
@@ -60,7 +68,7 @@ int sh_bce2_grid(int B, long HW, int C, int n_coarse);
  * stages: bit 0 = label prep, bit 1 = fused loss kernel, bit 2 = reduction of the per-CTA partials; bit 8 (256)
  * is a hint from the host table builder that the buckets are disjoint ranges (no fine class in two buckets,
  * hierarchy.py::two_level_is_tree): the tree-order kernel k_bce2_fast runs then, else the any-bucket kernel. */
-int sh_bce2_fwdbwd(const void* logits, int dtype, const long long* label, void* grad, int B, long HW, int n_fine,
+int sh_bce2_fwdbwd(const void* logits, int dtype, const void* label, int label_dtype, void* grad, int B, long HW, int n_fine,
                    int n_coarse, const int* hier_tab, int n_fb, int lut_size, float eps, float loss_weight,
                    unsigned char* lab8, unsigned long long* counts, float* partials, double* sums, int stages,
                    void* stream);
@@ -93,7 +101,7 @@ int sh_rmi3_fast_path(const void* logits, const void* grad, int dtype, int H, in
  * sh_loss3_final need in `workspace`.
  * hier_tab (device int32): [f2m nf][f2h nf][mh_ptr nm+1][mh_idx n_mh][hsmask nm][order C][fast_order C][fast_aux C]
  * (seghiero_b200/hierarchy.py::three_level_tables). */
-int sh_rmi3_forward(const void* logits, int dtype, const long long* label, int B, int H, int W, int nf, int nm, int nh,
+int sh_rmi3_forward(const void* logits, int dtype, const void* label, int label_dtype, int B, int H, int W, int nf, int nm, int nh,
                     const int* hier_tab, int n_mh, int fast_tab_ok, float lam, float loss_weight, void* workspace,
                     int stages, void* stream);
 
@@ -114,7 +122,7 @@ int sh_rmi3_backward(const void* logits, int dtype, void* grad, int B, int H, in
  * tab: mode 0 -> [bucket_lo ncls][bucket_hi ncls]; mode 1 -> group per label value [256] (0/1/-1), ncls = 256.
  * Workspaces: lab_ds [B*h*w] int32, sel [ncls*3*max_triplet] int32, kcount [ncls] int32, tl [ncls*max_triplet] f32.
  * Outputs: trip[0] = loss, trip[1] = #contributing classes; status[0] = ready, status[1] = label error. */
-int sh_triplet_forward(const void* feats, int dtype, const long long* label, int B, int D, int h, int w, int H, int W,
+int sh_triplet_forward(const void* feats, int dtype, const void* label, int label_dtype, int B, int D, int h, int w, int H, int W,
                        int mode, const int* tab, int ncls, int max_triplet, int* lab_ds, int* sel, int* kcount,
                        float* tl, float* trip, int* status, void* stream);
 
@@ -122,6 +130,31 @@ int sh_triplet_forward(const void* feats, int dtype, const long long* label, int
 int sh_triplet_backward(const void* feats, int dtype, int B, int D, int h, int w, int ncls, int max_triplet,
                         const int* sel, const int* kcount, const float* tl, const float* trip, const float* tscale,
                         const float* gscale, float* gfeat, void* stream);
+
+/* ---- upsample-fused variants: the head's logits stay at their own resolution ---- */
+
+/* F.interpolate(x, size=(H, W), mode="bilinear", align_corners=False) of train.py:282-284 for `planes` = B*C planes
+ * [h, w] -> [H, W], same dtype; feeds the loss kernels when the caller hands the head's H/4 logits to the loss. */
+int sh_upsample_bilinear(const void* in, int dtype, void* out, long planes, int h, int w, int H, int W, void* stream);
+
+/* Exact adjoint of the above (deterministic gather): full-resolution gradient [planes, H, W] -> [planes, h, w]. */
+int sh_upsample_bilinear_adjoint(const void* gout, int dtype, void* gin, long planes, int h, int w, int H, int W,
+                                 void* stream);
+
+/* Aux-head loss of train.py:309-313: nn.CrossEntropyLoss(ignore_index=255)(F.interpolate(aux_logits, (H, W)), label)
+ * computed from the LOW-resolution aux logits [B, C, h, w] (any H, W), forward value and (grad != NULL) gradient w.r.t.
+ * the low-resolution logits in one fused kernel; no [B, C, H, W] tensor exists.  out_loss[0] = mean over valid pixels.
+ * grad_out: device scalar multiplied into the gradient (NULL = 1).  workspace: sh_aux_ce_workspace_bytes. */
+size_t sh_aux_ce_workspace_bytes(int B, int C, int h, int w);
+int sh_aux_ce_fwdbwd(const void* logits, int dtype, const void* label, int label_dtype, int B, int C, int h, int w, int H,
+                     int W, void* grad, const float* grad_out, float* out_loss, void* workspace, void* stream);
+
+/* Validation / inference decode of train.py:350-385 and infer.py:296-312 without the full-resolution logits: per-level
+ * argmax of the bilinearly upsampled logits + fine pixel-accuracy counts straight from [B, C, h, w], for H = 4h, W = 4w
+ * (the head's geometry); other sizes return SH_ERR_UNSUPPORTED (-2) and the host runs sh_upsample_bilinear + sh_decode. */
+int sh_decode_upsampled(const void* logits, int dtype, int B, int C, int h, int w, int H, int W, int n0, int n1, int n2,
+                        void* out0, void* out1, void* out2, int out_is_u8, const void* label, int label_dtype,
+                        unsigned long long* counts, void* stream);
 
 #ifdef __cplusplus
 }

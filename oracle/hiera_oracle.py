@@ -431,3 +431,62 @@ def pixel_accuracy_counts(pred, target, ignore_index=IGNORE):
     pred, target = np.asarray(pred), np.asarray(target)
     valid = target != ignore_index
     return int(((pred == target) & valid).sum()), int(valid.sum())
+
+
+# --------------------------------------------------------------------------- #
+# the callers either side of the loss
+# --------------------------------------------------------------------------- #
+def _bilinear_axis(n_in: int, n_out: int, device):
+    """Source rows and weights of F.interpolate(mode='bilinear', align_corners=False) along one axis, fp32 like ATen:
+    src = (in / out) * (dst + 0.5) - 0.5 clamped at 0; i0 = floor(src); i1 = i0 + (i0 < in - 1); l1 = src - i0."""
+    scale = np.float32(n_in) / np.float32(n_out)
+    dst = np.arange(n_out, dtype=np.float32)
+    src = np.maximum(scale * (dst + np.float32(0.5)) - np.float32(0.5), np.float32(0.0)).astype(np.float32)
+    i0 = np.minimum(src.astype(np.int64), n_in - 1)
+    i1 = i0 + (i0 < n_in - 1)
+    l1 = (src - i0.astype(np.float32)).astype(np.float32)
+    l0 = (np.float32(1.0) - l1).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).to(device)
+    return t(i0), t(i1), t(l0), t(l1)
+
+
+def interpolate_bilinear(x: torch.Tensor, size) -> torch.Tensor:
+    """F.interpolate(x, size=size, mode='bilinear', align_corners=False) as train.py:282-284, 309-312 and
+    infer.py:296-299 call it, restated with explicit gathers (differentiable; result in x's dtype)."""
+    hh, ww = int(size[0]), int(size[1])
+    y0, y1, h0, h1 = _bilinear_axis(x.shape[2], hh, x.device)
+    x0, x1, w0, w1 = _bilinear_axis(x.shape[3], ww, x.device)
+    xf = x.float()
+    top, bot = xf[:, :, y0, :], xf[:, :, y1, :]
+    h0, h1 = h0.view(1, 1, hh, 1), h1.view(1, 1, hh, 1)
+    w0, w1 = w0.view(1, 1, 1, ww), w1.view(1, 1, 1, ww)
+    out = h0 * (w0 * top[:, :, :, x0] + w1 * top[:, :, :, x1]) + h1 * (w0 * bot[:, :, :, x0] + w1 * bot[:, :, :, x1])
+    return out.to(x.dtype)
+
+
+def aux_cross_entropy(x_low: torch.Tensor, label) -> torch.Tensor:
+    """train.py:309-313: nn.CrossEntropyLoss(ignore_index=255) of the bilinearly upsampled aux logits
+    (mean over the NON-ignored pixels, unlike the loss modules' own CE wrapper)."""
+    lab = _as_long(label, x_low.device)
+    full = interpolate_bilinear(x_low, lab.shape[-2:]).float()
+    valid = lab != IGNORE
+    logp = torch.log_softmax(full, dim=1)
+    picked = _pick(logp, torch.where(valid, lab, torch.zeros_like(lab)))
+    return -(picked * valid).double().sum().float() / valid.sum().float()
+
+
+def argmax_decode_upsampled(x_low: torch.Tensor, level_sizes, size):
+    """train.py:345-352, 382-385 / infer.py:296-312: per-level argmax of the upsampled logits."""
+    return argmax_decode(interpolate_bilinear(x_low, size), level_sizes)
+
+
+def colorize(mask, colormap) -> np.ndarray:
+    """infer.py:117-131 (`mask_to_color_image`): negative ids black, others colormap[id]; [H,W] -> uint8 [H,W,3]."""
+    m = np.asarray(mask)
+    cm = np.asarray(colormap, dtype=np.uint8).reshape(-1, 3)
+    if m.size and m.max() >= len(cm):
+        raise IndexError("list index out of range")
+    out = np.zeros(m.shape + (3,), dtype=np.uint8)
+    pos = m >= 0
+    out[pos] = cm[m[pos]]
+    return out

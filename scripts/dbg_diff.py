@@ -2,13 +2,11 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.nn.functional as F
 import seghiero_b200 as sb
-from seghiero_b200 import ops
 from tests.util import F2H, F2M, blob_labels
 
 def run(x, lab, emb, fast):
-    ops.FAST_PATH["enabled"] = fast
     xc = x.clone().requires_grad_(True)
-    mod = sb.RMIHieraTripletLoss(19, 7, 2, torch.tensor(F2M), torch.tensor(F2H))
+    mod = sb.RMIHieraTripletLoss(19, 7, 2, torch.tensor(F2M), torch.tensor(F2H), fast_path=fast)
     loss = mod(torch.tensor([100000]).cuda(), emb, None, xc, lab)
     loss.backward()
     torch.cuda.synchronize()

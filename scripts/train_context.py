@@ -44,4 +44,4 @@ class ContextSegNet(nn.Module):
         low = self.low(feats[0])
         y = F.interpolate(y, size=low.shape[2:], mode="bilinear", align_corners=False)
         logits = self.cls(self.refine(torch.cat([y, low], dim=1)))            # [B, C, H/4, W/4]
-        return logits, emb
+        return logits, emb, feats[2]                                          # c3 (stride 16) feeds the aux head

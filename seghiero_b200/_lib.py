@@ -14,22 +14,28 @@ _p, _i, _l, _f, _d, _sz = C.c_void_p, C.c_int, C.c_long, C.c_float, C.c_double, 
 
 # name -> (restype, argtypes); mirrors include/seghiero_b200.h one to one
 SIGNATURES = {
-    "sh_targets_two_level": (_i, [_p, _p, _l, _p, _i, _p]),
-    "sh_targets_three_level": (_i, [_p, _p, _p, _l, _p, _p, _i, _p, _p]),
-    "sh_targets_gather": (_i, [_p, _p, _l, _p, _i, _p, _p]),
-    "sh_decode": (_i, [_p, _i, _i, _i, _l, _i, _i, _i, _p, _p, _p, _i, _p, _p, _p]),
+    "sh_targets_two_level": (_i, [_p, _i, _p, _l, _p, _i, _p]),
+    "sh_targets_three_level": (_i, [_p, _i, _p, _p, _l, _p, _p, _i, _p, _p]),
+    "sh_targets_gather": (_i, [_p, _i, _p, _l, _p, _i, _p, _p]),
+    "sh_colorize": (_i, [_p, _i, _l, _p, _i, _p, _p, _p]),
+    "sh_decode": (_i, [_p, _i, _i, _i, _l, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p]),
     "sh_bce2_grid": (_i, [_i, _l, _i, _i]),
-    "sh_bce2_fwdbwd": (_i, [_p, _i, _p, _p, _i, _l, _i, _i, _p, _i, _i, _f, _f, _p, _p, _p, _p, _i, _p]),
+    "sh_bce2_fwdbwd": (_i, [_p, _i, _p, _i, _p, _i, _l, _i, _i, _p, _i, _i, _f, _f, _p, _p, _p, _p, _i, _p]),
     "sh_loss2_final": (_i, [_p, _p, _i, _i, _d, _p, _d, _p, _p, _f, _p, _p]),
     "sh_scale_inplace": (_i, [_p, _i, _l, _p, _p]),
     "sh_rmi3_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "sh_rmi3_workspace_offsets": (_i, [_i, _i, _i, _i, _i, _i, _p]),
     "sh_rmi3_fast_path": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i]),
-    "sh_rmi3_forward": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _f, _f, _p, _i, _p]),
+    "sh_rmi3_forward": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _f, _f, _p, _i, _p]),
     "sh_loss3_final": (_i, [_i, _i, _i, _i, _i, _i, _p, _f, _p, _d, _p, _p, _f, _p, _p]),
     "sh_rmi3_backward": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _f, _p, _p, _i, _p]),
-    "sh_triplet_forward": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "sh_triplet_forward": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "sh_triplet_backward": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "sh_upsample_bilinear": (_i, [_p, _i, _p, _l, _i, _i, _i, _i, _p]),
+    "sh_upsample_bilinear_adjoint": (_i, [_p, _i, _p, _l, _i, _i, _i, _i, _p]),
+    "sh_aux_ce_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "sh_aux_ce_fwdbwd": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "sh_decode_upsampled": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p]),
 }
 
 _lib = None

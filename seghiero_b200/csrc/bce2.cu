@@ -29,13 +29,14 @@ struct Hier2 {
 
 // Label pre-pass: int64 -> uint8 labels, valid counts per level, range check.
 // counts[0]=#fine-valid, counts[1]=#coarse-valid, counts[2]=error flag.
-__global__ void __launch_bounds__(256) k_prep2(const long long* __restrict__ label, unsigned char* __restrict__ lab8,
+template <typename L>
+__global__ void __launch_bounds__(256) k_prep2(const L* __restrict__ label, unsigned char* __restrict__ lab8,
                                                long n, int nf, const int* __restrict__ lut, int lut_size,
                                                unsigned long long* __restrict__ counts) {
   long long nvf = 0, nvc = 0;
   bool bad = false;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    long long t = label[i];
+    const long long t = lab_ld(label, i);
     unsigned char o = SH_IGNORE;
     if (t != SH_IGNORE) {
       if (t >= 0 && t < nf) {
@@ -518,6 +519,8 @@ __global__ void k_loss2_final(const double* __restrict__ sums, const unsigned lo
   }
   loss *= loss_weight;
   if (counts[2] != 0) loss = __longlong_as_double(0x7ff8000000000000LL);  // out-of-range labels poison the loss
+  // a label the triplet tables do not know (the reference raises IndexError from hiera_map[ii]) poisons it too
+  if (ready != nullptr && ready[1] != 0) loss = __longlong_as_double(0x7ff8000000000000LL);
   out[0] = (float)loss;
   out[1] = (float)tscale;
 }
@@ -590,7 +593,7 @@ int sh_bce2_grid(int B, long HW, int C, int n_coarse) {
 
 // hier_tab: device int32 blob laid out as
 //   [bstart nc][bend nc][owner nf][fb_ptr nf+1][fb_idx n_fb][lut lut_size]
-int sh_bce2_fwdbwd(const void* logits, int dtype, const long long* label, void* grad /* nullable */, int B, long HW,
+int sh_bce2_fwdbwd(const void* logits, int dtype, const void* label, int label_dtype, void* grad /* nullable */, int B, long HW,
                    int n_fine, int n_coarse, const int* hier_tab, int n_fb, int lut_size, float eps, float loss_weight,
                    unsigned char* lab8 /* [B*HW] */, unsigned long long* counts /* [4], zeroed by callee */,
                    float* partials /* [grid*4] */, double* sums /* [4] */, int stages, void* stream) {
@@ -611,7 +614,9 @@ int sh_bce2_fwdbwd(const void* logits, int dtype, const long long* label, void* 
     const long n = (long)B * HW;
     long pb = (n + 255) / 256;
     if (pb > SH_NUM_SMS * 8L) pb = SH_NUM_SMS * 8L;
-    sh::k_prep2<<<(unsigned)pb, 256, 0, st>>>(label, lab8, n, n_fine, h.lut, lut_size, counts);
+    SH_LABEL_SWITCH(label_dtype, L, {
+      sh::k_prep2<L><<<(unsigned)pb, 256, 0, st>>>((const L*)label, lab8, n, n_fine, h.lut, lut_size, counts);
+    })
     SH_CHECK_LAUNCH();
   }
   const int grid = sh_bce2_grid(B, HW, n_fine + n_coarse, n_coarse);

@@ -13,6 +13,11 @@
 #define SH_DT_BF16 1
 #define SH_DT_F16 2
 
+// label element types accepted at the C ABI (the reference uses int64; uint8 / int32 cut the label traffic 8x / 2x)
+#define SH_LAB_I64 0
+#define SH_LAB_I32 1
+#define SH_LAB_U8 2
+
 #define SH_IGNORE 255
 #define SH_NUM_SMS 148
 
@@ -22,7 +27,63 @@
     if (e__ != cudaSuccess) return (int)e__;       \
   } while (0)
 
+// run `...` with the label element type bound to the name L; returns SH_ERR_BAD_ARG for an unknown code
+#define SH_LABEL_SWITCH(code, L, ...)                                   \
+  switch (code) {                                                       \
+    case SH_LAB_I64: { using L = long long; __VA_ARGS__; } break;       \
+    case SH_LAB_I32: { using L = int; __VA_ARGS__; } break;             \
+    case SH_LAB_U8: { using L = unsigned char; __VA_ARGS__; } break;    \
+    default: return SH_ERR_BAD_ARG;                                     \
+  }
+
 namespace sh {
+
+// labels of any accepted element type as int64 values (uint8 255 stays 255 = ignore; int32 sign-extends)
+template <typename L>
+__device__ __forceinline__ long long lab_ld(const L* p, long i) { return (long long)p[i]; }
+// two consecutive labels; `vec` = the pair is naturally aligned (one load)
+template <typename L>
+__device__ __forceinline__ void lab_ld2(const L* p, bool vec, long long& a, long long& b) {
+  if (sizeof(L) == 8) {
+    if (vec) { const longlong2 v = __ldg(reinterpret_cast<const longlong2*>(p)); a = v.x; b = v.y; return; }
+  } else if (sizeof(L) == 4) {
+    if (vec) { const int2 v = __ldg(reinterpret_cast<const int2*>(p)); a = v.x; b = v.y; return; }
+  } else {
+    if (vec) { const unsigned short v = __ldg(reinterpret_cast<const unsigned short*>(p)); a = v & 0xffu; b = v >> 8; return; }
+  }
+  a = (long long)p[0]; b = (long long)p[1];
+}
+// 16 bytes of labels = 16 / sizeof(L) values
+template <typename L>
+__device__ __forceinline__ void lab_ld16(const L* p, long long (&o)[16 / sizeof(L)]) {
+  const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+  const unsigned int w[4] = {r.x, r.y, r.z, r.w};
+  if (sizeof(L) == 8) {
+    o[0] = (long long)((unsigned long long)w[0] | ((unsigned long long)w[1] << 32));
+    o[1 % (16 / sizeof(L))] = (long long)((unsigned long long)w[2] | ((unsigned long long)w[3] << 32));
+  } else if (sizeof(L) == 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k % (16 / sizeof(L))] = (long long)(int)w[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) o[k % (16 / sizeof(L))] = (long long)((w[k >> 2] >> (8 * (k & 3))) & 0xffu);
+  }
+}
+template <typename L>
+__device__ __forceinline__ void lab_st16(L* p, const long long (&o)[16 / sizeof(L)]) {
+  unsigned int w[4] = {0u, 0u, 0u, 0u};
+  if (sizeof(L) == 8) {
+    w[0] = (unsigned int)o[0]; w[1] = (unsigned int)((unsigned long long)o[0] >> 32);
+    w[2] = (unsigned int)o[1 % (16 / sizeof(L))]; w[3] = (unsigned int)((unsigned long long)o[1 % (16 / sizeof(L))] >> 32);
+  } else if (sizeof(L) == 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = (unsigned int)o[k % (16 / sizeof(L))];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) w[k >> 2] |= ((unsigned int)o[k % (16 / sizeof(L))] & 0xffu) << (8 * (k & 3));
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;

@@ -71,7 +71,8 @@ constexpr int PTH2 = 32;         // tile height of k3f_prep
 
 constexpr int PREP_MULT = 4;     // CTAs of k3f_prep per persistent-CTA record (occupancy: the kernel is load-latency bound)
 
-__global__ void __launch_bounds__(256) k3f_prep(const long long* __restrict__ label, int B, int H, int W, FastHier hg,
+template <typename L>
+__global__ void __launch_bounds__(256) k3f_prep(const L* __restrict__ label, int B, int H, int W, FastHier hg,
                                                 Ws3 ws, int cpi, int lab_vec) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C = hg.nf + hg.nm + hg.nh;
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(256) k3f_prep(const long long* __restrict__ la
   const int b = blockIdx.x / cpb, j0 = blockIdx.x - b * cpb;
   const int tiles_x = (W + TW - 1) / TW, ntiles = tiles_x * ((H + PTH2 - 1) / PTH2);
   const long HW = (long)H * W;
-  const long long* lb = label + (long)b * HW;
+  const L* lb = label + (long)b * HW;
   unsigned char* lab8 = ws.lab8 + (long)b * HW;
   const int ty = tid >> 4, tx = (tid & 15) << 2;
   const int level_base[3] = {0, hg.nf, hg.nf + hg.nm};
@@ -104,16 +105,14 @@ __global__ void __launch_bounds__(256) k3f_prep(const long long* __restrict__ la
 #pragma unroll 1
   for (int tile = j0; tile < ntiles; tile += cpb) {
     const TileCoord tc = tile_coord(tile, tiles_x, PTH2);
-    longlong2 v[NIT];
+    struct { long long x, y; } v[NIT];
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
       const int e = tid + 256 * it, r = e / NP, j = (e - r * NP) * 2;
       const int y = tc.y0 + r, xx = tc.x0 - 2 + j;
-      v[it] = make_longlong2(-1, -1);                      // outside the image
+      v[it].x = v[it].y = -1;                              // outside the image
       if (e < NITEM && y < H && xx >= 0 && xx < W) {
-        const long long* p = lb + (long)y * W + xx;
-        if (lab_vec) v[it] = __ldg(reinterpret_cast<const longlong2*>(p));
-        else v[it] = make_longlong2(p[0], p[1]);
+        lab_ld2<L>(lb + (long)y * W + xx, lab_vec != 0, v[it].x, v[it].y);
       }
     }
 #pragma unroll

@@ -16,20 +16,21 @@ namespace sh {
 // ---------------------------------------------------------------------------------------------
 // k3_prep: tile 64x16, 256 threads, one thread = 4 consecutive pixels
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k3_prep(const long long* __restrict__ label, int B, int H, int W, Hier3 h,
+template <typename L>
+__global__ void __launch_bounds__(256) k3_prep(const L* __restrict__ label, int B, int H, int W, Hier3 h,
                                                unsigned char* __restrict__ lab8, unsigned char* __restrict__ flags,
                                                unsigned long long* __restrict__ counts) {
   constexpr int TH = 16;
   __shared__ __align__(8) unsigned char rl[3][TH + 4][kLabPitch];
   const int b = blockIdx.z, y0 = blockIdx.y * TH, x0 = blockIdx.x * kTW;
-  const long long* lb = label + (long)b * H * W;
+  const L* lb = label + (long)b * H * W;
   bool bad = false;
   for (int e = threadIdx.x; e < (TH + 4) * kPitch; e += 256) {
     const int r = e / kPitch, j = e - r * kPitch;
     const int y = y0 - 2 + r, x = x0 - 2 + j;
     unsigned char f = 0xff, m = 0xff, g = 0xff;
     if (y >= 0 && y < H && x >= 0 && x < W) {
-      const long long t = lb[(long)y * W + x];
+      const long long t = lab_ld(lb, (long)y * W + x);
       f = m = g = 0;  // void pixels are one-hot of class 0 at every level inside RMI
       if (t != SH_IGNORE) {
         if (t >= 0 && t < h.nf) { f = (unsigned char)t; m = (unsigned char)h.f2m[t]; g = (unsigned char)h.f2h[t]; }
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(256) k3_prep(const long long* __restrict__ lab
     const int nvalid = min(4, W - xg);
     for (int k = 0; k < nvalid; ++k) {
       const int x = xg + k;
-      const long long t = lb[(long)y * W + x];
+      const long long t = lab_ld(lb, (long)y * W + x);
       const bool valid = (t != SH_IGNORE);
       nv += valid;
       unsigned int fl = 0;
@@ -83,8 +84,10 @@ __global__ void __launch_bounds__(256) k3_prep(const long long* __restrict__ lab
     store4_u8(flags + off, fl4, nvalid, al);
   }
   nv = warp_sum(nv);
-  if ((threadIdx.x & 31) == 0 && nv) atomicAdd(counts, (unsigned long long)nv);
-  if (bad) atomicOr((unsigned int*)(counts + 2), 1u);
+  if (counts != nullptr) {        // null: a fast forward pass that already counted runs this kernel for the flags only
+    if ((threadIdx.x & 31) == 0 && nv) atomicAdd(counts, (unsigned long long)nv);
+    if (bad) atomicOr((unsigned int*)(counts + 2), 1u);
+  }
 }
 
 // Slow path of k3_pass1 (kept out of line so that its registers do not burden the streaming loop):
@@ -936,6 +939,9 @@ __global__ void __launch_bounds__(256) k3_loss(int B, int C, int nf, int nm, int
     }
     loss *= lw;
     if (ws.counts[2] != 0) loss = __longlong_as_double(0x7ff8000000000000LL);
+    // a present class in neither id list: the reference raises ValueError from list.remove; without a host
+    // sync the device-side equivalent is a poisoned loss (strict=True on the module turns it into the exception)
+    if (ready != nullptr && ready[1] != 0) loss = __longlong_as_double(0x7ff8000000000000LL);
     out[0] = (float)loss;
     out[1] = (float)tscale;
     out[2] = r;
@@ -979,8 +985,8 @@ bool fast_path_ok(const void* x, const void* grad, int elem, int H, int W, int n
   return true;
 }
 
-template <typename T>
-static int run_forward3_fast(const void* x, const long long* label, int B, int H, int W, const Hier3& h, const Ws3& ws,
+template <typename T, typename L>
+static int run_forward3_fast(const void* x, const L* label, int B, int H, int W, const Hier3& h, const Ws3& ws,
                              float* bandR, float* bandC, float eps, double scale, int stages, cudaStream_t st) {
   const int C = h.nf + h.nm + h.nh;
   const bool fast_bwd_ok = fast_bwd_smem(C, h.nf, h.nm, h.nh) <= 227 * 1024;
@@ -993,17 +999,17 @@ static int run_forward3_fast(const void* x, const long long* label, int B, int H
     // uint8 labels, #valid, range check and the label-label counts in one kernel; the per-pixel uniformity flags of
     // k3_prep are only read by the generic kernels
     const size_t smem = fast::prep_smem(C, h.nf);
-    cudaFuncSetAttribute(fast::k3f_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(fast::k3f_prep<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     e = cudaMemsetAsync(ws.llrec, 0, (size_t)grid * C * 16 * sizeof(unsigned int), st);
     if (e != cudaSuccess) return (int)e;
     e = cudaMemsetAsync(ws.strips, 0, (size_t)B * 2 * sizeof(unsigned int), st);
     if (e != cudaSuccess) return (int)e;
-    fast::k3f_prep<<<grid * fast::PREP_MULT, 256, smem, st>>>(label, B, H, W, fh, ws, cpi,
-                                                             (uintptr_t)label % 16 == 0 ? 1 : 0);
+    fast::k3f_prep<L><<<grid * fast::PREP_MULT, 256, smem, st>>>(label, B, H, W, fh, ws, cpi,
+                                                                (uintptr_t)label % 16 == 0 ? 1 : 0);
     SH_CHECK_LAUNCH();
     if (!fast_bwd_ok) {     // the backward pass will run the generic kernel, which wants the flags
       dim3 gp((W + kTW - 1) / kTW, (H + 15) / 16, B);
-      k3_prep<<<gp, 256, 0, st>>>(label, B, H, W, h, ws.lab8, ws.flags, ws.counts + 3);
+      k3_prep<L><<<gp, 256, 0, st>>>(label, B, H, W, h, ws.lab8, ws.flags, nullptr);
       SH_CHECK_LAUNCH();
     }
   }
@@ -1031,8 +1037,8 @@ static int run_forward3_fast(const void* x, const long long* label, int B, int H
   return SH_OK;
 }
 
-template <typename T>
-static int run_forward3(const void* x, const long long* label, int B, int H, int W, const Hier3& h, const Ws3& ws,
+template <typename T, typename L>
+static int run_forward3(const void* x, const L* label, int B, int H, int W, const Hier3& h, const Ws3& ws,
                         float* bandR, float* bandC, float eps, double scale, int stages, cudaStream_t st) {
   const int C = h.nf + h.nm + h.nh;
   if (stages & 1) {
@@ -1041,7 +1047,7 @@ static int run_forward3(const void* x, const long long* label, int B, int H, int
     e = cudaMemsetAsync(ws.strips, 0, (size_t)B * 2 * sizeof(unsigned int), st);
     if (e != cudaSuccess) return (int)e;
     dim3 gp((W + kTW - 1) / kTW, (H + 15) / 16, B);
-    k3_prep<<<gp, 256, 0, st>>>(label, B, H, W, h, ws.lab8, ws.flags, ws.counts);
+    k3_prep<L><<<gp, 256, 0, st>>>(label, B, H, W, h, ws.lab8, ws.flags, ws.counts);
     SH_CHECK_LAUNCH();
   }
   if (stages & 2) {
@@ -1095,7 +1101,7 @@ int sh_rmi3_fast_path(const void* logits, const void* grad, int dtype, int H, in
   return sh::fast_path_ok(logits, grad, dtype == SH_DT_F32 ? 4 : 2, H, W, nf, nm, nh, fast_tab_ok) ? 1 : 0;
 }
 
-int sh_rmi3_forward(const void* logits, int dtype, const long long* label, int B, int H, int W, int nf, int nm, int nh,
+int sh_rmi3_forward(const void* logits, int dtype, const void* label, int label_dtype, int B, int H, int W, int nf, int nm, int nh,
                     const int* hier_tab, int n_mh, int fast_tab_ok, float lam, float loss_weight, void* workspace,
                     int stages, void* stream) {
   if (B <= 0 || H < 8 || W < 8 || nf <= 0 || nm <= 0 || nh <= 0 || nf + nm + nh > 254 || nh > 32)
@@ -1108,9 +1114,9 @@ int sh_rmi3_forward(const void* logits, int dtype, const long long* label, int B
     const double sc = (double)lam * (double)loss_weight / (9.0 * B);
     cudaStream_t s2 = (cudaStream_t)stream;
     switch (dtype) {
-      case SH_DT_F32: return sh::run_forward3_fast<float>(logits, label, B, H, W, hf, wsf, bR, bC, 1e-6f, sc, stages, s2);
-      case SH_DT_BF16: return sh::run_forward3_fast<__nv_bfloat16>(logits, label, B, H, W, hf, wsf, bR, bC, 1e-6f, sc, stages, s2);
-      case SH_DT_F16: return sh::run_forward3_fast<__half>(logits, label, B, H, W, hf, wsf, bR, bC, 1e-6f, sc, stages, s2);
+      case SH_DT_F32: SH_LABEL_SWITCH(label_dtype, L, { return sh::run_forward3_fast<float, L>(logits, (const L*)label, B, H, W, hf, wsf, bR, bC, 1e-6f, sc, stages, s2); }) break;
+      case SH_DT_BF16: SH_LABEL_SWITCH(label_dtype, L, { return sh::run_forward3_fast<__nv_bfloat16, L>(logits, (const L*)label, B, H, W, hf, wsf, bR, bC, 1e-6f, sc, stages, s2); }) break;
+      case SH_DT_F16: SH_LABEL_SWITCH(label_dtype, L, { return sh::run_forward3_fast<__half, L>(logits, (const L*)label, B, H, W, hf, wsf, bR, bC, 1e-6f, sc, stages, s2); }) break;
     }
     return SH_ERR_UNSUPPORTED;
   }
@@ -1121,9 +1127,9 @@ int sh_rmi3_forward(const void* logits, int dtype, const long long* label, int B
   const double scale = (double)lam * (double)loss_weight / (9.0 * B);
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case SH_DT_F32: return sh::run_forward3<float>(logits, label, B, H, W, h, ws, bandR, bandC, 1e-6f, scale, stages, st);
-    case SH_DT_BF16: return sh::run_forward3<__nv_bfloat16>(logits, label, B, H, W, h, ws, bandR, bandC, 1e-6f, scale, stages, st);
-    case SH_DT_F16: return sh::run_forward3<__half>(logits, label, B, H, W, h, ws, bandR, bandC, 1e-6f, scale, stages, st);
+    case SH_DT_F32: SH_LABEL_SWITCH(label_dtype, L, { return sh::run_forward3<float, L>(logits, (const L*)label, B, H, W, h, ws, bandR, bandC, 1e-6f, scale, stages, st); }) break;
+    case SH_DT_BF16: SH_LABEL_SWITCH(label_dtype, L, { return sh::run_forward3<__nv_bfloat16, L>(logits, (const L*)label, B, H, W, h, ws, bandR, bandC, 1e-6f, scale, stages, st); }) break;
+    case SH_DT_F16: SH_LABEL_SWITCH(label_dtype, L, { return sh::run_forward3<__half, L>(logits, (const L*)label, B, H, W, h, ws, bandR, bandC, 1e-6f, scale, stages, st); }) break;
   }
   return SH_ERR_UNSUPPORTED;
 }

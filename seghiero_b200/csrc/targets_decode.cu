@@ -10,48 +10,111 @@ namespace sh {
 // :21-63 (gather with literal-255 passthrough), dataset/dataloader.py:166-177
 // (plain gather).  torch advanced indexing wraps negative indices, so do we.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_targets_two_level(const long long* __restrict__ label,
-                                                           long long* __restrict__ coarse, long n,
+// One thread = 16 bytes of labels (2 int64 / 4 int32 / 16 uint8) in, the same out; the scalar form takes tensors
+// that are not 16-byte aligned (e.g. a batch slice of an odd-sized image) and the tail.
+template <typename L, bool VEC>
+__global__ void __launch_bounds__(256) k_targets_two_level(const L* __restrict__ label, L* __restrict__ coarse, long n,
                                                            const int* __restrict__ lut, int lut_size) {
-  long i = (blockIdx.x * (long)blockDim.x + threadIdx.x) * 2;
-  const long stride = (long)gridDim.x * blockDim.x * 2;
+  constexpr int N = VEC ? 16 / (int)sizeof(L) : 1;
+  long i = (blockIdx.x * (long)blockDim.x + threadIdx.x) * N;
+  const long stride = (long)gridDim.x * blockDim.x * N;
   for (; i < n; i += stride) {
-    if (i + 1 < n) {
-      longlong2 t = *reinterpret_cast<const longlong2*>(label + i);
-      longlong2 o;
-      o.x = (t.x >= 0 && t.x < lut_size) ? lut[t.x] : SH_IGNORE;
-      o.y = (t.y >= 0 && t.y < lut_size) ? lut[t.y] : SH_IGNORE;
-      *reinterpret_cast<longlong2*>(coarse + i) = o;
+    if (VEC && i + N <= n) {
+      long long t[16 / sizeof(L)];
+      lab_ld16<L>(label + i, t);
+#pragma unroll
+      for (int k = 0; k < N; ++k) t[k] = (t[k] >= 0 && t[k] < lut_size) ? lut[t[k]] : SH_IGNORE;
+      lab_st16<L>(coarse + i, t);
     } else {
-      long long t = label[i];
-      coarse[i] = (t >= 0 && t < lut_size) ? lut[t] : SH_IGNORE;
+      for (long j = i; j < min(i + N, n); ++j) {
+        const long long t = lab_ld(label, j);
+        coarse[j] = (L)((t >= 0 && t < lut_size) ? lut[t] : SH_IGNORE);
+      }
     }
   }
 }
 
-// mode 0: three-level builder (255 passes through, two maps); mode 1: dataloader gather (one map, no passthrough)
-__global__ void __launch_bounds__(256) k_targets_gather(const long long* __restrict__ label,
-                                                        long long* __restrict__ out_a, long long* __restrict__ out_b,
-                                                        long n, const long long* __restrict__ map_a,
+// mode 0: three-level builder (255 passes through, two maps); mode 1: dataloader gather (one map, no passthrough).
+// Same vector form; the maps (a few hundred int64 at most) are copied to shared memory first.
+template <typename L, bool VEC>
+__global__ void __launch_bounds__(256) k_targets_gather(const L* __restrict__ label, L* __restrict__ out_a,
+                                                        L* __restrict__ out_b, long n,
+                                                        const long long* __restrict__ map_a,
                                                         const long long* __restrict__ map_b, int map_size,
                                                         int passthrough_255, int* __restrict__ err) {
-  long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  const long stride = (long)gridDim.x * blockDim.x;
+  extern __shared__ long long s_map[];          // [map_size] a, then [map_size] b
+  for (int i = threadIdx.x; i < map_size; i += blockDim.x) {
+    s_map[i] = map_a[i];
+    if (map_b) s_map[map_size + i] = map_b[i];
+  }
+  __syncthreads();
+  constexpr int N = VEC ? 16 / (int)sizeof(L) : 1;
+  long i = (blockIdx.x * (long)blockDim.x + threadIdx.x) * N;
+  const long stride = (long)gridDim.x * blockDim.x * N;
   bool bad = false;
-  for (; i < n; i += stride) {
-    long long t = label[i];
-    long long a = SH_IGNORE, b = SH_IGNORE;
+  auto one = [&](long long t, long long& a, long long& b) {
+    a = SH_IGNORE; b = SH_IGNORE;
     if (!(passthrough_255 && t == SH_IGNORE)) {
-      long long u = t < 0 ? t + map_size : t;
+      const long long u = t < 0 ? t + map_size : t;       // torch advanced indexing wraps negative indices
       if (u >= 0 && u < map_size) {
-        a = map_a[u];
-        if (map_b) b = map_b[u];
+        a = s_map[u];
+        if (map_b) b = s_map[map_size + u];
       } else {
         bad = true;
       }
     }
-    out_a[i] = a;
-    if (out_b) out_b[i] = b;
+  };
+  for (; i < n; i += stride) {
+    if (VEC && i + N <= n) {
+      long long t[16 / sizeof(L)], a[16 / sizeof(L)], b[16 / sizeof(L)];
+      lab_ld16<L>(label + i, t);
+#pragma unroll
+      for (int k = 0; k < N; ++k) one(t[k], a[k], b[k]);
+      lab_st16<L>(out_a + i, a);
+      if (out_b) lab_st16<L>(out_b + i, b);
+    } else {
+      for (long j = i; j < min(i + N, n); ++j) {
+        long long a, b;
+        one(lab_ld(label, j), a, b);
+        out_a[j] = (L)a;
+        if (out_b) out_b[j] = (L)b;
+      }
+    }
+  }
+  if (bad) atomicOr(err, 1);
+}
+
+// Class-id mask -> RGB image (infer.py:117-131, a per-pixel Python loop in the reference): negative ids are black,
+// ids >= n_colors raise IndexError there and set *err here.  One thread = 4 pixels = 12 output bytes (3 words).
+template <typename L>
+__global__ void __launch_bounds__(256) k_colorize(const L* __restrict__ mask, long n, const unsigned char* __restrict__ pal,
+                                                  int n_colors, unsigned char* __restrict__ rgb, int* __restrict__ err) {
+  extern __shared__ unsigned int s_pal[];       // packed r | g << 8 | b << 16
+  for (int i = threadIdx.x; i < n_colors; i += blockDim.x)
+    s_pal[i] = (unsigned int)pal[3 * i] | ((unsigned int)pal[3 * i + 1] << 8) | ((unsigned int)pal[3 * i + 2] << 16);
+  __syncthreads();
+  bool bad = false;
+  const bool al = ((uintptr_t)rgb & 3) == 0;
+  for (long q = blockIdx.x * (long)blockDim.x + threadIdx.x; 4 * q < n; q += (long)gridDim.x * blockDim.x) {
+    unsigned int c[4] = {0u, 0u, 0u, 0u};
+    const int m = (int)min(4L, n - 4 * q);
+    for (int k = 0; k < m; ++k) {
+      const long long t = lab_ld(mask, 4 * q + k);
+      if (t >= n_colors) bad = true;
+      else if (t >= 0) c[k] = s_pal[t];
+    }
+    if (m == 4 && al) {
+      unsigned int* o = reinterpret_cast<unsigned int*>(rgb + 12 * q);
+      o[0] = c[0] | (c[1] << 24);
+      o[1] = (c[1] >> 8) | (c[2] << 16);
+      o[2] = (c[2] >> 16) | (c[3] << 8);
+    } else {
+      for (int k = 0; k < m; ++k) {
+        rgb[12 * q + 3 * k] = (unsigned char)c[k];
+        rgb[12 * q + 3 * k + 1] = (unsigned char)(c[k] >> 8);
+        rgb[12 * q + 3 * k + 2] = (unsigned char)(c[k] >> 16);
+      }
+    }
   }
   if (bad) atomicOr(err, 1);
 }
@@ -61,10 +124,10 @@ __global__ void __launch_bounds__(256) k_targets_gather(const long long* __restr
 // first max wins, NaN counts as max (torch.argmax).  Optional fine-level pixel
 // accuracy counts (train.py:37-49, 382-385).  Logits are read exactly once.
 // ---------------------------------------------------------------------------
-template <typename T, int VEC, typename OutT>
+template <typename T, int VEC, typename OutT, typename L>
 __global__ void __launch_bounds__(256) k_decode(const T* __restrict__ x, int B, int C, long HW, int n0, int n1, int n2,
                                                 OutT* __restrict__ o0, OutT* __restrict__ o1, OutT* __restrict__ o2,
-                                                const long long* __restrict__ label,
+                                                const L* __restrict__ label,
                                                 unsigned long long* __restrict__ counts, int vec_ok) {
   const long groups_per_img = (HW + VEC - 1) / VEC;
   const long total = groups_per_img * B;
@@ -99,7 +162,7 @@ __global__ void __launch_bounds__(256) k_decode(const T* __restrict__ x, int B, 
         if (p + v < HW) {
           out[(long)b * HW + p + v] = (OutT)arg[v];
           if (lvl == 0 && label != nullptr) {
-            long long t = label[(long)b * HW + p + v];
+            const long long t = lab_ld(label, (long)b * HW + p + v);
             if (t != SH_IGNORE) { valid++; correct += (t == arg[v]); }
           }
         }
@@ -166,10 +229,10 @@ __device__ __forceinline__ void store_args<8, unsigned char>(unsigned char* dst,
   *reinterpret_cast<uint2*>(dst) = v;
 }
 
-template <typename T, int VEC, typename OutT>
+template <typename T, int VEC, typename OutT, typename L>
 __global__ void __launch_bounds__(256, 3) k_decode_vec(const T* __restrict__ x, int B, int C, long HW, int n0, int n1, int n2,
                                                     OutT* __restrict__ o0, OutT* __restrict__ o1, OutT* __restrict__ o2,
-                                                    const long long* __restrict__ label,
+                                                    const L* __restrict__ label,
                                                     unsigned long long* __restrict__ counts) {
   constexpr int DEPTH = 8;
   const long groups_per_img = HW / VEC;
@@ -214,7 +277,7 @@ __global__ void __launch_bounds__(256, 3) k_decode_vec(const T* __restrict__ x, 
           if (lvl == 0 && label != nullptr) {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-              const long long t = label[(long)b * HW + p + v];
+              const long long t = lab_ld(label, (long)b * HW + p + v);
               if (t != SH_IGNORE) { valid++; correct += (t == arg[v]); }
             }
           }
@@ -235,9 +298,9 @@ __global__ void __launch_bounds__(256, 3) k_decode_vec(const T* __restrict__ x, 
   }
 }
 
-template <typename T, typename OutT>
+template <typename T, typename OutT, typename L>
 static int launch_decode(const void* x, int B, int C, long HW, int n0, int n1, int n2, void* o0, void* o1, void* o2,
-                         const long long* label, unsigned long long* counts, cudaStream_t st) {
+                         const L* label, unsigned long long* counts, cudaStream_t st) {
   constexpr int VEC = sizeof(T) == 4 ? 4 : 8;  // 128-bit loads
   bool vec_ok = (HW % VEC == 0) && ((uintptr_t)x % (VEC * sizeof(T)) == 0);
   long groups = ((HW + VEC - 1) / VEC) * B;
@@ -246,12 +309,12 @@ static int launch_decode(const void* x, int B, int C, long HW, int n0, int n1, i
   if (blocks < 1) blocks = 1;
   const bool out_al = ((uintptr_t)o0 | (uintptr_t)o1 | (uintptr_t)o2) % 16 == 0;
   if (vec_ok && out_al && n0 > 0) {
-    k_decode_vec<T, VEC, OutT><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, B, C, HW, n0, n1, n2, (OutT*)o0, (OutT*)o1,
+    k_decode_vec<T, VEC, OutT, L><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, B, C, HW, n0, n1, n2, (OutT*)o0, (OutT*)o1,
                                                                   (OutT*)o2, label, counts);
     SH_CHECK_LAUNCH();
     return SH_OK;
   }
-  k_decode<T, VEC, OutT><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, B, C, HW, n0, n1, n2, (OutT*)o0, (OutT*)o1,
+  k_decode<T, VEC, OutT, L><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, B, C, HW, n0, n1, n2, (OutT*)o0, (OutT*)o1,
                                                             (OutT*)o2, label, counts, vec_ok ? 1 : 0);
   SH_CHECK_LAUNCH();
   return SH_OK;
@@ -261,50 +324,84 @@ static int launch_decode(const void* x, int B, int C, long HW, int n0, int n1, i
 
 extern "C" {
 
-int sh_targets_two_level(const long long* label, long long* coarse, long n, const int* lut, int lut_size,
+static long sh_stream_blocks(long items) {
+  long blocks = (items + 255) / 256;
+  if (blocks > SH_NUM_SMS * 16L) blocks = SH_NUM_SMS * 16L;
+  return blocks < 1 ? 1 : blocks;
+}
+
+int sh_targets_two_level(const void* label, int label_dtype, void* coarse, long n, const int* lut, int lut_size,
                          void* stream) {
   if (n <= 0) return SH_OK;
-  if (((uintptr_t)label | (uintptr_t)coarse) % 16) return SH_ERR_BAD_ARG;
-  long blocks = (n / 2 + 255) / 256;
-  if (blocks > SH_NUM_SMS * 16L) blocks = SH_NUM_SMS * 16L;
-  if (blocks < 1) blocks = 1;
-  sh::k_targets_two_level<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(label, coarse, n, lut, lut_size);
+  const bool al = (((uintptr_t)label | (uintptr_t)coarse) % 16) == 0;
+  SH_LABEL_SWITCH(label_dtype, L, {
+    constexpr int N = 16 / (int)sizeof(L);
+    if (al)
+      sh::k_targets_two_level<L, true><<<(unsigned)sh_stream_blocks((n + N - 1) / N), 256, 0, (cudaStream_t)stream>>>(
+          (const L*)label, (L*)coarse, n, lut, lut_size);
+    else
+      sh::k_targets_two_level<L, false><<<(unsigned)sh_stream_blocks(n), 256, 0, (cudaStream_t)stream>>>(
+          (const L*)label, (L*)coarse, n, lut, lut_size);
+  })
   SH_CHECK_LAUNCH();
   return SH_OK;
 }
 
-int sh_targets_three_level(const long long* label, long long* mid, long long* high, long n, const long long* f2m,
+static int sh_gather_launch(const void* label, int label_dtype, void* out_a, void* out_b, long n, const long long* map_a,
+                            const long long* map_b, int map_size, int passthrough, int* err_flag, cudaStream_t st) {
+  if (map_size <= 0 || map_size > 2048) return SH_ERR_BAD_ARG;
+  const bool al = (((uintptr_t)label | (uintptr_t)out_a | (uintptr_t)out_b) % 16) == 0;
+  const size_t smem = (size_t)map_size * 8 * (map_b ? 2 : 1);
+  SH_LABEL_SWITCH(label_dtype, L, {
+    constexpr int N = 16 / (int)sizeof(L);
+    if (al)
+      sh::k_targets_gather<L, true><<<(unsigned)sh_stream_blocks((n + N - 1) / N), 256, smem, st>>>(
+          (const L*)label, (L*)out_a, (L*)out_b, n, map_a, map_b, map_size, passthrough, err_flag);
+    else
+      sh::k_targets_gather<L, false><<<(unsigned)sh_stream_blocks(n), 256, smem, st>>>(
+          (const L*)label, (L*)out_a, (L*)out_b, n, map_a, map_b, map_size, passthrough, err_flag);
+  })
+  SH_CHECK_LAUNCH();
+  return SH_OK;
+}
+
+int sh_targets_three_level(const void* label, int label_dtype, void* mid, void* high, long n, const long long* f2m,
                            const long long* f2h, int n_fine, int* err_flag, void* stream) {
   if (n <= 0) return SH_OK;
-  long blocks = (n + 255) / 256;
-  if (blocks > SH_NUM_SMS * 16L) blocks = SH_NUM_SMS * 16L;
-  sh::k_targets_gather<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(label, mid, high, n, f2m, f2h, n_fine, 1,
-                                                                          err_flag);
-  SH_CHECK_LAUNCH();
-  return SH_OK;
+  return sh_gather_launch(label, label_dtype, mid, high, n, f2m, f2h, n_fine, 1, err_flag, (cudaStream_t)stream);
 }
 
-int sh_targets_gather(const long long* label, long long* out, long n, const long long* map, int map_size,
+int sh_targets_gather(const void* label, int label_dtype, void* out, long n, const long long* map, int map_size,
                       int* err_flag, void* stream) {
   if (n <= 0) return SH_OK;
-  long blocks = (n + 255) / 256;
-  if (blocks > SH_NUM_SMS * 16L) blocks = SH_NUM_SMS * 16L;
-  sh::k_targets_gather<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(label, out, nullptr, n, map, nullptr,
-                                                                          map_size, 0, err_flag);
+  return sh_gather_launch(label, label_dtype, out, nullptr, n, map, nullptr, map_size, 0, err_flag, (cudaStream_t)stream);
+}
+
+int sh_colorize(const void* mask, int label_dtype, long n, const unsigned char* palette, int n_colors,
+                unsigned char* rgb, int* err_flag, void* stream) {
+  if (n <= 0) return SH_OK;
+  if (n_colors <= 0 || n_colors > 4096) return SH_ERR_BAD_ARG;
+  SH_LABEL_SWITCH(label_dtype, L, {
+    sh::k_colorize<L><<<(unsigned)sh_stream_blocks((n + 3) / 4), 256, (size_t)n_colors * 4, (cudaStream_t)stream>>>(
+        (const L*)mask, n, palette, n_colors, rgb, err_flag);
+  })
   SH_CHECK_LAUNCH();
   return SH_OK;
 }
 
 int sh_decode(const void* logits, int dtype, int B, int C, long HW, int n0, int n1, int n2, void* out0, void* out1,
-              void* out2, int out_is_u8, const long long* label, unsigned long long* counts, void* stream) {
+              void* out2, int out_is_u8, const void* label, int label_dtype, unsigned long long* counts, void* stream) {
   if (B <= 0 || HW <= 0) return SH_OK;
   if (n0 + (n1 > 0 ? n1 : 0) + (n2 > 0 ? n2 : 0) > C) return SH_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-#define SH_DECODE_DISPATCH(T)                                                                                  \
-  return out_is_u8 ? sh::launch_decode<T, unsigned char>(logits, B, C, HW, n0, n1, n2, out0, out1, out2, label, \
-                                                         counts, st)                                            \
-                   : sh::launch_decode<T, long long>(logits, B, C, HW, n0, n1, n2, out0, out1, out2, label,     \
-                                                     counts, st)
+#define SH_DECODE_DISPATCH(T)                                                                                        \
+  SH_LABEL_SWITCH(label_dtype, L, {                                                                                  \
+    return out_is_u8 ? sh::launch_decode<T, unsigned char, L>(logits, B, C, HW, n0, n1, n2, out0, out1, out2,        \
+                                                              (const L*)label, counts, st)                           \
+                     : sh::launch_decode<T, long long, L>(logits, B, C, HW, n0, n1, n2, out0, out1, out2,            \
+                                                          (const L*)label, counts, st);                              \
+  })                                                                                                                 \
+  break
   switch (dtype) {
     case SH_DT_F32: SH_DECODE_DISPATCH(float);
     case SH_DT_BF16: SH_DECODE_DISPATCH(__nv_bfloat16);

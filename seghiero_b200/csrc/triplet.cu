@@ -13,7 +13,8 @@ __device__ __forceinline__ int nearest_src(int dst, float scale, int n_in) {
   return s < n_in - 1 ? s : n_in - 1;
 }
 
-__global__ void __launch_bounds__(256) k_trip_labels(const long long* __restrict__ label, int B, int H, int W, int h,
+template <typename L>
+__global__ void __launch_bounds__(256) k_trip_labels(const L* __restrict__ label, int B, int H, int W, int h,
                                                      int w, int mode, const int* __restrict__ tab, int ncls,
                                                      int* __restrict__ lab_ds, int* __restrict__ status) {
   const float sy = (float)H / (float)h, sx = (float)W / (float)w;
@@ -22,7 +23,7 @@ __global__ void __launch_bounds__(256) k_trip_labels(const long long* __restrict
   for (long r = blockIdx.x * (long)blockDim.x + threadIdx.x; r < R; r += (long)gridDim.x * blockDim.x) {
     const int b = (int)(r / (h * w)), rem = (int)(r - (long)b * h * w);
     const int i = rem / w, j = rem - i * w;
-    const long long t = label[((long)b * H + nearest_src(i, sy, H)) * W + nearest_src(j, sx, W)];
+    const long long t = lab_ld(label, ((long)b * H + nearest_src(i, sy, H)) * W + nearest_src(j, sx, W));
     int v = (t >= 0 && t < 0x7fffffff) ? (int)t : -1;
     if (mode == 0) { if (v != SH_IGNORE && (v < 0 || v >= ncls)) bad = true; }
     else { if (v != SH_IGNORE && v != 0 && (v < 0 || v >= 256 || tab[v] < 0)) bad = true; }
@@ -200,7 +201,7 @@ extern "C" {
 
 // tab (device int32): mode 0 -> [bucket_lo ncls][bucket_hi ncls]; mode 1 -> group id per label [256] (0/1, -1 = none)
 // status: [0] ready flag (#classes>0), [1] error flag (label outside the tables; the reference raises)
-int sh_triplet_forward(const void* feats, int dtype, const long long* label, int B, int D, int h, int w, int H, int W,
+int sh_triplet_forward(const void* feats, int dtype, const void* label, int label_dtype, int B, int D, int h, int w, int H, int W,
                        int mode, const int* tab, int ncls, int max_triplet, int* lab_ds, int* sel, int* kcount,
                        float* tl, float* trip, int* status, void* stream) {
   if (B <= 0 || D <= 0 || h <= 0 || w <= 0 || ncls <= 0 || max_triplet <= 0) return SH_ERR_BAD_ARG;
@@ -211,7 +212,9 @@ int sh_triplet_forward(const void* feats, int dtype, const long long* label, int
   if (e != cudaSuccess) return (int)e;
   long blocks = (R + 255) / 256;
   if (blocks > SH_NUM_SMS * 4L) blocks = SH_NUM_SMS * 4L;
-  sh::k_trip_labels<<<(unsigned)blocks, 256, 0, st>>>(label, B, H, W, h, w, mode, tab, ncls, lab_ds, status);
+  SH_LABEL_SWITCH(label_dtype, L, {
+    sh::k_trip_labels<L><<<(unsigned)blocks, 256, 0, st>>>((const L*)label, B, H, W, h, w, mode, tab, ncls, lab_ds, status);
+  })
   SH_CHECK_LAUNCH();
   sh::k_trip_select<<<ncls, 256, 0, st>>>(lab_ds, R, mode, tab, ncls, max_triplet, sel, kcount);
   SH_CHECK_LAUNCH();

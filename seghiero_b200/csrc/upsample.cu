@@ -1,0 +1,456 @@
+// Bilinear upsampling (align_corners=False) of the head's logits, its adjoint, and the two consumers that never
+// need the full-resolution tensor at all: the aux-head cross entropy (train.py:309-313) and the validation /
+// inference decode (train.py:350-385, infer.py:296-312).  SURVEY section 8f rows N1-N3.
+//
+// Arithmetic of F.interpolate(mode="bilinear", align_corners=False, size=(H, W)) as torch computes it on CUDA
+// (aten/src/ATen/native/cuda/UpSample.cuh, area_pixel_compute_source_index):
+//   scale = in / out (float);  src = scale * (dst + 0.5) - 0.5, clamped at 0;  i0 = (int)src;
+//   i1 = i0 + (i0 < in - 1);  l1 = src - i0;  l0 = 1 - l1
+//   val = h0 * (w0 * x[i0][j0] + w1 * x[i0][j1]) + h1 * (w0 * x[i1][j0] + w1 * x[i1][j1])
+// and the result is rounded to the tensor's dtype (bf16 / fp16 logits stay 16-bit, like the reference's tensors).
+#include "common.cuh"
+
+namespace sh {
+
+struct Lerp {
+  int i0, i1;
+  float l0, l1;
+};
+__device__ __forceinline__ Lerp lerp_src(int dst, float scale, int n_in) {
+  float src = scale * ((float)dst + 0.5f) - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  Lerp r;
+  r.i0 = min((int)src, n_in - 1);
+  r.i1 = r.i0 + (r.i0 < n_in - 1 ? 1 : 0);
+  r.l1 = src - (float)r.i0;
+  r.l0 = 1.0f - r.l1;
+  return r;
+}
+__device__ __forceinline__ float bilerp(float a, float b, float c, float d, float w0, float w1, float h0, float h1) {
+  return h0 * (w0 * a + w1 * b) + h1 * (w0 * c + w1 * d);
+}
+// what the value becomes when torch stores it in a tensor of type T
+template <typename T>
+__device__ __forceinline__ float round_as(float v) { return to_f32<T>(from_f32<T>(v)); }
+
+// ---------------------------------------------------------------------------------------------
+// N1, first form: the full-resolution logits are produced by our own kernel (one write of the tensor the loss
+// kernels stream), and the gradient comes back to the head's resolution through the exact adjoint.
+// Thread = 4 consecutive output pixels of one row (one 16 / 8 byte store).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_upsample(const T* __restrict__ in, T* __restrict__ out, long planes, int h, int w,
+                                                  int H, int W, int vec_ok) {
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+  const int W4 = (W + 3) >> 2;
+  const long total = planes * H * W4;
+  for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+    const int x4 = (int)(g % W4);
+    const long r = g / W4;
+    const int y = (int)(r % H);
+    const long p = r / H;
+    const Lerp ly = lerp_src(y, sy, h);
+    const T* r0 = in + (p * h + ly.i0) * w;
+    const T* r1 = in + (p * h + ly.i1) * w;
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int x = min(4 * x4 + k, W - 1);
+      const Lerp lx = lerp_src(x, sx, w);
+      v[k] = bilerp(to_f32<T>(__ldg(r0 + lx.i0)), to_f32<T>(__ldg(r0 + lx.i1)), to_f32<T>(__ldg(r1 + lx.i0)),
+                    to_f32<T>(__ldg(r1 + lx.i1)), lx.l0, lx.l1, ly.l0, ly.l1);
+    }
+    T* o = out + (p * H + y) * (long)W + 4 * x4;
+    if (vec_ok) {
+      VecIO<T, 4>::store(o, v);
+    } else {
+      for (int k = 0; k < 4 && 4 * x4 + k < W; ++k) o[k] = from_f32<T>(v[k]);
+    }
+  }
+}
+
+// Adjoint (what autograd does for F.interpolate, but as a gather: deterministic, no atomics): thread = one
+// low-resolution pixel; the contributing output rows / columns are those whose (i0, i1) of the forward formula hit it.
+template <typename T>
+__global__ void __launch_bounds__(256) k_upsample_adjoint(const T* __restrict__ gout, T* __restrict__ gin, long planes,
+                                                          int h, int w, int H, int W) {
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+  const float ry = (float)H / (float)h, rx = (float)W / (float)w;
+  const long total = planes * h * w;
+  for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+    const int X = (int)(g % w);
+    const long r = g / w;
+    const int Y = (int)(r % h);
+    const long p = r / h;
+    // candidate ranges (one pixel of slack on each side; the exact test is the forward formula itself)
+    const int ylo = max(0, (int)floorf(((float)Y - 0.5f) * ry - 0.5f) - 1);
+    const int yhi = min(H - 1, (int)ceilf(((float)Y + 1.5f) * ry - 0.5f) + 1);
+    const int xlo = max(0, (int)floorf(((float)X - 0.5f) * rx - 0.5f) - 1);
+    const int xhi = min(W - 1, (int)ceilf(((float)X + 1.5f) * rx - 0.5f) + 1);
+    const T* gp = gout + p * (long)H * W;
+    float acc = 0.f;
+    for (int y = ylo; y <= yhi; ++y) {
+      const Lerp ly = lerp_src(y, sy, h);
+      const float wy = (ly.i0 == Y ? ly.l0 : 0.f) + (ly.i1 == Y ? ly.l1 : 0.f);
+      if (wy == 0.f) continue;
+      float rowacc = 0.f;
+      for (int x = xlo; x <= xhi; ++x) {
+        const Lerp lx = lerp_src(x, sx, w);
+        const float wx = (lx.i0 == X ? lx.l0 : 0.f) + (lx.i1 == X ? lx.l1 : 0.f);
+        if (wx != 0.f) rowacc = fmaf(wx, to_f32<T>(__ldg(gp + (long)y * W + x)), rowacc);
+      }
+      acc = fmaf(wy, rowacc, acc);
+    }
+    gin[g] = from_f32<T>(acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// N2: aux-head loss  nn.CrossEntropyLoss(ignore_index=255)(F.interpolate(aux_logits, (H, W)), label)  and its
+// gradient w.r.t. the LOW-resolution aux logits, fused: nothing of size [B, C, H, W] is ever written.
+// CTA = 32 x 8 output tile; thread = one output pixel, channels in a loop (online log-sum-exp over the interpolated
+// logits, then softmax - one-hot scattered to the <= 4 source pixels through shared-memory accumulators that are
+// flushed to the low-resolution gradient once per CTA).  `gin` must be zeroed by the caller.
+// ---------------------------------------------------------------------------------------------
+constexpr int AUX_TW = 32, AUX_TH = 8;
+
+template <typename T, typename L>
+__global__ void __launch_bounds__(AUX_TW * AUX_TH) k_aux_ce(const T* __restrict__ in, const L* __restrict__ label,
+                                                           float* __restrict__ gin, int B, int C, int h, int w, int H,
+                                                           int W, int fh, int fw, double* __restrict__ sums) {
+  extern __shared__ float s_acc[];       // [C][fh][fw] gradient footprint of the tile at low resolution
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+  const int tiles_x = (W + AUX_TW - 1) / AUX_TW, tiles_y = (H + AUX_TH - 1) / AUX_TH;
+  const int tile = blockIdx.x % (tiles_x * tiles_y), b = blockIdx.x / (tiles_x * tiles_y);
+  const int ty0 = (tile / tiles_x) * AUX_TH, tx0 = (tile % tiles_x) * AUX_TW;
+  const int tid = threadIdx.x;
+  const int fsz = C * fh * fw;
+  for (int i = tid; i < fsz; i += AUX_TW * AUX_TH) s_acc[i] = 0.f;
+  // low-resolution origin of the tile's footprint
+  const int Y0 = lerp_src(ty0, sy, h).i0, X0 = lerp_src(tx0, sx, w).i0;
+  __syncthreads();
+  const int x = tx0 + (tid & (AUX_TW - 1)), y = ty0 + tid / AUX_TW;
+  float loss = 0.f;
+  int nvalid = 0;
+  if (x < W && y < H) {
+    const long long t = lab_ld(label, ((long)b * H + y) * W + x);
+    if (t != SH_IGNORE && t >= 0 && t < C) {
+      const Lerp ly = lerp_src(y, sy, h), lx = lerp_src(x, sx, w);
+      const T* base = in + (long)b * C * h * w;
+      const int o00 = ly.i0 * w + lx.i0, o01 = ly.i0 * w + lx.i1, o10 = ly.i1 * w + lx.i0, o11 = ly.i1 * w + lx.i1;
+      // pass 1: max and sum of exp (two sweeps over <= a few dozen channels, all L1 hits)
+      float mx = -INFINITY, xt = 0.f;
+      for (int c = 0; c < C; ++c) {
+        const T* pc = base + (long)c * h * w;
+        const float v = round_as<T>(bilerp(to_f32<T>(__ldg(pc + o00)), to_f32<T>(__ldg(pc + o01)),
+                                           to_f32<T>(__ldg(pc + o10)), to_f32<T>(__ldg(pc + o11)), lx.l0, lx.l1, ly.l0, ly.l1));
+        mx = fmaxf(mx, v);
+        if (c == (int)t) xt = v;
+      }
+      float se = 0.f;
+      for (int c = 0; c < C; ++c) {
+        const T* pc = base + (long)c * h * w;
+        const float v = round_as<T>(bilerp(to_f32<T>(__ldg(pc + o00)), to_f32<T>(__ldg(pc + o01)),
+                                           to_f32<T>(__ldg(pc + o10)), to_f32<T>(__ldg(pc + o11)), lx.l0, lx.l1, ly.l0, ly.l1));
+        se += ex2((v - mx) * kLog2e);
+      }
+      loss = (mx - xt) + lg2(se) * kLn2;
+      nvalid = 1;
+      if (gin != nullptr) {
+        const float inv = rcp(se);
+        const int a00 = ((ly.i0 - Y0) * fw + (lx.i0 - X0)), a01 = ((ly.i0 - Y0) * fw + (lx.i1 - X0));
+        const int a10 = ((ly.i1 - Y0) * fw + (lx.i0 - X0)), a11 = ((ly.i1 - Y0) * fw + (lx.i1 - X0));
+        const float w00 = ly.l0 * lx.l0, w01 = ly.l0 * lx.l1, w10 = ly.l1 * lx.l0, w11 = ly.l1 * lx.l1;
+        for (int c = 0; c < C; ++c) {
+          const T* pc = base + (long)c * h * w;
+          const float v = round_as<T>(bilerp(to_f32<T>(__ldg(pc + o00)), to_f32<T>(__ldg(pc + o01)),
+                                             to_f32<T>(__ldg(pc + o10)), to_f32<T>(__ldg(pc + o11)), lx.l0, lx.l1, ly.l0, ly.l1));
+          const float gq = ex2((v - mx) * kLog2e) * inv - (c == (int)t ? 1.f : 0.f);
+          float* a = s_acc + c * fh * fw;
+          atomicAdd(a + a00, w00 * gq);
+          if (w01 != 0.f) atomicAdd(a + a01, w01 * gq);
+          if (w10 != 0.f) atomicAdd(a + a10, w10 * gq);
+          if (w11 != 0.f) atomicAdd(a + a11, w11 * gq);
+        }
+      }
+    } else if (t != SH_IGNORE) {
+      nvalid = 0x10000;        // out-of-range label: the reference's cross_entropy asserts on the device
+    }
+  }
+  // CTA totals -> global (fp64 atomics: a few thousand per launch)
+  __shared__ float s_l[AUX_TW * AUX_TH / 32];
+  __shared__ int s_n[AUX_TW * AUX_TH / 32];
+  loss = warp_sum(loss);
+  nvalid = __reduce_add_sync(0xffffffffu, nvalid);
+  if ((tid & 31) == 0) { s_l[tid >> 5] = loss; s_n[tid >> 5] = nvalid; }
+  __syncthreads();
+  if (tid == 0) {
+    float l = 0.f;
+    int n = 0;
+    for (int q = 0; q < AUX_TW * AUX_TH / 32; ++q) { l += s_l[q]; n += s_n[q]; }
+    if (l != 0.f) atomicAdd(sums, (double)l);
+    if (n & 0xffff) atomicAdd(sums + 1, (double)(n & 0xffff));
+    if (n >> 16) atomicAdd(sums + 2, 1.0);
+  }
+  if (gin != nullptr) {
+    for (int i = tid; i < fsz; i += AUX_TW * AUX_TH) {
+      const float v = s_acc[i];
+      if (v == 0.f) continue;
+      const int c = i / (fh * fw), rem = i - c * fh * fw, fy = rem / fw, fx = rem - fy * fw;
+      const int Y = Y0 + fy, X = X0 + fx;
+      if (Y < h && X < w) atomicAdd(gin + (((long)b * C + c) * h + Y) * w + X, v);
+    }
+  }
+}
+
+// loss = sums[0] / sums[1] (NaN when nothing is valid, as torch), gradient scale = gscale / sums[1]
+template <typename T>
+__global__ void __launch_bounds__(256) k_aux_finish(const float* __restrict__ gacc, T* __restrict__ gin, long n,
+                                                    const double* __restrict__ sums, const float* __restrict__ gscale,
+                                                    float* __restrict__ out) {
+  const double nv = sums[1];
+  if (blockIdx.x == 0 && threadIdx.x == 0 && out != nullptr) {
+    double l = sums[0] / nv;
+    if (sums[2] != 0.0) l = __longlong_as_double(0x7ff8000000000000LL);
+    out[0] = (float)l;
+  }
+  if (gin == nullptr) return;
+  const float s = (float)((gscale ? (double)*gscale : 1.0) / nv);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    gin[i] = from_f32<T>(gacc[i] * s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// N3: decode straight from the head's H/4 logits (out = 4 x in exactly): per-level argmax of the interpolated
+// logits + fine pixel-accuracy counts, uint8 or int64 predictions.  Thread = 4 x 4 output block = the 16 pixels whose
+// sources are the 3 x 3 low-resolution neighbourhood around (Y, X): 9 loads per channel for 16 outputs.
+//   output row 4Y + j, j = 0..3: src = Y + (2j - 3) / 8  ->  rows (Y-1, Y) for j < 2, (Y, Y+1) for j >= 2, clamped
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_args4(long long* dst, const int (&a)[4]) {
+  __stcs(reinterpret_cast<longlong2*>(dst), make_longlong2(a[0], a[1]));
+  __stcs(reinterpret_cast<longlong2*>(dst) + 1, make_longlong2(a[2], a[3]));
+}
+__device__ __forceinline__ void store_args4(unsigned char* dst, const int (&a)[4]) {
+  *reinterpret_cast<unsigned int*>(dst) = (unsigned)a[0] | ((unsigned)a[1] << 8) | ((unsigned)a[2] << 16) | ((unsigned)a[3] << 24);
+}
+__device__ __forceinline__ float pick3(const float (&v)[3], int i) { return i == 0 ? v[0] : (i == 1 ? v[1] : v[2]); }
+
+template <typename T, typename OutT, typename L>
+__global__ void __launch_bounds__(128) k_decode_up4(const T* __restrict__ in, int B, int C, int h, int w, int n0, int n1,
+                                                    int n2, OutT* __restrict__ o0, OutT* __restrict__ o1,
+                                                    OutT* __restrict__ o2, const L* __restrict__ label,
+                                                    unsigned long long* __restrict__ counts) {
+  const int H = 4 * h, W = 4 * w;
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+  const long total = (long)B * h * w;
+  long long correct = 0, valid = 0;
+  for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+    const int X = (int)(g % w);
+    const long r = g / w;
+    const int Y = (int)(r % h), b = (int)(r / h);
+    // the forward formula gives the weights (identical numbers to the unfused path); away from row / column 0 the
+    // source rows of output row 4Y + j are (Y-1, Y) for j < 2 and (Y, Y+1) for j >= 2, the neighbourhood index is static
+    Lerp ly[4], lx[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { ly[j] = lerp_src(4 * Y + j, sy, h); lx[j] = lerp_src(4 * X + j, sx, w); }
+    const int ym = max(Y - 1, 0), yp = min(Y + 1, h - 1), xm = max(X - 1, 0), xp = min(X + 1, w - 1);
+    const bool stat = Y > 0 && X > 0;
+    const int roff[3] = {ym * w, Y * w, yp * w}, cols[3] = {xm, X, xp};
+    const T* base = in + (long)b * C * h * w;
+    float best[4][4];
+    int arg[4][4];
+    int lvl = 0, cbeg = 0;
+    const int e0 = n0, e1 = n0 + max(n1, 0), e2 = e1 + max(n2, 0);
+#pragma unroll 1
+    for (int c = 0; c < e2; ++c) {
+      const T* pc = base + (long)c * h * w;
+      float v[3][3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) v[a][q] = to_f32<T>(__ldg(pc + roff[a] + cols[q]));
+      float val[4][4];
+      if (stat) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            val[j][k] = bilerp(v[j >> 1][k >> 1], v[j >> 1][(k >> 1) + 1], v[(j >> 1) + 1][k >> 1],
+                               v[(j >> 1) + 1][(k >> 1) + 1], lx[k].l0, lx[k].l1, ly[j].l0, ly[j].l1);
+      } else {       // row 0 / column 0 of the low-resolution map: the clamped source index pairs (0, 1) with weight (1, 0)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r0 = ly[j].i0 == Y ? 1 : (ly[j].i0 < Y ? 0 : 2), r1 = ly[j].i1 == Y ? 1 : (ly[j].i1 < Y ? 0 : 2);
+          float top[3], bot[3];
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            top[q] = r0 == 0 ? v[0][q] : (r0 == 1 ? v[1][q] : v[2][q]);
+            bot[q] = r1 == 0 ? v[0][q] : (r1 == 1 ? v[1][q] : v[2][q]);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int c0 = lx[k].i0 == X ? 1 : (lx[k].i0 < X ? 0 : 2), c1 = lx[k].i1 == X ? 1 : (lx[k].i1 < X ? 0 : 2);
+            val[j][k] = bilerp(pick3(top, c0), pick3(top, c1), pick3(bot, c0), pick3(bot, c1), lx[k].l0, lx[k].l1,
+                               ly[j].l0, ly[j].l1);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float vv = round_as<T>(val[j][k]);
+          if (c == cbeg) { best[j][k] = vv; arg[j][k] = 0; }
+          else if ((vv > best[j][k]) || (vv != vv && best[j][k] == best[j][k])) { best[j][k] = vv; arg[j][k] = c - cbeg; }
+        }
+      const int lend = lvl == 0 ? e0 : (lvl == 1 ? e1 : e2);
+      if (c + 1 == lend) {
+        OutT* out = lvl == 0 ? o0 : (lvl == 1 ? o1 : o2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const long off = ((long)b * H + 4 * Y + j) * W + 4 * X;
+          if (out != nullptr) store_args4(out + off, arg[j]);
+          if (lvl == 0 && label != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const long long t = lab_ld(label, off + k);
+              if (t != SH_IGNORE) { valid++; correct += (t == arg[j][k]); }
+            }
+          }
+        }
+        cbeg = lend;
+        ++lvl;
+        while (lvl < 3 && (lvl == 1 ? e1 : e2) == cbeg) ++lvl;
+      }
+    }
+  }
+  if (label != nullptr && counts != nullptr) {
+    correct = warp_sum(correct);
+    valid = warp_sum(valid);
+    if ((threadIdx.x & 31) == 0 && valid) {
+      atomicAdd(counts, (unsigned long long)correct);
+      atomicAdd(counts + 1, (unsigned long long)valid);
+    }
+  }
+}
+
+}  // namespace sh
+
+extern "C" {
+
+static long sh_up_blocks(long items, int per) {
+  long blocks = (items + per - 1) / per;
+  if (blocks > SH_NUM_SMS * 16L) blocks = SH_NUM_SMS * 16L;
+  return blocks < 1 ? 1 : blocks;
+}
+
+int sh_upsample_bilinear(const void* in, int dtype, void* out, long planes, int h, int w, int H, int W, void* stream) {
+  if (planes <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return SH_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long items = planes * H * ((W + 3) / 4);
+#define SH_UP(T)                                                                                          \
+  {                                                                                                       \
+    const int vec_ok = (W % 4 == 0) && ((uintptr_t)out % (4 * sizeof(T)) == 0);                           \
+    sh::k_upsample<T><<<(unsigned)sh_up_blocks(items, 256), 256, 0, st>>>((const T*)in, (T*)out, planes, h, w, H, W, vec_ok); \
+  }                                                                                                       \
+  break
+  switch (dtype) {
+    case SH_DT_F32: SH_UP(float);
+    case SH_DT_BF16: SH_UP(__nv_bfloat16);
+    case SH_DT_F16: SH_UP(__half);
+    default: return SH_ERR_UNSUPPORTED;
+  }
+#undef SH_UP
+  SH_CHECK_LAUNCH();
+  return SH_OK;
+}
+
+int sh_upsample_bilinear_adjoint(const void* gout, int dtype, void* gin, long planes, int h, int w, int H, int W,
+                                 void* stream) {
+  if (planes <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return SH_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)sh_up_blocks(planes * h * w, 256);
+  switch (dtype) {
+    case SH_DT_F32: sh::k_upsample_adjoint<float><<<blocks, 256, 0, st>>>((const float*)gout, (float*)gin, planes, h, w, H, W); break;
+    case SH_DT_BF16: sh::k_upsample_adjoint<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)gout, (__nv_bfloat16*)gin, planes, h, w, H, W); break;
+    case SH_DT_F16: sh::k_upsample_adjoint<__half><<<blocks, 256, 0, st>>>((const __half*)gout, (__half*)gin, planes, h, w, H, W); break;
+    default: return SH_ERR_UNSUPPORTED;
+  }
+  SH_CHECK_LAUNCH();
+  return SH_OK;
+}
+
+// footprint (low-resolution pixels per axis) of an AUX_T-pixel output span
+static int sh_aux_footprint(int span, int n_in, int n_out) {
+  const int f = (int)(((long)span * n_in + n_out - 1) / n_out) + 3;
+  return f > n_in ? n_in : f;
+}
+
+size_t sh_aux_ce_workspace_bytes(int B, int C, int h, int w) { return (size_t)B * C * h * w * 4 + 64; }
+
+int sh_aux_ce_fwdbwd(const void* logits, int dtype, const void* label, int label_dtype, int B, int C, int h, int w, int H,
+                     int W, void* grad /* nullable, [B,C,h,w] */, const float* grad_out /* nullable */, float* out_loss,
+                     void* workspace, void* stream) {
+  if (B <= 0 || C <= 0 || C > 4096 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return SH_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* sums = (double*)workspace;                       // [0] loss sum, [1] #valid, [2] error flag
+  float* gacc = (float*)((unsigned char*)workspace + 64);  // fp32 accumulator of the low-resolution gradient
+  const long n = (long)B * C * h * w;
+  cudaError_t e = cudaMemsetAsync(workspace, 0, grad ? 64 + (size_t)n * 4 : 64, st);
+  if (e != cudaSuccess) return (int)e;
+  const int fh = sh_aux_footprint(sh::AUX_TH, h, H), fw = sh_aux_footprint(sh::AUX_TW, w, W);
+  const size_t smem = (size_t)C * fh * fw * 4;
+  if (smem > 200 * 1024) return SH_ERR_UNSUPPORTED;
+  const int tiles = ((W + sh::AUX_TW - 1) / sh::AUX_TW) * ((H + sh::AUX_TH - 1) / sh::AUX_TH);
+#define SH_AUX(T)                                                                                                  \
+  SH_LABEL_SWITCH(label_dtype, L, {                                                                                \
+    auto kern = sh::k_aux_ce<T, L>;                                                                                \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                            \
+    kern<<<B * tiles, sh::AUX_TW * sh::AUX_TH, smem, st>>>((const T*)logits, (const L*)label, grad ? gacc : nullptr, B, C, \
+                                                           h, w, H, W, fh, fw, sums);                              \
+  })                                                                                                               \
+  SH_CHECK_LAUNCH();                                                                                               \
+  sh::k_aux_finish<T><<<(unsigned)sh_up_blocks(grad ? n : 1, 256), 256, 0, st>>>(gacc, (T*)grad, n, sums, grad_out, out_loss); \
+  break
+  switch (dtype) {
+    case SH_DT_F32: SH_AUX(float);
+    case SH_DT_BF16: SH_AUX(__nv_bfloat16);
+    case SH_DT_F16: SH_AUX(__half);
+    default: return SH_ERR_UNSUPPORTED;
+  }
+#undef SH_AUX
+  SH_CHECK_LAUNCH();
+  return SH_OK;
+}
+
+int sh_decode_upsampled(const void* logits, int dtype, int B, int C, int h, int w, int H, int W, int n0, int n1, int n2,
+                        void* out0, void* out1, void* out2, int out_is_u8, const void* label, int label_dtype,
+                        unsigned long long* counts, void* stream) {
+  if (B <= 0 || h <= 0 || w <= 0) return SH_OK;
+  if (n0 <= 0 || n0 + (n1 > 0 ? n1 : 0) + (n2 > 0 ? n2 : 0) > C) return SH_ERR_BAD_ARG;
+  if (H != 4 * h || W != 4 * w) return SH_ERR_UNSUPPORTED;    // other sizes: sh_upsample_bilinear + sh_decode
+  if (((uintptr_t)out0 | (uintptr_t)out1 | (uintptr_t)out2) % (out_is_u8 ? 4 : 16)) return SH_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)sh_up_blocks((long)B * h * w, 128);
+#define SH_DU(T)                                                                                                   \
+  SH_LABEL_SWITCH(label_dtype, L, {                                                                                \
+    if (out_is_u8)                                                                                                 \
+      sh::k_decode_up4<T, unsigned char, L><<<blocks, 128, 0, st>>>((const T*)logits, B, C, h, w, n0, n1, n2,       \
+          (unsigned char*)out0, (unsigned char*)out1, (unsigned char*)out2, (const L*)label, counts);              \
+    else                                                                                                           \
+      sh::k_decode_up4<T, long long, L><<<blocks, 128, 0, st>>>((const T*)logits, B, C, h, w, n0, n1, n2,          \
+          (long long*)out0, (long long*)out1, (long long*)out2, (const L*)label, counts);                          \
+  })                                                                                                               \
+  break
+  switch (dtype) {
+    case SH_DT_F32: SH_DU(float);
+    case SH_DT_BF16: SH_DU(__nv_bfloat16);
+    case SH_DT_F16: SH_DU(__half);
+    default: return SH_ERR_UNSUPPORTED;
+  }
+#undef SH_DU
+  SH_CHECK_LAUNCH();
+  return SH_OK;
+}
+
+}  // extern "C"

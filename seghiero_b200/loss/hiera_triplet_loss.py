@@ -42,7 +42,7 @@ class HieraTripletLoss(nn.Module):
     """
 
     def __init__(self, num_classes: int, hiera_map: list, hiera_index: list, ignore_index: int = 255,
-                 use_sigmoid: bool = False, loss_weight: float = 1.0, strict: bool = False):
+                 use_sigmoid: bool = False, loss_weight: float = 1.0, strict: bool = False, fast_path: bool = True):
         super().__init__()
         if ignore_index != 255:
             raise ValueError("only ignore_index=255 is supported (the reference's builders hard-code 255)")
@@ -55,19 +55,30 @@ class HieraTripletLoss(nn.Module):
                                                hiera_index=hiera_index, ignore_index=ignore_index)
         self.loss_weight = loss_weight
         self.strict = strict
+        self.fast_path = fast_path      # False: run the any-bucket kernels even for tree-shaped hierarchies (tests)
         self.last_stats: dict = {}
+        if not ops.two_level_supported(int(num_classes), len(hiera_index), True):
+            raise ValueError(f"HieraTripletLoss on sm_100a: {int(num_classes) + len(hiera_index)} channels exceed the "
+                             "shared-memory tiling of the 2-level kernels (<= 64 channels for tree-shaped hierarchies, "
+                             "<= ~110 for overlapping buckets); use RMIHieraTripletLoss-style tiling or fewer classes")
 
     def forward(self, step, embedding, cls_score_before, cls_score, label, weight=None, **kwargs):
-        cfg = ops.Hier2Config(n_fine=int(self.num_classes), n_coarse=len(self.hiera_index),
-                              hiera_map=list(self.hiera_map), hiera_index=[list(r) for r in self.hiera_index],
-                              loss_weight=float(self.loss_weight))
-        self.last_stats = {}
+        """`cls_score` [B, n_fine+n_coarse, H, W] at the label's resolution as in the reference, or at the head's own
+        (e.g. H/4): it is then upsampled inside the op exactly like train.py:282-284 does outside
+        (F.interpolate(size=label.shape[-2:], mode="bilinear", align_corners=False)) and the gradient arrives at the
+        head's resolution.  `label` may be int64 (reference), int32 or uint8."""
         step_d = ops.step_tensor(step, cls_score.device)
-        loss = ops.HieraTriplet2Fn.apply(cls_score, embedding, label, step_d, cfg, self.last_stats)
+        want = cls_score.requires_grad and torch.is_grad_enabled()
+        index_flat = [int(v) for r in self.hiera_index for v in r]
+        out, _grad, counts, _sel, _kc, _tl, trip, status = ops.hier2_fwd(
+            cls_score, label, embedding, step_d, int(self.num_classes), [int(v) for v in self.hiera_map], index_flat,
+            float(self.loss_weight), 80000.0, bool(self.fast_path), want)
+        if not torch.compiler.is_compiling():
+            # detached: a live grad_fn here would keep the whole autograd graph of the call alive until the next one
+            self.last_stats = {"out": out.detach(), "counts": counts, "trip": trip, "status": status}
         if self.strict:
-            if int(self.last_stats["counts"][2].item()):
+            if int(counts[2].item()):
                 raise RuntimeError("Class values must be smaller than num_classes.")
-            st = self.last_stats.get("triplet")
-            if st is not None and int(st.status[1].item()):
+            if status.numel() and int(status[1].item()):
                 raise IndexError("label outside hiera_map in the triplet term")
-        return loss
+        return out[0]

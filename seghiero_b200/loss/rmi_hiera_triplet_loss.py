@@ -22,7 +22,7 @@ class RMIHieraTripletLoss(nn.Module):
     def __init__(self, n_fine: int, n_mid: int, n_high: int, fine_to_mid: torch.Tensor, fine_to_high: torch.Tensor,
                  rmi_radius: int = 3, rmi_pool_way: int = 0, rmi_pool_size: int = 3, rmi_pool_stride: int = 3,
                  loss_weight_lambda: float = 0.5, loss_weight: float = 1.0, ignore_index: int = 255,
-                 strict: bool = False):
+                 strict: bool = False, fast_path: bool = True):
         super().__init__()
         assert fine_to_mid.dtype == torch.long
         assert fine_to_high.dtype == torch.long
@@ -56,27 +56,41 @@ class RMIHieraTripletLoss(nn.Module):
                                             lower_ids=self.lower_ids, ignore_index=self.ignore_index)
         self.ce = FusedCrossEntropy(ignore_index)
         self.strict = strict
+        self.fast_path = fast_path      # False: run the generic kernels even for tree-shaped hierarchies (tests)
         self.last_stats: dict = {}
-        # validate once on the host (raises ValueError on out-of-range map entries)
-        H.three_level_tables(n_fine, n_mid, n_high, self.fine_to_mid.cpu().numpy(), self.fine_to_high.cpu().numpy())
+        # host copies of the maps (the kernels' tables are built from them once per device); validated here
+        # (raises ValueError on out-of-range map entries)
+        self._f2m = [int(v) for v in self.fine_to_mid.cpu().tolist()]
+        self._f2h = [int(v) for v in self.fine_to_high.cpu().tolist()]
+        H.three_level_tables(n_fine, n_mid, n_high, self._f2m, self._f2h)
 
     def forward(self, step, embedding, cls_score_before, cls_score, label, weight=None, **kwargs):
-        cfg = ops.Hier3Config(
-            n_fine=int(self.n_fine), n_mid=int(self.n_mid), n_high=int(self.n_high),
-            fine_to_mid=tuple(int(v) for v in self.fine_to_mid.tolist()),
-            fine_to_high=tuple(int(v) for v in self.fine_to_high.tolist()),
-            upper_ids=tuple(self.upper_ids), lower_ids=tuple(self.lower_ids),
-            lam=float(self.loss_weight_lambda), loss_weight=float(self.loss_weight),
-            total_steps=160000.0 if self.n_fine > 15 else 60000.0,
-            use_triplet=self.triplet_loss is not None)
-        self.last_stats = {}
+        """`cls_score` [B, n_fine+n_mid+n_high, H, W] at the label's resolution as in the reference, or at the head's
+        own (e.g. H/4): it is then upsampled inside the op exactly like train.py:282-284 does outside and the gradient
+        arrives at the head's resolution.  `label` may be int64 (reference), int32 or uint8."""
         step_d = ops.step_tensor(step, cls_score.device)
-        loss = ops.RMIHieraTriplet3Fn.apply(cls_score, embedding, label, step_d, cfg, self.last_stats)
+        use_triplet = self.triplet_loss is not None
+        out, ws, _xf, _sel, _kc, _tl, trip, status = ops.hier3_fwd(
+            cls_score, label, embedding, step_d, int(self.n_fine), int(self.n_mid), int(self.n_high), self._f2m,
+            self._f2h, [int(v) for v in self.upper_ids], [int(v) for v in self.lower_ids],
+            float(self.loss_weight_lambda), float(self.loss_weight), 160000.0 if self.n_fine > 15 else 60000.0,
+            bool(self.fast_path), use_triplet)
+        if not torch.compiler.is_compiling():
+            # detached: a live grad_fn here would keep the whole autograd graph of the call alive until the next one
+            self.last_stats = {"out": out.detach(), "trip": trip, "status": status}
         if self.strict:
-            ws = self.last_stats["workspace"]
             if int(ws[16:24].view(torch.int64).item()):
                 raise RuntimeError("Class values must be smaller than num_classes.")
-            st = self.last_stats.get("triplet")
-            if st is not None and int(st.status[1].item()):
+            if status.numel() and int(status[1].item()):
                 raise ValueError("list.remove(x): x not in list (label in neither upper_ids nor lower_ids)")
-        return loss
+        return out[0]
+
+    def uses_fast_path(self, cls_score, label) -> bool:
+        """Whether the warp-specialised / tiled kernels (not the generic ones) serve this call (diagnostics)."""
+        from .. import _lib
+        tab, n_mh, fast_ok = H.three_level_tables(self.n_fine, self.n_mid, self.n_high, self._f2m, self._f2h)
+        hh, ww = label.shape[-2:]
+        same = tuple(cls_score.shape[-2:]) == (hh, ww)
+        return bool(self.fast_path and _lib.load().sh_rmi3_fast_path(
+            ops._p(cls_score) if same else None, None, ops._dtype_code(cls_score), int(hh), int(ww), self.n_fine,
+            self.n_mid, self.n_high, int(fast_ok)))

@@ -4,7 +4,6 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .. import hierarchy as H
 from .. import ops
 
 
@@ -21,17 +20,12 @@ class TreeTripletLoss(nn.Module):
         self.lower_ids = lower_ids
 
     def forward(self, feats, labels=None, max_triplet=200):
-        ops._need_cuda(feats, labels)
-        key = ("t1", tuple(int(v) for v in self.upper_ids), tuple(int(v) for v in self.lower_ids))
-        tab, ncls = ops.device_table(key, lambda: H.triplet_tables_id_lists(self.upper_ids, self.lower_ids),
-                                     feats.device)
-        holder = {}
-        loss = ops.TripletFn.apply(feats, labels, 1, tab, ncls, int(max_triplet), holder)
-        st = holder["state"]
-        ready, err = (int(v) for v in st.status.tolist())
+        trip, status, _sel, _kc, _tl = ops.triplet_fwd(feats, labels, 1, [int(v) for v in self.upper_ids], [int(v) for v in self.lower_ids],
+                                                       int(max_triplet))
+        ready, err = (int(v) for v in status.tolist())
         if err:
             raise ValueError("list.remove(x): x not in list (label in neither upper_ids nor lower_ids)")
-        count = st.trip[1:2].to(torch.int64)
+        count = trip[1:2].to(torch.int64)
         if not ready:
             return None, count
-        return loss, count
+        return trip[0], count

@@ -4,7 +4,6 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .. import hierarchy as H
 from .. import ops
 
 
@@ -25,18 +24,12 @@ class TreeTripletLoss(nn.Module):
         self.hiera_index = hiera_index
 
     def forward(self, feats, labels=None, max_triplet=200):
-        ops._need_cuda(feats, labels)
-        key = ("t0", tuple(int(v) for v in self.hiera_map),
-               tuple(tuple(int(v) for v in r) for r in self.hiera_index))
-        tab, ncls = ops.device_table(key, lambda: H.triplet_tables_hierarchy(self.hiera_map, self.hiera_index),
-                                     feats.device)
-        holder = {}
-        loss = ops.TripletFn.apply(feats, labels, 0, tab, ncls, int(max_triplet), holder)
-        st = holder["state"]
-        ready, err = (int(v) for v in st.status.tolist())
+        trip, status, _sel, _kc, _tl = ops.triplet_fwd(feats, labels, 0, [int(v) for v in self.hiera_map], [int(v) for r in self.hiera_index for v in r],
+                                                       int(max_triplet))
+        ready, err = (int(v) for v in status.tolist())
         if err:
             raise IndexError("TreeTripletLoss: label outside [0, num_classes) (hiera_map lookup)")
-        count = st.trip[1:2].to(torch.int64)
+        count = trip[1:2].to(torch.int64)
         if not ready:
             return None, count
-        return loss, count
+        return trip[0], count

@@ -1,40 +1,58 @@
 """Host side of the C-ABI custom ops: tensor plumbing, workspaces and autograd glue.
 
-PyTorch is used for device memory, streams and autograd bookkeeping only; every
-computation is a kernel of libseghiero_b200.so.  Nothing here touches the host
-inside forward/backward (no .item(), no .tolist()): `step`, the `ready` gate and
+Every computation is a kernel of libseghiero_b200.so reached through ctypes (`_lib`); PyTorch is used for device
+memory, streams and autograd bookkeeping only.  The fused losses are registered torch custom ops
+(`torch.library.custom_op` + `register_autograd` + fake implementations, namespace `seghiero_b200`), so they are
+opaque, traceable nodes for `torch.compile(fullgraph=True)` and save their tensors through `save_for_backward`
+(in-place edits of the logits between forward and backward are detected by autograd's version counters).
+Nothing here touches the host inside forward/backward (no .item(), no .tolist()): `step`, the `ready` gate and
 `grad_output` stay on the device.
 """
 from __future__ import annotations
 
 import contextlib
 import ctypes
-from dataclasses import dataclass
-from typing import Optional, Sequence
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
-from torch.autograd.function import once_differentiable
+from torch import Tensor
 
 from . import _lib
 from . import hierarchy as H
 
 _DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+_LAB = {torch.int64: 0, torch.int32: 1, torch.uint8: 2}
 _table_cache: dict = {}
 
 # kernels launched per C-ABI call (per stage bit for the multi-kernel entry points); bench.py reads
 # LAUNCHES["n"] to report how many of OUR kernels ran inside its timed region
 _KERNELS = {
-    "sh_targets_two_level": 1, "sh_targets_three_level": 1, "sh_targets_gather": 1, "sh_decode": 1,
+    "sh_targets_two_level": 1, "sh_targets_three_level": 1, "sh_targets_gather": 1, "sh_decode": 1, "sh_colorize": 1,
     "sh_loss2_final": 1, "sh_loss3_final": 1, "sh_scale_inplace": 1, "sh_triplet_forward": 4,
-    "sh_triplet_backward": 1,
+    "sh_triplet_backward": 1, "sh_upsample_bilinear": 1, "sh_upsample_bilinear_adjoint": 1, "sh_aux_ce_fwdbwd": 2,
+    "sh_decode_upsampled": 1,
     ("sh_bce2_fwdbwd", 1): 1, ("sh_bce2_fwdbwd", 2): 1, ("sh_bce2_fwdbwd", 4): 1,
     ("sh_rmi3_forward", 1): 1, ("sh_rmi3_forward", 2): 1, ("sh_rmi3_forward", 4): 2, ("sh_rmi3_forward", 8): 2,
     ("sh_rmi3_backward", 1): 2, ("sh_rmi3_backward", 2): 1,
 }
 LAUNCHES = {"n": 0}
-FAST_PATH = {"enabled": True}   # tests flip this to cover the generic kernels on shapes the fast path would take
-STAGE_TIMER = None   # bench.py installs an object with start(name, bit) / stop(name, bit)
+
+
+class _Debug:
+    """Measurement hook, off in the product path: bench.py brackets single kernels of the multi-kernel entry points
+    with CUDA events through `stage_timing(timer)` (one C call per stage bit instead of one per entry point)."""
+    timer = None
+
+
+@contextlib.contextmanager
+def stage_timing(timer):
+    """`timer` has start(name, bit) / stop(name, bit); active inside the with-block only."""
+    prev, _Debug.timer = _Debug.timer, timer
+    try:
+        yield timer
+    finally:
+        _Debug.timer = prev
 
 
 def _call(name, *args):
@@ -42,10 +60,20 @@ def _call(name, *args):
     LAUNCHES["n"] += _KERNELS.get(name, 0)
 
 
+def _timed_call(name, *args):
+    """Single-kernel entry point that bench.py may want to see as a stage of its own."""
+    timer = _Debug.timer
+    if timer is not None:
+        timer.start(name, 0)
+    _call(name, *args)
+    if timer is not None:
+        timer.stop(name, 0)
+
+
 def _staged(name, bits, make_args):
     """Run a multi-kernel entry point.  Normally one C call with every stage bit set; with a stage
     timer installed, one call per stage so that each kernel can be bracketed by CUDA events."""
-    timer = STAGE_TIMER
+    timer = _Debug.timer
     if timer is None:
         _lib.call(name, *make_args(sum(bits)))
     else:
@@ -76,10 +104,13 @@ def _dtype_code(t: torch.Tensor) -> int:
     return _DT[t.dtype]
 
 
-def _labels(label: torch.Tensor) -> torch.Tensor:
-    if label.dtype != torch.int64:
+def _labels(label: torch.Tensor) -> Tuple[torch.Tensor, int]:
+    """Labels as the kernels read them: int64 (the reference's dtype), int32 or uint8 pass through untouched
+    (1 byte per pixel from the dataloader to the loss); any other integer type is widened."""
+    if label.dtype not in _LAB:
         label = label.long()
-    return label.contiguous()
+    label = label.contiguous()
+    return label, _LAB[label.dtype]
 
 
 def device_table(key, builder, device):
@@ -139,11 +170,33 @@ class _Fork:
 
 
 # ----------------------------------------------------------------------------------------------
-# targets / decode
+# targets / decode / colourise (integer outputs, no autograd)
 # ----------------------------------------------------------------------------------------------
+def build_fine_to_level_map(map_cfg, n_fine: int) -> torch.Tensor:
+    """Drop-in for dataset/dataloader.py:12-34: a list of [lbl] / [start, end] (inclusive) entries, one per level
+    class -> LongTensor [n_fine] mapping each fine id to its level id.  Same assertions and ValueErrors."""
+    mapping = [-1] * n_fine
+    for lvl, sub in enumerate(map_cfg):
+        if len(sub) == 1:
+            lbl = int(sub[0])
+            assert 0 <= lbl < n_fine, f"Label {lbl} outside [0..{n_fine-1}]"
+            mapping[lbl] = lvl
+        elif len(sub) == 2:
+            start, end = int(sub[0]), int(sub[1])
+            assert 0 <= start <= end < n_fine, f"Range [{start},{end}] invalid"
+            mapping[start:end + 1] = [lvl] * (end + 1 - start)
+        else:
+            raise ValueError(f"Each entry must be [lbl] or [start,end], got {sub}")
+    missing = [i for i, m in enumerate(mapping) if m < 0]
+    if missing:
+        raise ValueError(f"Fine‐labels not mapped: {missing}")
+    return torch.tensor(mapping, dtype=torch.long)
+
+
 def targets_two_level(label: torch.Tensor, hiera_index):
+    """hiera_triplet_loss.py:11-38.  The output has the dtype of `label` (int64 / int32 / uint8 without a copy)."""
     _need_cuda(label)
-    lab = _labels(label)
+    lab, lcode = _labels(label)
     key = ("lut2", tuple(tuple(int(v) for v in r) for r in hiera_index))
 
     def build():
@@ -157,315 +210,581 @@ def targets_two_level(label: torch.Tensor, hiera_index):
     (lut,) = device_table(key, build, lab.device)
     out = torch.empty_like(lab)
     with torch.cuda.device(lab.device):
-        _call("sh_targets_two_level", _p(lab), _p(out), lab.numel(), _p(lut), lut.numel(), _stream())
-    return out.to(label.dtype) if label.dtype != torch.int64 else out
+        _call("sh_targets_two_level", _p(lab), lcode, _p(out), lab.numel(), _p(lut), lut.numel(), _stream())
+    return out.to(label.dtype) if label.dtype != lab.dtype else out
 
 
 def targets_three_level(label: torch.Tensor, fine_to_mid: torch.Tensor, fine_to_high: torch.Tensor, check=True):
+    """rmi_hiera_triplet_loss.py:21-63 (255 passes through; out-of-range labels raise IndexError when `check`)."""
     _need_cuda(label)
-    lab = _labels(label)
+    lab, lcode = _labels(label)
     f2m = fine_to_mid.to(device=lab.device, dtype=torch.int64).contiguous()
     f2h = fine_to_high.to(device=lab.device, dtype=torch.int64).contiguous()
     mid, high = torch.empty_like(lab), torch.empty_like(lab)
     err = torch.zeros(1, dtype=torch.int32, device=lab.device)
     with torch.cuda.device(lab.device):
-        _call("sh_targets_three_level", _p(lab), _p(mid), _p(high), lab.numel(), _p(f2m), _p(f2h), f2m.numel(),
-                  _p(err), _stream())
+        _call("sh_targets_three_level", _p(lab), lcode, _p(mid), _p(high), lab.numel(), _p(f2m), _p(f2h), f2m.numel(),
+              _p(err), _stream())
     if check and int(err.item()):
         raise IndexError("fine label out of range for fine_to_mid / fine_to_high")
     return mid, high
 
 
 def targets_gather(fine_mask: torch.Tensor, level_map: torch.Tensor, check=True):
+    """`level_map[fine_mask]` of dataset/dataloader.py:166-177 on the GPU (no ignore handling: 255 raises IndexError
+    like the reference's gather unless the map has 256 entries)."""
     _need_cuda(fine_mask)
-    lab = _labels(fine_mask)
+    lab, lcode = _labels(fine_mask)
     m = level_map.to(device=lab.device, dtype=torch.int64).contiguous()
     out = torch.empty_like(lab)
     err = torch.zeros(1, dtype=torch.int32, device=lab.device)
     with torch.cuda.device(lab.device):
-        _call("sh_targets_gather", _p(lab), _p(out), lab.numel(), _p(m), m.numel(), _p(err), _stream())
+        _call("sh_targets_gather", _p(lab), lcode, _p(out), lab.numel(), _p(m), m.numel(), _p(err), _stream())
     if check and int(err.item()):
         raise IndexError("index out of range in target gather")
     return out
 
 
+def colorize(mask: torch.Tensor, colormap, check=True) -> torch.Tensor:
+    """GPU form of infer.py:117-131 (`mask_to_color_image`, a per-pixel Python loop in the reference): class-id mask
+    [..., H, W] (any integer dtype) + colormap (list of (r, g, b)) -> uint8 [..., H, W, 3].  Negative ids are black,
+    ids beyond the colormap raise IndexError."""
+    _need_cuda(mask)
+    m, lcode = _labels(mask)
+    pal = torch.as_tensor(np.asarray(colormap, dtype=np.uint8).reshape(-1, 3)).to(m.device)
+    out = torch.empty(tuple(m.shape) + (3,), dtype=torch.uint8, device=m.device)
+    err = torch.zeros(1, dtype=torch.int32, device=m.device)
+    with torch.cuda.device(m.device):
+        _call("sh_colorize", _p(m), lcode, m.numel(), _p(pal), pal.shape[0], _p(out), _p(err), _stream())
+    if check and int(err.item()):
+        raise IndexError("list index out of range (class id beyond the colormap)")
+    return out
+
+
 def hierarchical_argmax(logits: torch.Tensor, level_sizes: Sequence[int], label: Optional[torch.Tensor] = None,
-                        out_dtype=torch.int64):
+                        out_dtype=torch.int64, size: Optional[Sequence[int]] = None):
     """Per-level argmax over channel slices (+ fine pixel-accuracy counts when `label` is given).
-    Returns (list of [B,H,W] predictions, counts int64[2] = (#correct, #valid) or None)."""
+    Returns (list of [B,H,W] predictions, counts int64[2] = (#correct, #valid) or None).
+
+    `size=(H, W)` (or a `label` larger than the logits) decodes F.interpolate(logits, size, "bilinear",
+    align_corners=False) as train.py:345-352 / infer.py:296-312 do -- fused for the head's 4x geometry (the
+    full-resolution logits are never written), through our upsample kernel otherwise."""
     _need_cuda(logits)
     if out_dtype not in (torch.int64, torch.uint8):
         raise TypeError("out_dtype must be torch.int64 or torch.uint8")
     x = logits.contiguous()
-    b, c = x.shape[0], x.shape[1]
-    hw = x[0, 0].numel()
+    if x.dim() != 4:
+        raise ValueError("logits must be [B,C,H,W]")
+    b, c, h, w = x.shape
+    if size is None and label is not None and tuple(label.shape[-2:]) != (h, w):
+        size = tuple(label.shape[-2:])
+    hh, ww = (int(size[0]), int(size[1])) if size is not None else (h, w)
     sizes = [int(s) for s in level_sizes] + [0, 0]
     n0, n1, n2 = sizes[:3]
     if len(level_sizes) > 3 or n0 + n1 + n2 > c:
         raise ValueError("level_sizes must be <= 3 levels and fit the channel count")
-    outs = [torch.empty((b,) + tuple(x.shape[2:]), dtype=out_dtype, device=x.device) if n > 0 else None
-            for n in (n0, n1, n2)]
+    outs = [torch.empty((b, hh, ww), dtype=out_dtype, device=x.device) if n > 0 else None for n in (n0, n1, n2)]
     counts = None
-    lab = None
+    lab, lcode = None, 0
     if label is not None:
-        lab = _labels(label)
+        lab, lcode = _labels(label)
         counts = torch.zeros(2, dtype=torch.int64, device=x.device)
+    u8 = 1 if out_dtype == torch.uint8 else 0
     with torch.cuda.device(x.device):
-        _call("sh_decode", _p(x), _dtype_code(x), b, c, hw, n0, n1, n2, _p(outs[0]), _p(outs[1]), _p(outs[2]),
-                  1 if out_dtype == torch.uint8 else 0, _p(lab), _p(counts), _stream())
+        if (hh, ww) != (h, w):
+            lib = _lib.load()
+            rc = lib.sh_decode_upsampled(_p(x), _dtype_code(x), b, c, h, w, hh, ww, n0, n1, n2, _p(outs[0]), _p(outs[1]),
+                                         _p(outs[2]), u8, _p(lab), lcode, _p(counts), _stream())
+            if rc == 0:
+                LAUNCHES["n"] += 1
+                return [o for o in outs if o is not None], counts
+            if rc != -2:
+                _lib.check(rc, "sh_decode_upsampled")
+            full = torch.empty((b, c, hh, ww), dtype=x.dtype, device=x.device)
+            _call("sh_upsample_bilinear", _p(x), _dtype_code(x), _p(full), b * c, h, w, hh, ww, _stream())
+            x = full
+        _call("sh_decode", _p(x), _dtype_code(x), b, c, hh * ww, n0, n1, n2, _p(outs[0]), _p(outs[1]), _p(outs[2]),
+              u8, _p(lab), lcode, _p(counts), _stream())
     return [o for o in outs if o is not None], counts
 
 
 # ----------------------------------------------------------------------------------------------
-# triplet
+# shared pieces of the fused ops
 # ----------------------------------------------------------------------------------------------
-@dataclass
-class TripletState:
-    mode: int
-    ncls: int
-    max_triplet: int
-    dims: tuple
-    sel: torch.Tensor
-    kcount: torch.Tensor
-    tl: torch.Tensor
-    trip: torch.Tensor      # [loss, #classes] float32
-    status: torch.Tensor    # [ready, error] int32
-    lab_ds: torch.Tensor
+def _empty(dev, dtype=torch.float32):
+    return torch.empty(0, dtype=dtype, device=dev)
 
 
-def triplet_forward(feats: torch.Tensor, label: torch.Tensor, mode: int, tab: torch.Tensor, ncls: int,
-                    max_triplet: int = 200, fork: Optional[_Fork] = None, world_ready: bool = False) -> TripletState:
-    _need_cuda(feats, label)
+def _opt(t: Tensor) -> Optional[Tensor]:
+    return t if t.numel() else None
+
+
+def _upsampled(x: Tensor, hh: int, ww: int) -> Tensor:
+    """The head's logits at label resolution (train.py:282-284) when the caller passed them at their own."""
+    b, c, h, w = x.shape
+    if (h, w) == (hh, ww):
+        return x
+    full = torch.empty((b, c, hh, ww), dtype=x.dtype, device=x.device)
+    _timed_call("sh_upsample_bilinear", _p(x), _dtype_code(x), _p(full), b * c, h, w, hh, ww, _stream())
+    return full
+
+
+def _triplet_alloc(dev, rows: int, ncls: int, max_triplet: int):
+    return (torch.empty(rows, dtype=torch.int32, device=dev),                      # lab_ds
+            torch.empty(ncls * 3 * max_triplet, dtype=torch.int32, device=dev),    # sel
+            torch.empty(ncls, dtype=torch.int32, device=dev),                      # kcount
+            torch.empty(ncls * max_triplet, dtype=torch.float32, device=dev),      # tl
+            torch.empty(2, dtype=torch.float32, device=dev),                       # trip  [loss, #classes]
+            torch.empty(2, dtype=torch.int32, device=dev))                         # status [ready, error]
+
+
+def _triplet_forward(feats: Tensor, lab: Tensor, lcode: int, mode: int, tab: Tensor, ncls: int, max_triplet: int,
+                     fork: Optional[_Fork], world_ready: bool):
     b, d, h, w = feats.shape
-    hh, ww = label.shape[-2:]
-    dev = feats.device
-    rows = b * h * w
-    lab_ds = torch.empty(rows, dtype=torch.int32, device=dev)
-    sel = torch.empty(ncls * 3 * max_triplet, dtype=torch.int32, device=dev)
-    kcount = torch.empty(ncls, dtype=torch.int32, device=dev)
-    tl = torch.empty(ncls * max_triplet, dtype=torch.float32, device=dev)
-    trip = torch.empty(2, dtype=torch.float32, device=dev)
-    status = torch.empty(2, dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev), (fork if fork is not None else contextlib.nullcontext()):
-        _call("sh_triplet_forward", _p(feats), _dtype_code(feats), _p(label), b, d, h, w, hh, ww, mode, _p(tab),
-                  ncls, max_triplet, _p(lab_ds), _p(sel), _p(kcount), _p(tl), _p(trip), _p(status), _stream())
+    hh, ww = lab.shape[-2:]
+    lab_ds, sel, kcount, tl, trip, status = _triplet_alloc(feats.device, b * h * w, ncls, max_triplet)
+    with (fork if fork is not None else contextlib.nullcontext()):
+        _call("sh_triplet_forward", _p(feats), _dtype_code(feats), _p(lab), lcode, b, d, h, w, hh, ww, mode, _p(tab),
+              ncls, max_triplet, _p(lab_ds), _p(sel), _p(kcount), _p(tl), _p(trip), _p(status), _stream())
         if world_ready:
             _world_ready(status)      # on the side stream too: the all-reduce overlaps the loss kernels
-    return TripletState(mode, ncls, max_triplet, (b, d, h, w), sel, kcount, tl, trip, status, lab_ds)
+    return sel, kcount, tl, trip, status
 
 
-def triplet_backward(feats: torch.Tensor, st: TripletState, tscale: torch.Tensor,
-                     gscale: Optional[torch.Tensor], fork: Optional[_Fork] = None) -> torch.Tensor:
-    """fp32 gradient of the embedding; with a fork the caller joins and then converts (`_grad_as`)."""
-    b, d, h, w = st.dims
+def _triplet_backward(feats: Tensor, ncls: int, max_triplet: int, sel, kcount, tl, trip, tscale: Tensor,
+                      gscale: Tensor, fork: Optional[_Fork]) -> Tensor:
+    """fp32 gradient of the embedding (the caller joins the fork and converts to the embedding's dtype)."""
+    b, d, h, w = feats.shape
     gfeat = torch.empty((b, d, h, w), dtype=torch.float32, device=feats.device)
-    with torch.cuda.device(feats.device), (fork if fork is not None else contextlib.nullcontext()):
-        _call("sh_triplet_backward", _p(feats), _dtype_code(feats), b, d, h, w, st.ncls, st.max_triplet,
-                  _p(st.sel), _p(st.kcount), _p(st.tl), _p(st.trip), _p(tscale), _p(gscale), _p(gfeat), _stream())
-    return gfeat if fork is not None else _grad_as(gfeat, feats)
+    with (fork if fork is not None else contextlib.nullcontext()):
+        _call("sh_triplet_backward", _p(feats), _dtype_code(feats), b, d, h, w, ncls, max_triplet, _p(sel), _p(kcount),
+              _p(tl), _p(trip), _p(tscale), _p(gscale), _p(gfeat), _stream())
+    return gfeat
 
 
 def _grad_as(gfeat: torch.Tensor, feats: torch.Tensor) -> torch.Tensor:
     return gfeat if feats.dtype == torch.float32 else gfeat.to(feats.dtype)
 
 
-class TripletFn(torch.autograd.Function):
-    """Standalone triplet loss value (mean over classes); 0 when no class contributes."""
-
-    @staticmethod
-    def forward(ctx, feats, label, mode, tab, ncls, max_triplet, holder):
-        feats_c = feats.contiguous()
-        st = triplet_forward(feats_c, _labels(label), mode, tab, ncls, max_triplet)
-        holder["state"] = st
-        ctx.st = st
-        ctx.save_for_backward(feats_c)
-        return st.trip[0].clone()
-
-    @staticmethod
-    @once_differentiable
-    def backward(ctx, gout):
-        (feats,) = ctx.saved_tensors
-        one = torch.ones(1, dtype=torch.float32, device=feats.device)
-        g = gout.detach().to(torch.float32).reshape(1).contiguous()
-        return triplet_backward(feats, ctx.st, one, g), None, None, None, None, None, None
+def _gscale(g: Tensor) -> Tensor:
+    """grad_output of the loss vector -> the device scalar of its first entry (the loss)."""
+    return g.detach().reshape(-1)[:1].to(torch.float32).contiguous()
 
 
 # ----------------------------------------------------------------------------------------------
-# two-level fused loss
+# standalone triplet loss
 # ----------------------------------------------------------------------------------------------
-@dataclass
-class Hier2Config:
-    n_fine: int
-    n_coarse: int
-    hiera_map: list
-    hiera_index: list
-    loss_weight: float
-    total_steps: float = 80000.0
-    eps: float = 1e-8
+def _triplet_tab(mode: int, a: Sequence[int], bflat: Sequence[int], dev):
+    if mode == 0:
+        hi = tuple((int(bflat[2 * i]), int(bflat[2 * i + 1])) for i in range(len(bflat) // 2))
+        key = ("t0", tuple(int(v) for v in a), hi)
+        return device_table(key, lambda: H.triplet_tables_hierarchy(list(a), [list(r) for r in hi]), dev)
+    key = ("t1", tuple(int(v) for v in a), tuple(int(v) for v in bflat))
+    return device_table(key, lambda: H.triplet_tables_id_lists(list(a), list(bflat)), dev)
 
 
-class HieraTriplet2Fn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, cls_score, embedding, label, step_d, cfg: Hier2Config, stats: dict):
-        _need_cuda(cls_score, label, embedding)
-        x = cls_score.contiguous()
-        lab = _labels(label)
-        dev = x.device
-        b, c = x.shape[0], x.shape[1]
-        hw = x[0, 0].numel()
-        if c != cfg.n_fine + cfg.n_coarse:
-            raise ValueError(f"cls_score has {c} channels, expected n_fine+n_coarse={cfg.n_fine + cfg.n_coarse}")
-        if tuple(lab.shape) != (b,) + tuple(x.shape[2:]):
-            raise ValueError("label must be [B,H,W] matching cls_score")
-        key = ("h2", cfg.n_fine, tuple(tuple(int(v) for v in r) for r in cfg.hiera_index))
-        tab, n_fb, lut_size = device_table(key, lambda: H.two_level_tables(cfg.n_fine, cfg.hiera_index), dev)
+@torch.library.custom_op("seghiero_b200::triplet_fwd", mutates_args=())
+def triplet_fwd(feats: Tensor, label: Tensor, mode: int, list_a: List[int], list_b: List[int],
+                max_triplet: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """-> (trip [loss, #classes], status [ready, error], sel, kcount, tl).  mode 0: list_a = hiera_map, list_b =
+    flattened hiera_index (tree_triplet_loss.py:15-65); mode 1: upper_ids / lower_ids (rmi_tree_triplet_loss.py:14-70)."""
+    _need_cuda(feats, label)
+    with torch.cuda.device(feats.device):
+        tab, ncls = _triplet_tab(mode, list_a, list_b, feats.device)
+        lab, lcode = _labels(label)
+        sel, kcount, tl, trip, status = _triplet_forward(feats.contiguous(), lab, lcode, mode, tab, ncls, max_triplet,
+                                                         None, False)
+    return trip, status, sel, kcount, tl
 
-        st = None
+
+@triplet_fwd.register_fake
+def _(feats, label, mode, list_a, list_b, max_triplet):
+    ncls = len(list_a) if mode == 0 else 256
+    dev = feats.device
+    return (torch.empty(2, dtype=torch.float32, device=dev), torch.empty(2, dtype=torch.int32, device=dev),
+            torch.empty(ncls * 3 * max_triplet, dtype=torch.int32, device=dev),
+            torch.empty(ncls, dtype=torch.int32, device=dev),
+            torch.empty(ncls * max_triplet, dtype=torch.float32, device=dev))
+
+
+@torch.library.custom_op("seghiero_b200::triplet_bwd", mutates_args=())
+def triplet_bwd(gout: Tensor, feats: Tensor, sel: Tensor, kcount: Tensor, tl: Tensor, trip: Tensor, tscale: Tensor,
+                max_triplet: int) -> Tensor:
+    with torch.cuda.device(feats.device):
+        f = feats.contiguous()
+        g = _triplet_backward(f, kcount.numel(), max_triplet, sel, kcount, tl, trip, tscale, _gscale(gout), None)
+    return _grad_as(g, feats)
+
+
+@triplet_bwd.register_fake
+def _(gout, feats, sel, kcount, tl, trip, tscale, max_triplet):
+    return torch.empty_like(feats, memory_format=torch.contiguous_format)
+
+
+def _triplet_setup(ctx, inputs, output):
+    feats, _label, _mode, _a, _b, max_triplet = inputs
+    trip, status, sel, kcount, tl = output
+    ctx.save_for_backward(feats, sel, kcount, tl, trip)
+    ctx.max_triplet = max_triplet
+    ctx.mark_non_differentiable(status, sel, kcount, tl)
+
+
+def _triplet_backward_fn(ctx, g_trip, *_unused):
+    feats, sel, kcount, tl, trip = ctx.saved_tensors
+    one = torch.ones(1, dtype=torch.float32, device=feats.device)
+    return triplet_bwd(g_trip, feats, sel, kcount, tl, trip, one, ctx.max_triplet), None, None, None, None, None
+
+
+triplet_fwd.register_autograd(_triplet_backward_fn, setup_context=_triplet_setup)
+
+
+# ----------------------------------------------------------------------------------------------
+# two-level fused loss: HieraTripletLoss.forward, models/loss/hiera_triplet_loss.py:152-211
+# ----------------------------------------------------------------------------------------------
+def _hier2_tables(n_fine: int, index_flat: Sequence[int], dev):
+    hi = tuple((int(index_flat[2 * i]), int(index_flat[2 * i + 1])) for i in range(len(index_flat) // 2))
+    key = ("h2", n_fine, hi)
+    tab, n_fb, lut_size = device_table(key, lambda: H.two_level_tables(n_fine, [list(r) for r in hi]), dev)
+    return tab, n_fb, lut_size, H.two_level_is_tree(n_fine, [list(r) for r in hi]), hi
+
+
+def two_level_supported(n_fine: int, n_coarse: int, fast: bool) -> bool:
+    """Shared-memory limits of the 2-level kernels (csrc/bce2.cu): the tree-order kernel parks e^-x of <= 64 channels,
+    the any-bucket kernel parks sigmoid and e^x of every channel for 256 pixels."""
+    c = n_fine + n_coarse
+    return (fast and c <= 64) or (c * 256 * 8 + n_coarse * 256 <= 227 * 1024)
+
+
+@torch.library.custom_op("seghiero_b200::hier2_fwd", mutates_args=())
+def hier2_fwd(cls_score: Tensor, label: Tensor, embedding: Optional[Tensor], step: Tensor, n_fine: int,
+              hiera_map: List[int], hiera_index: List[int], loss_weight: float, total_steps: float, fast_path: bool,
+              want_grad: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """-> (out [loss, triplet scale, -, -], grad (for grad_output = 1; empty unless want_grad), counts [#valid fine,
+    #valid coarse, label error, -], sel, kcount, tl, trip, status).  `cls_score` may be at the label's resolution (the
+    reference's contract) or at the head's: it is then upsampled here and `grad` comes back at the head's resolution."""
+    _need_cuda(cls_score, label, embedding)
+    dev = cls_score.device
+    nc = len(hiera_index) // 2
+    x_in = cls_score.contiguous()
+    lab, lcode = _labels(label)
+    if x_in.dim() != 4 or lab.dim() != 3:
+        raise ValueError("cls_score must be [B,C,H,W] and label [B,H,W]")
+    b, c, h_in, w_in = x_in.shape
+    hh, ww = int(lab.shape[1]), int(lab.shape[2])
+    if c != n_fine + nc:
+        raise ValueError(f"cls_score has {c} channels, expected n_fine+n_coarse={n_fine + nc}")
+    if lab.shape[0] != b:
+        raise ValueError("label must be [B,H,W] with the batch size of cls_score")
+    with torch.cuda.device(dev):
+        tab, n_fb, lut_size, is_tree, hi = _hier2_tables(n_fine, hiera_index, dev)
+        tree = 256 if (fast_path and is_tree) else 0
+        if not two_level_supported(n_fine, nc, bool(tree)):
+            raise ValueError(f"HieraTripletLoss on sm_100a: {c} channels exceed the shared-memory tiling of the 2-level "
+                             "kernels (tree-shaped hierarchies: <= 64 channels; overlapping buckets: <= ~110)")
+        fork = None
         if embedding is not None:
-            tkey = ("t0", tuple(int(v) for v in cfg.hiera_map), key[2])
-            ttab, ncls = device_table(tkey, lambda: H.triplet_tables_hierarchy(cfg.hiera_map, cfg.hiera_index), dev)
-            emb = embedding.contiguous()
+            ttab, ncls = _triplet_tab(0, hiera_map, hiera_index, dev)
             fork = _Fork(dev)
-            st = triplet_forward(emb, lab, 0, ttab, ncls, fork=fork, world_ready=True)
-
-        want_grad = ctx.needs_input_grad[0]
-        grad = torch.empty_like(x) if want_grad else None
+            sel, kcount, tl, trip, status = _triplet_forward(embedding.contiguous(), lab, lcode, 0, ttab, ncls, 200,
+                                                             fork, True)
+        else:
+            sel, kcount, tl, trip, status = (_empty(dev, torch.int32), _empty(dev, torch.int32), _empty(dev),
+                                             _empty(dev), _empty(dev, torch.int32))
+        x = _upsampled(x_in, hh, ww)
+        hw = hh * ww
+        grad_full = torch.empty_like(x) if want_grad else None
         lab8 = torch.empty(b * hw, dtype=torch.uint8, device=dev)
         counts = torch.empty(4, dtype=torch.int64, device=dev)
-        with torch.cuda.device(dev):
-            grid = _lib.load().sh_bce2_grid(b, hw, c, cfg.n_coarse)
-            partials = torch.empty(grid * 4, dtype=torch.float32, device=dev)
-            sums = torch.empty(4, dtype=torch.float64, device=dev)
-            out = torch.empty(4, dtype=torch.float32, device=dev)
-            tree = 256 if (FAST_PATH["enabled"] and H.two_level_is_tree(cfg.n_fine, cfg.hiera_index)) else 0
-            _staged("sh_bce2_fwdbwd", (1, 2, 4), lambda st_bits: (
-                _p(x), _dtype_code(x), _p(lab), _p(grad), b, hw, cfg.n_fine, cfg.n_coarse, _p(tab), n_fb, lut_size,
-                cfg.eps, cfg.loss_weight, _p(lab8), _p(counts), _p(partials), _p(sums), st_bits | tree, _stream()))
-            if st is not None:
-                fork.join()
-            _call("sh_loss2_final", _p(sums), _p(counts), cfg.n_fine, cfg.n_coarse, float(b * hw), _p(step_d),
-                      cfg.total_steps, _p(st.trip) if st else None, _p(st.status) if st else None, cfg.loss_weight,
-                      _p(out), _stream())
-        stats.update(sums=sums, counts=counts, out=out, triplet=st,
-                     fast_path=bool(tree) and hw % 4 == 0 and c <= 64 and x.data_ptr() % 16 == 0)
-        ctx.grad = grad
-        ctx.st = st
-        ctx.out = out
-        ctx.emb = emb if st is not None else None
-        return out[0].clone()
-
-    @staticmethod
-    @once_differentiable
-    def backward(ctx, gout):
-        g = gout.detach().to(torch.float32).reshape(1).contiguous()
-        gx = None
-        gemb = fork = None
-        if ctx.st is not None and ctx.needs_input_grad[1]:
-            fork = _Fork(ctx.emb.device)
-            gemb = triplet_backward(ctx.emb, ctx.st, ctx.out[1:2], g, fork=fork)
-        if ctx.needs_input_grad[0]:
-            gx = ctx.grad
-            if gx is None:
-                raise RuntimeError("seghiero_b200: backward through the fused loss can run only once")
-            ctx.grad = None
-            with torch.cuda.device(gx.device):
-                _call("sh_scale_inplace", _p(gx), _dtype_code(gx), gx.numel(), _p(g), _stream())
+        grid = _lib.load().sh_bce2_grid(b, hw, c, nc)
+        partials = torch.empty(grid * 4, dtype=torch.float32, device=dev)
+        sums = torch.empty(4, dtype=torch.float64, device=dev)
+        out = torch.empty(4, dtype=torch.float32, device=dev)
+        _staged("sh_bce2_fwdbwd", (1, 2, 4), lambda st_bits: (
+            _p(x), _dtype_code(x), _p(lab), lcode, _p(grad_full), b, hw, n_fine, nc, _p(tab), n_fb, lut_size,
+            1e-8, loss_weight, _p(lab8), _p(counts), _p(partials), _p(sums), st_bits | tree, _stream()))
         if fork is not None:
             fork.join()
-            gemb = _grad_as(gemb, ctx.emb)
-        return gx, gemb, None, None, None, None
+        _call("sh_loss2_final", _p(sums), _p(counts), n_fine, nc, float(b * hw), _p(step), total_steps,
+              _p(_opt(trip)), _p(_opt(status)), loss_weight, _p(out), _stream())
+        grad = _empty(dev, x.dtype)
+        if want_grad:
+            grad = grad_full
+            if x is not x_in:        # back to the head's resolution through the adjoint of the interpolation
+                grad = torch.empty_like(x_in)
+                _timed_call("sh_upsample_bilinear_adjoint", _p(grad_full), _dtype_code(x), _p(grad), b * c, h_in, w_in,
+                            hh, ww, _stream())
+    return out, grad, counts, sel, kcount, tl, trip, status
 
 
-# ----------------------------------------------------------------------------------------------
-# three-level fused loss
-# ----------------------------------------------------------------------------------------------
-@dataclass
-class Hier3Config:
-    n_fine: int
-    n_mid: int
-    n_high: int
-    fine_to_mid: tuple
-    fine_to_high: tuple
-    upper_ids: tuple
-    lower_ids: tuple
-    lam: float
-    loss_weight: float
-    total_steps: float
-    use_triplet: bool = True
+@hier2_fwd.register_fake
+def _(cls_score, label, embedding, step, n_fine, hiera_map, hiera_index, loss_weight, total_steps, fast_path, want_grad):
+    dev = cls_score.device
+    ncls, mt = len(hiera_map), 200
+    has = embedding is not None
+    i32, f32 = torch.int32, torch.float32
+    return (torch.empty(4, dtype=f32, device=dev),
+            torch.empty_like(cls_score, memory_format=torch.contiguous_format) if want_grad
+            else torch.empty(0, dtype=cls_score.dtype, device=dev),
+            torch.empty(4, dtype=torch.int64, device=dev),
+            torch.empty(ncls * 3 * mt if has else 0, dtype=i32, device=dev),
+            torch.empty(ncls if has else 0, dtype=i32, device=dev),
+            torch.empty(ncls * mt if has else 0, dtype=f32, device=dev),
+            torch.empty(2 if has else 0, dtype=f32, device=dev),
+            torch.empty(2 if has else 0, dtype=i32, device=dev))
 
 
-class RMIHieraTriplet3Fn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, cls_score, embedding, label, step_d, cfg: Hier3Config, stats: dict):
-        _need_cuda(cls_score, label, embedding)
-        x = cls_score.contiguous()
-        lab = _labels(label)
-        dev = x.device
-        if x.dim() != 4:
-            raise ValueError("cls_score must be [B,C,H,W]")
-        b, c, hh, ww = x.shape
-        if c != cfg.n_fine + cfg.n_mid + cfg.n_high:
-            raise ValueError(f"cls_score has {c} channels, expected {cfg.n_fine + cfg.n_mid + cfg.n_high}")
-        if tuple(lab.shape) != (b, hh, ww):
-            raise ValueError("label must be [B,H,W] matching cls_score")
-        if hh < 8 or ww < 8:
-            raise ValueError("the CUDA RMI path needs H, W >= 8 (the reference needs >= 3)")
-        key = ("h3", cfg.n_fine, cfg.n_mid, cfg.n_high, cfg.fine_to_mid, cfg.fine_to_high)
-        tab, n_mh, fast_ok = device_table(key, lambda: H.three_level_tables(cfg.n_fine, cfg.n_mid, cfg.n_high,
-                                                                            cfg.fine_to_mid, cfg.fine_to_high), dev)
-        if not FAST_PATH["enabled"]:
-            fast_ok = 0
-        st = None
-        if embedding is not None and cfg.use_triplet:
-            tkey = ("t1", cfg.upper_ids, cfg.lower_ids)
-            ttab, ncls = device_table(tkey, lambda: H.triplet_tables_id_lists(cfg.upper_ids, cfg.lower_ids), dev)
-            emb = embedding.contiguous()
+@torch.library.custom_op("seghiero_b200::hier2_bwd", mutates_args=("grad",))
+def hier2_bwd(gout: Tensor, grad: Tensor, embedding: Optional[Tensor], sel: Tensor, kcount: Tensor, tl: Tensor,
+              trip: Tensor, out: Tensor, need_x: bool, need_emb: bool) -> Tensor:
+    """Scales the precomputed logits gradient in place by grad_output (a no-op kernel exit when it is 1) and returns
+    the embedding gradient (empty when there is none)."""
+    dev = gout.device
+    g = _gscale(gout)
+    gemb = _empty(dev)
+    with torch.cuda.device(dev):
+        fork = None
+        if need_emb and embedding is not None:
             fork = _Fork(dev)
-            st = triplet_forward(emb, lab, 1, ttab, ncls, fork=fork, world_ready=True)
-        with torch.cuda.device(dev):
-            lib = _lib.load()
-            nbytes = lib.sh_rmi3_workspace_bytes(b, hh, ww, cfg.n_fine, cfg.n_mid, cfg.n_high)
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            out = torch.empty(4, dtype=torch.float32, device=dev)
-            _staged("sh_rmi3_forward", (1, 2, 4, 8), lambda st_bits: (
-                _p(x), _dtype_code(x), _p(lab), b, hh, ww, cfg.n_fine, cfg.n_mid, cfg.n_high, _p(tab), n_mh, fast_ok,
-                cfg.lam, cfg.loss_weight, _p(ws), st_bits, _stream()))
-            if st is not None:
-                fork.join()
-            _call("sh_loss3_final", b, hh, ww, cfg.n_fine, cfg.n_mid, cfg.n_high, _p(ws), cfg.lam, _p(step_d),
-                      cfg.total_steps, _p(st.trip) if st else None, _p(st.status) if st else None, cfg.loss_weight,
-                      _p(out), _stream())
-        stats.update(out=out, triplet=st, workspace=ws,
-                     fast_path=bool(lib.sh_rmi3_fast_path(_p(x), None, _dtype_code(x), hh, ww, cfg.n_fine, cfg.n_mid,
-                                                          cfg.n_high, fast_ok)))
-        ctx.cfg = cfg
-        ctx.tab, ctx.n_mh, ctx.fast_ok = tab, n_mh, fast_ok
-        ctx.st = st
-        ctx.out = out
-        ctx.ws = ws if ctx.needs_input_grad[0] else None
-        ctx.x = x if ctx.needs_input_grad[0] else None
-        ctx.emb = emb if st is not None else None
-        return out[0].clone()
-
-    @staticmethod
-    @once_differentiable
-    def backward(ctx, gout):
-        g = gout.detach().to(torch.float32).reshape(1).contiguous()
-        cfg = ctx.cfg
-        gx = None
-        gemb = fork = None
-        if ctx.st is not None and ctx.needs_input_grad[1]:
-            fork = _Fork(ctx.emb.device)
-            gemb = triplet_backward(ctx.emb, ctx.st, ctx.out[1:2], g, fork=fork)
-        if ctx.needs_input_grad[0]:
-            x = ctx.x
-            b, c, hh, ww = x.shape
-            gx = torch.empty_like(x)
-            with torch.cuda.device(x.device):
-                _staged("sh_rmi3_backward", (1, 2), lambda st_bits: (
-                    _p(x), _dtype_code(x), _p(gx), b, hh, ww, cfg.n_fine, cfg.n_mid, cfg.n_high, _p(ctx.tab), ctx.n_mh,
-                    ctx.fast_ok, cfg.loss_weight, _p(ctx.ws), _p(g), st_bits, _stream()))
+            emb = embedding.contiguous()
+            gemb = _triplet_backward(emb, kcount.numel(), 200, sel, kcount, tl, trip, out[1:2], g, fork)
+        if need_x and grad.numel():
+            _call("sh_scale_inplace", _p(grad), _dtype_code(grad), grad.numel(), _p(g), _stream())
         if fork is not None:
             fork.join()
-            gemb = _grad_as(gemb, ctx.emb)
-        return gx, gemb, None, None, None, None
+            gemb = _grad_as(gemb, embedding)
+    return gemb
+
+
+@hier2_bwd.register_fake
+def _(gout, grad, embedding, sel, kcount, tl, trip, out, need_x, need_emb):
+    if need_emb and embedding is not None:
+        return torch.empty_like(embedding, memory_format=torch.contiguous_format)
+    return torch.empty(0, dtype=torch.float32, device=gout.device)
+
+
+def _hier2_setup(ctx, inputs, output):
+    embedding = inputs[2]
+    out, grad, counts, sel, kcount, tl, trip, status = output
+    ctx.save_for_backward(grad, embedding, sel, kcount, tl, trip, out)
+    ctx.mark_non_differentiable(grad, counts, sel, kcount, tl, trip, status)
+    ctx.consumed = False
+
+
+def _hier2_backward_fn(ctx, g_out, *_unused):
+    grad, embedding, sel, kcount, tl, trip, out = ctx.saved_tensors
+    need_x, need_emb = ctx.needs_input_grad[0], ctx.needs_input_grad[2]
+    if need_x and ctx.consumed:
+        raise RuntimeError("seghiero_b200: backward through the fused 2-level loss can run only once "
+                           "(its gradient is computed in the forward kernel and scaled in place)")
+    ctx.consumed = True
+    gemb = hier2_bwd(g_out, grad, embedding, sel, kcount, tl, trip, out, need_x, need_emb)
+    gx = grad if need_x else None
+    ge = gemb if (need_emb and embedding is not None) else None
+    return (gx, None, ge) + (None,) * 8
+
+
+hier2_fwd.register_autograd(_hier2_backward_fn, setup_context=_hier2_setup)
+
+
+# ----------------------------------------------------------------------------------------------
+# three-level fused loss: RMIHieraTripletLoss.forward, models/loss/rmi_hiera_triplet_loss.py:323-546
+# ----------------------------------------------------------------------------------------------
+def _hier3_tables(nf: int, nm: int, nh: int, f2m: Sequence[int], f2h: Sequence[int], dev):
+    key = ("h3", nf, nm, nh, tuple(int(v) for v in f2m), tuple(int(v) for v in f2h))
+    return device_table(key, lambda: H.three_level_tables(nf, nm, nh, list(f2m), list(f2h)), dev)
+
+
+@torch.library.custom_op("seghiero_b200::hier3_fwd", mutates_args=())
+def hier3_fwd(cls_score: Tensor, label: Tensor, embedding: Optional[Tensor], step: Tensor, n_fine: int, n_mid: int,
+              n_high: int, fine_to_mid: List[int], fine_to_high: List[int], upper_ids: List[int], lower_ids: List[int],
+              lam: float, loss_weight: float, total_steps: float, fast_path: bool, use_triplet: bool
+              ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """-> (out [loss, triplet scale, rmi term, -], workspace, x_full (the upsampled logits when `cls_score` came at the
+    head's resolution, else empty), sel, kcount, tl, trip, status)."""
+    _need_cuda(cls_score, label, embedding)
+    dev = cls_score.device
+    x_in = cls_score.contiguous()
+    lab, lcode = _labels(label)
+    if x_in.dim() != 4 or lab.dim() != 3:
+        raise ValueError("cls_score must be [B,C,H,W] and label [B,H,W]")
+    b, c, _, _ = x_in.shape
+    hh, ww = int(lab.shape[1]), int(lab.shape[2])
+    if c != n_fine + n_mid + n_high:
+        raise ValueError(f"cls_score has {c} channels, expected {n_fine + n_mid + n_high}")
+    if lab.shape[0] != b:
+        raise ValueError("label must be [B,H,W] with the batch size of cls_score")
+    if hh < 8 or ww < 8:
+        raise ValueError("the CUDA RMI path needs H, W >= 8 (the reference needs >= 3)")
+    with torch.cuda.device(dev):
+        tab, n_mh, fast_ok = _hier3_tables(n_fine, n_mid, n_high, fine_to_mid, fine_to_high, dev)
+        if not fast_path:
+            fast_ok = 0
+        fork = None
+        if embedding is not None and use_triplet:
+            ttab, ncls = _triplet_tab(1, upper_ids, lower_ids, dev)
+            fork = _Fork(dev)
+            sel, kcount, tl, trip, status = _triplet_forward(embedding.contiguous(), lab, lcode, 1, ttab, ncls, 200,
+                                                             fork, True)
+        else:
+            sel, kcount, tl, trip, status = (_empty(dev, torch.int32), _empty(dev, torch.int32), _empty(dev),
+                                             _empty(dev), _empty(dev, torch.int32))
+        x = _upsampled(x_in, hh, ww)
+        lib = _lib.load()
+        ws = torch.empty(lib.sh_rmi3_workspace_bytes(b, hh, ww, n_fine, n_mid, n_high), dtype=torch.uint8, device=dev)
+        out = torch.empty(4, dtype=torch.float32, device=dev)
+        _staged("sh_rmi3_forward", (1, 2, 4, 8), lambda st_bits: (
+            _p(x), _dtype_code(x), _p(lab), lcode, b, hh, ww, n_fine, n_mid, n_high, _p(tab), n_mh, fast_ok,
+            lam, loss_weight, _p(ws), st_bits, _stream()))
+        if fork is not None:
+            fork.join()
+        _call("sh_loss3_final", b, hh, ww, n_fine, n_mid, n_high, _p(ws), lam, _p(step), total_steps,
+              _p(_opt(trip)), _p(_opt(status)), loss_weight, _p(out), _stream())
+    x_full = x if x is not x_in else _empty(dev, x.dtype)
+    return out, ws, x_full, sel, kcount, tl, trip, status
+
+
+@hier3_fwd.register_fake
+def _(cls_score, label, embedding, step, n_fine, n_mid, n_high, fine_to_mid, fine_to_high, upper_ids, lower_ids, lam,
+      loss_weight, total_steps, fast_path, use_triplet):
+    dev = cls_score.device
+    b, c = cls_score.shape[0], cls_score.shape[1]
+    hh, ww = label.shape[1], label.shape[2]
+    has = embedding is not None and use_triplet
+    ncls, mt = 256, 200
+    i32, f32 = torch.int32, torch.float32
+    nbytes = _lib.load().sh_rmi3_workspace_bytes(int(b), int(hh), int(ww), n_fine, n_mid, n_high)
+    up = (cls_score.shape[2], cls_score.shape[3]) != (hh, ww)
+    return (torch.empty(4, dtype=f32, device=dev), torch.empty(nbytes, dtype=torch.uint8, device=dev),
+            torch.empty((b, c, hh, ww) if up else (0,), dtype=cls_score.dtype, device=dev),
+            torch.empty(ncls * 3 * mt if has else 0, dtype=i32, device=dev),
+            torch.empty(ncls if has else 0, dtype=i32, device=dev),
+            torch.empty(ncls * mt if has else 0, dtype=f32, device=dev),
+            torch.empty(2 if has else 0, dtype=f32, device=dev),
+            torch.empty(2 if has else 0, dtype=i32, device=dev))
+
+
+@torch.library.custom_op("seghiero_b200::hier3_bwd", mutates_args=())
+def hier3_bwd(gout: Tensor, cls_score: Tensor, x_full: Tensor, ws: Tensor, embedding: Optional[Tensor], sel: Tensor,
+              kcount: Tensor, tl: Tensor, trip: Tensor, out: Tensor, n_fine: int, n_mid: int, n_high: int,
+              fine_to_mid: List[int], fine_to_high: List[int], loss_weight: float, fast_path: bool, need_x: bool,
+              need_emb: bool) -> Tuple[Tensor, Tensor]:
+    """Pass 2 (+ the image frame) -> d loss / d cls_score at the resolution `cls_score` came in, and the embedding
+    gradient."""
+    dev = cls_score.device
+    g = _gscale(gout)
+    gx, gemb = _empty(dev, cls_score.dtype), _empty(dev)
+    with torch.cuda.device(dev):
+        fork = None
+        if need_emb and embedding is not None and sel.numel():
+            fork = _Fork(dev)
+            emb = embedding.contiguous()
+            gemb = _triplet_backward(emb, kcount.numel(), 200, sel, kcount, tl, trip, out[1:2], g, fork)
+        if need_x:
+            x_in = cls_score.contiguous()
+            x = x_full if x_full.numel() else x_in
+            b, c, hh, ww = x.shape
+            tab, n_mh, fast_ok = _hier3_tables(n_fine, n_mid, n_high, fine_to_mid, fine_to_high, dev)
+            if not fast_path:
+                fast_ok = 0
+            gfull = torch.empty_like(x)
+            _staged("sh_rmi3_backward", (1, 2), lambda st_bits: (
+                _p(x), _dtype_code(x), _p(gfull), b, hh, ww, n_fine, n_mid, n_high, _p(tab), n_mh, fast_ok,
+                loss_weight, _p(ws), _p(g), st_bits, _stream()))
+            gx = gfull
+            if x is not x_in:
+                gx = torch.empty_like(x_in)
+                _timed_call("sh_upsample_bilinear_adjoint", _p(gfull), _dtype_code(x), _p(gx), b * c, x_in.shape[2],
+                            x_in.shape[3], hh, ww, _stream())
+        if fork is not None:
+            fork.join()
+            gemb = _grad_as(gemb, embedding)
+    return gx, gemb
+
+
+@hier3_bwd.register_fake
+def _(gout, cls_score, x_full, ws, embedding, sel, kcount, tl, trip, out, n_fine, n_mid, n_high, fine_to_mid,
+      fine_to_high, loss_weight, fast_path, need_x, need_emb):
+    dev = cls_score.device
+    gx = (torch.empty_like(cls_score, memory_format=torch.contiguous_format) if need_x
+          else torch.empty(0, dtype=cls_score.dtype, device=dev))
+    if need_emb and embedding is not None and sel.numel():
+        ge = torch.empty_like(embedding, memory_format=torch.contiguous_format)
+    else:
+        ge = torch.empty(0, dtype=torch.float32, device=dev)
+    return gx, ge
+
+
+def _hier3_setup(ctx, inputs, output):
+    (cls_score, _label, embedding, _step, n_fine, n_mid, n_high, f2m, f2h, _up, _lo, _lam, loss_weight, _ts, fast_path,
+     _ut) = inputs
+    out, ws, x_full, sel, kcount, tl, trip, status = output
+    ctx.save_for_backward(cls_score, x_full, ws, embedding, sel, kcount, tl, trip, out)
+    ctx.mark_non_differentiable(ws, x_full, sel, kcount, tl, trip, status)
+    ctx.cfg = (n_fine, n_mid, n_high, list(f2m), list(f2h), float(loss_weight), bool(fast_path))
+
+
+def _hier3_backward_fn(ctx, g_out, *_unused):
+    cls_score, x_full, ws, embedding, sel, kcount, tl, trip, out = ctx.saved_tensors
+    need_x, need_emb = ctx.needs_input_grad[0], ctx.needs_input_grad[2]
+    nf, nm, nh, f2m, f2h, lw, fast = ctx.cfg
+    gx, gemb = hier3_bwd(g_out, cls_score, x_full, ws, embedding, sel, kcount, tl, trip, out, nf, nm, nh, f2m, f2h, lw,
+                         fast, need_x, need_emb)
+    has_emb = need_emb and embedding is not None and sel.numel() > 0
+    return (gx if need_x else None, None, gemb if has_emb else None) + (None,) * 13
+
+
+hier3_fwd.register_autograd(_hier3_backward_fn, setup_context=_hier3_setup)
+
+
+# ----------------------------------------------------------------------------------------------
+# aux-head cross entropy fused with its upsample (train.py:309-313), SURVEY 8f N2
+# ----------------------------------------------------------------------------------------------
+@torch.library.custom_op("seghiero_b200::aux_ce_fwd", mutates_args=())
+def aux_ce_fwd(logits: Tensor, label: Tensor, want_grad: bool) -> Tuple[Tensor, Tensor]:
+    """-> (loss [1], gradient w.r.t. the low-resolution logits for grad_output = 1 (empty unless want_grad))."""
+    _need_cuda(logits, label)
+    x = logits.contiguous()
+    lab, lcode = _labels(label)
+    if x.dim() != 4 or lab.dim() != 3 or lab.shape[0] != x.shape[0]:
+        raise ValueError("logits must be [B,C,h,w] and label [B,H,W]")
+    b, c, h, w = x.shape
+    hh, ww = int(lab.shape[1]), int(lab.shape[2])
+    dev = x.device
+    with torch.cuda.device(dev):
+        lib = _lib.load()
+        ws = torch.empty(lib.sh_aux_ce_workspace_bytes(b, c, h, w), dtype=torch.uint8, device=dev)
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        grad = torch.empty_like(x) if want_grad else None
+        _timed_call("sh_aux_ce_fwdbwd", _p(x), _dtype_code(x), _p(lab), lcode, b, c, h, w, hh, ww, _p(grad), None,
+                    _p(out), _p(ws), _stream())
+    return out, (grad if want_grad else _empty(dev, x.dtype))
+
+
+@aux_ce_fwd.register_fake
+def _(logits, label, want_grad):
+    return (torch.empty(1, dtype=torch.float32, device=logits.device),
+            torch.empty_like(logits, memory_format=torch.contiguous_format) if want_grad
+            else torch.empty(0, dtype=logits.dtype, device=logits.device))
+
+
+def _aux_setup(ctx, inputs, output):
+    out, grad = output
+    ctx.save_for_backward(grad)
+    ctx.mark_non_differentiable(grad)
+
+
+def _aux_backward_fn(ctx, g_out, _g_grad):
+    (grad,) = ctx.saved_tensors
+    # out-of-place: the loss is usually weighted (0.4 * aux) and small ([B, C, H/16, W/16])
+    return grad * g_out.reshape(-1)[:1].to(grad.dtype), None, None
+
+
+aux_ce_fwd.register_autograd(_aux_backward_fn, setup_context=_aux_setup)
+
+
+def aux_cross_entropy(logits: Tensor, label: Tensor) -> Tensor:
+    """nn.CrossEntropyLoss(ignore_index=255)(F.interpolate(logits, label.shape[-2:], mode="bilinear",
+    align_corners=False), label) -- the aux-head loss of train.py:309-313 -- from the LOW-resolution logits."""
+    want = logits.requires_grad and torch.is_grad_enabled()
+    out, _ = aux_ce_fwd(logits, label, want)
+    return out[0]

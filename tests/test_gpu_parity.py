@@ -154,8 +154,7 @@ def test_two_level_golden(sb, golden, name):
         assert float(emb.grad.abs().max()) == 0.0
     else:
         assert rel(to_np(emb.grad), g["demb"]) <= FP32_TOL
-    st = mod.last_stats
-    assert int(st["triplet"].trip[1].item()) == int(g["count"][0])
+    assert int(mod.last_stats["trip"][1].item()) == int(g["count"][0])
 
 
 @pytest.mark.parametrize("case", [
@@ -171,12 +170,7 @@ def test_two_level_golden(sb, golden, name):
     dict(b=1, h=64, w=96, hi=HI, hm=HM, step=40000, dtype=torch.float32, labels="blob", generic=True),
 ])
 def test_two_level_vs_oracle(sb, case):
-    from seghiero_b200 import ops
-    ops.FAST_PATH["enabled"] = not case.get("generic", False)   # generic=True: the any-bucket kernel on a tree-shaped case
-    try:
-        _two_level_vs_oracle(sb, case)
-    finally:
-        ops.FAST_PATH["enabled"] = True
+    _two_level_vs_oracle(sb, case)
 
 
 def _two_level_vs_oracle(sb, case):
@@ -195,7 +189,8 @@ def _two_level_vs_oracle(sb, case):
     (ref * 0.7).backward()
     xc = x.cuda().requires_grad_(True)
     ec = emb.cuda().requires_grad_(True)
-    mod = sb.HieraTripletLoss(nf, case["hm"], case["hi"], loss_weight=1.3)
+    # generic=True: the any-bucket kernel on a tree-shaped case
+    mod = sb.HieraTripletLoss(nf, case["hm"], case["hi"], loss_weight=1.3, fast_path=not case.get("generic", False))
     loss = mod(torch.tensor([case["step"]]).cuda(), ec, None, xc, lab.cuda())
     (loss * 0.7).backward()                                                  # non-unit grad_output
     tol = FP32_TOL if case["dtype"] == torch.float32 else BF16_TOL
@@ -246,7 +241,7 @@ def test_three_level_golden(sb, golden, name):
         assert rel(to_np(x.grad), g["dx" + tag]) <= tol, (tag, rel(to_np(x.grad), g["dx" + tag]))
         if tag == "" and not bool(g["demb_none"]):
             assert rel(to_np(emb.grad), g["demb"]) <= FP32_TOL
-        assert int(mod.last_stats["triplet"].trip[1].item()) == int(g["count"][0])
+        assert int(mod.last_stats["trip"][1].item()) == int(g["count"][0])
 
 
 def test_three_level_flat_predictions(sb, golden):
@@ -274,12 +269,7 @@ def test_three_level_flat_predictions(sb, golden):
     dict(b=2, h=66, w=132, labels="blob", step=100000, lam=0.5, dtype=torch.float32, noisy_second=True),
 ])
 def test_three_level_vs_oracle(sb, case):
-    from seghiero_b200 import ops
-    ops.FAST_PATH["enabled"] = not case.get("generic", False)   # generic=True: the any-hierarchy kernels on a fast-path shape
-    try:
-        _three_level_vs_oracle(sb, case)
-    finally:
-        ops.FAST_PATH["enabled"] = True
+    _three_level_vs_oracle(sb, case)
 
 
 def _three_level_vs_oracle(sb, case):
@@ -301,8 +291,9 @@ def _three_level_vs_oracle(sb, case):
     (ref * 1.5).backward()
     xc = x.cuda().requires_grad_(True)
     ec = emb.cuda().requires_grad_(True)
+    # generic=True: the any-hierarchy kernels on a fast-path shape
     mod = sb.RMIHieraTripletLoss(19, 7, 2, torch.tensor(F2M), torch.tensor(F2H), loss_weight_lambda=case["lam"],
-                                 loss_weight=0.9)
+                                 loss_weight=0.9, fast_path=not case.get("generic", False))
     loss = mod(torch.tensor([case["step"]]).cuda(), ec, None, xc, lab.cuda())
     (loss * 1.5).backward()
     tol = case.get("tol", FP32_TOL if case["dtype"] == torch.float32 else BF16_TOL)
@@ -358,7 +349,7 @@ def test_three_level_other_hierarchies(sb, maps):
     xc = x.cuda().requires_grad_(True)
     loss = mod(torch.tensor([0]), None, None, xc, lab.cuda())
     loss.backward()
-    assert mod.last_stats["fast_path"] == ("m2h" in maps)
+    assert mod.uses_fast_path(xc, lab) == ("m2h" in maps)
     assert abs(float(loss) - float(ref)) <= FP32_TOL * abs(float(ref)), (float(loss), float(ref), parts)
     assert rel(to_np(xc.grad), to_np(xr.grad)) <= FP32_TOL
 
@@ -498,7 +489,7 @@ def test_config4_image_against_oracle_on_cuda(sb):
     xc = x.clone().requires_grad_(True)
     loss = mod(torch.tensor([0], device=dev), None, None, xc, lab)
     loss.backward()
-    assert mod.last_stats["fast_path"]
+    assert mod.uses_fast_path(xc, lab)
     assert abs(float(loss.detach()) - float(ref.detach())) <= FP32_TOL * abs(float(ref.detach()))
     _assert_grad_close_up_to_tie_flips(xc.grad, xr.grad, FP32_TOL)
 
