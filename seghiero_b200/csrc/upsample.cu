@@ -105,6 +105,139 @@ __global__ void __launch_bounds__(256) k_upsample_adjoint(const T* __restrict__ 
   }
 }
 
+// The head's geometry (out = 4 x in exactly) without index arithmetic: thread = 4 x 4 output block whose sources are
+// the 3 x 3 low-resolution neighbourhood of (Y, X); weights are the constants (2j - 3) / 8 of the forward formula
+// (scale = 0.25 is exact in fp32, so these are the very numbers lerp_src produces).  Blocks that touch row / column 0
+// (clamped source index) take the generic formula.
+template <typename T>
+__global__ void __launch_bounds__(256) k_upsample4(const T* __restrict__ in, T* __restrict__ out, long planes, int h, int w) {
+  const int H = 4 * h, W = 4 * w;
+  const long total = planes * h * w;
+  for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+    const int X = (int)(g % w);
+    const long r = g / w;
+    const int Y = (int)(r % h);
+    const long p = r / h;
+    const T* base = in + p * (long)h * w;
+    T* ob = out + (p * H + 4 * Y) * (long)W + 4 * X;
+    if (Y > 0 && X > 0) {
+      const int yp = min(Y + 1, h - 1), xp = min(X + 1, w - 1);
+      float v[3][3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const T* row = base + (long)(a == 0 ? Y - 1 : (a == 1 ? Y : yp)) * w;
+        v[a][0] = to_f32<T>(__ldg(row + X - 1));
+        v[a][1] = to_f32<T>(__ldg(row + X));
+        v[a][2] = to_f32<T>(__ldg(row + xp));
+      }
+      const float l1[4] = {0.625f, 0.875f, 0.125f, 0.375f};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          o[k] = bilerp(v[j >> 1][k >> 1], v[j >> 1][(k >> 1) + 1], v[(j >> 1) + 1][k >> 1], v[(j >> 1) + 1][(k >> 1) + 1],
+                        1.0f - l1[k], l1[k], 1.0f - l1[j], l1[j]);
+        VecIO<T, 4>::store(ob + (long)j * W, o);
+      }
+    } else {
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        const Lerp ly = lerp_src(4 * Y + j, 0.25f, h);
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const Lerp lx = lerp_src(4 * X + k, 0.25f, w);
+          o[k] = bilerp(to_f32<T>(__ldg(base + (long)ly.i0 * w + lx.i0)), to_f32<T>(__ldg(base + (long)ly.i0 * w + lx.i1)),
+                        to_f32<T>(__ldg(base + (long)ly.i1 * w + lx.i0)), to_f32<T>(__ldg(base + (long)ly.i1 * w + lx.i1)),
+                        lx.l0, lx.l1, ly.l0, ly.l1);
+        }
+        VecIO<T, 4>::store(ob + (long)j * W, o);
+      }
+    }
+  }
+}
+
+// Adjoint for out = 4 x in: thread = one low-resolution pixel, gathering its 8 x 8 output window with the separable
+// constant weights {1,3,5,7,7,5,3,1} / 8; pixels on the low-resolution border (clamped sources) take the generic gather.
+template <typename T>
+__device__ __forceinline__ float adjoint_generic(const T* __restrict__ gp, int Y, int X, int h, int w, int H, int W) {
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+  const int ylo = max(0, 4 * Y - 3), yhi = min(H - 1, 4 * Y + 6), xlo = max(0, 4 * X - 3), xhi = min(W - 1, 4 * X + 6);
+  float acc = 0.f;
+  for (int y = ylo; y <= yhi; ++y) {
+    const Lerp ly = lerp_src(y, sy, h);
+    const float wy = (ly.i0 == Y ? ly.l0 : 0.f) + (ly.i1 == Y ? ly.l1 : 0.f);
+    if (wy == 0.f) continue;
+    float rowacc = 0.f;
+    for (int x = xlo; x <= xhi; ++x) {
+      const Lerp lx = lerp_src(x, sx, w);
+      const float wx = (lx.i0 == X ? lx.l0 : 0.f) + (lx.i1 == X ? lx.l1 : 0.f);
+      if (wx != 0.f) rowacc = fmaf(wx, to_f32<T>(__ldg(gp + (long)y * W + x)), rowacc);
+    }
+    acc = fmaf(wy, rowacc, acc);
+  }
+  return acc;
+}
+
+// CTA = 8 x 32 low-resolution pixels of one plane: the 36 x 136 output pixels they gather from are staged in shared
+// memory with coalesced 16-byte loads (each gradient byte crosses HBM once), thread = one low-resolution pixel
+// (3 x LDS.128 per window row, separable weights).
+constexpr int ADJ_TH = 8, ADJ_TW = 32, ADJ_SR = 4 * ADJ_TH + 4, ADJ_SC = 4 * ADJ_TW + 8;
+template <typename T>
+__global__ void __launch_bounds__(ADJ_TH * ADJ_TW) k_upsample4_adjoint(const T* __restrict__ gout, T* __restrict__ gin,
+                                                                      long planes, int h, int w, int tiles_x, int tiles_y) {
+  __shared__ __align__(16) float tile[ADJ_SR][ADJ_SC];        // rows 4Y0-2 .. 4Y0+33, cols 4X0-4 .. 4X0+131
+  const int H = 4 * h, W = 4 * w;
+  const int tid = threadIdx.x;
+  for (long t = blockIdx.x; t < planes * tiles_x * tiles_y; t += gridDim.x) {
+    const int tx = (int)(t % tiles_x);
+    const long r = t / tiles_x;
+    const int ty = (int)(r % tiles_y);
+    const long p = r / tiles_y;
+    const int Y0 = ty * ADJ_TH, X0 = tx * ADJ_TW;
+    const T* gp = gout + p * (long)H * W;
+    __syncthreads();
+    for (int e = tid; e < ADJ_SR * (ADJ_SC / 4); e += ADJ_TH * ADJ_TW) {
+      const int rr = e / (ADJ_SC / 4), q = e - rr * (ADJ_SC / 4);
+      const int y = 4 * Y0 - 2 + rr, x = 4 * X0 - 4 + 4 * q;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (y >= 0 && y < H && x >= 0 && x < W) VecIO<T, 4>::load(gp + (long)y * W + x, v);
+      *reinterpret_cast<float4*>(&tile[rr][4 * q]) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    __syncthreads();
+    const int ly = tid / ADJ_TW, lx = tid - ly * ADJ_TW;
+    const int Y = Y0 + ly, X = X0 + lx;
+    if (Y >= h || X >= w) continue;
+    float acc = 0.f;
+    if (h >= 2 && w >= 2) {
+      // weights of the 8 window rows / columns 4Y-2 .. 4Y+5 on low-resolution row Y: the interior pattern, or the clamped
+      // patterns of the first / last row (sources outside the map fold onto it; rows outside the image weigh 0)
+      float wy[8], wx[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float in = i < 4 ? 0.125f + 0.25f * i : 0.875f - 0.25f * (i - 4);
+        wy[i] = Y == 0 ? (i < 2 ? 0.f : (i < 4 ? 1.f : in)) : (Y == h - 1 ? (i >= 6 ? 0.f : (i >= 4 ? 1.f : in)) : in);
+        wx[i] = X == 0 ? (i < 2 ? 0.f : (i < 4 ? 1.f : in)) : (X == w - 1 ? (i >= 6 ? 0.f : (i >= 4 ? 1.f : in)) : in);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(&tile[4 * ly + i][4 * lx]);
+        const float4 b = *reinterpret_cast<const float4*>(&tile[4 * ly + i][4 * lx + 4]);
+        const float4 c = *reinterpret_cast<const float4*>(&tile[4 * ly + i][4 * lx + 8]);
+        // window columns 4X-2 .. 4X+5 = tile columns 4lx+2 .. 4lx+9
+        float rs = wx[0] * a.z;
+        rs = fmaf(wx[1], a.w, rs); rs = fmaf(wx[2], b.x, rs); rs = fmaf(wx[3], b.y, rs);
+        rs = fmaf(wx[4], b.z, rs); rs = fmaf(wx[5], b.w, rs); rs = fmaf(wx[6], c.x, rs); rs = fmaf(wx[7], c.y, rs);
+        acc = fmaf(wy[i], rs, acc);
+      }
+    } else {
+      acc = adjoint_generic<T>(gp, Y, X, h, w, H, W);
+    }
+    gin[(p * h + Y) * (long)w + X] = from_f32<T>(acc);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // N2: aux-head loss  nn.CrossEntropyLoss(ignore_index=255)(F.interpolate(aux_logits, (H, W)), label)  and its
 // gradient w.r.t. the LOW-resolution aux logits, fused: nothing of size [B, C, H, W] is ever written.
@@ -351,7 +484,10 @@ int sh_upsample_bilinear(const void* in, int dtype, void* out, long planes, int 
 #define SH_UP(T)                                                                                          \
   {                                                                                                       \
     const int vec_ok = (W % 4 == 0) && ((uintptr_t)out % (4 * sizeof(T)) == 0);                           \
-    sh::k_upsample<T><<<(unsigned)sh_up_blocks(items, 256), 256, 0, st>>>((const T*)in, (T*)out, planes, h, w, H, W, vec_ok); \
+    if (H == 4 * h && W == 4 * w && vec_ok)                                                               \
+      sh::k_upsample4<T><<<(unsigned)sh_up_blocks(planes * h * w, 256), 256, 0, st>>>((const T*)in, (T*)out, planes, h, w); \
+    else                                                                                                  \
+      sh::k_upsample<T><<<(unsigned)sh_up_blocks(items, 256), 256, 0, st>>>((const T*)in, (T*)out, planes, h, w, H, W, vec_ok); \
   }                                                                                                       \
   break
   switch (dtype) {
@@ -370,12 +506,24 @@ int sh_upsample_bilinear_adjoint(const void* gout, int dtype, void* gin, long pl
   if (planes <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return SH_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned blocks = (unsigned)sh_up_blocks(planes * h * w, 256);
+#define SH_ADJ(T)                                                                                                   \
+  if (H == 4 * h && W == 4 * w && (uintptr_t)gout % (4 * sizeof(T)) == 0) {                                         \
+    const int txn = (w + sh::ADJ_TW - 1) / sh::ADJ_TW, tyn = (h + sh::ADJ_TH - 1) / sh::ADJ_TH;                      \
+    long nb = planes * txn * tyn;                                                                                   \
+    if (nb > SH_NUM_SMS * 32L) nb = SH_NUM_SMS * 32L;                                                               \
+    sh::k_upsample4_adjoint<T><<<(unsigned)nb, sh::ADJ_TH * sh::ADJ_TW, 0, st>>>((const T*)gout, (T*)gin, planes, h, \
+                                                                                w, txn, tyn);                       \
+  }                                                                                                                 \
+  else                                                                                                              \
+    sh::k_upsample_adjoint<T><<<blocks, 256, 0, st>>>((const T*)gout, (T*)gin, planes, h, w, H, W);                  \
+  break
   switch (dtype) {
-    case SH_DT_F32: sh::k_upsample_adjoint<float><<<blocks, 256, 0, st>>>((const float*)gout, (float*)gin, planes, h, w, H, W); break;
-    case SH_DT_BF16: sh::k_upsample_adjoint<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)gout, (__nv_bfloat16*)gin, planes, h, w, H, W); break;
-    case SH_DT_F16: sh::k_upsample_adjoint<__half><<<blocks, 256, 0, st>>>((const __half*)gout, (__half*)gin, planes, h, w, H, W); break;
+    case SH_DT_F32: SH_ADJ(float);
+    case SH_DT_BF16: SH_ADJ(__nv_bfloat16);
+    case SH_DT_F16: SH_ADJ(__half);
     default: return SH_ERR_UNSUPPORTED;
   }
+#undef SH_ADJ
   SH_CHECK_LAUNCH();
   return SH_OK;
 }

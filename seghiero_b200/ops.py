@@ -425,12 +425,15 @@ def _triplet_setup(ctx, inputs, output):
     feats, _label, _mode, _a, _b, max_triplet = inputs
     trip, status, sel, kcount, tl = output
     ctx.save_for_backward(feats, sel, kcount, tl, trip)
+    ctx.set_materialize_grads(False)      # no zero-filled "gradients" for the bookkeeping outputs
     ctx.max_triplet = max_triplet
     ctx.mark_non_differentiable(status, sel, kcount, tl)
 
 
 def _triplet_backward_fn(ctx, g_trip, *_unused):
     feats, sel, kcount, tl, trip = ctx.saved_tensors
+    if g_trip is None:
+        return (None,) * 6
     one = torch.ones(1, dtype=torch.float32, device=feats.device)
     return triplet_bwd(g_trip, feats, sel, kcount, tl, trip, one, ctx.max_triplet), None, None, None, None, None
 
@@ -566,12 +569,15 @@ def _hier2_setup(ctx, inputs, output):
     embedding = inputs[2]
     out, grad, counts, sel, kcount, tl, trip, status = output
     ctx.save_for_backward(grad, embedding, sel, kcount, tl, trip, out)
+    ctx.set_materialize_grads(False)      # no zero-filled "gradients" for the bookkeeping outputs
     ctx.mark_non_differentiable(grad, counts, sel, kcount, tl, trip, status)
     ctx.consumed = False
 
 
 def _hier2_backward_fn(ctx, g_out, *_unused):
     grad, embedding, sel, kcount, tl, trip, out = ctx.saved_tensors
+    if g_out is None:
+        return (None,) * 11
     need_x, need_emb = ctx.needs_input_grad[0], ctx.needs_input_grad[2]
     if need_x and ctx.consumed:
         raise RuntimeError("seghiero_b200: backward through the fused 2-level loss can run only once "
@@ -719,12 +725,15 @@ def _hier3_setup(ctx, inputs, output):
      _ut) = inputs
     out, ws, x_full, sel, kcount, tl, trip, status = output
     ctx.save_for_backward(cls_score, x_full, ws, embedding, sel, kcount, tl, trip, out)
+    ctx.set_materialize_grads(False)      # else autograd zero-fills a "gradient" for the 0.5 GB workspace every step
     ctx.mark_non_differentiable(ws, x_full, sel, kcount, tl, trip, status)
     ctx.cfg = (n_fine, n_mid, n_high, list(f2m), list(f2h), float(loss_weight), bool(fast_path))
 
 
 def _hier3_backward_fn(ctx, g_out, *_unused):
     cls_score, x_full, ws, embedding, sel, kcount, tl, trip, out = ctx.saved_tensors
+    if g_out is None:
+        return (None,) * 16
     need_x, need_emb = ctx.needs_input_grad[0], ctx.needs_input_grad[2]
     nf, nm, nh, f2m, f2h, lw, fast = ctx.cfg
     gx, gemb = hier3_bwd(g_out, cls_score, x_full, ws, embedding, sel, kcount, tl, trip, out, nf, nm, nh, f2m, f2h, lw,
@@ -770,11 +779,14 @@ def _(logits, label, want_grad):
 def _aux_setup(ctx, inputs, output):
     out, grad = output
     ctx.save_for_backward(grad)
+    ctx.set_materialize_grads(False)
     ctx.mark_non_differentiable(grad)
 
 
 def _aux_backward_fn(ctx, g_out, _g_grad):
     (grad,) = ctx.saved_tensors
+    if g_out is None:
+        return None, None, None
     # out-of-place: the loss is usually weighted (0.4 * aux) and small ([B, C, H/16, W/16])
     return grad * g_out.reshape(-1)[:1].to(grad.dtype), None, None
 
