@@ -7,6 +7,9 @@
 // Analytic RMI backward: see oracle/rmi_taps.py (checked against autograd on the CPU).
 #include "rmi3_common.cuh"
 #include "rmi3_fast_bwd.cuh"
+#include "rmi3_fast_bwd2.cuh"
+#include <cstdlib>
+#include <cstring>
 
 namespace sh {
 
@@ -453,6 +456,44 @@ static size_t pass2_smem_bytes() {
 bool fast_path_ok(const void* x, const void* grad, int elem, int H, int W, int nf, int nm, int nh, int fast_tab_ok);
 size_t fast_bwd_smem(int C, int nf, int nm, int nh) { return fast2::pass2_smem(C, nf, nm, nh); }
 
+// ---- TMA tensor maps (driver entry point fetched through the runtime: the library links cudart only) -------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;           // pure function pointer, resolved once
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// planes of [H][W] elements, box = boxw x boxh of one plane, out-of-bounds elements read as zero
+static bool make_plane_map(CUtensorMap* m, CUtensorMapDataType dt, int esize, const void* base, int W, int H, long planes,
+                           int boxw, int boxh) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr || ((uintptr_t)base & 15) || ((long)W * esize) % 16 || (boxw * esize) % 16) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+  const cuuint64_t strides[2] = {(cuuint64_t)W * esize, (cuuint64_t)W * H * esize};
+  const cuuint32_t box[3] = {(cuuint32_t)boxw, (cuuint32_t)boxh, 1u};
+  const cuuint32_t es[3] = {1u, 1u, 1u};
+  return enc(m, dt, 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+template <typename T> struct TmaType;
+template <> struct TmaType<float> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; };
+template <> struct TmaType<__nv_bfloat16> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; };
+template <> struct TmaType<__half> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_FLOAT16; };
+
+// which pass-2 kernel serves the fast path: "tma" (default) or "legacy" (SEGHIERO_B200_PASS2, for A/B measurements)
+static bool pass2_want_tma() {
+  const char* e = std::getenv("SEGHIERO_B200_PASS2");
+  return e == nullptr || std::strcmp(e, "legacy") != 0;
+}
+
 template <typename T>
 static int run_backward3(const void* x, void* grad, int B, int H, int W, const Hier3& h, const Ws3& ws,
                          const float* bandR, const float* bandC, float eps, float lw, const float* gscale, int stages,
@@ -468,6 +509,38 @@ static int run_backward3(const void* x, void* grad, int B, int H, int W, const H
     fh.nf = h.nf; fh.nm = h.nm; fh.nh = h.nh; fh.f2m = h.f2m; fh.f2h = h.f2h;
     fh.order = h.order + C; fh.aux = h.order + 2 * C;
     const int tiles_x = (W + fast2::TW - 1) / fast2::TW, tiles_y = (H + fast2::TH - 1) / fast2::TH;
+    // TMA form: needs 16-byte row pitches for the three maps (logits, 1/sum e^x, holder bytes)
+    CUtensorMap mx, mi, mh;
+    size_t tsmem = fast3::pass2_smem<T>(C, h.nf, h.nm, h.nh);
+    const char* dbg_e = std::getenv("SEGHIERO_B200_P2DBG");
+    const int dbg = dbg_e ? std::atoi(dbg_e) : 0;
+    if (pass2_want_tma() && tsmem <= 56 * 1024 &&
+        make_plane_map(&mx, TmaType<T>::v, (int)sizeof(T), x, W, H, (long)B * C, fast3::XBox<T>::COLS, fast3::PR) &&
+        make_plane_map(&mi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ws.inv, W, H, 3L * B, fast3::TW, fast3::TH) &&
+        make_plane_map(&mh, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, ws.hold, W, H, (long)(h.nm + h.nh + 2) * B, fast3::TW, fast3::TH)) {
+      // 4 CTAs per SM under a 128-register cap, or 3 with the compiler's own allocation (SEGHIERO_B200_P2DBG bit 3)
+      void (*t0)(CUtensorMap, CUtensorMap, CUtensorMap, const T*, T*, int, int, int, fast2::Hier2, Ws3, float, float,
+                 const float*, int, int, int) = (dbg & 8) ? fast3::k3t_pass2<T, false, 3> : fast3::k3t_pass2<T, false, 4>;
+      void (*t1)(CUtensorMap, CUtensorMap, CUtensorMap, const T*, T*, int, int, int, fast2::Hier2, Ws3, float, float,
+                 const float*, int, int, int) = (dbg & 8) ? fast3::k3t_pass2<T, true, 3> : fast3::k3t_pass2<T, true, 4>;
+      const char* stg_e = std::getenv("SEGHIERO_B200_P2STAGGER");
+      const int stagger = stg_e ? std::atoi(stg_e) : 0;
+      if (dbg & 2) tsmem = 120 * 1024;        // one CTA per SM
+      if (dbg & 4) tsmem = 75 * 1024;         // two
+      cudaFuncSetAttribute(t0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
+      cudaFuncSetAttribute(t1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
+      t0<<<B * tiles_x * tiles_y, fast3::NT, tsmem, st>>>(mx, mi, mh, (const T*)x, (T*)grad, B, H, W, fh, ws, eps, lw, gscale,
+                                                         tiles_x, tiles_x * tiles_y, stagger);
+      SH_CHECK_LAUNCH();
+      t1<<<B * tiles_x * tiles_y, fast3::NT, tsmem, st>>>(mx, mi, mh, (const T*)x, (T*)grad, B, H, W, fh, ws, eps, lw, gscale,
+                                                         tiles_x, tiles_x * tiles_y, stagger);
+      SH_CHECK_LAUNCH();
+      if (stages & 2) {
+        k3_frame2<T><<<dim3(B * C, ws.nseg), 256, 0, st>>>((T*)grad, B, H, W, h, ws, bandR, bandC, gscale);
+        SH_CHECK_LAUNCH();
+      }
+      return SH_OK;
+    }
     auto kern0 = fast2::k3f_pass2<T, false>;
     auto kern1 = fast2::k3f_pass2<T, true>;
     cudaFuncSetAttribute(kern0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);

@@ -1,79 +1,104 @@
-// Fast path of the three-level loss, backward side (pass 2): gradient of tree BCE + CE + RMI w.r.t. the logits.
-//
-// Applies to tree-shaped maps, W % 4 == 0, 16-byte aligned tensors, C <= 254 (the forward side may be either the
-// fast or the generic pass 1: both leave the same summaries).
+// Pass 2 of the three-level loss, TMA form (sm_100a): the same arithmetic and thread mapping as rmi3_fast_bwd.cuh
+// (read that file first), with every per-channel global read moved out of the threads:
+//   * the logit tile of the next channel INCLUDING its 2-pixel ring arrives as one cp.async.bulk.tensor box
+//     (68 x 36, out-of-image elements zero-filled by the TMA unit), 1/sum e^x of the channel's level as a second box and
+//     the holder bytes at group starts as a third / fourth; one elected thread issues them, an mbarrier with
+//     complete_tx hands them over.  The legacy kernel spends ~215 of its ~1600 instructions per (thread, channel) on
+//     cp.async address arithmetic and carries the addresses in ~20 registers.
+//   * with those registers gone the kernel fits 128 registers -> 4 CTAs per SM (16 warps instead of 12).
 // Reference arithmetic: models/loss/rmi_hiera_triplet_loss.py:349-526 (autograd of it); analytic RMI backward in
-// oracle/rmi_taps.py.  The generic kernel (rmi3_bwd.cu::k3_pass2) computes the same thing for every other case.
-//
-// One CTA = one 64 x 32 tile of one image, 128 threads, thread = 4 x 4 pixel block (+ one piece of the tile's
-// 2-pixel ring).  Per channel, in tree order (fine children, their mid, ..., the high):
-//   phase A  sigmoid / e^x (3 MUFU), tree-BCE + CE gradient from the per-pixel summaries of pass 1 (holder
-//            bytes, 1/sum e^x) -> 16 registers; P = s*valid + 1e-6 -> shared-memory plane (own block + ring piece)
-//   phase B  5x5 stencil over the plane (weights from k3f_finalize), + the one-hot stencil where the block's
-//            labels are mixed, combine, 128-bit store
-// Planes are double buffered: phase B of channel c and phase A of channel c+1 sit between the same pair of
-// barriers.  Everything a thread reads from global memory for channel c+1 (logits, 1/sum e^x of the channel's
-// level, holder bytes at group starts) travels with cp.async into the thread's own shared-memory slots while
-// phase B of channel c runs; no thread reads another thread's slots, so the only barrier is the plane hand-over.
-// Shared memory per CTA is ~57 KB and registers <= 168, so three CTAs share an SM.
+// oracle/rmi_taps.py.
 #pragma once
+#include <cuda.h>
 #include <type_traits>
-#include "rmi3_common.cuh"
+#include "rmi3_fast_bwd.cuh"
 
 namespace sh {
-namespace fast2 {
+namespace fast3 {
 
-constexpr int TW = 64, TH = 32;
-constexpr int NT = (TH / 4) * 16;         // 128 threads, each a 4 x 4 block
-constexpr int PW = TW + 4, PR = TH + 4, PLANE = PR * PW;
-constexpr int LP = TW + 8;                // label tile pitch (bytes): cols x0-2 .. x0+65 (+4 pad)
-constexpr int WS = 64;                    // floats per staged weight record: W1 at 0, W2 at 28, W2full at 56
-constexpr int SLOT = NT * 16;             // bytes of one staging row (16 bytes per thread)
+using fast2::Hier2;
+using fast2::byte_is_zero;
+constexpr int TW = fast2::TW, TH = fast2::TH, NT = fast2::NT, PW = fast2::PW, PR = fast2::PR, PLANE = fast2::PLANE;
+constexpr int LP = fast2::LP, WS = fast2::WS, SLOT = fast2::SLOT;
+constexpr int PLANE_B = ((PLANE * 4 + 127) / 128) * 128;          // bytes of one P plane, padded to the TMA alignment
 
-struct Hier2 {
-  int nf, nm, nh;
-  const int* f2m;             // [nf]
-  const int* f2h;             // [nf]
-  const unsigned int* order;  // [C] kind | class << 8 | flags << 16 | channel << 24 ; flags bit0/bit2 = first of a mid/high group
-  const unsigned int* aux;    // [C] mid id | high id << 8 (0xff = none)
+// the logit box: columns x0-2-XO .. x0+65+XO; the XO extra columns on each side make the box START a multiple of 16 bytes
+// (a TMA requirement for the innermost coordinate: an unaligned start is an illegal-instruction fault, measured with
+// scripts/ubench/tma_probe.cu) and keep its inner extent one
+template <typename T> struct XBox {
+  static constexpr int XO = sizeof(T) == 4 ? 2 : 6;
+  static constexpr int COLS = PW + 2 * XO;
+  static constexpr int BYTES = PR * COLS * (int)sizeof(T);
+  static constexpr int PAD = ((BYTES + 127) / 128) * 128;
 };
+constexpr int INV_B = TH * TW * 4, HOLD_B = TH * TW;
 
+template <typename T>
 inline size_t pass2_smem(int C, int nf, int nm, int nh) {
-  size_t s = (size_t)2 * PLANE * 4;                 // planes
-  s += (size_t)4 * SLOT;                            // logits of the next channel (4 rows per thread)
-  s += (size_t)4 * SLOT;                            // 1 / sum e^x of the next channel's level
-  s += (size_t)2 * SLOT;                            // ring pieces: strip / pair + corner pair
-  s += (size_t)4 * SLOT;                            // holder bytes: mid group, high group, fine target, mid target (4 rows x 4 bytes)
+  size_t s = (size_t)2 * PLANE_B;                   // P planes
+  s += XBox<T>::PAD;                                // logit box of the next channel
+  s += INV_B + 2 * HOLD_B;                          // 1 / sum e^x of its level; holder bytes of its mid / high group
+  s += (size_t)2 * SLOT;                            // holders of the positive terms (per-thread cp.async slots)
   s += (size_t)3 * PR * LP;                         // label tile
   s += (size_t)3 * WS * 4;                          // stencil weights (2 buffers) + their cp.async staging
-  s += (size_t)C * 16 + (size_t)2 * nf * 4 + 64;    // tables
-  s += (size_t)256 * 2 + 16;                        // deferred one-hot stencils: work list + counter
-  return (s + 15) & ~(size_t)15;
+  s += (size_t)C * 8 + (size_t)2 * nf * 4 + 64;     // tables
+  s += (size_t)256 * 2 + 16 + 16;                   // deferred one-hot stencils: work list + counter; mbarrier
+  return (s + 127) & ~(size_t)127;
 }
 
-__device__ __forceinline__ bool byte_is_zero(unsigned int z, int k) { return ((z >> (8 * k)) & 0xffu) == 0u; }
+__device__ __forceinline__ void mbar_expect_tx(unsigned int addr, unsigned int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(unsigned int dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned int mbar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(mbar) : "memory");
+}
+// acquire-wait on the box barrier; a transaction-count mistake must surface as a launch error, not as a hung GPU
+__device__ __forceinline__ void mbar_wait_or_trap(unsigned int addr, unsigned int parity) {
+  unsigned int ok, spins = 0;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 24)) __trap();
+  } while (!ok);
+}
+// 4 / 2 consecutive staged elements -> fp32
+template <typename T>
+__device__ __forceinline__ void ld4(const T* p, float (&o)[4]) {
+  staged_vec4<T>(p, o);      // 16-byte aligned for fp32 (column 4 + 4 st of the box), 8-byte for the 16-bit types
+}
+template <typename T>
+__device__ __forceinline__ void ld2(const T* p, float& a, float& b) {
+  if (sizeof(T) == 4) { const float2 t2 = *reinterpret_cast<const float2*>(p); a = t2.x; b = t2.y; }
+  else { a = staged_elem<T>(p, 0); b = staged_elem<T>(p, 1); }
+}
 
-template <typename T, bool INLINE_OH>
-__global__ void __launch_bounds__(NT, 3)
-k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hier2 hg, Ws3 ws, float eps,
-          float loss_weight, const float* __restrict__ gscale_ptr, int tiles_x, int tiles_per_img) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+template <typename T, bool INLINE_OH, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+k3t_pass2(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_inv,
+          const __grid_constant__ CUtensorMap map_hold, const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W,
+          Hier2 hg, Ws3 ws, float eps, float loss_weight, const float* __restrict__ gscale_ptr, int tiles_x,
+          int tiles_per_img, int stagger_ns) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int C = hg.nf + hg.nm + hg.nh;
-  float* planes = reinterpret_cast<float*>(smem_raw);                                  // [2][PLANE]
-  unsigned char* xst = reinterpret_cast<unsigned char*>(planes + 2 * PLANE);           // [4][NT] x 16 B
-  unsigned char* ist = xst + 4 * SLOT;                                                 // [4][NT] x 16 B
-  unsigned char* rst = ist + 4 * SLOT;                                                 // [2][NT] x 16 B
-  unsigned char* hst = rst + 2 * SLOT;                                                 // [4 kinds][NT] x (4 rows x 4 B)
-  unsigned char* LT = hst + 4 * SLOT;                                                  // [3][PR][LP]
+  constexpr int XO = XBox<T>::XO, XC = XBox<T>::COLS;
+  float* planes = reinterpret_cast<float*>(smem_raw);                                  // [2][PLANE_B / 4]
+  T* xbox = reinterpret_cast<T*>(smem_raw + 2 * PLANE_B);                              // [PR][XC] logits of the next channel
+  float* ibox = reinterpret_cast<float*>(smem_raw + 2 * PLANE_B + XBox<T>::PAD);       // [TH][TW] 1 / sum e^x
+  unsigned char* hbox = reinterpret_cast<unsigned char*>(ibox) + INV_B;                // [2][TH][TW] holder bytes (mid, high group)
+  unsigned char* hst = hbox + 2 * HOLD_B;                                              // [2 kinds][NT] x (4 rows x 4 B): positive-term holders
+  unsigned char* LT = hst + 2 * SLOT;                                                  // [3][PR][LP]
   float* wsm = reinterpret_cast<float*>(LT + 3 * PR * LP);                             // [2][WS]
   float* wst = wsm + 2 * WS;                                                           // [WS] raw weights of the next channel
-  long long* s_chb = reinterpret_cast<long long*>(wst + WS);                           // [C]
-  unsigned int* s_order = reinterpret_cast<unsigned int*>(s_chb + C);                  // [C]
+  unsigned int* s_order = reinterpret_cast<unsigned int*>(wst + WS);                   // [C]
   unsigned int* s_aux = s_order + C;                                                   // [C]
   int* s_f2m = reinterpret_cast<int*>(s_aux + C);                                      // [nf]
   int* s_f2h = s_f2m + hg.nf;                                                          // [nf]
   int* s_nwork = s_f2h + hg.nf;                                                        // [4] (one used)
   unsigned short* s_work = reinterpret_cast<unsigned short*>(s_nwork + 4);             // [256] block | order index << 7
+  unsigned long long* s_mbar = reinterpret_cast<unsigned long long*>(
+      (reinterpret_cast<uintptr_t>(s_work + 256) + 15) & ~(uintptr_t)15);               // [1]
+  const unsigned int mbar = (unsigned int)__cvta_generic_to_shared(s_mbar);
 
   const int tid = threadIdx.x;
   {
@@ -84,19 +109,25 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
     const bool noisy = 2u * ws.strips[2 * bb] > ws.strips[2 * bb + 1];
     if (noisy != INLINE_OH) return;
   }
-  if (tid == 0) s_nwork[0] = 0;
+  // The CTAs that share an SM run identical work: launched together they stay in lockstep, all in the MUFU / ALU
+  // heavy phase A or all in the FMA-bound phase B at the same time, and the pipes are used one after the other.  The
+  // first wave is therefore started a fraction of a channel period apart (later CTAs inherit the offsets, they
+  // start when an earlier one retires).
+  if (stagger_ns > 0 && blockIdx.x < (unsigned)(SH_NUM_SMS * MINB)) __nanosleep((blockIdx.x / SH_NUM_SMS) * stagger_ns);
+  if (tid == 0) {
+    s_nwork[0] = 0;
+    mbar_init(mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   const long HW = (long)H * W, BHW = (long)B * HW;
   const int b = blockIdx.x / tiles_per_img, tile = blockIdx.x - b * tiles_per_img;
   const int tyi = tile / tiles_x, ty0 = tyi * TH, tx0 = (tile - tyi * tiles_x) * TW;
   const unsigned char* lab8 = ws.lab8 + (long)b * HW;
-  const char* xbb = reinterpret_cast<const char*>(x + (long)b * C * HW);
   const bool border = ty0 < 2 || ty0 + TH > H - 2 || tx0 < 2 || tx0 + TW > W - 2;
 
   for (int i = tid; i < C; i += NT) {
-    const unsigned int oe = hg.order[i];
-    s_order[i] = oe;
+    s_order[i] = hg.order[i];
     s_aux[i] = hg.aux[i];
-    s_chb[i] = (long long)(oe >> 24) * HW * (long long)sizeof(T);
   }
   for (int i = tid; i < hg.nf; i += NT) { s_f2m[i] = hg.f2m[i]; s_f2h[i] = hg.f2h[i]; }
   __syncthreads();                                     // tables are in place
@@ -135,7 +166,7 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
   const float wCE = loss_weight * gscale / ((float)B * (float)HW);
 
   bool rowok[4];
-  long roff[4];                       // pixel offset of the strip inside one channel plane (clamped into the image)
+  int roff[4];                        // pixel offset of the strip inside one channel plane (clamped into the image)
   unsigned int tc0[4], tc1[4], tc2[4], hmN[4], hhN[4];
   // classes (mod 64, per level) that are the target of some pixel of the block: a set bit sends the channel through
   // the positive-term path; a collision only costs that detour
@@ -144,7 +175,7 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
   for (int j = 0; j < 4; ++j) {
     const int y = ty0 + 4 * rq + j;
     rowok[j] = y < H && colok;
-    roff[j] = (long)min(y, H - 1) * W + (colok ? xg : 0);
+    roff[j] = min(y, H - 1) * W + (colok ? xg : 0);
     const unsigned int t4 = rowok[j] ? *reinterpret_cast<const unsigned int*>(lab8 + roff[j]) : 0xffffffffu;
     tc0[j] = t4; tc1[j] = 0xffffffffu; tc2[j] = 0xffffffffu;
     hmN[j] = hhN[j] = 0xffffffffu;
@@ -175,8 +206,8 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
   }
   // ---- this thread's piece of the ring: tid < 64: 4-pixel strip of plane rows 0,1,TH+2,TH+3 ; tid >= 64: 2-pixel pair
   //      left / right of a body row ; tid < 8 also a 2-pixel corner pair ----
-  int pidx0, pidx1;
-  long goff0, goff1;
+  int pidx0, pidx1, xidx0, xidx1;     // plane index / logit-box index of this thread's ring piece(s)
+  int goff0, goff1;                   // only for the validity bytes below
   bool in0, in1;
   float hv[6];
   const bool is_strip = tid < 64;
@@ -184,21 +215,24 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
     const int hrow = tid >> 4, pr = hrow < 2 ? hrow : TH + hrow, strip = tid & 15;
     const int yy = ty0 - 2 + pr, xx = tx0 + 4 * strip;
     pidx0 = pr * PW + 2 + 4 * strip;
+    xidx0 = pr * XC + XO + 2 + 4 * strip;
     in0 = yy >= 0 && yy < H && xx < W;
-    goff0 = in0 ? (long)yy * W + xx : 0;
+    goff0 = in0 ? yy * W + xx : 0;
   } else {
     const int hl = tid - 64, srow = hl >> 1, side = hl & 1;
     const int yy = ty0 + srow, xx = side ? tx0 + TW : tx0 - 2;
     pidx0 = (2 + srow) * PW + (side ? TW + 2 : 0);
+    xidx0 = (2 + srow) * XC + XO + (side ? TW + 2 : 0);
     in0 = yy < H && xx >= 0 && xx < W;
-    goff0 = in0 ? (long)yy * W + xx : 0;
+    goff0 = in0 ? yy * W + xx : 0;
   }
   {
     const int crow = (tid >> 1) & 3, pr = crow < 2 ? crow : TH + crow, side = tid & 1;
     const int yy = ty0 - 2 + pr, xx = side ? tx0 + TW : tx0 - 2;
     pidx1 = pr * PW + (side ? TW + 2 : 0);
+    xidx1 = pr * XC + XO + (side ? TW + 2 : 0);
     in1 = tid < 8 && yy >= 0 && yy < H && xx >= 0 && xx < W;
-    goff1 = in1 ? (long)yy * W + xx : 0;
+    goff1 = in1 ? yy * W + xx : 0;
   }
   {
     unsigned int t4 = 0xffffffffu;
@@ -211,54 +245,27 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
     hv[5] = (t2 >> 8) != SH_IGNORE ? 1.f : 0.f;
   }
 
-  // ---- staging slots of this thread ----
-  const unsigned int xs_base = (unsigned int)__cvta_generic_to_shared(xst + tid * 16);
-  const unsigned int is_base = (unsigned int)__cvta_generic_to_shared(ist + tid * 16);
-  const unsigned int rs_base = (unsigned int)__cvta_generic_to_shared(rst + tid * 16);
+  // ---- staging ----
   const unsigned int hs_base = (unsigned int)__cvta_generic_to_shared(hst + tid * 16);
-  const unsigned char* xs_gen = xst + tid * 16;
-  const unsigned char* is_gen = ist + tid * 16;
-  const unsigned char* rs_gen = rst + tid * 16;
   const unsigned char* hs_gen = hst + tid * 16;
   const unsigned char* holdb = ws.hold + (long)b * HW;
-  const float* invb = ws.inv + (long)b * HW;
+  const unsigned int xbox_s = (unsigned int)__cvta_generic_to_shared(xbox);
+  const unsigned int ibox_s = (unsigned int)__cvta_generic_to_shared(ibox);
+  const unsigned int hbox_s = (unsigned int)__cvta_generic_to_shared(hbox);
 
-  // everything phase A of channel ci needs from global memory -> this thread's slots (one commit group)
+  // everything phase A of channel ci needs from global memory: three or four TMA boxes issued by one thread (the
+  // mbarrier's transaction count covers them), plus the channel's stencil weights (25 + 25 + 1 floats, cp.async)
   auto prefetch = [&](int ci) {
     const unsigned int oe = s_order[ci], ax = s_aux[ci];
     const int kind = oe & 3;
     const unsigned int fl = (oe >> 16) & 0xffu;
-    const char* g = xbb + s_chb[ci];
-    const float* ivl = invb + (long)kind * BHW;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const char* gp = g + roff[j] * (long)sizeof(T);
-      if (sizeof(T) == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(xs_base + j * SLOT), "l"(gp));
-      else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(xs_base + j * SLOT), "l"(gp));
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(is_base + j * SLOT), "l"(ivl + roff[j]));
-    }
-    if (is_strip) {
-      if (sizeof(T) == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rs_base), "l"(g + goff0 * 4));
-      else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(rs_base), "l"(g + goff0 * 2));
-    } else {
-      if (sizeof(T) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(rs_base), "l"(g + goff0 * 4));
-      else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(rs_base), "l"(g + goff0 * 2));
-    }
-    if (tid < 8) {
-      if (sizeof(T) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(rs_base + SLOT), "l"(g + goff1 * 4));
-      else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(rs_base + SLOT), "l"(g + goff1 * 2));
-    }
-    if (fl & 1u) {       // first channel of a mid group: the bytes that say which channel holds the group's max
-      const unsigned char* hp = holdb + (long)(ax & 0xffu) * BHW;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(hs_base + 4 * j), "l"(hp + roff[j]));
-    }
-    if ((fl & 4u) && (ax >> 8) != 0xffu) {
-      const unsigned char* hp = holdb + (long)(hg.nm + (ax >> 8)) * BHW;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(hs_base + SLOT + 4 * j), "l"(hp + roff[j]));
+    if (tid == 0) {
+      const bool hm = (fl & 1u) != 0u, hh = (fl & 4u) && (ax >> 8) != 0xffu;
+      mbar_expect_tx(mbar, (unsigned int)(XBox<T>::BYTES + INV_B + (hm ? HOLD_B : 0) + (hh ? HOLD_B : 0)));
+      tma_load_3d(xbox_s, &map_x, tx0 - 2 - XO, ty0 - 2, b * C + (int)(oe >> 24), mbar);
+      tma_load_3d(ibox_s, &map_inv, tx0, ty0, kind * B + b, mbar);
+      if (hm) tma_load_3d(hbox_s, &map_hold, tx0, ty0, (int)(ax & 0xffu) * B + b, mbar);
+      if (hh) tma_load_3d(hbox_s + HOLD_B, &map_hold, tx0, ty0, (hg.nm + (int)(ax >> 8)) * B + b, mbar);
     }
     if (tid < 25 || tid == 28) {   // stencil weights of the channel (k3f_finalize: W1[25], W2[25], sum W2 at 50)
       const float* src = ws.wts + ((size_t)b * C + (oe >> 24)) * 64;
@@ -280,7 +287,7 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
       const unsigned char* hp = holdb + (long)(hg.nm + hg.nh + q) * BHW;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(hs_base + (2 + q) * SLOT + 4 * j), "l"(hp + roff[j]));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(hs_base + q * SLOT + 4 * j), "l"(hp + roff[j]));
     }
   }
   prefetch(0);
@@ -316,20 +323,21 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
     const int kind = oe & 3;
     const unsigned int fl = (oe >> 16) & 0xffu, ch = oe >> 24;
     const unsigned int cc = ch * 0x01010101u;
-    float* plane = planes + (ci & 1) * PLANE;
+    float* plane = planes + (ci & 1) * (PLANE_B / 4);
+    const unsigned char* hrow = hbox + (4 * rq) * TW + 4 * st;      // this thread's 4 x 4 bytes of a holder box
     if (fl & 1u) {       // where does the group's (1 - max) term count: everywhere but at pixels whose target is this mid
       const unsigned int midc = (unsigned int)(hg.nf + (ax & 0xffu)) * 0x01010101u;
-      const uint4 hm = *reinterpret_cast<const uint4*>(hs_gen);
-      hmN[0] = hm.x | __vcmpeq4(tc1[0], midc); hmN[1] = hm.y | __vcmpeq4(tc1[1], midc);
-      hmN[2] = hm.z | __vcmpeq4(tc1[2], midc); hmN[3] = hm.w | __vcmpeq4(tc1[3], midc);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        hmN[j] = *reinterpret_cast<const unsigned int*>(hrow + j * TW) | __vcmpeq4(tc1[j], midc);
     }
     if (fl & 4u) {
       const unsigned int high = ax >> 8;
       if (high != 0xffu) {
         const unsigned int highc = (unsigned int)(hg.nf + hg.nm + high) * 0x01010101u;
-        const uint4 hh = *reinterpret_cast<const uint4*>(hs_gen + SLOT);
-        hhN[0] = hh.x | __vcmpeq4(tc2[0], highc); hhN[1] = hh.y | __vcmpeq4(tc2[1], highc);
-        hhN[2] = hh.z | __vcmpeq4(tc2[2], highc); hhN[3] = hh.w | __vcmpeq4(tc2[3], highc);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          hhN[j] = *reinterpret_cast<const unsigned int*>(hrow + HOLD_B + j * TW) | __vcmpeq4(tc2[j], highc);
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) hhN[j] = 0xffffffffu;
@@ -338,10 +346,9 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
     // ---- ring piece(s): sigmoid only ----
     {
       float xv[4];
-      if (is_strip) staged_vec4<T>(rs_gen, xv);
+      if (is_strip) ld4<T>(xbox + xidx0, xv);
       else {
-        if (sizeof(T) == 4) { const float2 t2 = *reinterpret_cast<const float2*>(rs_gen); xv[0] = t2.x; xv[1] = t2.y; }
-        else { xv[0] = staged_elem<T>(rs_gen, 0); xv[1] = staged_elem<T>(rs_gen, 1); }
+        ld2<T>(xbox + xidx0, xv[0], xv[1]);
         xv[2] = xv[3] = 0.f;
       }
       if (in0) {
@@ -351,8 +358,7 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
       }
       if (in1) {
         float a0, a1;
-        if (sizeof(T) == 4) { const float2 t2 = *reinterpret_cast<const float2*>(rs_gen + SLOT); a0 = t2.x; a1 = t2.y; }
-        else { a0 = staged_elem<T>(rs_gen + SLOT, 0); a1 = staged_elem<T>(rs_gen + SLOT, 1); }
+        ld2<T>(xbox + xidx1, a0, a1);
         *reinterpret_cast<float2*>(plane + pidx1) = make_float2(fmaf(sig_only(a0), hv[4], 1e-6f), fmaf(sig_only(a1), hv[5], 1e-6f));
       }
     }
@@ -370,8 +376,8 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float xv[4];
-      staged_vec4<T>(xs_gen + j * SLOT, xv);
-      const float4 iv4 = *reinterpret_cast<const float4*>(is_gen + j * SLOT);
+      ld4<T>(xbox + (4 * rq + 2 + j) * XC + XO + 2 + 4 * st, xv);
+      const float4 iv4 = *reinterpret_cast<const float4*>(ibox + (4 * rq + j) * TW + 4 * st);
       const float ivk[4] = {iv4.x, iv4.y, iv4.z, iv4.w};       // 1 / sum e^x of the level; 0 on void pixels
       const unsigned int zM = hmN[j] ^ cc, zH = hhN[j] ^ cc;
       float s[4], E[4], t[4], oh[4], ds[4];
@@ -391,8 +397,8 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
       }
       if (pos) {
         const unsigned int zT = (kind == 0 ? tc0[j] : (kind == 1 ? tc1[j] : tc2[j])) ^ cc;
-        const unsigned int zPF = *reinterpret_cast<const unsigned int*>(hs_gen + 2 * SLOT + 4 * j) ^ cc;
-        const unsigned int zPM = *reinterpret_cast<const unsigned int*>(hs_gen + 3 * SLOT + 4 * j) ^ cc;
+        const unsigned int zPF = *reinterpret_cast<const unsigned int*>(hs_gen + 4 * j) ^ cc;
+        const unsigned int zPM = *reinterpret_cast<const unsigned int*>(hs_gen + SLOT + 4 * j) ^ cc;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           float Bp = byte_is_zero(zPF, k) ? wF : 0.f;
@@ -425,7 +431,7 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
     const int kind = oe & 3;
     const unsigned int cl = (oe >> 8) & 0xffu, ch = oe >> 24;
     const float* wp = wsm + (ci & 1) * WS;
-    const float* pl = planes + (ci & 1) * PLANE + (4 * rq) * PW + 4 * st;
+    const float* pl = planes + (ci & 1) * (PLANE_B / 4) + (4 * rq) * PW + 4 * st;
     const unsigned int ub = kind == 0 ? ublk[0] : (kind == 1 ? ublk[1] : ublk[2]);
     const unsigned int ph = kind == 0 ? pres[0] : (kind == 1 ? pres[1] : pres[2]);
     const float init = ub == cl ? wp[56] : 0.f;
@@ -608,7 +614,8 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
     if (ci >= 0 && ci + 1 < C) prefetch(ci + 1);
     if (ci >= 0) phaseB(ci);
     if (ci + 1 < C) {
-      cp_async_wait<0>();
+      cp_async_wait<0>();                              // this thread's weight words (and, once, the positive-term holders)
+      mbar_wait_or_trap(mbar, (unsigned int)(ci + 1) & 1u);    // the TMA boxes of channel ci + 1 have landed
       phaseA(ci + 1);
     }
     // planes handed over; gradient stores of phase B visible to the CTA; number of deferred stencils queued by phase B
@@ -619,5 +626,5 @@ k3f_pass2(const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W, Hi
   }
 }
 
-}  // namespace fast2
+}  // namespace fast3
 }  // namespace sh
