@@ -511,29 +511,25 @@ static int run_backward3(const void* x, void* grad, int B, int H, int W, const H
     const int tiles_x = (W + fast2::TW - 1) / fast2::TW, tiles_y = (H + fast2::TH - 1) / fast2::TH;
     // TMA form: needs 16-byte row pitches for the three maps (logits, 1/sum e^x, holder bytes)
     CUtensorMap mx, mi, mh;
-    size_t tsmem = fast3::pass2_smem<T>(C, h.nf, h.nm, h.nh);
-    const char* dbg_e = std::getenv("SEGHIERO_B200_P2DBG");
-    const int dbg = dbg_e ? std::atoi(dbg_e) : 0;
+    const size_t tsmem = fast3::pass2_smem<T>(C, h.nf, h.nm, h.nh);
+    const char* ctas_e = std::getenv("SEGHIERO_B200_P2CTAS");          // "4": the 128-register variant (A/B measurements)
+    const bool four = ctas_e != nullptr && std::atoi(ctas_e) == 4;
     if (pass2_want_tma() && tsmem <= 56 * 1024 &&
         make_plane_map(&mx, TmaType<T>::v, (int)sizeof(T), x, W, H, (long)B * C, fast3::XBox<T>::COLS, fast3::PR) &&
         make_plane_map(&mi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ws.inv, W, H, 3L * B, fast3::TW, fast3::TH) &&
         make_plane_map(&mh, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, ws.hold, W, H, (long)(h.nm + h.nh + 2) * B, fast3::TW, fast3::TH)) {
-      // 4 CTAs per SM under a 128-register cap, or 3 with the compiler's own allocation (SEGHIERO_B200_P2DBG bit 3)
+      // 3 CTAs per SM with the compiler's own register allocation (default), or 4 under a 128-register cap
       void (*t0)(CUtensorMap, CUtensorMap, CUtensorMap, const T*, T*, int, int, int, fast2::Hier2, Ws3, float, float,
-                 const float*, int, int, int) = (dbg & 8) ? fast3::k3t_pass2<T, false, 3> : fast3::k3t_pass2<T, false, 4>;
+                 const float*, int, int) = four ? fast3::k3t_pass2<T, false, 4> : fast3::k3t_pass2<T, false, 3>;
       void (*t1)(CUtensorMap, CUtensorMap, CUtensorMap, const T*, T*, int, int, int, fast2::Hier2, Ws3, float, float,
-                 const float*, int, int, int) = (dbg & 8) ? fast3::k3t_pass2<T, true, 3> : fast3::k3t_pass2<T, true, 4>;
-      const char* stg_e = std::getenv("SEGHIERO_B200_P2STAGGER");
-      const int stagger = stg_e ? std::atoi(stg_e) : 0;
-      if (dbg & 2) tsmem = 120 * 1024;        // one CTA per SM
-      if (dbg & 4) tsmem = 75 * 1024;         // two
+                 const float*, int, int) = four ? fast3::k3t_pass2<T, true, 4> : fast3::k3t_pass2<T, true, 3>;
       cudaFuncSetAttribute(t0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
       cudaFuncSetAttribute(t1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
-      t0<<<B * tiles_x * tiles_y, fast3::NT, tsmem, st>>>(mx, mi, mh, (const T*)x, (T*)grad, B, H, W, fh, ws, eps, lw, gscale,
-                                                         tiles_x, tiles_x * tiles_y, stagger);
+      t0<<<dim3(tiles_x * tiles_y, B), fast3::NT, tsmem, st>>>(mx, mi, mh, (const T*)x, (T*)grad, B, H, W, fh, ws, eps, lw, gscale,
+                                                         tiles_x, tiles_x * tiles_y);
       SH_CHECK_LAUNCH();
-      t1<<<B * tiles_x * tiles_y, fast3::NT, tsmem, st>>>(mx, mi, mh, (const T*)x, (T*)grad, B, H, W, fh, ws, eps, lw, gscale,
-                                                         tiles_x, tiles_x * tiles_y, stagger);
+      t1<<<dim3(tiles_x * tiles_y, B), fast3::NT, tsmem, st>>>(mx, mi, mh, (const T*)x, (T*)grad, B, H, W, fh, ws, eps, lw, gscale,
+                                                         tiles_x, tiles_x * tiles_y);
       SH_CHECK_LAUNCH();
       if (stages & 2) {
         k3_frame2<T><<<dim3(B * C, ws.nseg), 256, 0, st>>>((T*)grad, B, H, W, h, ws, bandR, bandC, gscale);

@@ -5,7 +5,9 @@
 //     the holder bytes at group starts as a third / fourth; one elected thread issues them, an mbarrier with
 //     complete_tx hands them over.  The legacy kernel spends ~215 of its ~1600 instructions per (thread, channel) on
 //     cp.async address arithmetic and carries the addresses in ~20 registers.
-//   * with those registers gone the kernel fits 128 registers -> 4 CTAs per SM (16 warps instead of 12).
+//   * with those registers gone the kernel fits 128 registers -> 4 CTAs per SM (MINB = 4); measured, 3 CTAs with the
+//     compiler's own 168 registers (MINB = 3, the default) is as fast: the kernel is bound by operand reads of the
+//     register file, not by latency.
 // Reference arithmetic: models/loss/rmi_hiera_triplet_loss.py:349-526 (autograd of it); analytic RMI backward in
 // oracle/rmi_taps.py.
 #pragma once
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(NT, MINB)
 k3t_pass2(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_inv,
           const __grid_constant__ CUtensorMap map_hold, const T* __restrict__ x, T* __restrict__ grad, int B, int H, int W,
           Hier2 hg, Ws3 ws, float eps, float loss_weight, const float* __restrict__ gscale_ptr, int tiles_x,
-          int tiles_per_img, int stagger_ns) {
+          int tiles_per_img) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int C = hg.nf + hg.nm + hg.nh;
   constexpr int XO = XBox<T>::XO, XC = XBox<T>::COLS;
@@ -105,22 +107,17 @@ k3t_pass2(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
     // Two instantiations are launched back to back; each image is served by one of them.  Images whose labels are
     // noisy (most 3x8 strips see more than one class, counted by k3f_prep) do their one-hot stencils inline, the
     // others defer them to a work list (see phase B).  Without statistics (generic pass 1) everything defers.
-    const int bb = blockIdx.x / tiles_per_img;
+    const int bb = blockIdx.y;          // grid = (tiles of one image, images): the image index stays on the uniform datapath
     const bool noisy = 2u * ws.strips[2 * bb] > ws.strips[2 * bb + 1];
     if (noisy != INLINE_OH) return;
   }
-  // The CTAs that share an SM run identical work: launched together they stay in lockstep, all in the MUFU / ALU
-  // heavy phase A or all in the FMA-bound phase B at the same time, and the pipes are used one after the other.  The
-  // first wave is therefore started a fraction of a channel period apart (later CTAs inherit the offsets, they
-  // start when an earlier one retires).
-  if (stagger_ns > 0 && blockIdx.x < (unsigned)(SH_NUM_SMS * MINB)) __nanosleep((blockIdx.x / SH_NUM_SMS) * stagger_ns);
   if (tid == 0) {
     s_nwork[0] = 0;
     mbar_init(mbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const long HW = (long)H * W, BHW = (long)B * HW;
-  const int b = blockIdx.x / tiles_per_img, tile = blockIdx.x - b * tiles_per_img;
+  const int b = blockIdx.y, tile = blockIdx.x;
   const int tyi = tile / tiles_x, ty0 = tyi * TH, tx0 = (tile - tyi * tiles_x) * TW;
   const unsigned char* lab8 = ws.lab8 + (long)b * HW;
   const bool border = ty0 < 2 || ty0 + TH > H - 2 || tx0 < 2 || tx0 + TW > W - 2;
