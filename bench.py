@@ -432,8 +432,11 @@ def run_ours(args, w):
     fast2 = w["kind"] == "2level"
     if fast3 or fast2:
         names.update(FAST_NAMES)
+    if fast3:
+        names[("sh_rmi3_backward", 1)] = mod.pass2_kernel(x, lab)       # k3t_pass2 (TMA) or k3f_pass2 (cp.async)
     stage_bytes = {"k3_pass1": ab.get("pass1"), "k3_pass2": ab.get("pass2"), "k_bce2_fused": ab.get("fused"),
-                   "k_bce2_fast": ab.get("fused"), "k3f_pass1": ab.get("pass1"), "k3f_pass2": ab.get("pass2")}
+                   "k_bce2_fast": ab.get("fused"), "k3f_pass1": ab.get("pass1"), "k3f_pass2": ab.get("pass2"),
+                   "k3t_pass2": ab.get("pass2")}
 
     def stage_ms(tm):
         return {names[k]: t / n for k, (t, n) in tm.totals().items() if k in names}

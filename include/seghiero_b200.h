@@ -110,6 +110,12 @@ int sh_loss3_final(int B, int H, int W, int nf, int nm, int nh, void* workspace,
                    double total_steps, const float* trip, const int* ready, float loss_weight, float* out,
                    void* stream);
 
+/* Which pass-2 kernel sh_rmi3_backward runs for this problem (host arithmetic only): 0 = generic, 1 = tiled kernel with
+ * per-thread cp.async staging (csrc/rmi3_fast_bwd.cuh), 2 = tiled kernel with TMA box loads (csrc/rmi3_fast_bwd2.cuh:
+ * needs W % 16 == 0 for the holder-byte tensor map). */
+int sh_rmi3_pass2_kind(const void* logits, const void* grad, int dtype, int H, int W, int nf, int nm, int nh,
+                       int fast_tab_ok);
+
 /* Pass 2: d loss / d logits written once (grad_out = device scalar handed over by autograd). */
 int sh_rmi3_backward(const void* logits, int dtype, void* grad, int B, int H, int W, int nf, int nm, int nh,
                      const int* hier_tab, int n_mh, int fast_tab_ok, float loss_weight, void* workspace,

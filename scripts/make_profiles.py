@@ -10,7 +10,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-STAGE = {"k3f_pass1": "k3f_pass1", "k3f_pass2": "k3f_pass2", "k3_pass1": "k3_pass1", "k3_pass2": "k3_pass2",
+STAGE = {"k3f_pass1": "k3f_pass1", "k3f_pass2": "k3f_pass2", "k3t_pass2": "k3t_pass2", "k_upsample4": "k_upsample", "k_upsample4_adjoint": "k_upsample_adjoint", "k3_pass1": "k3_pass1", "k3_pass2": "k3_pass2",
          "k_bce2_fast": "k_bce2_fast", "k_bce2_fused": "k_bce2_fused", "k_decode_vec": "k_decode", "k_decode": "k_decode", "k3f_prep": "k3f_prep"}
 
 
@@ -51,7 +51,7 @@ def main():
                           f"{os.path.basename(rep)}, {int(px)} pixels in the captured launch"}
         summ = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), rep, "25"],
                               capture_output=True, text=True).stdout
-        dst = os.path.join(ROOT, "profiles", "r01_ncu_" + os.path.basename(rep).replace(".ncu-rep", "") + ".txt")
+        dst = os.path.join(ROOT, "profiles", os.environ.get("PROFILE_ROUND", "r02") + "_ncu_" + os.path.basename(rep).replace(".ncu-rep", "") + ".txt")
         with open(dst, "w") as fh:
             fh.write(f"# {os.path.basename(rep)}: ncu --set full --clock-control none --import-source on, "
                      f"{int(px)} label-resolution pixels per launch ({workload})\n" + summ)

@@ -26,6 +26,7 @@ SIGNATURES = {
     "sh_rmi3_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "sh_rmi3_workspace_offsets": (_i, [_i, _i, _i, _i, _i, _i, _p]),
     "sh_rmi3_fast_path": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i]),
+    "sh_rmi3_pass2_kind": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i]),
     "sh_rmi3_forward": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _f, _f, _p, _i, _p]),
     "sh_loss3_final": (_i, [_i, _i, _i, _i, _i, _i, _p, _f, _p, _d, _p, _p, _f, _p, _p]),
     "sh_rmi3_backward": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _f, _p, _p, _i, _p]),

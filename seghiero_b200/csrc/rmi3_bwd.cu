@@ -570,6 +570,20 @@ static int run_backward3(const void* x, void* grad, int B, int H, int W, const H
 
 extern "C" {
 
+// Which pass-2 kernel sh_rmi3_backward launches for this problem: 0 = generic k3_pass2, 1 = tiled cp.async kernel
+// (k3f_pass2), 2 = tiled TMA kernel (k3t_pass2).  Pure host arithmetic (diagnostics, bench.py's stage names).
+int sh_rmi3_pass2_kind(const void* logits, const void* grad, int dtype, int H, int W, int nf, int nm, int nh,
+                       int fast_tab_ok) {
+  const int es = dtype == SH_DT_F32 ? 4 : 2, C = nf + nm + nh;
+  const bool fast = fast_tab_ok && (W & 3) == 0 && C <= 254 && (uintptr_t)logits % (4 * es) == 0 &&
+                    (uintptr_t)grad % (4 * es) == 0 && sh::fast2::pass2_smem(C, nf, nm, nh) <= 227 * 1024;
+  if (!fast) return 0;
+  const size_t tsmem = es == 4 ? sh::fast3::pass2_smem<float>(C, nf, nm, nh) : sh::fast3::pass2_smem<__half>(C, nf, nm, nh);
+  const bool tma = sh::pass2_want_tma() && tsmem <= 56 * 1024 && ((long)W * es) % 16 == 0 && W % 16 == 0 &&
+                   ((uintptr_t)logits & 15) == 0 && sh::encode_tiled_fn() != nullptr;
+  return tma ? 2 : 1;
+}
+
 int sh_rmi3_backward(const void* logits, int dtype, void* grad, int B, int H, int W, int nf, int nm, int nh,
                      const int* hier_tab, int n_mh, int fast_tab_ok, float loss_weight, void* workspace,
                      const float* grad_out, int stages, void* stream) {

@@ -85,6 +85,17 @@ class RMIHieraTripletLoss(nn.Module):
                 raise ValueError("list.remove(x): x not in list (label in neither upper_ids nor lower_ids)")
         return out[0]
 
+    def pass2_kernel(self, cls_score, label) -> str:
+        """Name of the pass-2 kernel that serves this call (diagnostics / bench stage names)."""
+        from .. import _lib
+        tab, n_mh, fast_ok = H.three_level_tables(self.n_fine, self.n_mid, self.n_high, self._f2m, self._f2h)
+        hh, ww = label.shape[-2:]
+        same = tuple(cls_score.shape[-2:]) == (hh, ww)
+        ptr = ops._p(cls_score) if same else None
+        kind = _lib.load().sh_rmi3_pass2_kind(ptr, ptr, ops._dtype_code(cls_score), int(hh), int(ww), self.n_fine, self.n_mid,
+                                              self.n_high, int(fast_ok) if self.fast_path else 0)
+        return ("k3_pass2", "k3f_pass2", "k3t_pass2")[kind]
+
     def uses_fast_path(self, cls_score, label) -> bool:
         """Whether the warp-specialised / tiled kernels (not the generic ones) serve this call (diagnostics)."""
         from .. import _lib
