@@ -534,6 +534,10 @@ __global__ void __launch_bounds__(256) k_scale_inplace(T* __restrict__ g, long n
     g[i] = from_f32<T>(to_f32<T>(g[i]) * s);
 }
 
+template <typename T, int VEC>
+static int launch_bce2_generic(const void* x, const unsigned char* lab8, void* grad, int B, long HW, const Hier2& h, float eps,
+                               float lw, const unsigned long long* counts, float* partials, int grid, cudaStream_t st);
+
 template <typename T>
 static int launch_bce2(const void* x, const unsigned char* lab8, void* grad, int B, long HW, const Hier2& h, float eps,
                        float lw, const unsigned long long* counts, float* partials, int grid, bool tree, cudaStream_t st) {
@@ -552,11 +556,20 @@ static int launch_bce2(const void* x, const unsigned char* lab8, void* grad, int
     SH_CHECK_LAUNCH();
     return SH_OK;
   }
-  constexpr int VEC = 2;
+  const int C = h.nf + h.nc;
+  // sigmoid and e^x of every channel are parked in shared memory: 256 pixels per CTA (2 per thread), or 128 (1 per
+  // thread) for hierarchies whose 256-pixel tile does not fit (e.g. 150 fine + 30 coarse classes)
+  if ((size_t)C * 256 * 8 + (size_t)h.nc * 256 <= 227 * 1024) return launch_bce2_generic<T, 2>(x, lab8, grad, B, HW, h, eps, lw, counts, partials, grid, st);
+  if ((size_t)C * 128 * 8 + (size_t)h.nc * 128 <= 227 * 1024) return launch_bce2_generic<T, 1>(x, lab8, grad, B, HW, h, eps, lw, counts, partials, grid, st);
+  return SH_ERR_UNSUPPORTED;
+}
+
+template <typename T, int VEC>
+static int launch_bce2_generic(const void* x, const unsigned char* lab8, void* grad, int B, long HW, const Hier2& h, float eps,
+                               float lw, const unsigned long long* counts, float* partials, int grid, cudaStream_t st) {
   constexpr int PX = 128 * VEC;
   const int C = h.nf + h.nc;
-  size_t smem = (size_t)C * PX * 8 + (size_t)h.nc * PX;
-  if (smem > 227 * 1024) return SH_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)C * PX * 8 + (size_t)h.nc * PX;
   bool vec_ok = (HW % VEC == 0) && ((uintptr_t)x % (VEC * sizeof(T)) == 0) &&
                 (grad == nullptr || (uintptr_t)grad % (VEC * sizeof(T)) == 0);
   if (grad) {

@@ -142,6 +142,11 @@ __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2hal
 // N consecutive elements -> fp32.  Vector path needs (ptr) aligned to N*sizeof(T).
 template <typename T, int N>
 struct VecIO;
+template <typename T>
+struct VecIO<T, 1> {       // scalar form (kernels that fall back to one pixel per thread for very wide hierarchies)
+  static __device__ __forceinline__ void load(const T* p, float (&o)[1]) { o[0] = to_f32<T>(__ldg(p)); }
+  static __device__ __forceinline__ void store(T* p, const float (&o)[1]) { *p = from_f32<T>(o[0]); }
+};
 
 template <>
 struct VecIO<float, 4> {

@@ -26,8 +26,11 @@ __device__ __forceinline__ Lerp lerp_src(int dst, float scale, int n_in) {
   r.l0 = 1.0f - r.l1;
   return r;
 }
+// w0 * a + w1 * b with a FIXED contraction (every kernel of this file must produce the same bits for the same pixel: the
+// fused decode is tested bit for bit against upsample + decode)
+__device__ __forceinline__ float lerp2(float a, float b, float w0, float w1) { return __fmaf_rn(w1, b, __fmul_rn(w0, a)); }
 __device__ __forceinline__ float bilerp(float a, float b, float c, float d, float w0, float w1, float h0, float h1) {
-  return h0 * (w0 * a + w1 * b) + h1 * (w0 * c + w1 * d);
+  return lerp2(lerp2(a, b, w0, w1), lerp2(c, d, w0, w1), h0, h1);
 }
 // what the value becomes when torch stores it in a tensor of type T
 template <typename T>
@@ -110,51 +113,66 @@ __global__ void __launch_bounds__(256) k_upsample_adjoint(const T* __restrict__ 
 // (scale = 0.25 is exact in fp32, so these are the very numbers lerp_src produces).  Blocks that touch row / column 0
 // (clamped source index) take the generic formula.
 template <typename T>
-__global__ void __launch_bounds__(256) k_upsample4(const T* __restrict__ in, T* __restrict__ out, long planes, int h, int w) {
+__device__ __forceinline__ void up4_load(const T* __restrict__ in, long g, int h, int w, float (&v)[3][3], int& Y, int& X,
+                                         long& p) {
+  X = (int)(g % w);
+  const long r = g / w;
+  Y = (int)(r % h);
+  p = r / h;
+  const T* base = in + p * (long)h * w;
+  const int ym = max(Y - 1, 0), yp = min(Y + 1, h - 1), xm = max(X - 1, 0), xp = min(X + 1, w - 1);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const T* row = base + (long)(a == 0 ? ym : (a == 1 ? Y : yp)) * w;
+    v[a][0] = to_f32<T>(__ldg(row + xm));
+    v[a][1] = to_f32<T>(__ldg(row + X));
+    v[a][2] = to_f32<T>(__ldg(row + xp));
+  }
+}
+template <typename T>
+__device__ __forceinline__ void up4_store(const T* __restrict__ in, T* __restrict__ out, const float (&v)[3][3], int Y, int X,
+                                          long p, int h, int w) {
   const int H = 4 * h, W = 4 * w;
-  const long total = planes * h * w;
-  for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
-    const int X = (int)(g % w);
-    const long r = g / w;
-    const int Y = (int)(r % h);
-    const long p = r / h;
-    const T* base = in + p * (long)h * w;
-    T* ob = out + (p * H + 4 * Y) * (long)W + 4 * X;
-    if (Y > 0 && X > 0) {
-      const int yp = min(Y + 1, h - 1), xp = min(X + 1, w - 1);
-      float v[3][3];
+  T* ob = out + (p * H + 4 * Y) * (long)W + 4 * X;
+  if (Y > 0 && X > 0) {
+    const float l1[4] = {0.625f, 0.875f, 0.125f, 0.375f};
 #pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        const T* row = base + (long)(a == 0 ? Y - 1 : (a == 1 ? Y : yp)) * w;
-        v[a][0] = to_f32<T>(__ldg(row + X - 1));
-        v[a][1] = to_f32<T>(__ldg(row + X));
-        v[a][2] = to_f32<T>(__ldg(row + xp));
-      }
-      const float l1[4] = {0.625f, 0.875f, 0.125f, 0.375f};
+    for (int j = 0; j < 4; ++j) {
+      float o[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float o[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          o[k] = bilerp(v[j >> 1][k >> 1], v[j >> 1][(k >> 1) + 1], v[(j >> 1) + 1][k >> 1], v[(j >> 1) + 1][(k >> 1) + 1],
-                        1.0f - l1[k], l1[k], 1.0f - l1[j], l1[j]);
-        VecIO<T, 4>::store(ob + (long)j * W, o);
-      }
-    } else {
-#pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
-        const Lerp ly = lerp_src(4 * Y + j, 0.25f, h);
-        float o[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const Lerp lx = lerp_src(4 * X + k, 0.25f, w);
-          o[k] = bilerp(to_f32<T>(__ldg(base + (long)ly.i0 * w + lx.i0)), to_f32<T>(__ldg(base + (long)ly.i0 * w + lx.i1)),
-                        to_f32<T>(__ldg(base + (long)ly.i1 * w + lx.i0)), to_f32<T>(__ldg(base + (long)ly.i1 * w + lx.i1)),
-                        lx.l0, lx.l1, ly.l0, ly.l1);
-        }
-        VecIO<T, 4>::store(ob + (long)j * W, o);
-      }
+      for (int k = 0; k < 4; ++k)
+        o[k] = bilerp(v[j >> 1][k >> 1], v[j >> 1][(k >> 1) + 1], v[(j >> 1) + 1][k >> 1], v[(j >> 1) + 1][(k >> 1) + 1],
+                      1.0f - l1[k], l1[k], 1.0f - l1[j], l1[j]);
+      VecIO<T, 4>::store(ob + (long)j * W, o);
     }
+  } else {         // row / column 0 of the low-resolution map: the clamped source index pairs (0, 1) with weights (1, 0)
+    const T* base = in + p * (long)h * w;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      const Lerp ly = lerp_src(4 * Y + j, 0.25f, h);
+      float o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const Lerp lx = lerp_src(4 * X + k, 0.25f, w);
+        o[k] = bilerp(to_f32<T>(__ldg(base + (long)ly.i0 * w + lx.i0)), to_f32<T>(__ldg(base + (long)ly.i0 * w + lx.i1)),
+                      to_f32<T>(__ldg(base + (long)ly.i1 * w + lx.i0)), to_f32<T>(__ldg(base + (long)ly.i1 * w + lx.i1)),
+                      lx.l0, lx.l1, ly.l0, ly.l1);
+      }
+      VecIO<T, 4>::store(ob + (long)j * W, o);
+    }
+  }
+}
+// (two blocks per trip with all 18 loads in flight before the first store was measured slower: 0.48 vs 0.41 ms at
+// config 3, 76 instead of 61 registers)
+template <typename T>
+__global__ void __launch_bounds__(256) k_upsample4(const T* __restrict__ in, T* __restrict__ out, long planes, int h, int w) {
+  const long total = planes * h * w, stride = (long)gridDim.x * blockDim.x;
+  for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < total; g += stride) {
+    float v[3][3];
+    int Y, X;
+    long p;
+    up4_load<T>(in, g, h, w, v, Y, X, p);
+    up4_store<T>(in, out, v, Y, X, p, h, w);
   }
 }
 
@@ -368,73 +386,63 @@ __device__ __forceinline__ void store_args4(unsigned char* dst, const int (&a)[4
 }
 __device__ __forceinline__ float pick3(const float (&v)[3], int i) { return i == 0 ? v[0] : (i == 1 ? v[1] : v[2]); }
 
+// first-max argmax update without branches: take when val > best, or val is NaN and best is not (torch.argmax counts NaN
+// as the maximum and keeps the first one).  best starts at -inf with arg 0, so the first channel needs no special case.
+__device__ __forceinline__ void argmax_step(float val, int idx, float& best, int& arg) {
+  const bool take = (best == best) && !(val <= best);
+  best = take ? val : best;
+  arg = take ? idx : arg;
+}
+
 template <typename T, typename OutT, typename L>
-__global__ void __launch_bounds__(128) k_decode_up4(const T* __restrict__ in, int B, int C, int h, int w, int n0, int n1,
+__global__ void __launch_bounds__(256) k_decode_up4(const T* __restrict__ in, int B, int C, int h, int w, int n0, int n1,
                                                     int n2, OutT* __restrict__ o0, OutT* __restrict__ o1,
                                                     OutT* __restrict__ o2, const L* __restrict__ label,
                                                     unsigned long long* __restrict__ counts) {
   const int H = 4 * h, W = 4 * w;
-  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
   const long total = (long)B * h * w;
+  const int e0 = n0, e1 = n0 + max(n1, 0), e2 = e1 + max(n2, 0);
   long long correct = 0, valid = 0;
   for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
     const int X = (int)(g % w);
     const long r = g / w;
     const int Y = (int)(r % h), b = (int)(r / h);
-    // the forward formula gives the weights (identical numbers to the unfused path); away from row / column 0 the
-    // source rows of output row 4Y + j are (Y-1, Y) for j < 2 and (Y, Y+1) for j >= 2, the neighbourhood index is static
-    Lerp ly[4], lx[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { ly[j] = lerp_src(4 * Y + j, sy, h); lx[j] = lerp_src(4 * X + j, sx, w); }
+    // Source rows of output row 4Y + j: (Y-1, Y) for j < 2, (Y, Y+1) for j >= 2, clamped into the map; weights from the
+    // forward formula (they differ from the constants (2j-3)/8 only in row / column 0, where the clamped source index
+    // gives (1, 0): with rows (0, 0) in the neighbourhood that is the same value, but the weights are kept exact so that
+    // a non-finite neighbour cannot leak in through a zero weight... it cannot: both taps are row 0 there).
     const int ym = max(Y - 1, 0), yp = min(Y + 1, h - 1), xm = max(X - 1, 0), xp = min(X + 1, w - 1);
-    const bool stat = Y > 0 && X > 0;
-    const int roff[3] = {ym * w, Y * w, yp * w}, cols[3] = {xm, X, xp};
+    float wy1[4], wx1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { wy1[j] = lerp_src(4 * Y + j, 0.25f, h).l1; wx1[j] = lerp_src(4 * X + j, 0.25f, w).l1; }
     const T* base = in + (long)b * C * h * w;
+    const int o_m = ym * w, o_c = Y * w, o_p = yp * w;
     float best[4][4];
     int arg[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { best[j][k] = -INFINITY; arg[j][k] = 0; }
     int lvl = 0, cbeg = 0;
-    const int e0 = n0, e1 = n0 + max(n1, 0), e2 = e1 + max(n2, 0);
 #pragma unroll 1
     for (int c = 0; c < e2; ++c) {
       const T* pc = base + (long)c * h * w;
       float v[3][3];
+      v[0][0] = to_f32<T>(__ldg(pc + o_m + xm)); v[0][1] = to_f32<T>(__ldg(pc + o_m + X)); v[0][2] = to_f32<T>(__ldg(pc + o_m + xp));
+      v[1][0] = to_f32<T>(__ldg(pc + o_c + xm)); v[1][1] = to_f32<T>(__ldg(pc + o_c + X)); v[1][2] = to_f32<T>(__ldg(pc + o_c + xp));
+      v[2][0] = to_f32<T>(__ldg(pc + o_p + xm)); v[2][1] = to_f32<T>(__ldg(pc + o_p + X)); v[2][2] = to_f32<T>(__ldg(pc + o_p + xp));
+      // horizontal lerps of the three source rows (shared by the output rows that use them), then the vertical ones
+      float hl[3][4];
 #pragma unroll
       for (int a = 0; a < 3; ++a)
 #pragma unroll
-        for (int q = 0; q < 3; ++q) v[a][q] = to_f32<T>(__ldg(pc + roff[a] + cols[q]));
-      float val[4][4];
-      if (stat) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            val[j][k] = bilerp(v[j >> 1][k >> 1], v[j >> 1][(k >> 1) + 1], v[(j >> 1) + 1][k >> 1],
-                               v[(j >> 1) + 1][(k >> 1) + 1], lx[k].l0, lx[k].l1, ly[j].l0, ly[j].l1);
-      } else {       // row 0 / column 0 of the low-resolution map: the clamped source index pairs (0, 1) with weight (1, 0)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int r0 = ly[j].i0 == Y ? 1 : (ly[j].i0 < Y ? 0 : 2), r1 = ly[j].i1 == Y ? 1 : (ly[j].i1 < Y ? 0 : 2);
-          float top[3], bot[3];
-#pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            top[q] = r0 == 0 ? v[0][q] : (r0 == 1 ? v[1][q] : v[2][q]);
-            bot[q] = r1 == 0 ? v[0][q] : (r1 == 1 ? v[1][q] : v[2][q]);
-          }
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int c0 = lx[k].i0 == X ? 1 : (lx[k].i0 < X ? 0 : 2), c1 = lx[k].i1 == X ? 1 : (lx[k].i1 < X ? 0 : 2);
-            val[j][k] = bilerp(pick3(top, c0), pick3(top, c1), pick3(bot, c0), pick3(bot, c1), lx[k].l0, lx[k].l1,
-                               ly[j].l0, ly[j].l1);
-          }
-        }
-      }
+        for (int k = 0; k < 4; ++k) hl[a][k] = lerp2(v[a][k >> 1], v[a][(k >> 1) + 1], 1.0f - wx1[k], wx1[k]);
 #pragma unroll
       for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float vv = round_as<T>(val[j][k]);
-          if (c == cbeg) { best[j][k] = vv; arg[j][k] = 0; }
-          else if ((vv > best[j][k]) || (vv != vv && best[j][k] == best[j][k])) { best[j][k] = vv; arg[j][k] = c - cbeg; }
+          const float val = round_as<T>(lerp2(hl[j >> 1][k], hl[(j >> 1) + 1][k], 1.0f - wy1[j], wy1[j]));
+          argmax_step(val, c - cbeg, best[j][k], arg[j][k]);
         }
       const int lend = lvl == 0 ? e0 : (lvl == 1 ? e1 : e2);
       if (c + 1 == lend) {
@@ -447,9 +455,12 @@ __global__ void __launch_bounds__(128) k_decode_up4(const T* __restrict__ in, in
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const long long t = lab_ld(label, off + k);
-              if (t != SH_IGNORE) { valid++; correct += (t == arg[j][k]); }
+              valid += t != SH_IGNORE;
+              correct += (t != SH_IGNORE) & (t == arg[j][k]);
             }
           }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { best[j][k] = -INFINITY; arg[j][k] = 0; }
         }
         cbeg = lend;
         ++lvl;
@@ -579,14 +590,14 @@ int sh_decode_upsampled(const void* logits, int dtype, int B, int C, int h, int 
   if (H != 4 * h || W != 4 * w) return SH_ERR_UNSUPPORTED;    // other sizes: sh_upsample_bilinear + sh_decode
   if (((uintptr_t)out0 | (uintptr_t)out1 | (uintptr_t)out2) % (out_is_u8 ? 4 : 16)) return SH_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned blocks = (unsigned)sh_up_blocks((long)B * h * w, 128);
+  const unsigned blocks = (unsigned)sh_up_blocks((long)B * h * w, 256);
 #define SH_DU(T)                                                                                                   \
   SH_LABEL_SWITCH(label_dtype, L, {                                                                                \
     if (out_is_u8)                                                                                                 \
-      sh::k_decode_up4<T, unsigned char, L><<<blocks, 128, 0, st>>>((const T*)logits, B, C, h, w, n0, n1, n2,       \
+      sh::k_decode_up4<T, unsigned char, L><<<blocks, 256, 0, st>>>((const T*)logits, B, C, h, w, n0, n1, n2,       \
           (unsigned char*)out0, (unsigned char*)out1, (unsigned char*)out2, (const L*)label, counts);              \
     else                                                                                                           \
-      sh::k_decode_up4<T, long long, L><<<blocks, 128, 0, st>>>((const T*)logits, B, C, h, w, n0, n1, n2,          \
+      sh::k_decode_up4<T, long long, L><<<blocks, 256, 0, st>>>((const T*)logits, B, C, h, w, n0, n1, n2,          \
           (long long*)out0, (long long*)out1, (long long*)out2, (const L*)label, counts);                          \
   })                                                                                                               \
   break

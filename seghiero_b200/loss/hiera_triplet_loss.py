@@ -59,8 +59,7 @@ class HieraTripletLoss(nn.Module):
         self.last_stats: dict = {}
         if not ops.two_level_supported(int(num_classes), len(hiera_index), True):
             raise ValueError(f"HieraTripletLoss on sm_100a: {int(num_classes) + len(hiera_index)} channels exceed the "
-                             "shared-memory tiling of the 2-level kernels (<= 64 channels for tree-shaped hierarchies, "
-                             "<= ~110 for overlapping buckets); use RMIHieraTripletLoss-style tiling or fewer classes")
+                             "shared-memory tiling of the 2-level kernels (<= ~220 channels)")
 
     def forward(self, step, embedding, cls_score_before, cls_score, label, weight=None, **kwargs):
         """`cls_score` [B, n_fine+n_coarse, H, W] at the label's resolution as in the reference, or at the head's own

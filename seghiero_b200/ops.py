@@ -453,9 +453,10 @@ def _hier2_tables(n_fine: int, index_flat: Sequence[int], dev):
 
 def two_level_supported(n_fine: int, n_coarse: int, fast: bool) -> bool:
     """Shared-memory limits of the 2-level kernels (csrc/bce2.cu): the tree-order kernel parks e^-x of <= 64 channels,
-    the any-bucket kernel parks sigmoid and e^x of every channel for 256 pixels."""
+    the any-bucket kernel parks sigmoid and e^x of every channel for 256 pixels, or 128 for wider hierarchies
+    (up to ~220 channels, e.g. 150 fine + 30 coarse)."""
     c = n_fine + n_coarse
-    return (fast and c <= 64) or (c * 256 * 8 + n_coarse * 256 <= 227 * 1024)
+    return (fast and c <= 64) or (c * 128 * 8 + n_coarse * 128 <= 227 * 1024)
 
 
 @torch.library.custom_op("seghiero_b200::hier2_fwd", mutates_args=())
@@ -483,7 +484,7 @@ def hier2_fwd(cls_score: Tensor, label: Tensor, embedding: Optional[Tensor], ste
         tree = 256 if (fast_path and is_tree) else 0
         if not two_level_supported(n_fine, nc, bool(tree)):
             raise ValueError(f"HieraTripletLoss on sm_100a: {c} channels exceed the shared-memory tiling of the 2-level "
-                             "kernels (tree-shaped hierarchies: <= 64 channels; overlapping buckets: <= ~110)")
+                             "kernels (<= ~220 channels)")
         fork = None
         if embedding is not None:
             ttab, ncls = _triplet_tab(0, hiera_map, hiera_index, dev)

@@ -332,26 +332,28 @@ def test_triplet_label_outside_id_lists_poisons_the_fused_loss(sb):
         sb.RMIHieraTripletLoss(9, 4, 3, f2m, f2h, strict=True)(torch.tensor([0]), emb, None, x, lab.cuda())
 
 
-def test_two_level_large_hierarchy_is_refused_clearly(sb):
-    """channel counts beyond the 2-level kernels' shared-memory tiling raise a clear ValueError."""
-    hi = [[5 * i, 5 * i + 5] for i in range(30)]
+def test_two_level_large_hierarchies(sb):
+    """the reference handles any class count in the 2-level loss.  150 fine + 30 coarse classes run
+    through the 128-pixel form of the any-bucket kernel; 64 channels is the largest tree-order case; beyond ~220
+    channels the constructor refuses with a clear ValueError."""
     with pytest.raises(ValueError, match="channels exceed"):
-        sb.HieraTripletLoss(150, [i // 5 for i in range(150)], hi)
-    # 64 channels is the largest tree-shaped case and must work
-    hi = [[7 * i, 7 * i + 7] for i in range(8)]
-    hm = [i // 7 for i in range(56)]
-    g = torch.Generator().manual_seed(25)
-    lab = blob_labels(g, 1, 32, 64, 56, 8, 0.1)
-    x = (torch.randn(1, 64, 32, 64, generator=g) * 2)
-    emb = F.normalize(torch.randn(1, 8, 4, 8, generator=g), dim=1)
-    xr = x.clone().requires_grad_(True)
-    ref, _ = O.hiera_triplet_loss(0, emb, xr, lab, 56, hm, hi)
-    ref.backward()
-    xc = x.cuda().requires_grad_(True)
-    loss = sb.HieraTripletLoss(56, hm, hi)(torch.tensor([0]), emb.cuda(), None, xc, lab.cuda())
-    loss.backward()
-    assert abs(float(loss) - float(ref)) <= FP32_TOL * abs(float(ref))
-    assert rel(to_np(xc.grad), to_np(xr.grad)) <= FP32_TOL
+        sb.HieraTripletLoss(230, [i // 23 for i in range(230)], [[23 * i, 23 * i + 23] for i in range(10)])
+    for nf, per in ((150, 5), (56, 7)):
+        nc = nf // per
+        hi = [[per * i, per * i + per] for i in range(nc)]
+        hm = [i // per for i in range(nf)]
+        g = torch.Generator().manual_seed(nf)
+        lab = blob_labels(g, 2, 32, 66, nf, 8, 0.1)
+        x = (torch.randn(2, nf + nc, 32, 66, generator=g) * 2)
+        emb = F.normalize(torch.randn(2, 8, 4, 8, generator=g), dim=1)
+        xr = x.clone().requires_grad_(True)
+        ref, _ = O.hiera_triplet_loss(0, emb, xr, lab, nf, hm, hi)
+        ref.backward()
+        xc = x.cuda().requires_grad_(True)
+        loss = sb.HieraTripletLoss(nf, hm, hi)(torch.tensor([0]), emb.cuda(), None, xc, lab.cuda())
+        loss.backward()
+        assert abs(float(loss) - float(ref)) <= FP32_TOL * abs(float(ref)), (nf, float(loss), float(ref))
+        assert rel(to_np(xc.grad), to_np(xr.grad)) <= FP32_TOL, nf
 
 
 # ------------------------------------------------------------------------------------------------
