@@ -198,61 +198,80 @@ __device__ __forceinline__ float adjoint_generic(const T* __restrict__ gp, int Y
   return acc;
 }
 
-// CTA = 8 x 32 low-resolution pixels of one plane: the 36 x 136 output pixels they gather from are staged in shared
-// memory with coalesced 16-byte loads (each gradient byte crosses HBM once), thread = one low-resolution pixel
-// (3 x LDS.128 per window row, separable weights).
+// CTA = 8 x 32 low-resolution pixels of one plane at a time (persistent over tiles): the 36 x 136 output pixels they
+// gather from are staged in shared memory with cp.async (16 bytes per request, zero-filled outside the image; each
+// gradient byte crosses HBM once), the tile after next is in flight while this one is gathered (two buffers);
+// thread = one low-resolution pixel (3 x LDS.128 per window row, separable weights).
 constexpr int ADJ_TH = 8, ADJ_TW = 32, ADJ_SR = 4 * ADJ_TH + 4, ADJ_SC = 4 * ADJ_TW + 8;
 template <typename T>
 __global__ void __launch_bounds__(ADJ_TH * ADJ_TW) k_upsample4_adjoint(const T* __restrict__ gout, T* __restrict__ gin,
                                                                       long planes, int h, int w, int tiles_x, int tiles_y) {
-  __shared__ __align__(16) float tile[ADJ_SR][ADJ_SC];        // rows 4Y0-2 .. 4Y0+33, cols 4X0-4 .. 4X0+131
+  __shared__ __align__(16) T tile[2][ADJ_SR][ADJ_SC];         // rows 4Y0-2 .. 4Y0+33, cols 4X0-4 .. 4X0+131
   const int H = 4 * h, W = 4 * w;
   const int tid = threadIdx.x;
-  for (long t = blockIdx.x; t < planes * tiles_x * tiles_y; t += gridDim.x) {
+  const long ntiles = planes * tiles_x * tiles_y;
+  auto issue = [&](long t, int buf) {
     const int tx = (int)(t % tiles_x);
     const long r = t / tiles_x;
     const int ty = (int)(r % tiles_y);
     const long p = r / tiles_y;
-    const int Y0 = ty * ADJ_TH, X0 = tx * ADJ_TW;
     const T* gp = gout + p * (long)H * W;
-    __syncthreads();
     for (int e = tid; e < ADJ_SR * (ADJ_SC / 4); e += ADJ_TH * ADJ_TW) {
       const int rr = e / (ADJ_SC / 4), q = e - rr * (ADJ_SC / 4);
-      const int y = 4 * Y0 - 2 + rr, x = 4 * X0 - 4 + 4 * q;
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      if (y >= 0 && y < H && x >= 0 && x < W) VecIO<T, 4>::load(gp + (long)y * W + x, v);
-      *reinterpret_cast<float4*>(&tile[rr][4 * q]) = make_float4(v[0], v[1], v[2], v[3]);
+      const int y = 4 * ty * ADJ_TH - 2 + rr, x = 4 * tx * ADJ_TW - 4 + 4 * q;
+      const bool in = y >= 0 && y < H && x >= 0 && x < W;
+      const unsigned int dst = (unsigned int)__cvta_generic_to_shared(&tile[buf][rr][4 * q]);
+      const T* src = in ? gp + (long)y * W + x : gout;
+      const int nbytes = in ? 4 * (int)sizeof(T) : 0;        // src-size 0: the slot is zero-filled
+      if (sizeof(T) == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes));
+      else asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(nbytes));
     }
+    cp_async_commit();
+  };
+  long t = blockIdx.x;
+  if (t < ntiles) issue(t, 0);
+  for (int it = 0; t < ntiles; t += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const bool more = t + gridDim.x < ntiles;
+    if (more) issue(t + gridDim.x, buf ^ 1);
+    if (more) cp_async_wait<1>(); else cp_async_wait<0>();
     __syncthreads();
+    const int tx = (int)(t % tiles_x);
+    const long r = t / tiles_x;
+    const int ty = (int)(r % tiles_y);
+    const long p = r / tiles_y;
     const int ly = tid / ADJ_TW, lx = tid - ly * ADJ_TW;
-    const int Y = Y0 + ly, X = X0 + lx;
-    if (Y >= h || X >= w) continue;
-    float acc = 0.f;
-    if (h >= 2 && w >= 2) {
-      // weights of the 8 window rows / columns 4Y-2 .. 4Y+5 on low-resolution row Y: the interior pattern, or the clamped
-      // patterns of the first / last row (sources outside the map fold onto it; rows outside the image weigh 0)
-      float wy[8], wx[8];
+    const int Y = ty * ADJ_TH + ly, X = tx * ADJ_TW + lx;
+    if (Y < h && X < w) {
+      float acc = 0.f;
+      if (h >= 2 && w >= 2) {
+        // weights of the 8 window rows / columns 4Y-2 .. 4Y+5 on low-resolution row Y: the interior pattern, or the clamped
+        // patterns of the first / last row (sources outside the map fold onto it; rows outside the image weigh 0)
+        float wy[8], wx[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float in = i < 4 ? 0.125f + 0.25f * i : 0.875f - 0.25f * (i - 4);
-        wy[i] = Y == 0 ? (i < 2 ? 0.f : (i < 4 ? 1.f : in)) : (Y == h - 1 ? (i >= 6 ? 0.f : (i >= 4 ? 1.f : in)) : in);
-        wx[i] = X == 0 ? (i < 2 ? 0.f : (i < 4 ? 1.f : in)) : (X == w - 1 ? (i >= 6 ? 0.f : (i >= 4 ? 1.f : in)) : in);
-      }
+        for (int i = 0; i < 8; ++i) {
+          const float in = i < 4 ? 0.125f + 0.25f * i : 0.875f - 0.25f * (i - 4);
+          wy[i] = Y == 0 ? (i < 2 ? 0.f : (i < 4 ? 1.f : in)) : (Y == h - 1 ? (i >= 6 ? 0.f : (i >= 4 ? 1.f : in)) : in);
+          wx[i] = X == 0 ? (i < 2 ? 0.f : (i < 4 ? 1.f : in)) : (X == w - 1 ? (i >= 6 ? 0.f : (i >= 4 ? 1.f : in)) : in);
+        }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 a = *reinterpret_cast<const float4*>(&tile[4 * ly + i][4 * lx]);
-        const float4 b = *reinterpret_cast<const float4*>(&tile[4 * ly + i][4 * lx + 4]);
-        const float4 c = *reinterpret_cast<const float4*>(&tile[4 * ly + i][4 * lx + 8]);
-        // window columns 4X-2 .. 4X+5 = tile columns 4lx+2 .. 4lx+9
-        float rs = wx[0] * a.z;
-        rs = fmaf(wx[1], a.w, rs); rs = fmaf(wx[2], b.x, rs); rs = fmaf(wx[3], b.y, rs);
-        rs = fmaf(wx[4], b.z, rs); rs = fmaf(wx[5], b.w, rs); rs = fmaf(wx[6], c.x, rs); rs = fmaf(wx[7], c.y, rs);
-        acc = fmaf(wy[i], rs, acc);
+        for (int i = 0; i < 8; ++i) {
+          float a[4], b4[4], c[4];
+          staged_vec4<T>(&tile[buf][4 * ly + i][4 * lx], a);
+          staged_vec4<T>(&tile[buf][4 * ly + i][4 * lx + 4], b4);
+          staged_vec4<T>(&tile[buf][4 * ly + i][4 * lx + 8], c);
+          // window columns 4X-2 .. 4X+5 = tile columns 4lx+2 .. 4lx+9
+          float rs = wx[0] * a[2];
+          rs = fmaf(wx[1], a[3], rs); rs = fmaf(wx[2], b4[0], rs); rs = fmaf(wx[3], b4[1], rs);
+          rs = fmaf(wx[4], b4[2], rs); rs = fmaf(wx[5], b4[3], rs); rs = fmaf(wx[6], c[0], rs); rs = fmaf(wx[7], c[1], rs);
+          acc = fmaf(wy[i], rs, acc);
+        }
+      } else {
+        acc = adjoint_generic<T>(gout + p * (long)H * W, Y, X, h, w, H, W);
       }
-    } else {
-      acc = adjoint_generic<T>(gp, Y, X, h, w, H, W);
+      gin[(p * h + Y) * (long)w + X] = from_f32<T>(acc);
     }
-    gin[(p * h + Y) * (long)w + X] = from_f32<T>(acc);
+    __syncthreads();           // everyone is done with this buffer before the next trip refills it
   }
 }
 
