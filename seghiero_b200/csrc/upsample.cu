@@ -373,6 +373,137 @@ __global__ void __launch_bounds__(AUX_TW * AUX_TH) k_aux_ce(const T* __restrict_
   }
 }
 
+// Integer scale k = 2 * PX (the aux head's x16, and x8 / x4): thread = a strip of PX consecutive output pixels of one row,
+// aligned to PX.  Such a strip lies inside one half of a k-block, so all its pixels interpolate between the SAME two
+// source columns (and, being one row, the same two source rows): the 4 source values are loaded once per channel and
+// strip, interpolated vertically once, and the gradient of the strip is summed in registers before it goes to the
+// shared-memory footprint -- 4 atomics per (strip, channel), at most 2 lanes of a warp on one address.  (With a thread
+// per output pixel every lane of a warp hits the same 2 - 3 accumulators: 32-way serialised atomics, 10 ms at config 3.)
+// CTA = 8 rows x 32 strips.  The interpolation is contracted vertically first here (the generic kernel follows ATen's
+// horizontal-first order): same value up to fp32 rounding, parity is to the loss / gradient tolerance, not bitwise.
+template <typename T, typename L, int PX>
+__global__ void __launch_bounds__(256) k_aux_ce_strip(const T* __restrict__ in, const L* __restrict__ label,
+                                                      float* __restrict__ gin, int B, int C, int h, int w, int H, int W,
+                                                      int fh, int fw, double* __restrict__ sums) {
+  extern __shared__ float s_acc[];       // [C][fh][fw]
+  constexpr int TWS = 32 * PX, THS = 8;
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+  const int tiles_x = (W + TWS - 1) / TWS, tiles_y = (H + THS - 1) / THS;
+  const int tile = blockIdx.x % (tiles_x * tiles_y), b = blockIdx.x / (tiles_x * tiles_y);
+  const int ty0 = (tile / tiles_x) * THS, tx0 = (tile % tiles_x) * TWS;
+  const int tid = threadIdx.x;
+  const int fsz = C * fh * fw;
+  for (int i = tid; i < fsz; i += 256) s_acc[i] = 0.f;
+  const int Y0 = lerp_src(ty0, sy, h).i0, X0 = lerp_src(tx0, sx, w).i0;
+  __syncthreads();
+  const int x0 = tx0 + (tid & 31) * PX, y = ty0 + (tid >> 5);
+  float loss = 0.f;
+  int nvalid = 0;
+  if (x0 < W && y < H) {
+    const Lerp ly = lerp_src(y, sy, h), lxs = lerp_src(x0, sx, w);
+    float l1[PX], mx[PX], xt[PX], se[PX];
+    int t[PX];
+    bool any = false;
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      const long long tt = lab_ld(label, ((long)b * H + y) * W + x0 + p);
+      t[p] = -1;
+      if (tt != SH_IGNORE) {
+        if (tt >= 0 && tt < C) { t[p] = (int)tt; any = true; }
+        else nvalid = 0x10000;                     // out-of-range label: the reference's cross_entropy asserts on the device
+      }
+      l1[p] = lerp_src(x0 + p, sx, w).l1;          // the strip shares i0 / i1; only the weight moves
+      mx[p] = -INFINITY; xt[p] = 0.f; se[p] = 0.f;
+    }
+    if (any) {
+      const T* base = in + (long)b * C * h * w;
+      const int o00 = ly.i0 * w + lxs.i0, o01 = ly.i0 * w + lxs.i1, o10 = ly.i1 * w + lxs.i0, o11 = ly.i1 * w + lxs.i1;
+      const long hw = (long)h * w;
+      // pass 1: max (and the target's logit); pass 2: sum of exp; pass 3: gradient.  The 4 source values per channel are L1 / L2 hits.
+#pragma unroll 1
+      for (int c = 0; c < C; ++c) {
+        const T* pc = base + c * hw;
+        const float A = lerp2(to_f32<T>(__ldg(pc + o00)), to_f32<T>(__ldg(pc + o10)), ly.l0, ly.l1);
+        const float Bv = lerp2(to_f32<T>(__ldg(pc + o01)), to_f32<T>(__ldg(pc + o11)), ly.l0, ly.l1);
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+          const float v = round_as<T>(lerp2(A, Bv, 1.0f - l1[p], l1[p]));
+          mx[p] = fmaxf(mx[p], v);
+          xt[p] = c == t[p] ? v : xt[p];
+        }
+      }
+#pragma unroll 1
+      for (int c = 0; c < C; ++c) {
+        const T* pc = base + c * hw;
+        const float A = lerp2(to_f32<T>(__ldg(pc + o00)), to_f32<T>(__ldg(pc + o10)), ly.l0, ly.l1);
+        const float Bv = lerp2(to_f32<T>(__ldg(pc + o01)), to_f32<T>(__ldg(pc + o11)), ly.l0, ly.l1);
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+          const float v = round_as<T>(lerp2(A, Bv, 1.0f - l1[p], l1[p]));
+          se[p] += ex2((v - mx[p]) * kLog2e);
+        }
+      }
+      float inv[PX];
+#pragma unroll
+      for (int p = 0; p < PX; ++p) {
+        const bool ok = t[p] >= 0;
+        if (ok) { loss += (mx[p] - xt[p]) + lg2(se[p]) * kLn2; ++nvalid; }
+        inv[p] = ok ? rcp(se[p]) : 0.f;            // ignored pixels: no gradient
+      }
+      if (gin != nullptr) {
+        const int a00 = (ly.i0 - Y0) * fw + (lxs.i0 - X0), a01 = (ly.i0 - Y0) * fw + (lxs.i1 - X0);
+        const int a10 = (ly.i1 - Y0) * fw + (lxs.i0 - X0), a11 = (ly.i1 - Y0) * fw + (lxs.i1 - X0);
+#pragma unroll 1
+        for (int c = 0; c < C; ++c) {
+          const T* pc = base + c * hw;
+          const float A = lerp2(to_f32<T>(__ldg(pc + o00)), to_f32<T>(__ldg(pc + o10)), ly.l0, ly.l1);
+          const float Bv = lerp2(to_f32<T>(__ldg(pc + o01)), to_f32<T>(__ldg(pc + o11)), ly.l0, ly.l1);
+          float gA = 0.f, gB = 0.f;
+#pragma unroll
+          for (int p = 0; p < PX; ++p) {
+            const float v = round_as<T>(lerp2(A, Bv, 1.0f - l1[p], l1[p]));
+            const float gq = fmaf(ex2((v - mx[p]) * kLog2e), inv[p], c == t[p] ? -1.f : 0.f);
+            gA = fmaf(1.0f - l1[p], gq, gA);
+            gB = fmaf(l1[p], gq, gB);
+          }
+          float* a = s_acc + c * fh * fw;
+          if (gA != 0.f) {
+            atomicAdd(a + a00, ly.l0 * gA);
+            if (ly.l1 != 0.f) atomicAdd(a + a10, ly.l1 * gA);
+          }
+          if (gB != 0.f) {
+            atomicAdd(a + a01, ly.l0 * gB);
+            if (ly.l1 != 0.f) atomicAdd(a + a11, ly.l1 * gB);
+          }
+        }
+      }
+    }
+  }
+  __shared__ float s_l[8];
+  __shared__ int s_n[8];
+  loss = warp_sum(loss);
+  nvalid = __reduce_add_sync(0xffffffffu, nvalid);
+  if ((tid & 31) == 0) { s_l[tid >> 5] = loss; s_n[tid >> 5] = nvalid; }
+  __syncthreads();
+  if (tid == 0) {
+    float l = 0.f;
+    int n = 0;
+    for (int q = 0; q < 8; ++q) { l += s_l[q]; n += s_n[q]; }
+    if (l != 0.f) atomicAdd(sums, (double)l);
+    if (n & 0xffff) atomicAdd(sums + 1, (double)(n & 0xffff));
+    if (n >> 16) atomicAdd(sums + 2, 1.0);
+  }
+  if (gin != nullptr) {
+    for (int i = tid; i < fsz; i += 256) {
+      const float v = s_acc[i];
+      if (v == 0.f) continue;
+      const int c = i / (fh * fw), rem = i - c * fh * fw, fy = rem / fw, fx = rem - fy * fw;
+      const int Y = Y0 + fy, X = X0 + fx;
+      if (Y < h && X < w) atomicAdd(gin + (((long)b * C + c) * h + Y) * w + X, v);
+    }
+  }
+}
+
 // loss = sums[0] / sums[1] (NaN when nothing is valid, as torch), gradient scale = gscale / sums[1]
 template <typename T>
 __global__ void __launch_bounds__(256) k_aux_finish(const float* __restrict__ gacc, T* __restrict__ gin, long n,
@@ -576,16 +707,28 @@ int sh_aux_ce_fwdbwd(const void* logits, int dtype, const void* label, int label
   const long n = (long)B * C * h * w;
   cudaError_t e = cudaMemsetAsync(workspace, 0, grad ? 64 + (size_t)n * 4 : 64, st);
   if (e != cudaSuccess) return (int)e;
-  const int fh = sh_aux_footprint(sh::AUX_TH, h, H), fw = sh_aux_footprint(sh::AUX_TW, w, W);
+  // integer scale 4 / 8 / 16 (W = k w, H = k h): the strip kernel, PX = k / 2 pixels per thread; anything else: a thread per pixel
+  const int k = (w > 0 && W % w == 0 && h > 0 && H % h == 0 && W / w == H / h) ? W / w : 0;
+  const int px = (k == 4 || k == 8 || k == 16) ? k / 2 : 0;
+  const int tw = px ? 32 * px : sh::AUX_TW, th = sh::AUX_TH;
+  const int fh = sh_aux_footprint(th, h, H), fw = sh_aux_footprint(tw, w, W);
   const size_t smem = (size_t)C * fh * fw * 4;
   if (smem > 200 * 1024) return SH_ERR_UNSUPPORTED;
-  const int tiles = ((W + sh::AUX_TW - 1) / sh::AUX_TW) * ((H + sh::AUX_TH - 1) / sh::AUX_TH);
+  const int tiles = ((W + tw - 1) / tw) * ((H + th - 1) / th);
+#define SH_AUX_LAUNCH(KERN)                                                                                        \
+  {                                                                                                                \
+    auto kern = KERN;                                                                                              \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                            \
+    kern<<<B * tiles, 256, smem, st>>>((const T_*)logits, (const L*)label, grad ? gacc : nullptr, B, C, h, w, H, W, \
+                                       fh, fw, sums);                                                              \
+  }
 #define SH_AUX(T)                                                                                                  \
   SH_LABEL_SWITCH(label_dtype, L, {                                                                                \
-    auto kern = sh::k_aux_ce<T, L>;                                                                                \
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                            \
-    kern<<<B * tiles, sh::AUX_TW * sh::AUX_TH, smem, st>>>((const T*)logits, (const L*)label, grad ? gacc : nullptr, B, C, \
-                                                           h, w, H, W, fh, fw, sums);                              \
+    using T_ = T;                                                                                                  \
+    if (px == 8) SH_AUX_LAUNCH((sh::k_aux_ce_strip<T, L, 8>))                                                      \
+    else if (px == 4) SH_AUX_LAUNCH((sh::k_aux_ce_strip<T, L, 4>))                                                 \
+    else if (px == 2) SH_AUX_LAUNCH((sh::k_aux_ce_strip<T, L, 2>))                                                 \
+    else SH_AUX_LAUNCH((sh::k_aux_ce<T, L>))                                                                       \
   })                                                                                                               \
   SH_CHECK_LAUNCH();                                                                                               \
   sh::k_aux_finish<T><<<(unsigned)sh_up_blocks(grad ? n : 1, 256), 256, 0, st>>>(gacc, (T*)grad, n, sums, grad_out, out_loss); \
@@ -597,6 +740,7 @@ int sh_aux_ce_fwdbwd(const void* logits, int dtype, const void* label, int label
     default: return SH_ERR_UNSUPPORTED;
   }
 #undef SH_AUX
+#undef SH_AUX_LAUNCH
   SH_CHECK_LAUNCH();
   return SH_OK;
 }

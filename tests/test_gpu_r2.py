@@ -205,6 +205,32 @@ def test_n2_aux_ce(sb, golden):
     assert abs(float(loss) - float(ref)) <= BF16_TOL * abs(float(ref))
 
 
+@pytest.mark.parametrize("k,h,w,dt", [(16, 9, 21, torch.float32), (8, 13, 40, torch.float32), (4, 19, 33, torch.float32),
+                                      (16, 6, 17, torch.bfloat16), (2, 24, 31, torch.float32), (16, 1, 1, torch.float32)])
+def test_n2_aux_ce_integer_scales(sb, k, h, w, dt):
+    """The strip kernel (thread = k/2 output pixels that share their source pixels) against torch on the same device:
+    x16 / x8 / x4, sizes that are not multiples of the CTA tile, void pixels, bf16 logits; x2 runs the per-pixel kernel."""
+    gen = torch.Generator().manual_seed(100 + k + h)
+    H, W = k * h, k * w
+    lab = iid_labels(gen, 2, H, W, 19, 0.15) if k != 8 else blob_labels(gen, 2, H, W, 19, 24, 0.1)
+    lab[0, : H // 3, : W // 2] = 255
+    xa = (torch.randn(2, 19, h, w, generator=gen) * 2).to(dt).cuda()
+    # 16-bit logits: the reference interpolates in fp32 here (torch's own bf16 backward accumulates the 256 contributions
+    # of a source pixel with bf16 atomics and is off by ~10 %); the kernel rounds the interpolated logits to bf16 like
+    # torch's forward does, which stays inside the 16-bit tolerance
+    xr = xa.float().clone().requires_grad_(True)
+    ref = torch.nn.CrossEntropyLoss(ignore_index=255)(
+        F.interpolate(xr, size=(H, W), mode="bilinear", align_corners=False), lab.cuda())
+    (1.7 * ref).backward()
+    xc = xa.clone().requires_grad_(True)
+    loss = sb.aux_cross_entropy(xc, lab.to(torch.uint8).cuda())
+    (1.7 * loss).backward()
+    tol = FP32_TOL if dt == torch.float32 else BF16_TOL
+    assert abs(float(loss) - float(ref)) <= tol * abs(float(ref))
+    assert rel(to_np(xc.grad.float()), to_np(xr.grad.float())) <= tol
+    assert xc.grad.dtype == dt
+
+
 # ------------------------------------------------------------------------------------------------
 # N3: decode from the head's logits
 # ------------------------------------------------------------------------------------------------
