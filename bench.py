@@ -698,7 +698,9 @@ def _e2e_loss(torch, dist, mod, w, world, dev, x, lab, emb, use_emb, step_t, clk
     e2e_step()
     drain()
     barrier()
-    k2 = max(2, min(steps, 10))
+    # steady-state throughput of the three-stream pipeline: the first H2D and the last D2H of the timed region (~5 ms
+    # together at config 3) overlap nothing, so the region is 3 K steps long (capped) when a step is a few ms
+    k2 = max(2, min(3 * steps, 30)) if low_res else max(2, min(steps, 10))
     t0 = time.time()
     for _ in range(k2):
         e2e_step()

@@ -456,38 +456,7 @@ static size_t pass2_smem_bytes() {
 bool fast_path_ok(const void* x, const void* grad, int elem, int H, int W, int nf, int nm, int nh, int fast_tab_ok);
 size_t fast_bwd_smem(int C, int nf, int nm, int nh) { return fast2::pass2_smem(C, nf, nm, nh); }
 
-// ---- TMA tensor maps (driver entry point fetched through the runtime: the library links cudart only) -------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;           // pure function pointer, resolved once
-  if (fn == nullptr) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-// planes of [H][W] elements, box = boxw x boxh of one plane, out-of-bounds elements read as zero
-static bool make_plane_map(CUtensorMap* m, CUtensorMapDataType dt, int esize, const void* base, int W, int H, long planes,
-                           int boxw, int boxh) {
-  EncodeTiledFn enc = encode_tiled_fn();
-  if (enc == nullptr || ((uintptr_t)base & 15) || ((long)W * esize) % 16 || (boxw * esize) % 16) return false;
-  const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
-  const cuuint64_t strides[2] = {(cuuint64_t)W * esize, (cuuint64_t)W * H * esize};
-  const cuuint32_t box[3] = {(cuuint32_t)boxw, (cuuint32_t)boxh, 1u};
-  const cuuint32_t es[3] = {1u, 1u, 1u};
-  return enc(m, dt, 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-template <typename T> struct TmaType;
-template <> struct TmaType<float> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; };
-template <> struct TmaType<__nv_bfloat16> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; };
-template <> struct TmaType<__half> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_FLOAT16; };
-
+// TMA tensor maps: tma.cuh
 // which pass-2 kernel serves the fast path: "tma" (default) or "legacy" (SEGHIERO_B200_PASS2, for A/B measurements)
 static bool pass2_want_tma() {
   const char* e = std::getenv("SEGHIERO_B200_PASS2");

@@ -11,9 +11,9 @@
 // Reference arithmetic: models/loss/rmi_hiera_triplet_loss.py:349-526 (autograd of it); analytic RMI backward in
 // oracle/rmi_taps.py.
 #pragma once
-#include <cuda.h>
 #include <type_traits>
 #include "rmi3_fast_bwd.cuh"
+#include "tma.cuh"
 
 namespace sh {
 namespace fast3 {
@@ -48,22 +48,6 @@ inline size_t pass2_smem(int C, int nf, int nm, int nh) {
   return (s + 127) & ~(size_t)127;
 }
 
-__device__ __forceinline__ void mbar_expect_tx(unsigned int addr, unsigned int bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(unsigned int dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned int mbar) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(mbar) : "memory");
-}
-// acquire-wait on the box barrier; a transaction-count mistake must surface as a launch error, not as a hung GPU
-__device__ __forceinline__ void mbar_wait_or_trap(unsigned int addr, unsigned int parity) {
-  unsigned int ok, spins = 0;
-  do {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    if (!ok && ++spins > (1u << 24)) __trap();
-  } while (!ok);
-}
 // 4 / 2 consecutive staged elements -> fp32
 template <typename T>
 __device__ __forceinline__ void ld4(const T* p, float (&o)[4]) {

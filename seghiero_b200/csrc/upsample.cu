@@ -8,7 +8,10 @@
 //   i1 = i0 + (i0 < in - 1);  l1 = src - i0;  l0 = 1 - l1
 //   val = h0 * (w0 * x[i0][j0] + w1 * x[i0][j1]) + h1 * (w0 * x[i1][j0] + w1 * x[i1][j1])
 // and the result is rounded to the tensor's dtype (bf16 / fp16 logits stay 16-bit, like the reference's tensors).
+#include <cstdlib>
+#include <cstring>
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace sh {
 
@@ -113,12 +116,7 @@ __global__ void __launch_bounds__(256) k_upsample_adjoint(const T* __restrict__ 
 // (scale = 0.25 is exact in fp32, so these are the very numbers lerp_src produces).  Blocks that touch row / column 0
 // (clamped source index) take the generic formula.
 template <typename T>
-__device__ __forceinline__ void up4_load(const T* __restrict__ in, long g, int h, int w, float (&v)[3][3], int& Y, int& X,
-                                         long& p) {
-  X = (int)(g % w);
-  const long r = g / w;
-  Y = (int)(r % h);
-  p = r / h;
+__device__ __forceinline__ void up4_load_at(const T* __restrict__ in, long p, int Y, int X, int h, int w, float (&v)[3][3]) {
   const T* base = in + p * (long)h * w;
   const int ym = max(Y - 1, 0), yp = min(Y + 1, h - 1), xm = max(X - 1, 0), xp = min(X + 1, w - 1);
 #pragma unroll
@@ -164,14 +162,17 @@ __device__ __forceinline__ void up4_store(const T* __restrict__ in, T* __restric
 }
 // (two blocks per trip with all 18 loads in flight before the first store was measured slower: 0.48 vs 0.41 ms at
 // config 3, 76 instead of 61 registers)
+// CTA = 8 x 32 low-resolution pixels of one plane (a warp = 32 consecutive X of one row: every store instruction of
+// the warp covers 512 contiguous bytes); grid = (tiles of a plane, planes), no 64-bit index arithmetic per thread.
 template <typename T>
-__global__ void __launch_bounds__(256) k_upsample4(const T* __restrict__ in, T* __restrict__ out, long planes, int h, int w) {
-  const long total = planes * h * w, stride = (long)gridDim.x * blockDim.x;
-  for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < total; g += stride) {
+__global__ void __launch_bounds__(256) k_upsample4(const T* __restrict__ in, T* __restrict__ out, long planes, int h, int w,
+                                                  int tiles_x) {
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int Y = ty * 8 + (threadIdx.x >> 5), X = tx * 32 + (threadIdx.x & 31);
+  if (Y >= h || X >= w) return;
+  for (long p = blockIdx.y; p < planes; p += gridDim.y) {
     float v[3][3];
-    int Y, X;
-    long p;
-    up4_load<T>(in, g, h, w, v, Y, X, p);
+    up4_load_at<T>(in, p, Y, X, h, w, v);
     up4_store<T>(in, out, v, Y, X, p, h, w);
   }
 }
@@ -272,6 +273,99 @@ __global__ void __launch_bounds__(ADJ_TH * ADJ_TW) k_upsample4_adjoint(const T* 
       gin[(p * h + Y) * (long)w + X] = from_f32<T>(acc);
     }
     __syncthreads();           // everyone is done with this buffer before the next trip refills it
+  }
+}
+
+// The same gather with the copy engine doing the staging: one thread issues the whole 36-row tile (zero-filled outside
+// the image) as ONE cp.async.bulk.tensor box per trip, ADJ_NST - 1 tiles ahead, an mbarrier per stage hands it over;
+// thread = TWO vertically adjacent low-resolution pixels (their windows share 4 of 12 rows: 18 instead of 24 LDS.128
+// per output).  The cp.async form above spends a seventh of its instructions on staging addresses and runs at 74 %
+// issue utilisation; it stays for maps that cannot be tensor-mapped (W * sizeof(T) not a multiple of 16 bytes).
+constexpr int ADJ_NST = 3, ADJ_NT2 = ADJ_TH / 2 * ADJ_TW;
+template <typename T> struct AdjBox {
+  static constexpr int XO = sizeof(T) == 4 ? 4 : 8;                 // the box starts XO columns left of the tile: 16-byte aligned start
+  static constexpr int SC = 4 * ADJ_TW + 2 * XO;
+  static constexpr int BYTES = ADJ_SR * SC * (int)sizeof(T);
+  static constexpr int STAGE = ((BYTES + 127) / 128) * 128;
+};
+template <typename T>
+__global__ void __launch_bounds__(ADJ_NT2) k_upsample4_adjoint_tma(const __grid_constant__ CUtensorMap map_g,
+                                                                   const T* __restrict__ gout, T* __restrict__ gin, long planes,
+                                                                   int h, int w, int tiles_x, int tiles_y) {
+  extern __shared__ __align__(128) unsigned char adj_smem[];
+  constexpr int XO = AdjBox<T>::XO, SC = AdjBox<T>::SC;
+  __shared__ __align__(8) unsigned long long s_mbar[ADJ_NST];
+  const int H = 4 * h, W = 4 * w;
+  const int tid = threadIdx.x;
+  const long ntiles = planes * tiles_x * tiles_y;
+  const unsigned int smem_s = (unsigned int)__cvta_generic_to_shared(adj_smem);
+  const unsigned int mbar_s = (unsigned int)__cvta_generic_to_shared(s_mbar);
+  if (tid == 0) {
+#pragma unroll
+    for (int q = 0; q < ADJ_NST; ++q) mbar_init(mbar_s + 8 * q, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](long t, int stage) {       // tid 0 only
+    const int tx = (int)(t % tiles_x);
+    const long r = t / tiles_x;
+    const int ty = (int)(r % tiles_y);
+    const int p = (int)(r / tiles_y);
+    mbar_expect_tx(mbar_s + 8 * stage, (unsigned int)AdjBox<T>::BYTES);
+    tma_load_3d(smem_s + stage * AdjBox<T>::STAGE, &map_g, 4 * tx * ADJ_TW - XO, 4 * ty * ADJ_TH - 2, p, mbar_s + 8 * stage);
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int q = 0; q < ADJ_NST - 1; ++q)
+      if (blockIdx.x + (long)q * gridDim.x < ntiles) issue(blockIdx.x + (long)q * gridDim.x, q);
+  }
+  const int ly2 = tid / ADJ_TW, lx = tid - ly2 * ADJ_TW;
+  int it = 0;
+  for (long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    const int stage = it % ADJ_NST;
+    if (tid == 0) {        // the stage consumed in the previous trip is free (barrier at the end of that trip)
+      const long tn = t + (long)(ADJ_NST - 1) * gridDim.x;
+      if (tn < ntiles) issue(tn, (it + ADJ_NST - 1) % ADJ_NST);
+    }
+    mbar_wait_or_trap(mbar_s + 8 * stage, (unsigned int)(it / ADJ_NST) & 1u);
+    const T* tile = reinterpret_cast<const T*>(adj_smem + stage * AdjBox<T>::STAGE);
+    const int tx = (int)(t % tiles_x);
+    const long r = t / tiles_x;
+    const int ty = (int)(r % tiles_y);
+    const long p = r / tiles_y;
+    const int Y = ty * ADJ_TH + 2 * ly2, X = tx * ADJ_TW + lx;
+    if (Y < h && X < w) {
+      float accA = 0.f, accB = 0.f;
+      if (h >= 2 && w >= 2) {
+        float wyA[8], wyB[8], wx[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float in = i < 4 ? 0.125f + 0.25f * i : 0.875f - 0.25f * (i - 4);
+          wyA[i] = Y == 0 ? (i < 2 ? 0.f : (i < 4 ? 1.f : in)) : (Y == h - 1 ? (i >= 6 ? 0.f : (i >= 4 ? 1.f : in)) : in);
+          wyB[i] = Y + 1 == h - 1 ? (i >= 6 ? 0.f : (i >= 4 ? 1.f : in)) : in;        // Y + 1 >= 1: never the first row
+          wx[i] = X == 0 ? (i < 2 ? 0.f : (i < 4 ? 1.f : in)) : (X == w - 1 ? (i >= 6 ? 0.f : (i >= 4 ? 1.f : in)) : in);
+        }
+        const T* base = tile + (8 * ly2) * SC + 4 * lx + XO - 4;      // window columns 4X-2 .. 4X+5 = base[2] .. base[9]
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          float a[4], b4[4], c[4];
+          staged_vec4<T>(base + i * SC, a);
+          staged_vec4<T>(base + i * SC + 4, b4);
+          staged_vec4<T>(base + i * SC + 8, c);
+          float rs = wx[0] * a[2];
+          rs = fmaf(wx[1], a[3], rs); rs = fmaf(wx[2], b4[0], rs); rs = fmaf(wx[3], b4[1], rs);
+          rs = fmaf(wx[4], b4[2], rs); rs = fmaf(wx[5], b4[3], rs); rs = fmaf(wx[6], c[0], rs); rs = fmaf(wx[7], c[1], rs);
+          if (i < 8) accA = fmaf(wyA[i], rs, accA);
+          if (i >= 4) accB = fmaf(wyB[i - 4], rs, accB);
+        }
+      } else {
+        accA = adjoint_generic<T>(gout + p * (long)H * W, Y, X, h, w, H, W);
+        if (Y + 1 < h) accB = adjoint_generic<T>(gout + p * (long)H * W, Y + 1, X, h, w, H, W);
+      }
+      gin[(p * h + Y) * (long)w + X] = from_f32<T>(accA);
+      if (Y + 1 < h) gin[(p * h + Y + 1) * (long)w + X] = from_f32<T>(accB);
+    }
+    __syncthreads();           // everyone is done with this stage before it is refilled
   }
 }
 
@@ -646,7 +740,11 @@ int sh_upsample_bilinear(const void* in, int dtype, void* out, long planes, int 
   {                                                                                                       \
     const int vec_ok = (W % 4 == 0) && ((uintptr_t)out % (4 * sizeof(T)) == 0);                           \
     if (H == 4 * h && W == 4 * w && vec_ok)                                                               \
-      sh::k_upsample4<T><<<(unsigned)sh_up_blocks(planes * h * w, 256), 256, 0, st>>>((const T*)in, (T*)out, planes, h, w); \
+    {                                                                                                     \
+      const int txn = (w + 31) / 32, tyn = (h + 7) / 8;                                                   \
+      const dim3 grid((unsigned)(txn * tyn), (unsigned)(planes < 65535 ? planes : 65535));                \
+      sh::k_upsample4<T><<<grid, 256, 0, st>>>((const T*)in, (T*)out, planes, h, w, txn);                  \
+    }                                                                                                     \
     else                                                                                                  \
       sh::k_upsample<T><<<(unsigned)sh_up_blocks(items, 256), 256, 0, st>>>((const T*)in, (T*)out, planes, h, w, H, W, vec_ok); \
   }                                                                                                       \
@@ -671,9 +769,21 @@ int sh_upsample_bilinear_adjoint(const void* gout, int dtype, void* gin, long pl
   if (H == 4 * h && W == 4 * w && (uintptr_t)gout % (4 * sizeof(T)) == 0) {                                         \
     const int txn = (w + sh::ADJ_TW - 1) / sh::ADJ_TW, tyn = (h + sh::ADJ_TH - 1) / sh::ADJ_TH;                      \
     long nb = planes * txn * tyn;                                                                                   \
-    if (nb > SH_NUM_SMS * 32L) nb = SH_NUM_SMS * 32L;                                                               \
-    sh::k_upsample4_adjoint<T><<<(unsigned)nb, sh::ADJ_TH * sh::ADJ_TW, 0, st>>>((const T*)gout, (T*)gin, planes, h, \
-                                                                                w, txn, tyn);                       \
+    CUtensorMap mg;                                                                                                 \
+    const char* adj_e = std::getenv("SEGHIERO_B200_ADJOINT");      /* "legacy": the cp.async form (A/B measurements) */ \
+    const bool want_tma = adj_e == nullptr || std::strcmp(adj_e, "legacy") != 0;                                    \
+    if (want_tma && planes < (1L << 30) &&                                                                          \
+        sh::make_plane_map(&mg, sh::TmaType<T>::v, (int)sizeof(T), gout, W, H, planes, sh::AdjBox<T>::SC, sh::ADJ_SR)) { \
+      const int smem = sh::ADJ_NST * sh::AdjBox<T>::STAGE;                                                          \
+      if (nb > SH_NUM_SMS * 3L) nb = SH_NUM_SMS * 3L;                                                               \
+      auto kern = sh::k_upsample4_adjoint_tma<T>;                                                                   \
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                                \
+      kern<<<(unsigned)nb, sh::ADJ_NT2, smem, st>>>(mg, (const T*)gout, (T*)gin, planes, h, w, txn, tyn);            \
+    } else {                                                                                                        \
+      if (nb > SH_NUM_SMS * 32L) nb = SH_NUM_SMS * 32L;                                                             \
+      sh::k_upsample4_adjoint<T><<<(unsigned)nb, sh::ADJ_TH * sh::ADJ_TW, 0, st>>>((const T*)gout, (T*)gin, planes, \
+                                                                                  h, w, txn, tyn);                  \
+    }                                                                                                               \
   }                                                                                                                 \
   else                                                                                                              \
     sh::k_upsample_adjoint<T><<<blocks, 256, 0, st>>>((const T*)gout, (T*)gin, planes, h, w, H, W);                  \
