@@ -172,6 +172,34 @@ def test_upsample_kernels_against_torch(sb):
             assert float((got.float() - ref.float()).abs().max()) <= tol * max(1.0, float(ref.float().abs().max()))
 
 
+@pytest.mark.parametrize("planes,h,w,dt", [(6, 9, 37, torch.float32), (3, 16, 64, torch.float32), (5, 1, 40, torch.float32),
+                                           (4, 33, 1, torch.float32), (2, 17, 45, torch.bfloat16), (7, 8, 32, torch.float16),
+                                           (66000, 2, 4, torch.float32), (3, 11, 34, torch.float32)])
+def test_x4_upsample_and_adjoint_edge_shapes(sb, planes, h, w, dt):
+    """The head's x4 geometry on maps whose size is not a multiple of the 8 x 32 tile (odd heights: the second row of a
+    thread's pair does not exist), one-pixel-wide / one-pixel-high maps (generic gather), 16-bit types (TMA box start 8
+    columns left of the tile), more planes than grid.y holds: upsample against F.interpolate, adjoint against torch's
+    backward of it and through the inner-product identity <up(x), g> = <x, adjoint(g)>."""
+    from seghiero_b200 import ops
+    gen = torch.Generator().manual_seed(planes + 10 * h + w)
+    x = torch.randn(1, planes, h, w, generator=gen).to(dt).cuda()
+    g = torch.randn(1, planes, 4 * h, 4 * w, generator=gen).to(dt).cuda()
+    up = ops._upsampled(x, 4 * h, 4 * w)
+    xr = x.float().clone().requires_grad_(True)
+    ref = F.interpolate(xr, size=(4 * h, 4 * w), mode="bilinear", align_corners=False)
+    ref.backward(g.float())
+    tol = 2e-6 if dt == torch.float32 else 1e-2
+    assert float((up.float() - ref.detach()).abs().max()) <= tol * max(1.0, float(ref.detach().abs().max()))
+    gin = torch.empty_like(x)
+    ops._call("sh_upsample_bilinear_adjoint", ops._p(g), ops._dtype_code(g), ops._p(gin), planes, h, w, 4 * h, 4 * w,
+              ops._stream())
+    assert rel(to_np(gin.float()), to_np(xr.grad)) <= (1e-6 if dt == torch.float32 else 1e-2)
+    if dt == torch.float32:
+        lhs = float((ref.detach().double() * g.double()).sum())
+        rhs = float((x.double() * gin.double()).sum())
+        assert abs(lhs - rhs) <= 1e-5 * max(1.0, abs(lhs))
+
+
 # ------------------------------------------------------------------------------------------------
 # N2: aux-head cross entropy
 # ------------------------------------------------------------------------------------------------
