@@ -132,10 +132,12 @@ int sh_triplet_forward(const void* feats, int dtype, const void* label, int labe
                        int mode, const int* tab, int ncls, int max_triplet, int* lab_ds, int* sel, int* kcount,
                        float* tl, float* trip, int* status, void* stream);
 
-/* gfeat: fp32 [B,D,h,w], zeroed here; weight = *tscale * *gscale / (k_c * #classes). */
+/* gfeat: fp32 [B,D,h,w], fully written; weight = *tscale * *gscale / (k_c * #classes).  scratch: B*D*h*w*8 bytes
+ * (zeroed here): the scatter accumulates in 64-bit fixed point with integer atomics, so the result is bitwise
+ * reproducible. */
 int sh_triplet_backward(const void* feats, int dtype, int B, int D, int h, int w, int ncls, int max_triplet,
                         const int* sel, const int* kcount, const float* tl, const float* trip, const float* tscale,
-                        const float* gscale, float* gfeat, void* stream);
+                        const float* gscale, float* gfeat, void* scratch, void* stream);
 
 /* ---- upsample-fused variants: the head's logits stay at their own resolution ---- */
 

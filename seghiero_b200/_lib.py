@@ -31,7 +31,7 @@ SIGNATURES = {
     "sh_loss3_final": (_i, [_i, _i, _i, _i, _i, _i, _p, _f, _p, _d, _p, _p, _f, _p, _p]),
     "sh_rmi3_backward": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _f, _p, _p, _i, _p]),
     "sh_triplet_forward": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
-    "sh_triplet_backward": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "sh_triplet_backward": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "sh_upsample_bilinear": (_i, [_p, _i, _p, _l, _i, _i, _i, _i, _p]),
     "sh_upsample_bilinear_adjoint": (_i, [_p, _i, _p, _l, _i, _i, _i, _i, _p]),
     "sh_aux_ce_workspace_bytes": (_sz, [_i, _i, _i, _i]),

@@ -19,7 +19,22 @@
 #define SH_LAB_U8 2
 
 #define SH_IGNORE 255
-#define SH_NUM_SMS 148
+// SM count of the current device (148 on a B200), queried once: grids of the persistent kernels are sized from it.
+// All devices of a box are the same part; the cached integer is the library's only other process-wide state besides
+// the cuTensorMapEncodeTiled entry point.
+inline int sh_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+        v > 0)
+      n = v;
+    else
+      n = 148;
+  }
+  return n;
+}
+#define SH_NUM_SMS sh_num_sms()
 
 #define SH_CHECK_LAUNCH()                          \
   do {                                             \

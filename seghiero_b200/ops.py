@@ -357,8 +357,9 @@ def _triplet_backward(feats: Tensor, ncls: int, max_triplet: int, sel, kcount, t
     b, d, h, w = feats.shape
     gfeat = torch.empty((b, d, h, w), dtype=torch.float32, device=feats.device)
     with (fork if fork is not None else contextlib.nullcontext()):
+        scratch = torch.empty((b, d, h, w), dtype=torch.int64, device=feats.device)   # fixed-point accumulator
         _call("sh_triplet_backward", _p(feats), _dtype_code(feats), b, d, h, w, ncls, max_triplet, _p(sel), _p(kcount),
-              _p(tl), _p(trip), _p(tscale), _p(gscale), _p(gfeat), _stream())
+              _p(tl), _p(trip), _p(tscale), _p(gscale), _p(gfeat), _p(scratch), _stream())
     return gfeat
 
 

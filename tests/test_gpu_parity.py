@@ -107,6 +107,24 @@ def test_triplet_hierarchy(sb, shape):
     assert abs(float(loss2) - float(ref2)) <= FP32_TOL * abs(float(ref2))
 
 
+def test_triplet_backward_is_bitwise_reproducible(sb):
+    """embedding.grad comes from plain read-modify-writes in a fixed (class, role) order, not from float atomics: two runs
+    give the same bits, for both triplet flavours, with every pixel taking part in many triplets (200 per class)."""
+    g = torch.Generator().manual_seed(5)
+    lab = iid_labels(g, 2, 64, 64, 19, 0.05)
+    emb = F.normalize(torch.randn(2, 40, 32, 32, generator=g), dim=1).cuda()
+    upper, lower = O.id_lists_for(19)
+    for mod in (sb.TreeTripletLoss(19, HM, HI), sb.IdListTreeTripletLoss(19, upper, lower)):
+        grads = []
+        for _ in range(3):
+            e = emb.clone().requires_grad_(True)
+            loss, _ = mod(e, lab.cuda())
+            loss.backward()
+            grads.append(e.grad.clone())
+        assert float(grads[0].abs().sum()) > 0
+        assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])
+
+
 def test_triplet_id_lists_and_edge_cases(sb):
     g = torch.Generator().manual_seed(77)
     lab = blob_labels(g, 2, 40, 56, 19, 4, 0.1)
