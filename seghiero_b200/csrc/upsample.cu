@@ -377,19 +377,23 @@ __global__ void __launch_bounds__(ADJ_NT2) k_upsample4_adjoint_tma(const __grid_
 // flushed to the low-resolution gradient once per CTA).  `gin` must be zeroed by the caller.
 // ---------------------------------------------------------------------------------------------
 constexpr int AUX_TW = 32, AUX_TH = 8;
+// The gradient is scattered with INTEGER atomics (fixed point, 2^-40): the sum does not depend on the order in which warps
+// and CTAs arrive, so the aux gradient is bitwise reproducible.  |softmax - onehot| <= 1 per output pixel: no overflow.
+constexpr float kAuxFix = 1099511627776.0f;      // 2^40
+__device__ __forceinline__ unsigned long long aux_fix(float v) { return (unsigned long long)__float2ll_rn(v * kAuxFix); }
 
 template <typename T, typename L>
 __global__ void __launch_bounds__(AUX_TW * AUX_TH) k_aux_ce(const T* __restrict__ in, const L* __restrict__ label,
-                                                           float* __restrict__ gin, int B, int C, int h, int w, int H,
+                                                           unsigned long long* __restrict__ gin, int B, int C, int h, int w, int H,
                                                            int W, int fh, int fw, double* __restrict__ sums) {
-  extern __shared__ float s_acc[];       // [C][fh][fw] gradient footprint of the tile at low resolution
+  extern __shared__ unsigned long long s_acc[];       // [C][fh][fw] gradient footprint of the tile at low resolution (fixed point)
   const float sy = (float)h / (float)H, sx = (float)w / (float)W;
   const int tiles_x = (W + AUX_TW - 1) / AUX_TW, tiles_y = (H + AUX_TH - 1) / AUX_TH;
   const int tile = blockIdx.x % (tiles_x * tiles_y), b = blockIdx.x / (tiles_x * tiles_y);
   const int ty0 = (tile / tiles_x) * AUX_TH, tx0 = (tile % tiles_x) * AUX_TW;
   const int tid = threadIdx.x;
   const int fsz = C * fh * fw;
-  for (int i = tid; i < fsz; i += AUX_TW * AUX_TH) s_acc[i] = 0.f;
+  for (int i = tid; i < fsz; i += AUX_TW * AUX_TH) s_acc[i] = 0ull;
   // low-resolution origin of the tile's footprint
   const int Y0 = lerp_src(ty0, sy, h).i0, X0 = lerp_src(tx0, sx, w).i0;
   __syncthreads();
@@ -430,11 +434,11 @@ __global__ void __launch_bounds__(AUX_TW * AUX_TH) k_aux_ce(const T* __restrict_
           const float v = round_as<T>(bilerp(to_f32<T>(__ldg(pc + o00)), to_f32<T>(__ldg(pc + o01)),
                                              to_f32<T>(__ldg(pc + o10)), to_f32<T>(__ldg(pc + o11)), lx.l0, lx.l1, ly.l0, ly.l1));
           const float gq = ex2((v - mx) * kLog2e) * inv - (c == (int)t ? 1.f : 0.f);
-          float* a = s_acc + c * fh * fw;
-          atomicAdd(a + a00, w00 * gq);
-          if (w01 != 0.f) atomicAdd(a + a01, w01 * gq);
-          if (w10 != 0.f) atomicAdd(a + a10, w10 * gq);
-          if (w11 != 0.f) atomicAdd(a + a11, w11 * gq);
+          unsigned long long* a = s_acc + c * fh * fw;
+          atomicAdd(a + a00, aux_fix(w00 * gq));
+          if (w01 != 0.f) atomicAdd(a + a01, aux_fix(w01 * gq));
+          if (w10 != 0.f) atomicAdd(a + a10, aux_fix(w10 * gq));
+          if (w11 != 0.f) atomicAdd(a + a11, aux_fix(w11 * gq));
         }
       }
     } else if (t != SH_IGNORE) {
@@ -458,8 +462,8 @@ __global__ void __launch_bounds__(AUX_TW * AUX_TH) k_aux_ce(const T* __restrict_
   }
   if (gin != nullptr) {
     for (int i = tid; i < fsz; i += AUX_TW * AUX_TH) {
-      const float v = s_acc[i];
-      if (v == 0.f) continue;
+      const unsigned long long v = s_acc[i];
+      if (v == 0ull) continue;
       const int c = i / (fh * fw), rem = i - c * fh * fw, fy = rem / fw, fx = rem - fy * fw;
       const int Y = Y0 + fy, X = X0 + fx;
       if (Y < h && X < w) atomicAdd(gin + (((long)b * C + c) * h + Y) * w + X, v);
@@ -477,9 +481,9 @@ __global__ void __launch_bounds__(AUX_TW * AUX_TH) k_aux_ce(const T* __restrict_
 // horizontal-first order): same value up to fp32 rounding, parity is to the loss / gradient tolerance, not bitwise.
 template <typename T, typename L, int PX>
 __global__ void __launch_bounds__(256) k_aux_ce_strip(const T* __restrict__ in, const L* __restrict__ label,
-                                                      float* __restrict__ gin, int B, int C, int h, int w, int H, int W,
+                                                      unsigned long long* __restrict__ gin, int B, int C, int h, int w, int H, int W,
                                                       int fh, int fw, double* __restrict__ sums) {
-  extern __shared__ float s_acc[];       // [C][fh][fw]
+  extern __shared__ unsigned long long s_acc[];       // [C][fh][fw], fixed point
   constexpr int TWS = 32 * PX, THS = 8;
   const float sy = (float)h / (float)H, sx = (float)w / (float)W;
   const int tiles_x = (W + TWS - 1) / TWS, tiles_y = (H + THS - 1) / THS;
@@ -487,7 +491,7 @@ __global__ void __launch_bounds__(256) k_aux_ce_strip(const T* __restrict__ in, 
   const int ty0 = (tile / tiles_x) * THS, tx0 = (tile % tiles_x) * TWS;
   const int tid = threadIdx.x;
   const int fsz = C * fh * fw;
-  for (int i = tid; i < fsz; i += 256) s_acc[i] = 0.f;
+  for (int i = tid; i < fsz; i += 256) s_acc[i] = 0ull;
   const int Y0 = lerp_src(ty0, sy, h).i0, X0 = lerp_src(tx0, sx, w).i0;
   __syncthreads();
   const int x0 = tx0 + (tid & 31) * PX, y = ty0 + (tid >> 5);
@@ -495,7 +499,7 @@ __global__ void __launch_bounds__(256) k_aux_ce_strip(const T* __restrict__ in, 
   int nvalid = 0;
   if (x0 < W && y < H) {
     const Lerp ly = lerp_src(y, sy, h), lxs = lerp_src(x0, sx, w);
-    float l1[PX], mx[PX], xt[PX], se[PX];
+    float l0[PX], l1[PX], mx[PX], xt[PX], se[PX];
     int t[PX];
     bool any = false;
 #pragma unroll
@@ -507,13 +511,16 @@ __global__ void __launch_bounds__(256) k_aux_ce_strip(const T* __restrict__ in, 
         else nvalid = 0x10000;                     // out-of-range label: the reference's cross_entropy asserts on the device
       }
       l1[p] = lerp_src(x0 + p, sx, w).l1;          // the strip shares i0 / i1; only the weight moves
+      l0[p] = 1.0f - l1[p];
       mx[p] = -INFINITY; xt[p] = 0.f; se[p] = 0.f;
     }
     if (any) {
       const T* base = in + (long)b * C * h * w;
       const int o00 = ly.i0 * w + lxs.i0, o01 = ly.i0 * w + lxs.i1, o10 = ly.i1 * w + lxs.i0, o11 = ly.i1 * w + lxs.i1;
       const long hw = (long)h * w;
-      // pass 1: max (and the target's logit); pass 2: sum of exp; pass 3: gradient.  The 4 source values per channel are L1 / L2 hits.
+      // sweep 1: online log-sum-exp (running max m and sum of e^(v - m); ONE ex2 per value: e = 2^-|v - m| serves both
+      // the case v <= m (sum += e) and v > m (sum = sum * e + 1)) and the target's logit; sweep 2: gradient.  The 4 source
+      // values per channel are L1 / L2 hits.
 #pragma unroll 1
       for (int c = 0; c < C; ++c) {
         const T* pc = base + c * hw;
@@ -521,20 +528,12 @@ __global__ void __launch_bounds__(256) k_aux_ce_strip(const T* __restrict__ in, 
         const float Bv = lerp2(to_f32<T>(__ldg(pc + o01)), to_f32<T>(__ldg(pc + o11)), ly.l0, ly.l1);
 #pragma unroll
         for (int p = 0; p < PX; ++p) {
-          const float v = round_as<T>(lerp2(A, Bv, 1.0f - l1[p], l1[p]));
+          const float v = round_as<T>(lerp2(A, Bv, l0[p], l1[p]));
+          const float dlt = v - mx[p];
+          const float e = ex2(-fabsf(dlt) * kLog2e);           // mx starts at -inf: e = 0, sum = 0 * 0 + 1
+          se[p] = dlt > 0.f ? fmaf(se[p], e, 1.0f) : se[p] + e;
           mx[p] = fmaxf(mx[p], v);
           xt[p] = c == t[p] ? v : xt[p];
-        }
-      }
-#pragma unroll 1
-      for (int c = 0; c < C; ++c) {
-        const T* pc = base + c * hw;
-        const float A = lerp2(to_f32<T>(__ldg(pc + o00)), to_f32<T>(__ldg(pc + o10)), ly.l0, ly.l1);
-        const float Bv = lerp2(to_f32<T>(__ldg(pc + o01)), to_f32<T>(__ldg(pc + o11)), ly.l0, ly.l1);
-#pragma unroll
-        for (int p = 0; p < PX; ++p) {
-          const float v = round_as<T>(lerp2(A, Bv, 1.0f - l1[p], l1[p]));
-          se[p] += ex2((v - mx[p]) * kLog2e);
         }
       }
       float inv[PX];
@@ -555,19 +554,19 @@ __global__ void __launch_bounds__(256) k_aux_ce_strip(const T* __restrict__ in, 
           float gA = 0.f, gB = 0.f;
 #pragma unroll
           for (int p = 0; p < PX; ++p) {
-            const float v = round_as<T>(lerp2(A, Bv, 1.0f - l1[p], l1[p]));
+            const float v = round_as<T>(lerp2(A, Bv, l0[p], l1[p]));
             const float gq = fmaf(ex2((v - mx[p]) * kLog2e), inv[p], c == t[p] ? -1.f : 0.f);
-            gA = fmaf(1.0f - l1[p], gq, gA);
+            gA = fmaf(l0[p], gq, gA);
             gB = fmaf(l1[p], gq, gB);
           }
-          float* a = s_acc + c * fh * fw;
+          unsigned long long* a = s_acc + c * fh * fw;
           if (gA != 0.f) {
-            atomicAdd(a + a00, ly.l0 * gA);
-            if (ly.l1 != 0.f) atomicAdd(a + a10, ly.l1 * gA);
+            atomicAdd(a + a00, aux_fix(ly.l0 * gA));
+            if (ly.l1 != 0.f) atomicAdd(a + a10, aux_fix(ly.l1 * gA));
           }
           if (gB != 0.f) {
-            atomicAdd(a + a01, ly.l0 * gB);
-            if (ly.l1 != 0.f) atomicAdd(a + a11, ly.l1 * gB);
+            atomicAdd(a + a01, aux_fix(ly.l0 * gB));
+            if (ly.l1 != 0.f) atomicAdd(a + a11, aux_fix(ly.l1 * gB));
           }
         }
       }
@@ -589,8 +588,8 @@ __global__ void __launch_bounds__(256) k_aux_ce_strip(const T* __restrict__ in, 
   }
   if (gin != nullptr) {
     for (int i = tid; i < fsz; i += 256) {
-      const float v = s_acc[i];
-      if (v == 0.f) continue;
+      const unsigned long long v = s_acc[i];
+      if (v == 0ull) continue;
       const int c = i / (fh * fw), rem = i - c * fh * fw, fy = rem / fw, fx = rem - fy * fw;
       const int Y = Y0 + fy, X = X0 + fx;
       if (Y < h && X < w) atomicAdd(gin + (((long)b * C + c) * h + Y) * w + X, v);
@@ -600,7 +599,7 @@ __global__ void __launch_bounds__(256) k_aux_ce_strip(const T* __restrict__ in, 
 
 // loss = sums[0] / sums[1] (NaN when nothing is valid, as torch), gradient scale = gscale / sums[1]
 template <typename T>
-__global__ void __launch_bounds__(256) k_aux_finish(const float* __restrict__ gacc, T* __restrict__ gin, long n,
+__global__ void __launch_bounds__(256) k_aux_finish(const unsigned long long* __restrict__ gacc, T* __restrict__ gin, long n,
                                                     const double* __restrict__ sums, const float* __restrict__ gscale,
                                                     float* __restrict__ out) {
   const double nv = sums[1];
@@ -610,9 +609,9 @@ __global__ void __launch_bounds__(256) k_aux_finish(const float* __restrict__ ga
     out[0] = (float)l;
   }
   if (gin == nullptr) return;
-  const float s = (float)((gscale ? (double)*gscale : 1.0) / nv);
+  const double s = (gscale ? (double)*gscale : 1.0) / nv / (double)kAuxFix;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
-    gin[i] = from_f32<T>(gacc[i] * s);
+    gin[i] = from_f32<T>((float)((double)(long long)gacc[i] * s));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -805,7 +804,7 @@ static int sh_aux_footprint(int span, int n_in, int n_out) {
   return f > n_in ? n_in : f;
 }
 
-size_t sh_aux_ce_workspace_bytes(int B, int C, int h, int w) { return (size_t)B * C * h * w * 4 + 64; }
+size_t sh_aux_ce_workspace_bytes(int B, int C, int h, int w) { return (size_t)B * C * h * w * 8 + 64; }
 
 int sh_aux_ce_fwdbwd(const void* logits, int dtype, const void* label, int label_dtype, int B, int C, int h, int w, int H,
                      int W, void* grad /* nullable, [B,C,h,w] */, const float* grad_out /* nullable */, float* out_loss,
@@ -813,16 +812,16 @@ int sh_aux_ce_fwdbwd(const void* logits, int dtype, const void* label, int label
   if (B <= 0 || C <= 0 || C > 4096 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return SH_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   double* sums = (double*)workspace;                       // [0] loss sum, [1] #valid, [2] error flag
-  float* gacc = (float*)((unsigned char*)workspace + 64);  // fp32 accumulator of the low-resolution gradient
+  unsigned long long* gacc = (unsigned long long*)((unsigned char*)workspace + 64);  // fixed-point accumulator of the low-resolution gradient
   const long n = (long)B * C * h * w;
-  cudaError_t e = cudaMemsetAsync(workspace, 0, grad ? 64 + (size_t)n * 4 : 64, st);
+  cudaError_t e = cudaMemsetAsync(workspace, 0, grad ? 64 + (size_t)n * 8 : 64, st);
   if (e != cudaSuccess) return (int)e;
   // integer scale 4 / 8 / 16 (W = k w, H = k h): the strip kernel, PX = k / 2 pixels per thread; anything else: a thread per pixel
   const int k = (w > 0 && W % w == 0 && h > 0 && H % h == 0 && W / w == H / h) ? W / w : 0;
   const int px = (k == 4 || k == 8 || k == 16) ? k / 2 : 0;
   const int tw = px ? 32 * px : sh::AUX_TW, th = sh::AUX_TH;
   const int fh = sh_aux_footprint(th, h, H), fw = sh_aux_footprint(tw, w, W);
-  const size_t smem = (size_t)C * fh * fw * 4;
+  const size_t smem = (size_t)C * fh * fw * 8;
   if (smem > 200 * 1024) return SH_ERR_UNSUPPORTED;
   const int tiles = ((W + tw - 1) / tw) * ((H + th - 1) / th);
 #define SH_AUX_LAUNCH(KERN)                                                                                        \

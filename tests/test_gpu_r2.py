@@ -257,6 +257,10 @@ def test_n2_aux_ce_integer_scales(sb, k, h, w, dt):
     assert abs(float(loss) - float(ref)) <= tol * abs(float(ref))
     assert rel(to_np(xc.grad.float()), to_np(xr.grad.float())) <= tol
     assert xc.grad.dtype == dt
+    # the scatter uses fixed-point integer atomics: a second run gives the same bits
+    xd = xa.clone().requires_grad_(True)
+    (1.7 * sb.aux_cross_entropy(xd, lab.to(torch.uint8).cuda())).backward()
+    assert torch.equal(xd.grad, xc.grad)
 
 
 # ------------------------------------------------------------------------------------------------
