@@ -483,7 +483,7 @@ static int run_backward3(const void* x, void* grad, int B, int H, int W, const H
     const size_t tsmem = fast3::pass2_smem<T>(C, h.nf, h.nm, h.nh);
     const char* ctas_e = std::getenv("SEGHIERO_B200_P2CTAS");          // "4": the 128-register variant (A/B measurements)
     const bool four = ctas_e != nullptr && std::atoi(ctas_e) == 4;
-    if (pass2_want_tma() && tsmem <= 56 * 1024 &&
+    if (pass2_want_tma() && tsmem <= 72 * 1024 &&      /* 3 CTAs per SM */
         make_plane_map(&mx, TmaType<T>::v, (int)sizeof(T), x, W, H, (long)B * C, fast3::XBox<T>::COLS, fast3::PR) &&
         make_plane_map(&mi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ws.inv, W, H, 3L * B, fast3::TW, fast3::TH) &&
         make_plane_map(&mh, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, ws.hold, W, H, (long)(h.nm + h.nh + 2) * B, fast3::TW, fast3::TH)) {
@@ -548,7 +548,7 @@ int sh_rmi3_pass2_kind(const void* logits, const void* grad, int dtype, int H, i
                     (uintptr_t)grad % (4 * es) == 0 && sh::fast2::pass2_smem(C, nf, nm, nh) <= 227 * 1024;
   if (!fast) return 0;
   const size_t tsmem = es == 4 ? sh::fast3::pass2_smem<float>(C, nf, nm, nh) : sh::fast3::pass2_smem<__half>(C, nf, nm, nh);
-  const bool tma = sh::pass2_want_tma() && tsmem <= 56 * 1024 && ((long)W * es) % 16 == 0 && W % 16 == 0 &&
+  const bool tma = sh::pass2_want_tma() && tsmem <= 72 * 1024 && ((long)W * es) % 16 == 0 && W % 16 == 0 &&
                    ((uintptr_t)logits & 15) == 0 && sh::encode_tiled_fn() != nullptr;
   return tma ? 2 : 1;
 }
