@@ -272,6 +272,8 @@ def bench_config(args, w, b, px, world, x_gb=None):
            "parallelism": f"dp{world} by sample, no data-path collective"}
     if x_gb is not None:
         cfg["l2"] = "inputs larger than L2 (logits %.2f GB per GPU)" % x_gb
+    if NUMA_NOTE["node"] is not None:
+        cfg["host_binding"] = "each rank's host threads and pinned buffers bound to its GPU's NUMA node (rank 0: node %d)" % NUMA_NOTE["node"]
     return cfg
 
 
@@ -312,12 +314,45 @@ FAST_NAMES = {("sh_rmi3_forward", 1): "k3f_prep", ("sh_rmi3_forward", 2): "k3f_p
               ("sh_bce2_fwdbwd", 2): "k_bce2_fast"}
 
 
+NUMA_NOTE = {"node": None}
+
+
+def _bind_to_gpu_numa_node(local):
+    """One process per GPU: run this rank's host threads (and first-touch its pinned staging buffers) on the NUMA node the
+    GPU hangs off.  torchrun does not bind ranks; unbound, the pinned buffers of all 8 ranks can land on one node and the
+    host<->device copies of the e2e path share that node's memory controllers (round 1: e2e flat from 1 to 8 GPUs)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else local
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = "/sys/bus/pci/devices/%s:%s/numa_node" % (dom[-4:].lower(), rest.lower())
+        node = int(open(path).read().strip())
+        if node < 0:
+            return
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            NUMA_NOTE["node"] = node
+    except Exception:      # noqa: BLE001 -- binding is an optimisation of the host side, never a requirement
+        pass
+
+
 def _dist_env():
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and os.environ.get("SEGHIERO_B200_NO_NUMA_BIND") is None:
+        _bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1 and not dist.is_initialized():
