@@ -637,6 +637,38 @@ __device__ __forceinline__ void argmax_step(float val, int idx, float& best, int
   arg = take ? idx : arg;
 }
 
+// 16-bit logits: the interpolated values are rounded to the logits' type anyway (as torch's tensors are), so two of them
+// travel as one packed word and the first-max update is two HSET2 masks and three bitwise selects per PAIR (see
+// targets_decode.cu): take the new channel when the running best is not NaN and NOT (value <= best).
+template <typename T> struct Pack2;
+template <> struct Pack2<__nv_bfloat16> {
+  static constexpr unsigned int NEG_INF = 0xff80ff80u;
+  static __device__ __forceinline__ unsigned int pack(float a, float b) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const unsigned int*>(&v);
+  }
+  static __device__ __forceinline__ unsigned int take(unsigned int v, unsigned int best) {
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&v), b = *reinterpret_cast<const __nv_bfloat162*>(&best);
+    return ~__hle2_mask(a, b) & __heq2_mask(b, b);
+  }
+};
+template <> struct Pack2<__half> {
+  static constexpr unsigned int NEG_INF = 0xfc00fc00u;
+  static __device__ __forceinline__ unsigned int pack(float a, float b) {
+    const __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const unsigned int*>(&v);
+  }
+  static __device__ __forceinline__ unsigned int take(unsigned int v, unsigned int best) {
+    const __half2 a = *reinterpret_cast<const __half2*>(&v), b = *reinterpret_cast<const __half2*>(&best);
+    return ~__hle2_mask(a, b) & __heq2_mask(b, b);
+  }
+};
+template <> struct Pack2<float> {
+  static constexpr unsigned int NEG_INF = 0u;
+  static __device__ __forceinline__ unsigned int pack(float, float) { return 0u; }
+  static __device__ __forceinline__ unsigned int take(unsigned int, unsigned int) { return 0u; }
+};
+
 template <typename T, typename OutT, typename L>
 __global__ void __launch_bounds__(256) k_decode_up4(const T* __restrict__ in, int B, int C, int h, int w, int n0, int n1,
                                                     int n2, OutT* __restrict__ o0, OutT* __restrict__ o1,
@@ -662,10 +694,14 @@ __global__ void __launch_bounds__(256) k_decode_up4(const T* __restrict__ in, in
     const int o_m = ym * w, o_c = Y * w, o_p = yp * w;
     float best[4][4];
     int arg[4][4];
+    unsigned int best2[4][2], arg2[4][2];      // 16-bit logits: packed pairs (k, k + 1)
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 4; ++j) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) { best[j][k] = -INFINITY; arg[j][k] = 0; }
+      best2[j][0] = best2[j][1] = Pack2<T>::NEG_INF;
+      arg2[j][0] = arg2[j][1] = 0u;
+    }
     int lvl = 0, cbeg = 0;
 #pragma unroll 1
     for (int c = 0; c < e2; ++c) {
@@ -680,16 +716,41 @@ __global__ void __launch_bounds__(256) k_decode_up4(const T* __restrict__ in, in
       for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int k = 0; k < 4; ++k) hl[a][k] = lerp2(v[a][k >> 1], v[a][(k >> 1) + 1], 1.0f - wx1[k], wx1[k]);
+      if (sizeof(T) == 2) {
+        const unsigned int cc = (unsigned int)(c - cbeg) * 0x00010001u;
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float val = round_as<T>(lerp2(hl[j >> 1][k], hl[(j >> 1) + 1][k], 1.0f - wy1[j], wy1[j]));
-          argmax_step(val, c - cbeg, best[j][k], arg[j][k]);
-        }
+          for (int kp = 0; kp < 2; ++kp) {
+            const unsigned int v2 = Pack2<T>::pack(lerp2(hl[j >> 1][2 * kp], hl[(j >> 1) + 1][2 * kp], 1.0f - wy1[j], wy1[j]),
+                                                   lerp2(hl[j >> 1][2 * kp + 1], hl[(j >> 1) + 1][2 * kp + 1], 1.0f - wy1[j], wy1[j]));
+            const unsigned int take = Pack2<T>::take(v2, best2[j][kp]);
+            best2[j][kp] = (best2[j][kp] & ~take) | (v2 & take);
+            arg2[j][kp] = (arg2[j][kp] & ~take) | (cc & take);
+          }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float val = round_as<T>(lerp2(hl[j >> 1][k], hl[(j >> 1) + 1][k], 1.0f - wy1[j], wy1[j]));
+            argmax_step(val, c - cbeg, best[j][k], arg[j][k]);
+          }
+      }
       const int lend = lvl == 0 ? e0 : (lvl == 1 ? e1 : e2);
       if (c + 1 == lend) {
         OutT* out = lvl == 0 ? o0 : (lvl == 1 ? o1 : o2);
+        if (sizeof(T) == 2) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int kp = 0; kp < 2; ++kp) {
+              arg[j][2 * kp] = (int)(arg2[j][kp] & 0xffffu);
+              arg[j][2 * kp + 1] = (int)(arg2[j][kp] >> 16);
+              best2[j][kp] = Pack2<T>::NEG_INF;
+              arg2[j][kp] = 0u;
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const long off = ((long)b * H + 4 * Y + j) * W + 4 * X;
